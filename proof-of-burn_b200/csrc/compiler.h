@@ -1,0 +1,26 @@
+// compiler.h -- layout compiler: circuit shape -> witness program (host C++, runs once per shape at create time).
+//
+// This is the B200-native counterpart of what `circom -c ... --O0` does for the reference (Makefile:2-3):
+// it fixes the witness numbering (SURVEY.md Appendix C rules R1-R4) and emits the program the GPU executes.
+// It never sees instance data and computes no witness values.
+#pragma once
+#include <string>
+#include <vector>
+#include "program.h"
+
+namespace pob {
+
+// main_name / params name the `component main = Name(params...)` expression, e.g. ("ProofOfBurn",
+// {16,4,16,50,31,2,10^19,10^20}) for circuits/main_proof_of_burn.circom:27 or ("Spend", {31}) for
+// circuits/main_spend.circom:6; every gadget the reference's suites instantiate (tests/test.py:146-201) is
+// accepted too.  hcreate selects creation-order numbering at the two sites where it differs from
+// completion order (Num2Bits_strict, MultiAND n>=3).  Throws std::runtime_error on unknown template/shape.
+Program compile_circuit(const std::string &main_name, const std::vector<Fr> &params, bool hcreate);
+
+// Input schema of a main template ("name[d0][d1],name2,...", dims are expressions over p0..p7) or nullptr.
+const char *main_input_schema(const std::string &main_name, int *nparams);
+
+// inverses of 0..INV_TABLE_N-1 (entry 0 = 0), computed with one inversion (Montgomery's trick)
+std::vector<Fr> build_inverse_table();
+
+}  // namespace pob

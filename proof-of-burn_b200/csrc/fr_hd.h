@@ -1,0 +1,156 @@
+// fr_hd.h -- BN254-Fr arithmetic for the B200 witness VM: 8 x 32-bit limbs, Montgomery (CIOS) multiply.
+//
+// Every signal of the proof-of-burn circuits is an element of this field (reference: the implicit field
+// ops under every `<==` -- circomlib/circuits/gates.circom:26,34,42, comparators.circom:30-33,
+// poseidon.circom:12-15; prime in tests/poseidon.py:1-3).  The reference's own implementation is the
+// fr.asm/fr.cpp the circom toolchain emits (not in the tree); this is an independent implementation.
+//
+// The functions are __host__ __device__ on purpose: the device build is the product; the host build is
+// used only by the compile-time constant folder of the layout compiler and by the test-only emulator
+// under tests/emu/ that lets the VM programs be checked against the oracle on a machine without a GPU.
+// Device code uses 32-bit limbs with 64-bit accumulators (IMAD.WIDE on sm_100a).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define POB_HD __host__ __device__ __forceinline__
+#else
+#define POB_HD inline
+#endif
+
+namespace pob {
+
+struct Fr { uint32_t l[8]; };   // canonical value in [0,p), little-endian limbs == 32-byte .wtns entry
+
+#define POB_P_LIMBS {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u}
+// R^2 mod p with R = 2^256 (Montgomery conversion factor)
+#define POB_R2_LIMBS {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u}
+#define POB_N0 0xefffffffu      // -p^-1 mod 2^32
+
+POB_HD uint32_t fr_p_limb(int i) {
+    constexpr uint32_t P[8] = POB_P_LIMBS;
+    return P[i];
+}
+POB_HD uint32_t fr_r2_limb(int i) {
+    constexpr uint32_t R2[8] = POB_R2_LIMBS;
+    return R2[i];
+}
+
+POB_HD Fr fr_zero() { Fr r; for (int i = 0; i < 8; i++) r.l[i] = 0; return r; }
+POB_HD Fr fr_from_u64(uint64_t v) { Fr r = fr_zero(); r.l[0] = (uint32_t)v; r.l[1] = (uint32_t)(v >> 32); return r; }
+POB_HD bool fr_is_zero(const Fr &a) { uint32_t o = 0; for (int i = 0; i < 8; i++) o |= a.l[i]; return o == 0; }
+POB_HD bool fr_eq(const Fr &a, const Fr &b) { uint32_t o = 0; for (int i = 0; i < 8; i++) o |= a.l[i] ^ b.l[i]; return o == 0; }
+POB_HD bool fr_fits64(const Fr &a) { uint32_t o = 0; for (int i = 2; i < 8; i++) o |= a.l[i]; return o == 0; }
+POB_HD uint64_t fr_lo64(const Fr &a) { return (uint64_t)a.l[0] | ((uint64_t)a.l[1] << 32); }
+// a >= p ?
+POB_HD bool fr_geq_p(const Fr &a) {
+    for (int i = 7; i >= 0; i--) { uint32_t p = fr_p_limb(i); if (a.l[i] > p) return true; if (a.l[i] < p) return false; }
+    return true;
+}
+POB_HD uint32_t fr_raw_add(Fr &r, const Fr &a, const Fr &b) {
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)a.l[i] + b.l[i]; r.l[i] = (uint32_t)c; c >>= 32; }
+    return (uint32_t)c;
+}
+POB_HD uint32_t fr_raw_sub(Fr &r, const Fr &a, const Fr &b) {
+    uint64_t br = 0;
+    for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)a.l[i] - b.l[i] - br; r.l[i] = (uint32_t)d; br = (d >> 32) & 1; }
+    return (uint32_t)br;
+}
+POB_HD Fr fr_p() { Fr r; for (int i = 0; i < 8; i++) r.l[i] = fr_p_limb(i); return r; }
+POB_HD Fr fr_add(const Fr &a, const Fr &b) {
+    Fr r; uint32_t c = fr_raw_add(r, a, b);
+    if (c || fr_geq_p(r)) { Fr t; fr_raw_sub(t, r, fr_p()); return t; }
+    return r;
+}
+POB_HD Fr fr_sub(const Fr &a, const Fr &b) {
+    Fr r; if (fr_raw_sub(r, a, b)) { Fr t; fr_raw_add(t, r, fr_p()); return t; }
+    return r;
+}
+POB_HD Fr fr_neg(const Fr &a) { if (fr_is_zero(a)) return a; Fr t; fr_raw_sub(t, fr_p(), a); return t; }
+
+// Montgomery product a*b*2^-256 mod p.  CIOS over 32-bit limbs; t never exceeds 2p so one conditional
+// subtraction suffices.
+POB_HD Fr fr_mont(const Fr &a, const Fr &b) {
+    uint32_t t[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { c += (uint64_t)a.l[j] * b.l[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
+        c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
+        uint32_t m = t[0] * POB_N0;
+        c = (uint64_t)m * fr_p_limb(0) + t[0]; c >>= 32;
+#pragma unroll
+        for (int j = 1; j < 8; j++) { c += (uint64_t)m * fr_p_limb(j) + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
+        c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32);
+    }
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = t[i];
+    if (t[8] || fr_geq_p(r)) { Fr s; fr_raw_sub(s, r, fr_p()); return s; }
+    return r;
+}
+POB_HD Fr fr_r2() { Fr r; for (int i = 0; i < 8; i++) r.l[i] = fr_r2_limb(i); return r; }
+POB_HD Fr fr_to_mont(const Fr &a) { return fr_mont(a, fr_r2()); }
+POB_HD Fr fr_from_mont(const Fr &a) { Fr one = fr_from_u64(1); return fr_mont(a, one); }
+// canonical * canonical -> canonical.  Small operands (the overwhelmingly common case: bits, bytes,
+// lengths) take a plain 64x64 product, which is < 2^128 < p and needs no reduction.
+POB_HD Fr fr_mul(const Fr &a, const Fr &b) {
+    if (fr_fits64(a) && fr_fits64(b)) {
+        uint64_t x = fr_lo64(a), y = fr_lo64(b);
+        uint64_t x0 = (uint32_t)x, x1 = x >> 32, y0 = (uint32_t)y, y1 = y >> 32;
+        uint64_t p00 = x0 * y0, p01 = x0 * y1, p10 = x1 * y0, p11 = x1 * y1;
+        uint64_t mid = (p00 >> 32) + (uint32_t)p01 + (uint32_t)p10;
+        uint64_t hi = p11 + (p01 >> 32) + (p10 >> 32) + (mid >> 32);
+        Fr r = fr_zero();
+        r.l[0] = (uint32_t)p00; r.l[1] = (uint32_t)mid; r.l[2] = (uint32_t)hi; r.l[3] = (uint32_t)(hi >> 32);
+        return r;
+    }
+    return fr_mont(fr_mont(a, b), fr_r2());
+}
+POB_HD int fr_bit(const Fr &a, unsigned i) { return (int)((a.l[i >> 5] >> (i & 31)) & 1u); }
+// a^-1 by Fermat (a != 0), Montgomery ladder over the fixed exponent p-2
+POB_HD Fr fr_inv(const Fr &a) {
+    Fr am = fr_to_mont(a);
+    Fr r = fr_to_mont(fr_from_u64(1));
+    Fr e; { Fr two = fr_from_u64(2); fr_raw_sub(e, fr_p(), two); }
+    for (int i = 253; i >= 0; i--) {
+        r = fr_mont(r, r);
+        if (fr_bit(e, (unsigned)i)) r = fr_mont(r, am);
+    }
+    return fr_from_mont(r);
+}
+// value < 2^n ?  (n <= 256)
+POB_HD bool fr_lt_pow2(const Fr &a, unsigned n) {
+    uint32_t bad = 0;
+#pragma unroll
+    for (unsigned i = 0; i < 8; i++) {
+        unsigned lo = 32 * i;
+        if (lo >= n) bad |= a.l[i];
+        else if (lo + 32 > n) bad |= a.l[i] >> (n - lo);
+    }
+    return bad == 0;
+}
+// integer quotient / remainder of canonical representatives by a divisor that fits 32 bits (the circuits
+// only divide by compile-time constants 136, 4 and 2: utils/keccak.circom:420, rlp/...leaf.circom:60)
+POB_HD void fr_divmod_u32(const Fr &a, uint32_t d, Fr &q, Fr &r) {
+    uint64_t rem = 0; q = fr_zero();
+    for (int i = 7; i >= 0; i--) { uint64_t cur = (rem << 32) | a.l[i]; q.l[i] = (uint32_t)(cur / d); rem = cur % d; }
+    r = fr_from_u64(rem);
+}
+// general 256/256 schoolbook (shift-subtract); rare path (divisor is a signal, e.g. the Divide(16) gadget suite)
+POB_HD void fr_divmod(const Fr &a, const Fr &b, Fr &q, Fr &r) {
+    if (fr_fits64(b) && (fr_lo64(b) >> 32) == 0) { fr_divmod_u32(a, b.l[0], q, r); return; }
+    q = fr_zero(); r = fr_zero();
+    for (int i = 255; i >= 0; i--) {
+        uint32_t c = 0;
+        for (int k = 0; k < 8; k++) { uint32_t n = (r.l[k] << 1) | c; c = r.l[k] >> 31; r.l[k] = n; }
+        r.l[0] |= (uint32_t)fr_bit(a, (unsigned)i);
+        Fr t; if (!fr_raw_sub(t, r, b)) { r = t; q.l[i >> 5] |= 1u << (i & 31); }
+    }
+}
+
+}  // namespace pob

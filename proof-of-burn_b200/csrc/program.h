@@ -1,0 +1,108 @@
+// program.h -- the compiled witness program: what the layout compiler (compiler.cpp, host, once per
+// circuit shape) hands to the GPU kernels (kernels.cu, once per proof instance).
+//
+// Design ("evaluate small, materialise big").  A circom --O0 witness for main_proof_of_burn is 215.9 M field
+// elements (6.9 GB) but only ~0.6 M of them are distinct computed values; the rest are copies, constants and
+// single bits of 64-bit Keccak lane words.  So one instance is processed in two stages:
+//   1. EVAL  -- a levelised straight-line program over a compact per-instance STORE (u64 words):
+//        lane-word region  W[0 .. n_words)          Keccak lanes, packed input blocks
+//        value region      V[slot] = 4 x u64         canonical BN254-Fr values (inputs first)
+//      thread ops (FMA over Fr, IsZero, inverse, integer div/mod, byte packing, constraint checks) and
+//      warp ops (one Keccak absorb = block XOR + 24 rounds, emitting every intermediate lane word).
+//   2. EXPAND -- every witness entry is described by one 32-bit operand CODE (constant, bit of a store word,
+//      store value, table constant); the expand kernel turns codes into 32-byte little-endian field
+//      elements and streams them to HBM.  All 2016 KeccakfRound blocks (102,656 signals each, 95.8 % of the
+//      witness) share ONE code table, addressed relative to the round's word base.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "fr_hd.h"
+
+namespace pob {
+
+// ---- operand / witness codes --------------------------------------------------------------------------------
+typedef uint32_t Code;
+enum : uint32_t { K_CONST = 0, K_BIT = 1, K_VAL = 2, K_KONST = 3 };
+POB_HD uint32_t code_kind(Code c) { return c >> 30; }
+POB_HD uint32_t code_payload(Code c) { return c & 0x3fffffffu; }
+POB_HD Code c_const(uint32_t v) { return v; }                                    // v < 2^30
+POB_HD Code c_bit(uint32_t u64idx, uint32_t bit) { return (1u << 30) | (u64idx << 6) | bit; }   // u64idx < 2^24
+POB_HD Code c_val(uint32_t slot) { return (2u << 30) | slot; }
+POB_HD Code c_konst(uint32_t idx) { return (3u << 30) | idx; }
+static const uint32_t MAX_STORE_U64 = 1u << 24;                                  // 128 MiB per instance store
+
+// ---- thread ops ---------------------------------------------------------------------------------------------
+enum Opc : uint32_t {
+    OP_FMA = 1,        // V[dst] = a*b + c
+    OP_ISZ = 2,        // V[dst] = (a == 0)                       comparators.circom:24-35 (out)
+    OP_INV = 3,        // V[dst] = a != 0 ? 1/a : 0               comparators.circom:30 (hint)
+    OP_DIV = 4,        // V[dst] = a \ b   (integer)              utils/divide.circom:23 ; c = raw component base
+    OP_MOD = 5,        // V[dst] = a % b   (integer)              utils/divide.circom:24
+    OP_PACK8 = 6,      // W[dst] = sum_k (aux[a+k] & 0xff) << 8k  utils/keccak.circom:467-482 (bytes -> lane)
+    OP_CHK_EQ = 7,     // a == b else fail(c)                     any `===`
+    OP_CHK_RANGE = 8,  // a < 2^b else fail(c)                    bitify.circom:38 (Num2Bits sum check)
+};
+struct Op { uint32_t opc_dst; Code a, b, c; };                    // opc in the top 6 bits, dst in the low 26
+POB_HD uint32_t op_opc(const Op &o) { return o.opc_dst >> 26; }
+POB_HD uint32_t op_dst(const Op &o) { return o.opc_dst & 0x3ffffffu; }
+
+// ---- warp op: one Absorb (utils/keccak.circom:304-323) = 17-lane XOR + Keccakf (24 KeccakfRound) -------------
+// Word layout written at W[out .. out + ABSORB_WORDS):
+//   out + 0..24                       aux[25]  (= s ^ block on the 17 rate lanes)
+//   round r base  rb = out + RW*r     rb+0..24 is the round INPUT (aux, or the previous round's OUT)
+//     rb + X5(i,k)  i<5,k<4   Xor5 chain of column i: xor_ab, xor_abc, xor_abcd, c[i]       keccak.circom:58-70
+//     rb + DD(i,k)  i<5,k<4   D: c<<1, c>>63, or, d[i]                                        :135-144
+//     rb + TH(l)    l<25      Theta out                                                       :151-170
+//     rb + RP(i,k)  i<24,k<3  stepRhoPi i: a>>shr, a<<shl, or                                 :177-204
+//     rb + CH(l,k)  l<25,k<3  stepChi of lane l: ~b, ~b&c, a^(~b&c)                           :212-241
+//     rb + RCW                round-constant word                                             :248-266
+//     rb + OUT(l)   l<25      Iota out = round output                                         :273-283
+static const uint32_t NONE_IDX = 0xffffffffu;
+struct AbsorbOp { uint32_t s_idx, blk_idx, out_idx, pad; };       // s_idx == NONE_IDX: all-zero state
+enum : uint32_t { RW = 238, RW_X5 = 25, RW_DD = 45, RW_TH = 65, RW_RP = 90, RW_CH = 162, RW_RC = 237, RW_OUT = 238,
+                  ROUND_WORDS_SPAN = 263, ABSORB_WORDS = 25 + 24 * 238, ROUND_SIGNALS = 102656 };
+POB_HD uint32_t rw_x5(int i, int k) { return RW_X5 + 4 * i + k; }
+POB_HD uint32_t rw_dd(int i, int k) { return RW_DD + 4 * i + k; }
+POB_HD uint32_t rw_th(int l) { return RW_TH + l; }
+POB_HD uint32_t rw_rp(int i, int k) { return RW_RP + 3 * i + k; }
+POB_HD uint32_t rw_ch(int l, int k) { return RW_CH + 3 * l + k; }
+POB_HD uint32_t rw_out(int l) { return RW_OUT + l; }
+
+struct Level { uint32_t t_begin, t_end, w_begin, w_end; };
+
+// ---- expand tiles: a contiguous run of witness entries and where its codes live -------------------------------
+struct Tile { uint64_t dst; uint32_t n, code_off, ubase, pad; };  // BIT codes are relative to ubase
+static const uint32_t TILE_SIGNALS = 8192;
+
+// ---- circuit identity ---------------------------------------------------------------------------------------
+enum CircuitKind : int32_t { CIRCUIT_SPEND = 0, CIRCUIT_PROOF_OF_BURN = 1, CIRCUIT_GADGET = 2 };
+
+struct Program {
+    // identity
+    std::string main_name;
+    std::vector<Fr> params;
+    bool hcreate = false;
+    // witness shape
+    uint64_t n_signals = 0;        // including witness[0] = 1
+    uint32_t n_outputs = 0, n_inputs = 0;
+    std::string input_schema;      // "name[d0][d1],name2,..." in declaration order
+    // store shape
+    uint32_t n_words = 0;          // lane-word region size (u64)
+    uint32_t val_base = 0;         // u64 index of V[0] (multiple of 4)
+    uint32_t n_vals = 0;           // value slots (inputs are slots 0..n_inputs-1)
+    uint64_t store_u64() const { return (uint64_t)val_base + 4ull * n_vals; }
+    // eval program
+    std::vector<Op> ops;           // sorted by level
+    std::vector<AbsorbOp> absorbs; // sorted by level
+    std::vector<Level> levels;
+    std::vector<Code> aux;         // PACK8 operand lists
+    std::vector<Fr> konst;         // big constants
+    // expand program
+    std::vector<Code> codes;       // [0, ROUND_SIGNALS) = shared KeccakfRound table, then flat codes
+    std::vector<Tile> tiles;
+    // statistics
+    uint64_t n_round_blocks = 0, n_flat_signals = 0;
+};
+
+}  // namespace pob

@@ -1,0 +1,150 @@
+// vm_exec.h -- semantics of one witness-VM thread op and of operand/witness code decoding.
+//
+// __host__ __device__: the device instantiation is what kernels.cu runs (the product); the host
+// instantiation exists only for tests/emu/ (a test-only emulator that checks compiled programs against the
+// oracle on a box without a GPU).  Nothing in the shipped library executes these on the host.
+#pragma once
+#include "program.h"
+
+namespace pob {
+
+static const uint32_t INV_TABLE_N = 1u << 16;     // inverses of 1 .. 65535 (most IsZero inputs are small differences)
+static const uint32_t STATUS_OK = 0xffffffffu;
+
+struct VmCtx {
+    uint64_t *U;            // instance store
+    uint32_t val_base;
+    const Fr *konst;
+    const Code *aux;
+    const Fr *invtab;
+    uint32_t *status;       // min over failing constraints of (component base + 1); STATUS_OK if none
+};
+
+POB_HD Fr vm_load_val(const uint64_t *p) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { uint64_t v = p[i]; r.l[2 * i] = (uint32_t)v; r.l[2 * i + 1] = (uint32_t)(v >> 32); }
+    return r;
+}
+POB_HD void vm_store_val(uint64_t *p, const Fr &v) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) p[i] = (uint64_t)v.l[2 * i] | ((uint64_t)v.l[2 * i + 1] << 32);
+}
+POB_HD Fr vm_load(const VmCtx &x, Code c) {
+    uint32_t k = code_kind(c), p = code_payload(c);
+    if (k == K_CONST) return fr_from_u64(p);
+    if (k == K_BIT) return fr_from_u64((x.U[p >> 6] >> (p & 63)) & 1ull);
+    if (k == K_VAL) return vm_load_val(x.U + x.val_base + 4ull * p);
+    return x.konst[p];
+}
+POB_HD void vm_fail(const VmCtx &x, uint32_t base) {
+#if defined(__CUDA_ARCH__)
+    atomicMin(x.status, base + 1u);
+#else
+    if (base + 1u < *x.status) *x.status = base + 1u;
+#endif
+}
+POB_HD Fr vm_inverse(const VmCtx &x, const Fr &a) {
+    if (fr_is_zero(a)) return a;
+    if (fr_fits64(a) && fr_lo64(a) < INV_TABLE_N) return x.invtab[fr_lo64(a)];
+    Fr n; fr_raw_sub(n, fr_p(), a);
+    if (fr_fits64(n) && fr_lo64(n) < INV_TABLE_N) return fr_neg(x.invtab[fr_lo64(n)]);
+    return fr_inv(a);
+}
+
+POB_HD void vm_exec_op(const VmCtx &x, const Op &op) {
+    uint32_t opc = op_opc(op), dst = op_dst(op);
+    uint64_t *vd = x.U + x.val_base + 4ull * dst;
+    switch (opc) {
+    case OP_FMA: {
+        Fr a = vm_load(x, op.a), b = vm_load(x, op.b), c = vm_load(x, op.c);
+        vm_store_val(vd, fr_add(fr_mul(a, b), c));
+        break; }
+    case OP_ISZ: { Fr a = vm_load(x, op.a); vm_store_val(vd, fr_from_u64(fr_is_zero(a) ? 1 : 0)); break; }
+    case OP_INV: { Fr a = vm_load(x, op.a); vm_store_val(vd, vm_inverse(x, a)); break; }
+    case OP_DIV:
+    case OP_MOD: {
+        Fr a = vm_load(x, op.a), b = vm_load(x, op.b), q = fr_zero(), r = fr_zero();
+        if (fr_is_zero(b)) vm_fail(x, op.c); else fr_divmod(a, b, q, r);
+        vm_store_val(vd, opc == OP_DIV ? q : r);
+        break; }
+    case OP_PACK8: {
+        uint64_t w = 0;
+        for (int k = 0; k < 8; k++) { Fr v = vm_load(x, x.aux[op.a + k]); w |= (uint64_t)(v.l[0] & 0xffu) << (8 * k); }
+        x.U[dst] = w;
+        break; }
+    case OP_CHK_EQ: { Fr a = vm_load(x, op.a), b = vm_load(x, op.b); if (!fr_eq(a, b)) vm_fail(x, op.c); break; }
+    case OP_CHK_RANGE: { Fr a = vm_load(x, op.a); if (!fr_lt_pow2(a, op.b)) vm_fail(x, op.c); break; }
+    default: break;
+    }
+}
+
+// Keccak-f round constants and rotation tables (utils/keccak.circom:195, 200, 253-262)
+POB_HD uint64_t keccak_rc(int r) {
+    constexpr uint64_t RC[24] = {
+        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL, 0x000000000000808BULL,
+        0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008AULL, 0x0000000000000088ULL,
+        0x0000000080008009ULL, 0x000000008000000AULL, 0x000000008000808BULL, 0x800000000000008BULL, 0x8000000000008089ULL,
+        0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800AULL, 0x800000008000000AULL,
+        0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    return RC[r];
+}
+POB_HD int keccak_rot(int i) {      // RhoPi lane walk, keccak.circom:195
+    constexpr int ROT[25] = {1, 10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+    return ROT[i];
+}
+POB_HD int keccak_shl(int i) { return ((i + 1) * (i + 2) / 2) % 64; }   // keccak.circom:200
+// (b, c) operand lanes of stepChi for output lane l, keccak.circom:233-239
+POB_HD int chi_b(int l) { return (l % 5 == 4) ? l - 4 : l + 1; }
+POB_HD int chi_c(int l) { return (l % 5 >= 3) ? l - 3 : l + 2; }
+
+// Scalar reference of the absorb warp op (HOST ONLY users: tests/emu).  The device implementation is the
+// warp-cooperative absorb_warp() in kernels.cu; both must write the word layout documented in program.h.
+inline void vm_absorb_scalar(uint64_t *W, const AbsorbOp &op) {
+    uint64_t st[25];
+    for (int l = 0; l < 25; l++) {
+        uint64_t s = op.s_idx == NONE_IDX ? 0 : W[op.s_idx + l];
+        st[l] = l < 17 ? (s ^ W[op.blk_idx + l]) : s;
+        W[op.out_idx + l] = st[l];
+    }
+    for (int r = 0; r < 24; r++) {
+        uint64_t *B = W + op.out_idx + RW * r;
+        uint64_t c[5], d[5], th[25], rp[25], ch[25];
+        for (int i = 0; i < 5; i++) {
+            uint64_t v = st[i] ^ st[5 + i]; B[rw_x5(i, 0)] = v;
+            v ^= st[10 + i]; B[rw_x5(i, 1)] = v;
+            v ^= st[15 + i]; B[rw_x5(i, 2)] = v;
+            v ^= st[20 + i]; B[rw_x5(i, 3)] = v; c[i] = v;
+        }
+        for (int i = 0; i < 5; i++) {
+            uint64_t a = c[(i + 1) % 5], b = c[(i + 4) % 5], s0 = a << 1, s1 = a >> 63, o = s0 | s1;
+            d[i] = b ^ o;
+            B[rw_dd(i, 0)] = s0; B[rw_dd(i, 1)] = s1; B[rw_dd(i, 2)] = o; B[rw_dd(i, 3)] = d[i];
+        }
+        for (int l = 0; l < 25; l++) { th[l] = st[l] ^ d[l % 5]; B[rw_th(l)] = th[l]; }
+        rp[0] = th[0];
+        for (int i = 0; i < 24; i++) {
+            int shl = keccak_shl(i); uint64_t a = th[keccak_rot(i)], a0 = a >> (64 - shl), a1 = a << shl, o = a0 | a1;
+            B[rw_rp(i, 0)] = a0; B[rw_rp(i, 1)] = a1; B[rw_rp(i, 2)] = o; rp[keccak_rot(i + 1)] = o;
+        }
+        for (int l = 0; l < 25; l++) {
+            uint64_t nb = ~rp[chi_b(l)], bc = nb & rp[chi_c(l)]; ch[l] = rp[l] ^ bc;
+            B[rw_ch(l, 0)] = nb; B[rw_ch(l, 1)] = bc; B[rw_ch(l, 2)] = ch[l];
+        }
+        B[RW_RC] = keccak_rc(r);
+        ch[0] ^= keccak_rc(r);
+        for (int l = 0; l < 25; l++) { B[rw_out(l)] = ch[l]; st[l] = ch[l]; }
+    }
+}
+
+// ---- expand: one witness code -> 32-byte little-endian field element (4 x u64) --------------------------------
+POB_HD void vm_expand(Code c, const uint64_t *U, uint32_t ubase, uint32_t val_base, const Fr *konst, uint64_t out[4]) {
+    uint32_t k = code_kind(c), p = code_payload(c);
+    out[1] = out[2] = out[3] = 0;
+    if (k == K_BIT) { out[0] = (U[ubase + (p >> 6)] >> (p & 63)) & 1ull; }
+    else if (k == K_CONST) { out[0] = p; }
+    else if (k == K_VAL) { const uint64_t *s = U + val_base + 4ull * p; out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; out[3] = s[3]; }
+    else { const uint32_t *l = konst[p].l; for (int i = 0; i < 4; i++) out[i] = (uint64_t)l[2 * i] | ((uint64_t)l[2 * i + 1] << 32); }
+}
+
+}  // namespace pob

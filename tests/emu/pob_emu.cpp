@@ -1,0 +1,64 @@
+// tests/emu/pob_emu.cpp -- TEST-ONLY host emulator of the witness VM.
+//
+// Runs a compiled Program (the product's layout compiler output) with the host instantiation of
+// vm_exec.h so that program correctness can be checked against the oracle on a machine without a GPU.
+// It is NOT part of the product: libpob_b200.so never contains or calls this file, and on a GPU box the
+// parity tests go through the CUDA kernels via the C-ABI.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "compiler.h"
+#include "vm_exec.h"
+
+using namespace pob;
+
+struct EmuProgram { Program P; std::vector<Fr> invtab; std::string err; };
+
+extern "C" {
+
+void *pob_emu_compile(const char *main_name, const uint64_t *params, int nparams, int hcreate, char *err, int errlen) {
+    try {
+        std::vector<Fr> ps((size_t)nparams);
+        for (int i = 0; i < nparams; i++) memcpy(ps[(size_t)i].l, params + 4 * i, 32);
+        EmuProgram *e = new EmuProgram();
+        e->P = compile_circuit(main_name, ps, hcreate != 0);
+        e->invtab = build_inverse_table();
+        return e;
+    } catch (const std::exception &ex) { if (err) snprintf(err, (size_t)errlen, "%s", ex.what()); return nullptr; }
+}
+void pob_emu_free(void *h) { delete (EmuProgram *)h; }
+
+// stats: n_signals, n_outputs, n_inputs, n_words, n_vals, n_ops, n_absorbs, n_levels, n_tiles, n_codes, n_konst, n_round_blocks
+void pob_emu_stats(void *h, uint64_t *out) {
+    const Program &P = ((EmuProgram *)h)->P;
+    out[0] = P.n_signals; out[1] = P.n_outputs; out[2] = P.n_inputs; out[3] = P.n_words; out[4] = P.n_vals;
+    out[5] = P.ops.size(); out[6] = P.absorbs.size(); out[7] = P.levels.size(); out[8] = P.tiles.size();
+    out[9] = P.codes.size(); out[10] = P.konst.size(); out[11] = P.n_round_blocks;
+}
+const char *pob_emu_schema(void *h) { return ((EmuProgram *)h)->P.input_schema.c_str(); }
+
+// inputs: n_inputs x 4 u64; witness: n_signals x 4 u64 (caller allocated) or NULL to skip expansion;
+// outputs: n_outputs x 4 u64.  Returns status (0 = accepted, else 1 + failing component base).
+uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_t *outputs) {
+    EmuProgram *e = (EmuProgram *)h; const Program &P = e->P;
+    std::vector<uint64_t> U(P.store_u64() + 4, 0);
+    memcpy(U.data() + P.val_base, inputs, (size_t)P.n_inputs * 32);
+    uint32_t status = STATUS_OK;
+    VmCtx x{U.data(), P.val_base, P.konst.data(), P.aux.data(), e->invtab.data(), &status};
+    for (const Level &lv : P.levels) {
+        for (uint32_t i = lv.t_begin; i < lv.t_end; i++) vm_exec_op(x, P.ops[i]);
+        for (uint32_t i = lv.w_begin; i < lv.w_end; i++) vm_absorb_scalar(U.data(), P.absorbs[i]);
+    }
+    if (witness)
+        for (const Tile &t : P.tiles)
+            for (uint32_t k = 0; k < t.n; k++)
+                vm_expand(P.codes[t.code_off + k], U.data(), t.ubase, P.val_base, P.konst.data(), witness + 4 * (t.dst + k));
+    if (outputs)
+        for (uint32_t i = 0; i < P.n_outputs; i++)
+            vm_expand(P.codes[ROUND_SIGNALS + 1 + i], U.data(), 0, P.val_base, P.konst.data(), outputs + 4 * i);
+    return status == STATUS_OK ? 0 : status;
+}
+}
