@@ -1,0 +1,452 @@
+// pob_b200.cu -- CUDA kernels (sm_100a) and the C-ABI of the batched witness generator (include/pob_b200.h).
+//
+// Kernels
+//   k_eval    one CTA per proof instance: runs the levelised witness program over the instance store.
+//             Thread ops: BN254-Fr FMA / IsZero / inverse / div-mod / byte packing / constraint checks
+//             (vm_exec.h).  Warp ops: one Keccak absorb per warp, state lane l held by thread l, Theta
+//             column parities / D, RhoPi lane walk and Chi neighbours exchanged with warp shuffles; every
+//             intermediate lane word the bit-level circuit exposes (utils/keccak.circom:58-297) is written
+//             to the store (238 words per round).
+//   k_expand  the HBM-bound kernel: turns 32-bit witness codes into 32-byte little-endian field elements and
+//             streams them with 256-bit stores (STG.E.ENL2.256).  Algorithmic bytes = 32 * n_signals per
+//             instance (6.909 GB for main_proof_of_burn); reads are ~4 B of L2-resident code per entry.
+//   k_digest  optional 64-bit digest of a materialised witness (parity tests at full size).
+// There is no host execution path for any of this: without a device pob_create fails.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/pob_b200.h"
+#include "compiler.h"
+#include "vm_exec.h"
+
+using namespace pob;
+
+// =============================================================================================================
+// device code
+// =============================================================================================================
+namespace {
+
+__device__ __forceinline__ int inv_rot(int L) {      // i such that rot[i + 1] == L  (L = 1..24)
+    constexpr int INV[25] = {0, 23, 17, 5, 11, 6, 22, 1, 8, 21, 0, 2, 16, 15, 19, 12, 7, 3, 4, 14, 18, 9, 20, 13, 10};
+    return INV[L];
+}
+
+// One Absorb (utils/keccak.circom:304-323) by one warp; lane l < 25 owns state lane l.
+__device__ void absorb_warp(uint64_t *W, const AbsorbOp op) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool act = lane < 25;
+    const int l = act ? lane : 0;
+    uint64_t st = (act && op.s_idx != NONE_IDX) ? W[op.s_idx + l] : 0ull;
+    if (lane < 17) st ^= W[op.blk_idx + lane];
+    if (act) W[op.out_idx + l] = st;
+    const int col = l % 5;
+#pragma unroll 1
+    for (int r = 0; r < 24; r++) {
+        uint64_t *B = W + op.out_idx + RW * r;
+        // Theta: Xor5 chain of my column (all lanes of a column compute it redundantly; lanes 0..4 store it)
+        uint64_t v0 = __shfl_sync(FULL, st, col), v1 = __shfl_sync(FULL, st, col + 5), v2 = __shfl_sync(FULL, st, col + 10),
+                 v3 = __shfl_sync(FULL, st, col + 15), v4 = __shfl_sync(FULL, st, col + 20);
+        uint64_t x0 = v0 ^ v1, x1 = x0 ^ v2, x2 = x1 ^ v3, c = x2 ^ v4;
+        if (lane < 5) { B[rw_x5(lane, 0)] = x0; B[rw_x5(lane, 1)] = x1; B[rw_x5(lane, 2)] = x2; B[rw_x5(lane, 3)] = c; }
+        // D(i) = c[(i+4)%5] ^ rotl(c[(i+1)%5], 1)
+        uint64_t ca = __shfl_sync(FULL, c, (col + 1) % 5), cb = __shfl_sync(FULL, c, (col + 4) % 5);
+        uint64_t s0 = ca << 1, s1 = ca >> 63, so = s0 | s1, d = cb ^ so;
+        if (lane < 5) { B[rw_dd(lane, 0)] = s0; B[rw_dd(lane, 1)] = s1; B[rw_dd(lane, 2)] = so; B[rw_dd(lane, 3)] = d; }
+        uint64_t th = st ^ d;
+        if (act) B[rw_th(l)] = th;
+        // RhoPi: lane i < 24 performs step i on theta[rot[i]], the result belongs to lane rot[i+1]
+        const int i = lane < 24 ? lane : 0;
+        uint64_t a = __shfl_sync(FULL, th, keccak_rot(i));
+        const int shl = keccak_shl(i);
+        uint64_t a0 = a >> (64 - shl), a1 = a << shl, ro = a0 | a1;
+        if (lane < 24) { B[rw_rp(lane, 0)] = a0; B[rw_rp(lane, 1)] = a1; B[rw_rp(lane, 2)] = ro; }
+        uint64_t rp = __shfl_sync(FULL, ro, inv_rot(l));
+        if (lane == 0) rp = th;
+        // Chi
+        uint64_t vb = __shfl_sync(FULL, rp, chi_b(l)), vc = __shfl_sync(FULL, rp, chi_c(l));
+        uint64_t nb = ~vb, bc = nb & vc, ch = rp ^ bc;
+        if (act) { B[rw_ch(l, 0)] = nb; B[rw_ch(l, 1)] = bc; B[rw_ch(l, 2)] = ch; }
+        // Iota
+        const uint64_t rc = keccak_rc(r);
+        if (lane == 0) { B[RW_RC] = rc; ch ^= rc; }
+        if (act) B[rw_out(l)] = ch;
+        st = ch;
+    }
+}
+
+struct EvalArgs {
+    const Op *ops; const AbsorbOp *absorbs; const Level *levels; uint32_t n_levels;
+    const Code *aux; const Fr *konst; const Fr *invtab;
+    const Code *out_codes; uint32_t n_outputs, n_inputs, val_base;
+    uint64_t *stores; uint64_t store_stride;     // u64 units
+    const uint64_t *inputs;                       // chunk base: instance j at inputs + j * n_inputs * 4
+    uint32_t *status; uint64_t *outputs;          // chunk base
+};
+
+__global__ void __launch_bounds__(256) k_eval(const EvalArgs a) {
+    const uint32_t inst = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    uint64_t *U = a.stores + (uint64_t)inst * a.store_stride;
+    __shared__ uint32_t s_status;
+    if (tid == 0) s_status = STATUS_OK;
+    const uint64_t *in = a.inputs + (uint64_t)inst * a.n_inputs * 4;
+    for (uint32_t i = tid; i < a.n_inputs * 4; i += nthr) U[a.val_base + i] = in[i];
+    __syncthreads();
+    VmCtx x{U, a.val_base, a.konst, a.aux, a.invtab, &s_status};
+    const uint32_t warp = tid >> 5, nwarp = nthr >> 5;
+    for (uint32_t lv = 0; lv < a.n_levels; lv++) {
+        const Level L = a.levels[lv];
+        for (uint32_t i = L.t_begin + tid; i < L.t_end; i += nthr) vm_exec_op(x, a.ops[i]);
+        for (uint32_t w = L.w_begin + warp; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]);
+        __syncthreads();
+    }
+    if (tid == 0) a.status[inst] = (s_status == STATUS_OK) ? 0u : s_status;
+    for (uint32_t i = tid; i < a.n_outputs; i += nthr) {
+        uint64_t v[4]; vm_expand(a.out_codes[i], U, 0, a.val_base, a.konst, v);
+        uint64_t *o = a.outputs + ((uint64_t)inst * a.n_outputs + i) * 4;
+        o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3];
+    }
+}
+
+__device__ __forceinline__ void st256(uint64_t *p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+struct ExpandArgs {
+    const Tile *tiles; const Code *codes; const Fr *konst;
+    const uint64_t *stores; uint64_t store_stride; uint32_t val_base;
+    uint64_t *const *wit;                         // per instance of the chunk: witness slot base
+};
+
+// grid = (n_tiles, instances in chunk); one CTA streams one tile (<= 8192 entries = 256 KiB) of one witness
+__global__ void __launch_bounds__(256) k_expand(const ExpandArgs a) {
+    const Tile t = a.tiles[blockIdx.x];
+    const uint64_t *U = a.stores + (uint64_t)blockIdx.y * a.store_stride;
+    uint64_t *W = a.wit[blockIdx.y] + t.dst * 4;
+    const Code *c = a.codes + t.code_off;
+    const uint64_t *Ub = U + t.ubase;
+#pragma unroll 4
+    for (uint32_t k = threadIdx.x; k < t.n; k += 256) {
+        const Code cd = __ldg(c + k);
+        const uint32_t kind = code_kind(cd), p = code_payload(cd);
+        uint64_t v0, v1 = 0, v2 = 0, v3 = 0;
+        if (kind == K_BIT) v0 = (Ub[p >> 6] >> (p & 63)) & 1ull;
+        else if (kind == K_CONST) v0 = p;
+        else if (kind == K_VAL) { const uint64_t *s = U + a.val_base + 4ull * p; v0 = s[0]; v1 = s[1]; v2 = s[2]; v3 = s[3]; }
+        else { const uint64_t *s = reinterpret_cast<const uint64_t *>(a.konst + p); v0 = s[0]; v1 = s[1]; v2 = s[2]; v3 = s[3]; }
+        st256(W + 4ull * k, v0, v1, v2, v3);
+    }
+}
+
+// digest = sum_i mix(i, limbs) mod 2^64 -- must equal oracle/pob_oracle.c:pob_oracle_digest
+__global__ void __launch_bounds__(256) k_digest(const uint64_t *wit, uint64_t n_signals, unsigned long long *out) {
+    uint64_t acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_signals; i += (uint64_t)gridDim.x * blockDim.x) {
+        const ulonglong4 v = *reinterpret_cast<const ulonglong4 *>(wit + 4 * i);
+        uint64_t h = (i + 1) * 0x9E3779B97F4A7C15ULL;
+        h ^= v.x * 0xBF58476D1CE4E5B9ULL + v.y * 0x94D049BB133111EBULL + v.z * 0xD6E8FEB86659FD93ULL + v.w * 0xA0761D6478BD642FULL;
+        h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 32;
+        acc += h;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    __shared__ uint64_t part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint64_t s = 0; for (int w = 0; w < 8; w++) s += part[w]; atomicAdd(out, (unsigned long long)s); }
+}
+
+}  // namespace
+
+// =============================================================================================================
+// host side of the C-ABI
+// =============================================================================================================
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct pob_handle {
+    Program P; int device = 0;
+    // device program
+    Op *d_ops = nullptr; AbsorbOp *d_abs = nullptr; Level *d_levels = nullptr; Code *d_aux = nullptr; Fr *d_konst = nullptr;
+    Code *d_codes = nullptr; Tile *d_tiles = nullptr; Fr *d_invtab = nullptr;
+    // stores (ring of RING chunks)
+    static const uint32_t RING = 2;
+    uint32_t chunk = 0; uint64_t store_stride = 0; uint64_t *d_stores = nullptr; uint64_t *d_inputs = nullptr;
+    // witness slots
+    std::vector<uint64_t *> slots;
+    // per-batch buffers
+    uint32_t cap_n = 0; uint32_t *d_status = nullptr; uint64_t *d_outputs = nullptr; unsigned long long *d_digests = nullptr;
+    uint64_t **d_witptr = nullptr; uint32_t *h_status = nullptr; uint64_t *h_outputs = nullptr; uint64_t *h_digests = nullptr;
+    uint64_t **h_witptr = nullptr;
+    uint64_t *d_staged = nullptr; uint32_t n_staged = 0;
+    cudaStream_t s_eval = nullptr, s_exp = nullptr;
+    cudaEvent_t ev_eval_done[RING] = {nullptr, nullptr}, ev_exp_done[RING] = {nullptr, nullptr}, ev_start = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
+    uint32_t last_n = 0; bool last_expanded = false;
+    pob_timing timing{};
+};
+
+static void fill_desc(const Program &P, pob_desc *d) {
+    memset(d, 0, sizeof *d);
+    d->n_signals = P.n_signals; d->n_outputs = P.n_outputs; d->n_inputs = P.n_inputs;
+    d->witness_bytes = 32ull * P.n_signals; d->wtns_file_bytes = 76ull + 32ull * P.n_signals;
+    d->store_bytes = 8ull * P.store_u64(); d->n_ops = P.ops.size(); d->n_absorbs = (uint32_t)P.absorbs.size();
+    d->n_levels = (uint32_t)P.levels.size(); d->n_tiles = (uint32_t)P.tiles.size();
+}
+static std::vector<Fr> params_vec(const uint64_t *params, int nparams) {
+    std::vector<Fr> ps((size_t)(nparams > 0 ? nparams : 0));
+    for (int i = 0; i < nparams; i++) memcpy(ps[(size_t)i].l, params + 4 * i, 32);
+    return ps;
+}
+template <class T> static T *upload(const std::vector<T> &v) {
+    T *d = nullptr; size_t bytes = std::max<size_t>(1, v.size()) * sizeof(T);
+    CU(cudaMalloc(&d, bytes));
+    if (!v.empty()) CU(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+extern "C" {
+
+const char *pob_last_error(void) { return g_err.c_str(); }
+const char *pob_version(void) { return "pob_b200 0.1 (sm_100a)"; }
+
+const char *pob_input_schema(const char *main_name, int *nparams) {
+    if (!main_name) return nullptr;
+    return main_input_schema(main_name, nparams);
+}
+
+int pob_layout_info(const char *main_name, const uint64_t *params, int nparams, int hcreate, pob_desc *out) {
+    if (!main_name || !out || (nparams > 0 && !params)) return fail(POB_E_BAD_ARG, "pob_layout_info: null argument");
+    try { Program P = compile_circuit(main_name, params_vec(params, nparams), hcreate != 0); fill_desc(P, out); }
+    catch (const std::exception &e) { return fail(POB_E_COMPILE, e.what()); }
+    return POB_OK;
+}
+
+void pob_destroy(pob_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->s_eval) cudaStreamSynchronize(h->s_eval);
+    if (h->s_exp) cudaStreamSynchronize(h->s_exp);
+    for (void *p : {(void *)h->d_ops, (void *)h->d_abs, (void *)h->d_levels, (void *)h->d_aux, (void *)h->d_konst, (void *)h->d_codes,
+                    (void *)h->d_tiles, (void *)h->d_invtab, (void *)h->d_stores, (void *)h->d_inputs, (void *)h->d_status,
+                    (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr, (void *)h->d_staged})
+        if (p) cudaFree(p);
+    for (uint64_t *s : h->slots) cudaFree(s);
+    for (void *p : {(void *)h->h_status, (void *)h->h_outputs, (void *)h->h_digests, (void *)h->h_witptr}) if (p) cudaFreeHost(p);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    for (uint32_t r = 0; r < pob_handle::RING; r++) { if (h->ev_eval_done[r]) cudaEventDestroy(h->ev_eval_done[r]); if (h->ev_exp_done[r]) cudaEventDestroy(h->ev_exp_done[r]); }
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_end) cudaEventDestroy(h->ev_end);
+    if (h->s_eval) cudaStreamDestroy(h->s_eval);
+    if (h->s_exp) cudaStreamDestroy(h->s_exp);
+    delete h;
+}
+
+int pob_create(const char *main_name, const uint64_t *params, int nparams, int hcreate, int device, uint32_t max_slots, pob_handle **out) {
+    if (!main_name || !out || (nparams > 0 && !params)) return fail(POB_E_BAD_ARG, "pob_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(POB_E_NO_DEVICE, "pob_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(POB_E_NO_DEVICE, "pob_create: device index out of range");
+    pob_handle *h = new pob_handle(); h->device = device;
+    try { h->P = compile_circuit(main_name, params_vec(params, nparams), hcreate != 0); }
+    catch (const std::exception &e) { delete h; return fail(POB_E_COMPILE, e.what()); }
+    try {
+        const Program &P = h->P;
+        CU(cudaSetDevice(device));
+        h->d_ops = upload(P.ops); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
+        h->d_konst = upload(P.konst); h->d_codes = upload(P.codes); h->d_tiles = upload(P.tiles);
+        h->d_invtab = upload(build_inverse_table());
+        CU(cudaStreamCreateWithFlags(&h->s_eval, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->s_exp, cudaStreamNonBlocking));
+        for (uint32_t r = 0; r < pob_handle::RING; r++) { CU(cudaEventCreateWithFlags(&h->ev_eval_done[r], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&h->ev_exp_done[r], cudaEventDisableTiming)); }
+        CU(cudaEventCreate(&h->ev_start)); CU(cudaEventCreate(&h->ev_end));
+        // witness slots: as many as fit in 80 % of free HBM after the store ring
+        size_t free_b = 0, total_b = 0; CU(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t wbytes = 32ull * P.n_signals;
+        h->store_stride = (P.store_u64() + 31) & ~31ull;
+        uint32_t chunk = 16;
+        const uint64_t ring_bytes_per_inst = pob_handle::RING * (h->store_stride * 8 + (uint64_t)P.n_inputs * 32);
+        uint64_t budget = (uint64_t)(free_b * 0.8);
+        uint64_t nslots = budget > chunk * ring_bytes_per_inst ? (budget - chunk * ring_bytes_per_inst) / wbytes : 0;
+        if (max_slots && nslots > max_slots) nslots = max_slots;
+        if (nslots > 4096) nslots = 4096;
+        if (nslots == 0) throw std::runtime_error("not even one witness slot fits in free HBM");
+        if (chunk > nslots) chunk = (uint32_t)nslots;
+        h->chunk = chunk;
+        CU(cudaMalloc(&h->d_stores, (size_t)pob_handle::RING * chunk * h->store_stride * 8));
+        CU(cudaMalloc(&h->d_inputs, std::max<size_t>(32, (size_t)pob_handle::RING * chunk * P.n_inputs * 32)));
+        for (uint64_t s = 0; s < nslots; s++) { uint64_t *p = nullptr; CU(cudaMalloc(&p, wbytes)); h->slots.push_back(p); }
+    } catch (const std::exception &e) {
+        std::string m = e.what(); pob_destroy(h);
+        return fail(m.find("slot") != std::string::npos ? POB_E_NO_MEMORY : POB_E_CUDA, "pob_create: " + m);
+    }
+    *out = h; return POB_OK;
+}
+
+int pob_describe(const pob_handle *h, pob_desc *out) {
+    if (!h || !out) return fail(POB_E_BAD_ARG, "pob_describe: null argument");
+    fill_desc(h->P, out); out->n_slots = (uint32_t)h->slots.size(); out->chunk = h->chunk; return POB_OK;
+}
+
+void *pob_alloc_pinned(uint64_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { g_err = "cudaMallocHost failed"; return nullptr; } return p; }
+void pob_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+static void ensure_batch_buffers(pob_handle *h, uint32_t n) {
+    if (n <= h->cap_n) return;
+    const Program &P = h->P;
+    for (void *p : {(void *)h->d_status, (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr}) if (p) cudaFree(p);
+    for (void *p : {(void *)h->h_status, (void *)h->h_outputs, (void *)h->h_digests, (void *)h->h_witptr}) if (p) cudaFreeHost(p);
+    const size_t no = std::max<uint32_t>(1, P.n_outputs);
+    CU(cudaMalloc(&h->d_status, (size_t)n * 4)); CU(cudaMalloc(&h->d_outputs, (size_t)n * no * 32));
+    CU(cudaMalloc(&h->d_digests, (size_t)n * 8)); CU(cudaMalloc(&h->d_witptr, (size_t)n * sizeof(uint64_t *)));
+    CU(cudaMallocHost(&h->h_status, (size_t)n * 4)); CU(cudaMallocHost(&h->h_outputs, (size_t)n * no * 32));
+    CU(cudaMallocHost(&h->h_digests, (size_t)n * 8)); CU(cudaMallocHost(&h->h_witptr, (size_t)n * sizeof(uint64_t *)));
+    h->cap_n = n;
+}
+
+int pob_stage_inputs(pob_handle *h, const uint64_t *inputs, uint32_t n) {
+    if (!h || !inputs || n == 0) return fail(POB_E_BAD_ARG, "pob_stage_inputs: bad argument");
+    try {
+        CU(cudaSetDevice(h->device));
+        if (h->d_staged) { cudaFree(h->d_staged); h->d_staged = nullptr; h->n_staged = 0; }
+        size_t bytes = std::max<size_t>(32, (size_t)n * h->P.n_inputs * 32);
+        CU(cudaMalloc(&h->d_staged, bytes));
+        if (h->P.n_inputs) CU(cudaMemcpy(h->d_staged, inputs, (size_t)n * h->P.n_inputs * 32, cudaMemcpyHostToDevice));
+        h->n_staged = n;
+    } catch (const std::exception &e) { return fail(POB_E_CUDA, e.what()); }
+    return POB_OK;
+}
+
+int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t flags, uint32_t *status, uint64_t *outputs, uint64_t *digests) {
+    if (!h || n == 0 || !status) return fail(POB_E_BAD_ARG, "pob_run_batch: bad argument");
+    const bool staged = (flags & POB_RUN_INPUTS_STAGED) != 0, expand = (flags & (POB_RUN_EXPAND | POB_RUN_DIGEST)) != 0, digest = (flags & POB_RUN_DIGEST) != 0;
+    if (staged ? (h->n_staged < n) : (inputs == nullptr && h->P.n_inputs)) return fail(POB_E_BAD_ARG, "pob_run_batch: no inputs");
+    if (digest && !digests) return fail(POB_E_BAD_ARG, "pob_run_batch: POB_RUN_DIGEST needs a digests array");
+    try {
+        const Program &P = h->P;
+        CU(cudaSetDevice(h->device));
+        ensure_batch_buffers(h, n);
+        const uint32_t E = h->chunk, R = pob_handle::RING, nchunks = (n + E - 1) / E, nslots = (uint32_t)h->slots.size();
+        const size_t in_stride = (size_t)P.n_inputs * 4, no = std::max<uint32_t>(1, P.n_outputs);
+        while (h->ev_pool.size() < (size_t)nchunks * 4) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
+        for (uint32_t i = 0; i < n; i++) h->h_witptr[i] = h->slots[i % nslots];
+        pob_timing T{};
+        CU(cudaEventRecord(h->ev_start, h->s_eval));
+        CU(cudaMemcpyAsync(h->d_witptr, h->h_witptr, (size_t)n * sizeof(uint64_t *), cudaMemcpyHostToDevice, h->s_eval));
+        if (digest) CU(cudaMemsetAsync(h->d_digests, 0, (size_t)n * 8, h->s_eval));
+        for (uint32_t c = 0; c < nchunks; c++) {
+            const uint32_t r = c % R, first = c * E, cnt = std::min(E, n - first);
+            if (c >= R) CU(cudaStreamWaitEvent(h->s_eval, h->ev_exp_done[r], 0));
+            const uint64_t *d_in;
+            if (staged) d_in = h->d_staged + (size_t)first * in_stride;
+            else {
+                uint64_t *dst = h->d_inputs + (size_t)r * E * in_stride;
+                if (in_stride) { CU(cudaMemcpyAsync(dst, inputs + (size_t)first * in_stride, (size_t)cnt * in_stride * 8, cudaMemcpyHostToDevice, h->s_eval)); T.h2d_bytes += (uint64_t)cnt * in_stride * 8; }
+                d_in = dst;
+            }
+            uint64_t *stores = h->d_stores + (size_t)r * E * h->store_stride;
+            EvalArgs ea{h->d_ops, h->d_abs, h->d_levels, (uint32_t)P.levels.size(), h->d_aux, h->d_konst, h->d_invtab,
+                        h->d_codes + ROUND_SIGNALS + 1, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
+                        h->d_status + first, h->d_outputs + (size_t)first * no * 4};
+            CU(cudaEventRecord(h->ev_pool[4 * c + 0], h->s_eval));
+            k_eval<<<cnt, 256, 0, h->s_eval>>>(ea);
+            CU(cudaEventRecord(h->ev_pool[4 * c + 1], h->s_eval));
+            CU(cudaEventRecord(h->ev_eval_done[r], h->s_eval));
+            T.eval_launches++;
+            if (expand) {
+                CU(cudaStreamWaitEvent(h->s_exp, h->ev_eval_done[r], 0));
+                ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, stores, h->store_stride, P.val_base, h->d_witptr + first};
+                CU(cudaEventRecord(h->ev_pool[4 * c + 2], h->s_exp));
+                k_expand<<<dim3((unsigned)P.tiles.size(), cnt), 256, 0, h->s_exp>>>(xa);
+                CU(cudaEventRecord(h->ev_pool[4 * c + 3], h->s_exp));
+                T.expand_launches++;
+                if (digest) for (uint32_t j = 0; j < cnt; j++) {
+                    k_digest<<<1184, 256, 0, h->s_exp>>>(h->slots[(first + j) % nslots], P.n_signals, h->d_digests + first + j);
+                    T.other_launches++;
+                }
+                CU(cudaEventRecord(h->ev_exp_done[r], h->s_exp));
+            } else {
+                CU(cudaEventRecord(h->ev_exp_done[r], h->s_eval));
+            }
+        }
+        CU(cudaGetLastError());
+        // results: status + outputs after the last eval; digests after the last expand
+        CU(cudaMemcpyAsync(h->h_status, h->d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, h->s_eval));
+        T.d2h_bytes += (uint64_t)n * 4;
+        if (P.n_outputs) { CU(cudaMemcpyAsync(h->h_outputs, h->d_outputs, (size_t)n * no * 32, cudaMemcpyDeviceToHost, h->s_eval)); T.d2h_bytes += (uint64_t)n * no * 32; }
+        CU(cudaEventRecord(h->ev_eval_done[0], h->s_eval));
+        CU(cudaStreamWaitEvent(h->s_exp, h->ev_eval_done[0], 0));
+        if (digest) { CU(cudaMemcpyAsync(h->h_digests, h->d_digests, (size_t)n * 8, cudaMemcpyDeviceToHost, h->s_exp)); T.d2h_bytes += (uint64_t)n * 8; }
+        CU(cudaEventRecord(h->ev_end, h->s_exp));
+        CU(cudaStreamSynchronize(h->s_exp)); CU(cudaStreamSynchronize(h->s_eval));
+        CU(cudaGetLastError());
+        memcpy(status, h->h_status, (size_t)n * 4);
+        if (outputs && P.n_outputs) memcpy(outputs, h->h_outputs, (size_t)n * no * 32);
+        if (digest) memcpy(digests, h->h_digests, (size_t)n * 8);
+        CU(cudaEventElapsedTime(&T.total_ms, h->ev_start, h->ev_end));
+        for (uint32_t c = 0; c < nchunks; c++) {
+            float ms = 0; CU(cudaEventElapsedTime(&ms, h->ev_pool[4 * c + 0], h->ev_pool[4 * c + 1])); T.eval_ms += ms;
+            if (expand) { CU(cudaEventElapsedTime(&ms, h->ev_pool[4 * c + 2], h->ev_pool[4 * c + 3])); T.expand_ms += ms; }
+        }
+        h->timing = T; h->last_n = n; h->last_expanded = expand;
+    } catch (const std::exception &e) { return fail(POB_E_CUDA, std::string("pob_run_batch: ") + e.what()); }
+    return POB_OK;
+}
+
+int pob_last_timing(const pob_handle *h, pob_timing *out) {
+    if (!h || !out) return fail(POB_E_BAD_ARG, "pob_last_timing: null argument");
+    *out = h->timing; return POB_OK;
+}
+
+static int resident_slot(pob_handle *h, uint32_t index, uint64_t **slot) {
+    if (!h->last_expanded || index >= h->last_n) return fail(POB_E_RANGE, "witness index not in the last expanded batch");
+    const uint32_t nslots = (uint32_t)h->slots.size();
+    if ((uint64_t)index + nslots < h->last_n) return fail(POB_E_RANGE, "witness slot already overwritten by a later instance");
+    *slot = h->slots[index % nslots]; return POB_OK;
+}
+
+int pob_witness_device_ptr(pob_handle *h, uint32_t index, void **dptr) {
+    if (!h || !dptr) return fail(POB_E_BAD_ARG, "pob_witness_device_ptr: null argument");
+    uint64_t *s = nullptr; int rc = resident_slot(h, index, &s); if (rc) return rc;
+    *dptr = s; return POB_OK;
+}
+
+int pob_copy_witness(pob_handle *h, uint32_t index, uint64_t first_signal, uint64_t n_signals, uint64_t *dst_host) {
+    if (!h || !dst_host) return fail(POB_E_BAD_ARG, "pob_copy_witness: null argument");
+    uint64_t *s = nullptr; int rc = resident_slot(h, index, &s); if (rc) return rc;
+    if (first_signal + n_signals > h->P.n_signals) return fail(POB_E_RANGE, "pob_copy_witness: range exceeds the witness");
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaMemcpy(dst_host, s + 4 * first_signal, (size_t)n_signals * 32, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(POB_E_CUDA, "pob_copy_witness: cudaMemcpy failed");
+    return POB_OK;
+}
+
+int pob_write_wtns(pob_handle *h, uint32_t index, const char *path) {
+    if (!h || !path) return fail(POB_E_BAD_ARG, "pob_write_wtns: null argument");
+    uint64_t *s = nullptr; int rc = resident_slot(h, index, &s); if (rc) return rc;
+    FILE *f = fopen(path, "wb"); if (!f) return fail(POB_E_IO, std::string("cannot open ") + path);
+    // iden3 binary witness format, version 2 (what the circom runtime's writeBinWitness emits)
+    const uint64_t n = h->P.n_signals; uint32_t u32; uint64_t u64; Fr p = fr_p();
+    bool ok = fwrite("wtns", 1, 4, f) == 4;
+    u32 = 2; ok &= fwrite(&u32, 4, 1, f) == 1; u32 = 2; ok &= fwrite(&u32, 4, 1, f) == 1;
+    u32 = 1; ok &= fwrite(&u32, 4, 1, f) == 1; u64 = 40; ok &= fwrite(&u64, 8, 1, f) == 1;
+    u32 = 32; ok &= fwrite(&u32, 4, 1, f) == 1; ok &= fwrite(p.l, 4, 8, f) == 8; u32 = (uint32_t)n; ok &= fwrite(&u32, 4, 1, f) == 1;
+    u32 = 2; ok &= fwrite(&u32, 4, 1, f) == 1; u64 = 32ull * n; ok &= fwrite(&u64, 8, 1, f) == 1;
+    const uint64_t CH = 1ull << 21;     // 2 Mi entries = 64 MiB per hop
+    void *buf = nullptr;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaMallocHost(&buf, CH * 32) != cudaSuccess) { fclose(f); return fail(POB_E_CUDA, "pob_write_wtns: cudaMallocHost failed"); }
+    for (uint64_t off = 0; ok && off < n; off += CH) {
+        uint64_t cnt = std::min(CH, n - off);
+        if (cudaMemcpy(buf, s + 4 * off, (size_t)cnt * 32, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaFreeHost(buf); fclose(f); return fail(POB_E_CUDA, "pob_write_wtns: cudaMemcpy failed"); }
+        ok &= fwrite(buf, 32, (size_t)cnt, f) == cnt;
+    }
+    cudaFreeHost(buf);
+    ok &= fclose(f) == 0;
+    return ok ? POB_OK : fail(POB_E_IO, std::string("short write to ") + path);
+}
+
+}  // extern "C"

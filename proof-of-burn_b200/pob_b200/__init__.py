@@ -1,0 +1,316 @@
+"""pob_b200 -- Python host of the B200-native batched witness generator (ctypes over libpob_b200.so).
+
+Mirrors the reference's interface for this path: the process CLI the circom toolchain emits,
+`./<circuit> input.json witness.wtns` (reference Makefile:5-6, tests/test.py:60-63), with the input-JSON
+schema tests/main.py:160-178 writes (keys = the main template's `signal input` names, values JSON ints or
+decimal strings, nested arrays, scalars possibly wrapped in 1-element arrays).
+
+    from pob_b200 import Circuit
+    c = Circuit("ProofOfBurn(16, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)")       # == circom -c + make
+    res = c.run([input_dict, ...])                                              # == N x ./main input.json w.wtns
+    res.status[i] == 0, res.outputs[i] -> [commitment]; c.write_wtns(i, "witness.wtns")
+
+All witness computation happens in hand-written CUDA (csrc/pob_b200.cu).  There is no CPU fallback: if the
+extension is missing or no GPU is visible, construction fails loudly.
+"""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+
+P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpob_b200.so")
+
+RUN_EXPAND, RUN_DIGEST, RUN_INPUTS_STAGED = 1, 2, 4
+MAIN_PROOF_OF_BURN = "ProofOfBurn(16, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)"   # circuits/main_proof_of_burn.circom:27
+MAIN_SPEND = "Spend(31)"                                                       # circuits/main_spend.circom:6
+TEST_PROOF_OF_BURN = "ProofOfBurn(4, 4, 5, 20, 31, 2, 10 ** 18, 10 ** 19)"     # tests/testcases/proof_of_burn.py:53
+
+
+class PobError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pob_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Desc(ctypes.Structure):
+    _fields_ = [("n_signals", ctypes.c_uint64), ("n_outputs", ctypes.c_uint32), ("n_inputs", ctypes.c_uint32),
+                ("witness_bytes", ctypes.c_uint64), ("wtns_file_bytes", ctypes.c_uint64), ("store_bytes", ctypes.c_uint64),
+                ("n_ops", ctypes.c_uint64), ("n_absorbs", ctypes.c_uint32), ("n_levels", ctypes.c_uint32),
+                ("n_tiles", ctypes.c_uint32), ("n_slots", ctypes.c_uint32), ("chunk", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved"}
+
+
+class Timing(ctypes.Structure):
+    _fields_ = [("total_ms", ctypes.c_float), ("expand_ms", ctypes.c_float), ("eval_ms", ctypes.c_float),
+                ("expand_launches", ctypes.c_uint32), ("eval_launches", ctypes.c_uint32), ("other_launches", ctypes.c_uint32),
+                ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
+
+    def as_dict(self):
+        return {k: (float(getattr(self, k)) if k.endswith("_ms") else int(getattr(self, k))) for k, _ in self._fields_}
+
+
+_LIB = None
+
+
+def lib():
+    """Load the CUDA extension.  Fails loudly when it has not been built (python __graft_entry__.py build)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("pob_b200: %s is missing -- build it with `make -C proof-of-burn_b200/csrc` "
+                              "(there is no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        vp, u32, u64, ci = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
+        L.pob_create.restype = ci
+        L.pob_create.argtypes = [ctypes.c_char_p, vp, ci, ci, ci, u32, ctypes.POINTER(vp)]
+        L.pob_destroy.argtypes = [vp]
+        L.pob_layout_info.restype = ci
+        L.pob_layout_info.argtypes = [ctypes.c_char_p, vp, ci, ci, ctypes.POINTER(Desc)]
+        L.pob_input_schema.restype = ctypes.c_char_p
+        L.pob_input_schema.argtypes = [ctypes.c_char_p, ctypes.POINTER(ci)]
+        L.pob_describe.restype = ci
+        L.pob_describe.argtypes = [vp, ctypes.POINTER(Desc)]
+        L.pob_alloc_pinned.restype = vp
+        L.pob_alloc_pinned.argtypes = [u64]
+        L.pob_free_pinned.argtypes = [vp]
+        L.pob_stage_inputs.restype = ci
+        L.pob_stage_inputs.argtypes = [vp, vp, u32]
+        L.pob_run_batch.restype = ci
+        L.pob_run_batch.argtypes = [vp, vp, u32, u32, vp, vp, vp]
+        L.pob_last_timing.restype = ci
+        L.pob_last_timing.argtypes = [vp, ctypes.POINTER(Timing)]
+        L.pob_copy_witness.restype = ci
+        L.pob_copy_witness.argtypes = [vp, u32, u64, u64, vp]
+        L.pob_write_wtns.restype = ci
+        L.pob_write_wtns.argtypes = [vp, u32, ctypes.c_char_p]
+        L.pob_witness_device_ptr.restype = ci
+        L.pob_witness_device_ptr.argtypes = [vp, u32, ctypes.POINTER(vp)]
+        L.pob_last_error.restype = ctypes.c_char_p
+        L.pob_version.restype = ctypes.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise PobError(rc, lib().pob_last_error().decode())
+
+
+# ---- field / schema helpers --------------------------------------------------------------------------------
+def parse_main(expr):
+    """'ProofOfBurn(4, 4, 5, 20, 31, 2, 10 ** 18, 10 ** 19)' -> ('ProofOfBurn', [4, 4, 5, 20, 31, 2, 10**18, 10**19])"""
+    m = re.match(r"\s*(\w+)\s*(?:\((.*)\))?\s*;?\s*$", expr, re.S)
+    if not m:
+        raise ValueError("cannot parse main expression %r" % expr)
+    args = (m.group(2) or "").strip()
+    return m.group(1), ([int(eval(a, {"__builtins__": {}})) for a in args.split(",")] if args else [])
+
+
+def to_limbs(vals):
+    """ints of any sign/size (reduced mod p like the circom loader) -> (n, 4) uint64 little-endian limbs"""
+    out = np.zeros((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        v = int(v) % P
+        if v >> 64:
+            for k in range(4):
+                out[i, k] = (v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+        else:
+            out[i, 0] = v
+    return out
+
+
+def from_limbs(row):
+    return int(row[0]) | (int(row[1]) << 64) | (int(row[2]) << 128) | (int(row[3]) << 192)
+
+
+def input_schema(name, params):
+    """[(input name, [dims])] in declaration order, from the library (single source of truth)."""
+    n = ctypes.c_int(0)
+    s = lib().pob_input_schema(name.encode(), ctypes.byref(n))
+    if s is None:
+        raise PobError(-1, "unknown main template %r" % name)
+    if len(params) < n.value:
+        raise PobError(-1, "%s needs %d template parameters" % (name, n.value))
+    env = {"p%d" % i: v for i, v in enumerate(params)}
+    out = []
+    for item in [x for x in s.decode().split(",") if x]:
+        m = re.match(r"(\w+)((?:\[[^\]]+\])*)$", item)
+        out.append((m.group(1), [int(eval(d, {"__builtins__": {}}, env)) for d in re.findall(r"\[([^\]]+)\]", m.group(2))]))
+    return out
+
+
+def _flatten(v, out):
+    if isinstance(v, (list, tuple)):
+        for e in v:
+            _flatten(e, out)
+    else:
+        out.append(int(v))
+
+
+def flatten_input(schema, inp):
+    """One input JSON object -> flat list of ints in declaration order.  Element counts must match the circuit
+    exactly, as with the circom loader; unknown keys are ignored, missing keys are an error."""
+    flat = []
+    for name, dims in schema:
+        if name not in inp:
+            raise KeyError("input signal %r missing" % name)
+        vals = []
+        _flatten(inp[name], vals)
+        want = int(np.prod(dims)) if dims else 1
+        if len(vals) != want:
+            raise ValueError("input %s: circuit expects %d values, got %d" % (name, want, len(vals)))
+        flat.extend(vals)
+    return flat
+
+
+def layout_info(main_expr, hcreate=False):
+    """Shape of a circuit's witness program; runs the host-side layout compiler only (no GPU needed)."""
+    name, params = parse_main(main_expr)
+    pl = to_limbs(params) if params else np.zeros((1, 4), dtype=np.uint64)
+    d = Desc()
+    _check(lib().pob_layout_info(name.encode(), pl.ctypes.data, len(params), int(hcreate), ctypes.byref(d)))
+    return d.as_dict()
+
+
+class PinnedArray:
+    """numpy view over cudaMallocHost memory (so H2D copies inside run() are asynchronous DMA)."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = lib().pob_alloc_pinned(max(1, self.nbytes))
+        if not self.ptr:
+            raise PobError(-3, "pob_alloc_pinned failed")
+        buf = (ctypes.c_uint8 * max(1, self.nbytes)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().pob_free_pinned(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class BatchResult:
+    def __init__(self, status, outputs, digests, timing):
+        self.status, self.outputs_limbs, self.digests, self.timing = status, outputs, digests, timing
+
+    @property
+    def n_ok(self):
+        return int((self.status == 0).sum())
+
+    @property
+    def outputs(self):
+        return [[from_limbs(r) for r in inst] for inst in self.outputs_limbs]
+
+
+class Circuit:
+    """One compiled circuit shape bound to one GPU (== the executable `circom -c ... && make` produces)."""
+
+    def __init__(self, main_expr, device=0, hcreate=False, max_slots=0):
+        self.main_expr = main_expr
+        self.name, self.params = parse_main(main_expr)
+        self.schema = input_schema(self.name, self.params)
+        pl = to_limbs(self.params) if self.params else np.zeros((1, 4), dtype=np.uint64)
+        h = ctypes.c_void_p()
+        _check(lib().pob_create(self.name.encode(), pl.ctypes.data, len(self.params), int(hcreate), int(device), int(max_slots), ctypes.byref(h)))
+        self._h = h
+        d = Desc()
+        _check(lib().pob_describe(self._h, ctypes.byref(d)))
+        self.desc = d.as_dict()
+        self.n_signals, self.n_inputs, self.n_outputs = self.desc["n_signals"], self.desc["n_inputs"], self.desc["n_outputs"]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pob_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- inputs ----
+    def pack(self, inputs, pinned=False):
+        """list of input JSON objects (or one) -> (n, n_inputs, 4) uint64 array"""
+        if isinstance(inputs, dict):
+            inputs = [inputs]
+        n = len(inputs)
+        shape = (n, max(1, self.n_inputs), 4)
+        holder = PinnedArray(shape, np.uint64) if pinned else None
+        arr = holder.array if pinned else np.zeros(shape, dtype=np.uint64)
+        for i, inp in enumerate(inputs):
+            arr[i, : self.n_inputs] = to_limbs(flatten_input(self.schema, inp))
+        return (arr, holder) if pinned else arr
+
+    def stage(self, packed):
+        packed = np.ascontiguousarray(packed, dtype=np.uint64)
+        _check(lib().pob_stage_inputs(self._h, packed.ctypes.data, packed.shape[0]))
+
+    # ---- run ----
+    def run_packed(self, packed, n=None, expand=True, digest=False, staged=False):
+        if staged:
+            assert n is not None
+            ptr = None
+        else:
+            packed = np.ascontiguousarray(packed, dtype=np.uint64)
+            n = packed.shape[0] if n is None else n
+            ptr = packed.ctypes.data
+        flags = (RUN_EXPAND if expand else 0) | (RUN_DIGEST if digest else 0) | (RUN_INPUTS_STAGED if staged else 0)
+        status = np.zeros(n, dtype=np.uint32)
+        outputs = np.zeros((n, max(1, self.n_outputs), 4), dtype=np.uint64)
+        digests = np.zeros(n, dtype=np.uint64)
+        _check(lib().pob_run_batch(self._h, ptr, n, flags, status.ctypes.data, outputs.ctypes.data, digests.ctypes.data if digest else None))
+        t = Timing()
+        _check(lib().pob_last_timing(self._h, ctypes.byref(t)))
+        return BatchResult(status, outputs[:, : self.n_outputs], digests if digest else None, t.as_dict())
+
+    def run(self, inputs, expand=True, digest=False):
+        return self.run_packed(self.pack(inputs), expand=expand, digest=digest)
+
+    # ---- witness access ----
+    def witness(self, index, first=0, count=None):
+        count = self.n_signals - first if count is None else count
+        out = np.zeros((count, 4), dtype=np.uint64)
+        _check(lib().pob_copy_witness(self._h, index, first, count, out.ctypes.data))
+        return out
+
+    def write_wtns(self, index, path):
+        _check(lib().pob_write_wtns(self._h, index, path.encode()))
+
+    def witness_device_ptr(self, index):
+        p = ctypes.c_void_p()
+        _check(lib().pob_witness_device_ptr(self._h, index, ctypes.byref(p)))
+        return p.value
+
+
+CIRCUIT_ALIASES = {"main_proof_of_burn": MAIN_PROOF_OF_BURN, "main_spend": MAIN_SPEND}
+
+
+def main(argv=None):
+    """CLI shim with the reference calculator's argv: `python -m pob_b200 <circuit> input.json witness.wtns`
+    (reference Makefile:5-6); <circuit> is main_proof_of_burn, main_spend or a `Template(params)` expression."""
+    import sys
+    argv = sys.argv[1:] if argv is None else argv
+    if len(argv) != 3:
+        print("usage: python -m pob_b200 <main_proof_of_burn|main_spend|Template(params)> input.json witness.wtns", file=sys.stderr)
+        return 2
+    c = Circuit(CIRCUIT_ALIASES.get(argv[0], argv[0]), max_slots=1)
+    res = c.run([json.load(open(argv[1]))])
+    if res.status[0] != 0:
+        print("Error: constraint failed in the component at witness index %d" % (int(res.status[0]) - 1), file=sys.stderr)
+        return 1
+    c.write_wtns(0, argv[2])
+    return 0
