@@ -1,0 +1,78 @@
+"""Host logic: synthetic input generator (valid instances), index sharding, and the N>1 reductions over gloo."""
+import os, sys
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+
+def test_synth_primitives_known_answers():
+    from pob_b200 import synth
+    assert synth.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"   # empty_account.circom:10
+    assert synth.keccak256(b"\x80").hex() == "56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421"  # :9
+    assert int.from_bytes(synth.keccak256(b"EIP-7503"), "big") % synth.P == synth.POSEIDON_PREFIX            # constants.circom:3-6
+    assert synth.poseidon([1, 2]) == 7853200120776062878684798364095072458815029376092732009249414926327459813530   # poseidoncircuit.js:52
+    assert synth.poseidon([3, 4]) == 14763215145315200506921711489642608356394854266165572616578112107564877678998  # :62
+
+
+def test_pow_pool_entries_satisfy_the_check():
+    from pob_b200 import synth
+    pool = synth.load_pow_pool()
+    assert len(pool) >= 16
+    for key, reveal, extra in pool[:8]:
+        h = synth.keccak256(int(key).to_bytes(32, "big") + int(reveal).to_bytes(32, "big") + int(extra).to_bytes(32, "big") + b"EIP-7503")
+        assert h[:2] == b"\x00\x00"
+
+
+def test_synthetic_instances_are_accepted_by_the_oracle():
+    """test-shape circuit (64 M entries) so this stays fast; the generator is shape-generic"""
+    from pob_b200 import synth
+    shape = (4, 4, 5, 20, 31, 2, 10 ** 18, 10 ** 19)
+    insts = synth.make_batch(2, shape, seed=11)
+    packed = synth.pack_instances(insts, shape)
+    for i, it in enumerate(insts):
+        j = synth.to_json(it, shape)
+        sch = oracle.schema("ProofOfBurn", list(shape))
+        assert np.array_equal(packed[i], oracle.to_limbs(oracle.flatten_inputs(sch, j)))
+        w = oracle.run_flat("ProofOfBurn", list(shape), packed[i])
+        try:
+            assert w.ok, "synthetic instance %d rejected: status %d" % (i, w.status)
+        finally:
+            w.free()
+    assert insts[0]["burnKey"] != insts[1]["burnKey"] or insts[0]["blockHeader"] != insts[1]["blockHeader"]
+
+
+def test_shard_ranges_cover_the_batch():
+    from pob_b200 import shard
+    for n, world in [(8192, 8), (1000, 3), (5, 8), (1, 1)]:
+        spans = [shard.shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "proof-of-burn_b200"))
+    from pob_b200 import shard
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    lo, hi = shard.shard_range(100, rank, world)
+    times, counts = shard.reduce_timing_and_counts(dist, "cpu", [10.0 + rank, 5.0 - rank], [hi - lo, rank])
+    dist.barrier()
+    if rank == 0:
+        out.put((times, counts))
+    dist.destroy_process_group()
+
+
+def test_two_rank_reduction_over_gloo():
+    """the N>1 path of bench.py on CPU: max-over-ranks timing and summed counts, world_size 2, gloo"""
+    import torch.multiprocessing as tmp
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    times, counts = q.get(timeout=120)
+    [p.join(timeout=60) for p in procs]
+    assert times == [11.0, 5.0] and counts == [100, 1]

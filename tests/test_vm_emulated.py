@@ -1,0 +1,64 @@
+"""The product's layout compiler, checked on the CPU: every compiled witness program is executed by the TEST-ONLY
+host emulator (tests/emu/, the host instantiation of csrc/vm_exec.h) and its complete witness vector, status code
+and outputs are compared entry by entry with the independent CPU oracle.  This validates layout + program on a box
+without a GPU; the CUDA kernels themselves are covered by tests/test_gpu_parity.py (-m gpu)."""
+import os, sys
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+from helpers import gold, suite, pob_fixture
+from oracle import oracle
+
+SMALL = [s for s in gold() if s["suite"] != "test_proof_of_burn"]
+
+
+def _compare(main, cases, hcreate=False):
+    import emu
+    name, params = oracle.parse_main(main)
+    pl = oracle.to_limbs(params) if params else np.zeros((1, 4), dtype=np.uint64)
+    prog = emu.EmuProgram(name, pl, len(params), hcreate)
+    sch = oracle.schema(name, params)
+    for k, inp in enumerate(cases):
+        flat = oracle.to_limbs(oracle.flatten_inputs(sch, inp))
+        w = oracle.run_flat(name, params, flat, hcreate)
+        try:
+            st, wit, outs = prog.run(flat)
+            assert prog.stats["n_signals"] == w.n_signals
+            assert st == w.status, "%s case %d: status %d vs oracle %d" % (main, k, st, w.status)
+            if w.ok:
+                neq = np.nonzero((wit != w.limbs).any(axis=1))[0]
+                assert len(neq) == 0, "%s case %d: %d entries differ, first at %d" % (main, k, len(neq), neq[0])
+                assert np.array_equal(outs, w.limbs[1:1 + w.n_outputs])
+        finally:
+            w.free()
+    return prog
+
+
+@pytest.mark.parametrize("s", SMALL, ids=[s["suite"] for s in SMALL])
+def test_program_matches_oracle(s):
+    _compare(s["main"], [c["input"] for c in s["cases"]])
+
+
+def test_proof_of_burn_program_matches_oracle():
+    """ProofOfBurn(4,4,5,...) on the reference fixture and one corrupted copy: 64.4 M entries each"""
+    s = suite("test_proof_of_burn")
+    prog = _compare(s["main"], [s["cases"][0]["input"], s["cases"][1]["input"]])
+    assert prog.stats["n_absorbs"] == 25 and prog.stats["n_round_blocks"] == 25 * 24
+
+
+def test_creation_order_policy_matches_oracle():
+    s = suite("test_spend")
+    _compare(s["main"], [s["cases"][0]["input"]], hcreate=True)
+    s = suite("test_leaf_detector_2")
+    _compare(s["main"], [s["cases"][0]["input"]], hcreate=True)
+
+
+def test_round_table_is_shared():
+    import emu
+    name, params = oracle.parse_main("KeccakBytes(2)")
+    prog = emu.EmuProgram(name, oracle.to_limbs(params), len(params))
+    st = prog.stats
+    assert st["n_round_blocks"] == 48
+    # codes = one shared 102,656-entry KeccakfRound table + the flat (non-round) signals
+    assert st["n_codes"] == 102656 + st["n_signals"] - 48 * 102656
