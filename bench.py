@@ -131,8 +131,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     shape = (a.layers,) + MAIN_SHAPE[1:]
     expr = shape_expr(shape)
-    workload = "main_proof_of_burn %s, batch %d synthetic valid test_pob_input.json-shaped inputs per GPU per step (trie depth 8-10 of %d layers)" % (
-        expr.replace(" ", ""), a.batch, a.layers)
+    workload = "main_proof_of_burn %s, batch %d synthetic valid test_pob_input.json-shaped inputs per GPU per step (trie depth %d-%d)" % (
+        expr.replace(" ", ""), a.batch, min(8, a.layers), min(10, a.layers))
 
     from pob_b200 import synth
     cores = host_cores()
@@ -227,7 +227,8 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        bytes_per_launch = 32.0 * desc["n_signals"] * min(desc["chunk"], a.batch)
+        # algorithmic bytes of all expand launches of the timed steps / their summed CUDA-event durations
+        bytes_per_launch = 32.0 * desc["n_signals"] * a.batch * a.steps / max(1, exp_launches)
         per_launch_ms = exp_ms / max(1, exp_launches)
         achieved = bytes_per_launch / (per_launch_ms / 1e3) / 1e9
         traffic = None

@@ -58,7 +58,7 @@ typedef struct {
     uint32_t n_tiles;          /* expand tiles per instance */
     uint32_t n_slots;          /* witness slots resident in HBM (0 when no device handle) */
     uint32_t chunk;            /* instances evaluated per eval launch */
-    uint32_t reserved;
+    uint32_t expand_group;     /* instances materialised per expand launch (<= n_slots) */
 } pob_desc;
 
 /* replaces: `circom -c <main>.circom --O0 && make` (reference Makefile:2-3, tests/test.py:32,55).

@@ -170,6 +170,44 @@ class Builder {
         Fr fa; if (const_val(a, fa)) return fr_is_zero(fa) ? ZERO : konst(fr_inv(fa));
         return emit_val(OP_INV, a, 0, 0, 1 + level_of(a));
     }
+    // (a > k) on canonical integers == prod_{j<=k} (1 - IsEqual(j, a))
+    Code gtc(Code a, uint32_t k) {
+        Fr fa; if (const_val(a, fa)) return (!fr_fits64(fa) || fr_lo64(fa) > k) ? ONE : ZERO;
+        return emit_val(OP_GTC, a, k, 0, 1 + level_of(a));
+    }
+    // sum_{j<=i} IsEqual(sel, j) * vals[j]  for every i < n, as n independent ops over one shared operand list
+    void selsum(Code sel, const Code *vals, size_t n, Code *out) {
+        uint32_t lv = level_of(sel);
+        for (size_t i = 0; i < n; i++) lv = std::max(lv, level_of(vals[i]));
+        uint32_t a0 = (uint32_t)aux.size();
+        aux.insert(aux.end(), vals, vals + n);
+        for (size_t i = 0; i < n; i++) {
+            uint32_t slot = new_val(lv + 1);
+            ops.push_back({Op{(OP_SELSUM << 26) | slot, sel, a0, (uint32_t)i}, lv + 1});
+            out[i] = c_val(slot);
+        }
+    }
+    // x_{k+1} = x_k * m[k] + ad[k], every x_k a signal: one thread walks the recurrence
+    void chain(Code x0, const Code *m, const Code *ad, size_t n, Code *out) {
+        uint32_t lv = level_of(x0);
+        for (size_t i = 0; i < n; i++) lv = std::max(lv, std::max(level_of(m[i]), level_of(ad[i])));
+        uint32_t a0 = (uint32_t)aux.size();
+        for (size_t i = 0; i < n; i++) { aux.push_back(m[i]); aux.push_back(ad[i]); }
+        uint32_t first = n_vals;
+        for (size_t i = 0; i < n; i++) { uint32_t slot = new_val(lv + 1); out[i] = c_val(slot); }
+        ops.push_back({Op{(OP_CHAIN << 26) | first, a0, (uint32_t)n, x0}, lv + 1});
+    }
+    // balanced sum of terms that are `var` accumulations in the circuit (only the total is a signal)
+    Code sum_tree(std::vector<Code> v) {
+        if (v.empty()) return ZERO;
+        while (v.size() > 1) {
+            std::vector<Code> nx; nx.reserve((v.size() + 1) / 2);
+            for (size_t i = 0; i + 1 < v.size(); i += 2) nx.push_back(add(v[i], v[i + 1]));
+            if (v.size() & 1) nx.push_back(v.back());
+            v.swap(nx);
+        }
+        return v[0];
+    }
     Code divmod(bool want_mod, Code a, Code b, uint64_t base) {
         uint32_t lv = 1 + std::max(level_of(a), level_of(b));
         return emit_val(want_mod ? OP_MOD : OP_DIV, a, b, (uint32_t)base, lv);
@@ -268,9 +306,8 @@ static Blk T_Num2Bits(Builder &B, int n, Code in) {
 // Bits2Num(n) :55-67  own: out, in[n]
 static Blk T_Bits2Num(Builder &B, int n, const Code *in) {
     Blk o = B.alloc((size_t)n + 1); B.copy(o.pos + 1, in, (size_t)n);
-    Code lc = ZERO;
-    for (int i = 0; i < n; i++) lc = B.fma(in[i], B.pow2((unsigned)i), lc);
-    B.at(o.pos) = lc; return o;
+    std::vector<Code> terms; for (int i = 0; i < n; i++) terms.push_back(B.mul(in[i], B.pow2((unsigned)i)));
+    B.at(o.pos) = B.sum_tree(terms); return o;
 }
 // CompConstant(ct) :25-73 with ct = p-1  own: out, in[254], parts[127], sout ; child Num2Bits(135)
 static Blk T_CompConstant(Builder &B, const Fr &ct, const Code *in) {
@@ -279,7 +316,7 @@ static Blk T_CompConstant(Builder &B, const Fr &ct, const Code *in) {
     Fr one = fr_from_u64(1);
     Fr b; { Fr t = fr_from_u64(1); for (int i = 0; i < 128; i++) t = fr_add(t, t); b = fr_sub(t, one); }
     Fr a = one, e = one;
-    Code sum = ZERO;
+    std::vector<Code> terms;
     for (int i = 0; i < 127; i++) {
         int clsb = fr_bit(ct, (unsigned)(2 * i)), cmsb = fr_bit(ct, (unsigned)(2 * i + 1));
         Code slsb = in[2 * i], smsb = in[2 * i + 1], ml = B.mul(smsb, slsb), p;
@@ -288,9 +325,10 @@ static Blk T_CompConstant(Builder &B, const Fr &ct, const Code *in) {
         else if (!cmsb && clsb)  p = B.fma(smsb, nka, B.fma(smsb, kb, B.fma(slsb, nka, B.fma(ml, ka, ka))));
         else if (cmsb && !clsb)  p = B.fma(smsb, nka, B.fma(ml, kb, ka));
         else                     p = B.fma(ml, nka, ka);
-        B.at(parts + (size_t)i) = p; sum = B.add(sum, p);
+        B.at(parts + (size_t)i) = p; terms.push_back(p);
         b = fr_sub(b, e); a = fr_add(a, e); e = fr_add(e, e);
     }
+    Code sum = B.sum_tree(terms);
     B.at(o.pos + 255 + 127) = sum;
     Blk nb = T_Num2Bits(B, 135, sum);
     B.at(o.pos) = B.at(nb.pos + 127);
@@ -474,8 +512,7 @@ static Blk T_Filter(Builder &B, int N, Code in) {
     for (size_t i = 0; i < n; i++) {
         Blk e = T_IsEqual(B, c_const((uint32_t)i), in);
         Code eq = B.at(e.pos); B.at(o.pos + n + 1 + i) = eq;
-        Code nf = B.not1(eq);
-        B.at(o.pos + i) = i > 0 ? B.mul(B.at(o.pos + i - 1), nf) : nf;
+        B.at(o.pos + i) = B.gtc(in, (uint32_t)i);      // prod_{j<=i} (1 - isEq[j]) == (in > i)
     }
     return o;
 }
@@ -503,8 +540,8 @@ static Blk T_Reverse(Builder &B, int N, const Code *in) {
 static Blk T_LittleEndianBytes2Num(Builder &B, int N, const Code *in) {
     Blk o = B.alloc(1 + (size_t)N); B.copy(o.pos + 1, in, (size_t)N);
     T_AssertByteString(B, N, in);
-    Code lc = ZERO; for (int i = 0; i < N; i++) lc = B.fma(in[i], B.pow2((unsigned)(8 * i)), lc);
-    B.at(o.pos) = lc; return o;
+    std::vector<Code> terms; for (int i = 0; i < N; i++) terms.push_back(B.mul(in[i], B.pow2((unsigned)(8 * i))));
+    B.at(o.pos) = B.sum_tree(terms); return o;
 }
 // BigEndianBytes2Num(N) :33-39  own: out, in[N], inReversed[N]
 static Blk T_BigEndianBytes2Num(Builder &B, int N, const Code *in) {
@@ -585,13 +622,10 @@ static Blk T_Selector(Builder &B, int n_, const Code *vals, Code select) {
     size_t n = (size_t)n_; Blk o = B.alloc(1 + n + 1 + n + n + 1);
     B.copy(o.pos + 1, vals, n); B.at(o.pos + 1 + n) = select;
     size_t isEq = o.pos + 2 + n, sum = isEq + n;
-    Code cnt = ZERO; B.at(sum) = ZERO;
-    for (size_t i = 0; i < n; i++) {
-        Blk e = T_IsEqual(B, select, c_const((uint32_t)i));
-        Code eq = B.at(e.pos); B.at(isEq + i) = eq; cnt = B.add(cnt, eq);
-        B.at(sum + i + 1) = B.fma(eq, vals[i], B.at(sum + i));
-    }
-    B.chk_eq(cnt, ONE, o.sig);
+    B.at(sum) = ZERO;
+    for (size_t i = 0; i < n; i++) { Blk e = T_IsEqual(B, select, c_const((uint32_t)i)); B.at(isEq + i) = B.at(e.pos); }
+    B.selsum(select, vals, n, &B.at(sum + 1));          // sum[i+1] = sum_{j<=i} isEq[j]*vals[j]
+    B.chk_eq(B.gtc(select, (uint32_t)(n - 1)), ZERO, o.sig);   // sumIsEq === 1  <=>  select in [0, n)
     B.at(o.pos) = B.at(sum + n); return o;
 }
 // SelectorArray1D(n,p) :62-77 / SelectorArray2D(n,p,q) :91-110  own: out[cols], arrays[n][cols], select, arraysT[cols][n]
@@ -614,13 +648,13 @@ static Blk T_ShiftLeft(Builder &B, int n_, const Code *in, Code count) {
     size_t isEq = o.pos + 2 * n + 1, temp = isEq + n * n;
     T_AssertLessEqThan(B, 16, count, c_const((uint32_t)n));
     for (size_t i = 0; i < n; i++) {
-        Code acc = ZERO;
+        std::vector<Code> terms;
         for (size_t j = 0; j < n; j++) {
             Blk e = T_IsEqual(B, c_const((uint32_t)i), B.sub(c_const((uint32_t)j), count));
             Code eq = B.at(e.pos); B.at(isEq + i * n + j) = eq;
-            Code tv = B.mul(eq, in[j]); B.at(temp + i * n + j) = tv; acc = B.add(acc, tv);
+            Code tv = B.mul(eq, in[j]); B.at(temp + i * n + j) = tv; terms.push_back(tv);
         }
-        B.at(o.pos + i) = acc;
+        B.at(o.pos + i) = B.sum_tree(terms);
     }
     return o;
 }
@@ -630,12 +664,13 @@ static Blk T_ShiftRight(Builder &B, int n_, int ms_, const Code *in, Code count)
     B.copy(o.pos + n + ms, in, n); B.at(o.pos + 2 * n + ms) = count;
     size_t isEq = o.pos + 2 * n + ms + 1, temps = isEq + ms + 1;
     T_AssertLessEqThan(B, 16, count, c_const((uint32_t)ms));
-    std::vector<Code> acc(n + ms, ZERO);
+    std::vector<std::vector<Code>> acc(n + ms);
     for (size_t i = 0; i <= ms; i++) {
         Blk e = T_IsEqual(B, c_const((uint32_t)i), count); Code eq = B.at(e.pos); B.at(isEq + i) = eq;
-        for (size_t j = 0; j < n; j++) { Code tv = B.mul(eq, in[j]); B.at(temps + i * n + j) = tv; acc[i + j] = B.add(acc[i + j], tv); }
+        for (size_t j = 0; j < n; j++) { Code tv = B.mul(eq, in[j]); B.at(temps + i * n + j) = tv; acc[i + j].push_back(tv); }
     }
-    B.copy(o.pos, acc.data(), n + ms); return o;
+    for (size_t k = 0; k < n + ms; k++) B.at(o.pos + k) = B.sum_tree(acc[k]);
+    return o;
 }
 // Mask(n) :18-30  own: out[n], in[n], count, filter[n]
 static Blk T_Mask(Builder &B, int n_, const Code *in, Code count) {
@@ -677,18 +712,24 @@ static Blk T_SubstringCheck(Builder &B, int maxMainLen, int subLen, const Code *
     Blk sn = T_LittleEndianBytes2Num(B, subLen, subInput); Code subN = B.at(sn.pos); B.at(subNum) = subN;
     B.at(Mo) = ZERO;
     Fr pw = fr_from_u64(1), c256 = fr_from_u64(256);
-    for (size_t i = 0; i < MM; i++) { B.at(Mo + i + 1) = B.fma(mainInput[i], B.konst(pw), B.at(Mo + i)); pw = fr_mul(pw, c256); }
+    {   // M[i+1] = mainInput[i]*256^i + M[i]
+        std::vector<Code> ones(MM, ONE), terms(MM);
+        for (size_t i = 0; i < MM; i++) { terms[i] = B.mul(mainInput[i], B.konst(pw)); pw = fr_mul(pw, c256); }
+        B.chain(ZERO, ones.data(), terms.data(), MM, &B.at(Mo + 1));
+    }
     B.at(allowed) = ONE; B.at(sums) = ZERO;
     pw = fr_from_u64(1);
     Code lastIdx = B.add(B.sub(mainLen, c_const((uint32_t)SL)), ONE);
+    std::vector<Code> sones(Kn, ONE), sterms(Kn);
     for (size_t i = 0; i < Kn; i++) {
-        Blk e1 = T_IsEqual(B, c_const((uint32_t)i), lastIdx); Code l = B.at(e1.pos); B.at(isLast + i) = l;
-        B.at(allowed + i + 1) = B.mul(B.at(allowed + i), B.not1(l));
+        Blk e1 = T_IsEqual(B, c_const((uint32_t)i), lastIdx); B.at(isLast + i) = B.at(e1.pos);
+        B.at(allowed + i + 1) = B.gtc(lastIdx, (uint32_t)i);       // allowed[i]*(1 - isLastIndex[i]) == (lastIdx > i)
         Blk e2 = T_IsEqual(B, B.mul(subN, B.konst(pw)), B.sub(B.at(Mo + i + SL), B.at(Mo + i)));
         Code ex = B.at(e2.pos); B.at(exists + i) = ex;
-        B.at(sums + i + 1) = B.fma(B.at(allowed + i + 1), ex, B.at(sums + i));
+        sterms[i] = B.mul(B.at(allowed + i + 1), ex);
         pw = fr_mul(pw, c256);
     }
+    B.chain(ZERO, sones.data(), sterms.data(), Kn, &B.at(sums + 1));   // sums[i+1] = sums[i] + allowed[i+1]*exists[i]
     Blk z = T_IsZero(B, B.at(sums + Kn)); B.at(dne) = B.at(z.pos);
     B.at(o.pos) = B.not1(B.at(z.pos));
     return o;
@@ -833,7 +874,7 @@ static Blk T_Pad(Builder &B, int maxBlocks, int blockSize, const Code *in, Code 
     B.at(filter) = ONE;
     for (size_t i = 0; i < Bn; i++) {
         Blk e = T_IsEqual(B, c_const((uint32_t)i), inLen); Code eq = B.at(e.pos); B.at(isEq + i) = eq;
-        B.at(filter + i + 1) = B.mul(B.at(filter + i), B.not1(eq));
+        B.at(filter + i + 1) = B.gtc(inLen, (uint32_t)i);          // filter[i]*(1 - isEq[i]) == (inLen > i)
     }
     Code lastPos = B.sub(B.mul(nbk, c_const((uint32_t)blockSize)), ONE);
     for (size_t i = 0; i < Bn; i++) {
@@ -948,12 +989,12 @@ static Blk T_ProofOfWorkChecker(Builder &B, Code burnKey, Code revealAmount, Cod
 static Blk T_CountBytes(Builder &B, int N, const Code *bytes) {
     size_t n = (size_t)N; Blk o = B.alloc(1 + 3 * n); B.copy(o.pos + 1, bytes, n);
     for (size_t i = 0; i < n; i++) { Blk z = T_IsZero(B, bytes[i]); B.at(o.pos + 1 + n + i) = B.at(z.pos); }
-    Code lead = ZERO;
+    std::vector<Code> terms;
     for (size_t i = 0; i < n; i++) {
         Code sz = i == 0 ? B.at(o.pos + 1 + n) : B.mul(B.at(o.pos + 1 + n + i), B.at(o.pos + 1 + 2 * n + i - 1));
-        B.at(o.pos + 1 + 2 * n + i) = sz; lead = B.add(lead, sz);
+        B.at(o.pos + 1 + 2 * n + i) = sz; terms.push_back(sz);
     }
-    B.at(o.pos) = B.sub(c_const((uint32_t)n), lead); return o;
+    B.at(o.pos) = B.sub(c_const((uint32_t)n), B.sum_tree(terms)); return o;
 }
 // RlpInteger(N) integer.circom:67-110
 static Blk T_RlpInteger(Builder &B, int N, Code in) {
@@ -1318,17 +1359,34 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     if (P.konst.empty()) P.konst.push_back(fr_zero());
     if (P.aux.empty()) P.aux.push_back(0);
     // ---- levelise ----
+    // OP_INV results (the `inv` hint signal of IsZero) are consumed by no other op, so they are pulled out of the
+    // dependency levels and run once at the end, batch-inverted (vm_inv_batch).
+    std::vector<uint8_t> is_inv_slot(B.n_vals, 0);
+    size_t n_inv = 0;
+    for (auto &o : B.ops) if (op_opc(o.op) == OP_INV) { is_inv_slot[op_dst(o.op)] = 1; n_inv++; }
+    auto uses_inv = [&](Code c) { return code_kind(c) == K_VAL && is_inv_slot[code_payload(c)]; };
+    for (auto &o : B.ops) {
+        uint32_t opc = op_opc(o.op);
+        bool bad = false;
+        if (opc == OP_FMA) bad = uses_inv(o.op.a) || uses_inv(o.op.b) || uses_inv(o.op.c);
+        else if (opc == OP_CHK_EQ || opc == OP_DIV || opc == OP_MOD) bad = uses_inv(o.op.a) || uses_inv(o.op.b);
+        else if (opc == OP_CHAIN) bad = uses_inv(o.op.c);
+        else if (opc != OP_PACK8) bad = uses_inv(o.op.a);
+        if (bad) throw std::runtime_error("pob: internal: an IsZero inverse is consumed by another op");
+    }
+    for (Code c : B.aux) if (uses_inv(c)) throw std::runtime_error("pob: internal: an IsZero inverse is consumed by an operand list");
     uint32_t max_level = 0;
-    for (auto &o : B.ops) max_level = std::max(max_level, o.level);
+    for (auto &o : B.ops) if (op_opc(o.op) != OP_INV) max_level = std::max(max_level, o.level);
     for (auto &a : B.absorbs) max_level = std::max(max_level, a.level);
     std::vector<uint32_t> tcount(max_level + 2, 0), wcount(max_level + 2, 0);
-    for (auto &o : B.ops) tcount[o.level]++;
+    for (auto &o : B.ops) if (op_opc(o.op) != OP_INV) tcount[o.level]++;
     for (auto &a : B.absorbs) wcount[a.level]++;
     std::vector<uint32_t> tstart(max_level + 2, 0), wstart(max_level + 2, 0);
     for (uint32_t l = 1; l <= max_level + 1; l++) { tstart[l] = tstart[l - 1] + tcount[l - 1]; wstart[l] = wstart[l - 1] + wcount[l - 1]; }
     P.ops.resize(B.ops.size()); P.absorbs.resize(B.absorbs.size());
-    { std::vector<uint32_t> tp = tstart, wp = wstart;
-      for (auto &o : B.ops) P.ops[tp[o.level]++] = o.op;
+    P.inv_begin = (uint32_t)(B.ops.size() - n_inv); P.inv_end = (uint32_t)B.ops.size();
+    { std::vector<uint32_t> tp = tstart, wp = wstart; uint32_t ip = P.inv_begin;
+      for (auto &o : B.ops) { if (op_opc(o.op) == OP_INV) P.ops[ip++] = o.op; else P.ops[tp[o.level]++] = o.op; }
       for (auto &a : B.absorbs) P.absorbs[wp[a.level]++] = a.op; }
     for (uint32_t l = 1; l <= max_level; l++) {
         if (tcount[l] == 0 && wcount[l] == 0) continue;

@@ -80,7 +80,7 @@ __device__ void absorb_warp(uint64_t *W, const AbsorbOp op) {
 }
 
 struct EvalArgs {
-    const Op *ops; const AbsorbOp *absorbs; const Level *levels; uint32_t n_levels;
+    const Op *ops; const AbsorbOp *absorbs; const Level *levels; uint32_t n_levels, inv_begin, inv_end;
     const Code *aux; const Fr *konst; const Fr *invtab;
     const Code *out_codes; uint32_t n_outputs, n_inputs, val_base;
     uint64_t *stores; uint64_t store_stride;     // u64 units
@@ -88,7 +88,8 @@ struct EvalArgs {
     uint32_t *status; uint64_t *outputs;          // chunk base
 };
 
-__global__ void __launch_bounds__(256) k_eval(const EvalArgs a) {
+static const int EVAL_THREADS = 1024;
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval(const EvalArgs a) {
     const uint32_t inst = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     uint64_t *U = a.stores + (uint64_t)inst * a.store_stride;
     __shared__ uint32_t s_status;
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(256) k_eval(const EvalArgs a) {
         for (uint32_t w = L.w_begin + warp; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]);
         __syncthreads();
     }
+    vm_inv_batch(x, a.ops, a.inv_begin, a.inv_end, tid, nthr);     // IsZero inverse hints: no consumers, done last
     if (tid == 0) a.status[inst] = (s_status == STATUS_OK) ? 0u : s_status;
     for (uint32_t i = tid; i < a.n_outputs; i += nthr) {
         uint64_t v[4]; vm_expand(a.out_codes[i], U, 0, a.val_base, a.konst, v);
@@ -183,8 +185,10 @@ struct pob_handle {
     uint64_t **d_witptr = nullptr; uint32_t *h_status = nullptr; uint64_t *h_outputs = nullptr; uint64_t *h_digests = nullptr;
     uint64_t **h_witptr = nullptr;
     uint64_t *d_staged = nullptr; uint32_t n_staged = 0;
-    cudaStream_t s_eval = nullptr, s_exp = nullptr;
-    cudaEvent_t ev_eval_done[RING] = {nullptr, nullptr}, ev_exp_done[RING] = {nullptr, nullptr}, ev_start = nullptr, ev_end = nullptr;
+    uint32_t xgroup = 0;                       // instances per expand launch (distinct witness slots)
+    cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
+    cudaEvent_t ev_eval_done[RING] = {nullptr, nullptr}, ev_exp_done[RING] = {nullptr, nullptr}, ev_h2d[RING] = {nullptr, nullptr},
+                ev_start = nullptr, ev_end = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     uint32_t last_n = 0; bool last_expanded = false;
     pob_timing timing{};
@@ -238,7 +242,12 @@ void pob_destroy(pob_handle *h) {
     for (uint64_t *s : h->slots) cudaFree(s);
     for (void *p : {(void *)h->h_status, (void *)h->h_outputs, (void *)h->h_digests, (void *)h->h_witptr}) if (p) cudaFreeHost(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
-    for (uint32_t r = 0; r < pob_handle::RING; r++) { if (h->ev_eval_done[r]) cudaEventDestroy(h->ev_eval_done[r]); if (h->ev_exp_done[r]) cudaEventDestroy(h->ev_exp_done[r]); }
+    for (uint32_t r = 0; r < pob_handle::RING; r++) {
+        if (h->ev_eval_done[r]) cudaEventDestroy(h->ev_eval_done[r]);
+        if (h->ev_exp_done[r]) cudaEventDestroy(h->ev_exp_done[r]);
+        if (h->ev_h2d[r]) cudaEventDestroy(h->ev_h2d[r]);
+    }
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_end) cudaEventDestroy(h->ev_end);
     if (h->s_eval) cudaStreamDestroy(h->s_eval);
@@ -261,22 +270,30 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         h->d_ops = upload(P.ops); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
         h->d_konst = upload(P.konst); h->d_codes = upload(P.codes); h->d_tiles = upload(P.tiles);
         h->d_invtab = upload(build_inverse_table());
-        CU(cudaStreamCreateWithFlags(&h->s_eval, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&h->s_exp, cudaStreamNonBlocking));
-        for (uint32_t r = 0; r < pob_handle::RING; r++) { CU(cudaEventCreateWithFlags(&h->ev_eval_done[r], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&h->ev_exp_done[r], cudaEventDisableTiming)); }
+        // the small eval grid must get SMs while the expand grid (hundreds of thousands of CTAs) is draining:
+        // eval runs on the highest-priority stream, expand on the lowest
+        int pr_least = 0, pr_greatest = 0; CU(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+        CU(cudaStreamCreateWithPriority(&h->s_eval, cudaStreamNonBlocking, pr_greatest));
+        CU(cudaStreamCreateWithPriority(&h->s_h2d, cudaStreamNonBlocking, pr_greatest));
+        CU(cudaStreamCreateWithPriority(&h->s_exp, cudaStreamNonBlocking, pr_least));
+        for (uint32_t r = 0; r < pob_handle::RING; r++) {
+            CU(cudaEventCreateWithFlags(&h->ev_eval_done[r], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->ev_exp_done[r], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->ev_h2d[r], cudaEventDisableTiming));
+        }
         CU(cudaEventCreate(&h->ev_start)); CU(cudaEventCreate(&h->ev_end));
         // witness slots: as many as fit in 80 % of free HBM after the store ring
         size_t free_b = 0, total_b = 0; CU(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t wbytes = 32ull * P.n_signals;
         h->store_stride = (P.store_u64() + 31) & ~31ull;
-        uint32_t chunk = 16;
+        uint32_t chunk = 32;
         const uint64_t ring_bytes_per_inst = pob_handle::RING * (h->store_stride * 8 + (uint64_t)P.n_inputs * 32);
         uint64_t budget = (uint64_t)(free_b * 0.8);
         uint64_t nslots = budget > chunk * ring_bytes_per_inst ? (budget - chunk * ring_bytes_per_inst) / wbytes : 0;
         if (max_slots && nslots > max_slots) nslots = max_slots;
         if (nslots > 4096) nslots = 4096;
         if (nslots == 0) throw std::runtime_error("not even one witness slot fits in free HBM");
-        if (chunk > nslots) chunk = (uint32_t)nslots;
+        h->xgroup = (uint32_t)std::min<uint64_t>(16, nslots);
         h->chunk = chunk;
         CU(cudaMalloc(&h->d_stores, (size_t)pob_handle::RING * chunk * h->store_stride * 8));
         CU(cudaMalloc(&h->d_inputs, std::max<size_t>(32, (size_t)pob_handle::RING * chunk * P.n_inputs * 32)));
@@ -290,7 +307,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
 
 int pob_describe(const pob_handle *h, pob_desc *out) {
     if (!h || !out) return fail(POB_E_BAD_ARG, "pob_describe: null argument");
-    fill_desc(h->P, out); out->n_slots = (uint32_t)h->slots.size(); out->chunk = h->chunk; return POB_OK;
+    fill_desc(h->P, out); out->n_slots = (uint32_t)h->slots.size(); out->chunk = h->chunk; out->expand_group = h->xgroup; return POB_OK;
 }
 
 void *pob_alloc_pinned(uint64_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { g_err = "cudaMallocHost failed"; return nullptr; } return p; }
@@ -331,46 +348,61 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
         const Program &P = h->P;
         CU(cudaSetDevice(h->device));
         ensure_batch_buffers(h, n);
-        const uint32_t E = h->chunk, R = pob_handle::RING, nchunks = (n + E - 1) / E, nslots = (uint32_t)h->slots.size();
+        const uint32_t E = h->chunk, R = pob_handle::RING, nchunks = (n + E - 1) / E, nslots = (uint32_t)h->slots.size(), X = h->xgroup;
         const size_t in_stride = (size_t)P.n_inputs * 4, no = std::max<uint32_t>(1, P.n_outputs);
-        while (h->ev_pool.size() < (size_t)nchunks * 4) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
+        const uint32_t groups_per_chunk = (E + X - 1) / X, ev_per_chunk = 2 + 2 * groups_per_chunk;
+        while (h->ev_pool.size() < (size_t)nchunks * ev_per_chunk) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
         for (uint32_t i = 0; i < n; i++) h->h_witptr[i] = h->slots[i % nslots];
         pob_timing T{};
         CU(cudaEventRecord(h->ev_start, h->s_eval));
         CU(cudaMemcpyAsync(h->d_witptr, h->h_witptr, (size_t)n * sizeof(uint64_t *), cudaMemcpyHostToDevice, h->s_eval));
         if (digest) CU(cudaMemsetAsync(h->d_digests, 0, (size_t)n * 8, h->s_eval));
+        CU(cudaEventRecord(h->ev_eval_done[0], h->s_eval));
+        CU(cudaStreamWaitEvent(h->s_h2d, h->ev_eval_done[0], 0));
+        std::vector<uint32_t> group_count;
         for (uint32_t c = 0; c < nchunks; c++) {
             const uint32_t r = c % R, first = c * E, cnt = std::min(E, n - first);
-            if (c >= R) CU(cudaStreamWaitEvent(h->s_eval, h->ev_exp_done[r], 0));
+            cudaEvent_t *ev = &h->ev_pool[(size_t)c * ev_per_chunk];
             const uint64_t *d_in;
             if (staged) d_in = h->d_staged + (size_t)first * in_stride;
             else {
+                // inputs travel on their own stream, one chunk ahead of the eval kernel that consumes them
                 uint64_t *dst = h->d_inputs + (size_t)r * E * in_stride;
-                if (in_stride) { CU(cudaMemcpyAsync(dst, inputs + (size_t)first * in_stride, (size_t)cnt * in_stride * 8, cudaMemcpyHostToDevice, h->s_eval)); T.h2d_bytes += (uint64_t)cnt * in_stride * 8; }
+                if (c >= R) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_eval_done[r], 0));
+                if (in_stride) { CU(cudaMemcpyAsync(dst, inputs + (size_t)first * in_stride, (size_t)cnt * in_stride * 8, cudaMemcpyHostToDevice, h->s_h2d)); T.h2d_bytes += (uint64_t)cnt * in_stride * 8; }
+                CU(cudaEventRecord(h->ev_h2d[r], h->s_h2d));
+                CU(cudaStreamWaitEvent(h->s_eval, h->ev_h2d[r], 0));
                 d_in = dst;
             }
+            if (c >= R) CU(cudaStreamWaitEvent(h->s_eval, h->ev_exp_done[r], 0));      // store ring slot r is free again
             uint64_t *stores = h->d_stores + (size_t)r * E * h->store_stride;
-            EvalArgs ea{h->d_ops, h->d_abs, h->d_levels, (uint32_t)P.levels.size(), h->d_aux, h->d_konst, h->d_invtab,
+            EvalArgs ea{h->d_ops, h->d_abs, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
                         h->d_codes + ROUND_SIGNALS + 1, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
                         h->d_status + first, h->d_outputs + (size_t)first * no * 4};
-            CU(cudaEventRecord(h->ev_pool[4 * c + 0], h->s_eval));
-            k_eval<<<cnt, 256, 0, h->s_eval>>>(ea);
-            CU(cudaEventRecord(h->ev_pool[4 * c + 1], h->s_eval));
+            CU(cudaEventRecord(ev[0], h->s_eval));
+            k_eval<<<cnt, EVAL_THREADS, 0, h->s_eval>>>(ea);
+            CU(cudaEventRecord(ev[1], h->s_eval));
             CU(cudaEventRecord(h->ev_eval_done[r], h->s_eval));
             T.eval_launches++;
             if (expand) {
                 CU(cudaStreamWaitEvent(h->s_exp, h->ev_eval_done[r], 0));
-                ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, stores, h->store_stride, P.val_base, h->d_witptr + first};
-                CU(cudaEventRecord(h->ev_pool[4 * c + 2], h->s_exp));
-                k_expand<<<dim3((unsigned)P.tiles.size(), cnt), 256, 0, h->s_exp>>>(xa);
-                CU(cudaEventRecord(h->ev_pool[4 * c + 3], h->s_exp));
-                T.expand_launches++;
-                if (digest) for (uint32_t j = 0; j < cnt; j++) {
-                    k_digest<<<1184, 256, 0, h->s_exp>>>(h->slots[(first + j) % nslots], P.n_signals, h->d_digests + first + j);
-                    T.other_launches++;
+                uint32_t g = 0;
+                for (uint32_t off = 0; off < cnt; off += X, g++) {
+                    const uint32_t gc = std::min(X, cnt - off);
+                    ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, stores + (size_t)off * h->store_stride, h->store_stride, P.val_base, h->d_witptr + first + off};
+                    CU(cudaEventRecord(ev[2 + 2 * g], h->s_exp));
+                    k_expand<<<dim3((unsigned)P.tiles.size(), gc), 256, 0, h->s_exp>>>(xa);
+                    CU(cudaEventRecord(ev[3 + 2 * g], h->s_exp));
+                    T.expand_launches++;
+                    if (digest) for (uint32_t j = 0; j < gc; j++) {
+                        k_digest<<<1184, 256, 0, h->s_exp>>>(h->slots[(first + off + j) % nslots], P.n_signals, h->d_digests + first + off + j);
+                        T.other_launches++;
+                    }
                 }
+                group_count.push_back(g);
                 CU(cudaEventRecord(h->ev_exp_done[r], h->s_exp));
             } else {
+                group_count.push_back(0);
                 CU(cudaEventRecord(h->ev_exp_done[r], h->s_eval));
             }
         }
@@ -383,15 +415,16 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
         CU(cudaStreamWaitEvent(h->s_exp, h->ev_eval_done[0], 0));
         if (digest) { CU(cudaMemcpyAsync(h->h_digests, h->d_digests, (size_t)n * 8, cudaMemcpyDeviceToHost, h->s_exp)); T.d2h_bytes += (uint64_t)n * 8; }
         CU(cudaEventRecord(h->ev_end, h->s_exp));
-        CU(cudaStreamSynchronize(h->s_exp)); CU(cudaStreamSynchronize(h->s_eval));
+        CU(cudaStreamSynchronize(h->s_exp)); CU(cudaStreamSynchronize(h->s_eval)); CU(cudaStreamSynchronize(h->s_h2d));
         CU(cudaGetLastError());
         memcpy(status, h->h_status, (size_t)n * 4);
         if (outputs && P.n_outputs) memcpy(outputs, h->h_outputs, (size_t)n * no * 32);
         if (digest) memcpy(digests, h->h_digests, (size_t)n * 8);
         CU(cudaEventElapsedTime(&T.total_ms, h->ev_start, h->ev_end));
         for (uint32_t c = 0; c < nchunks; c++) {
-            float ms = 0; CU(cudaEventElapsedTime(&ms, h->ev_pool[4 * c + 0], h->ev_pool[4 * c + 1])); T.eval_ms += ms;
-            if (expand) { CU(cudaEventElapsedTime(&ms, h->ev_pool[4 * c + 2], h->ev_pool[4 * c + 3])); T.expand_ms += ms; }
+            cudaEvent_t *ev = &h->ev_pool[(size_t)c * ev_per_chunk];
+            float ms = 0; CU(cudaEventElapsedTime(&ms, ev[0], ev[1])); T.eval_ms += ms;
+            for (uint32_t g = 0; g < group_count[c]; g++) { CU(cudaEventElapsedTime(&ms, ev[2 + 2 * g], ev[3 + 2 * g])); T.expand_ms += ms; }
         }
         h->timing = T; h->last_n = n; h->last_expanded = expand;
     } catch (const std::exception &e) { return fail(POB_E_CUDA, std::string("pob_run_batch: ") + e.what()); }

@@ -42,6 +42,12 @@ enum Opc : uint32_t {
     OP_PACK8 = 6,      // W[dst] = sum_k (aux[a+k] & 0xff) << 8k  utils/keccak.circom:467-482 (bytes -> lane)
     OP_CHK_EQ = 7,     // a == b else fail(c)                     any `===`
     OP_CHK_RANGE = 8,  // a < 2^b else fail(c)                    bitify.circom:38 (Num2Bits sum check)
+    // closed forms of the circuits' one-hot prefix patterns (identical values, no dependency chain):
+    OP_GTC = 9,        // V[dst] = (a > b) as canonical integers, b raw u32.  prod_{j<=i}(1 - IsEqual(j, a)) == (a > i):
+                       //   utils/keccak.circom:427-433 (Pad filter), array.circom:26-40 (Filter), substring_check.circom:87-88
+    OP_SELSUM = 10,    // V[dst] = (a <= c) ? aux[b + a] : 0, b/c raw.  sum_{j<=c} IsEqual(a, j)*vals[j]: selector.circom:31-41
+    OP_CHAIN = 11,     // x = c; for k < b: x = x*aux[a+2k] + aux[a+2k+1]; V[dst+k] = x   (one thread walks an affine
+                       //   recurrence whose every step is a signal: substring_check.circom:47-49, 95)
 };
 struct Op { uint32_t opc_dst; Code a, b, c; };                    // opc in the top 6 bits, dst in the low 26
 POB_HD uint32_t op_opc(const Op &o) { return o.opc_dst >> 26; }
@@ -93,7 +99,8 @@ struct Program {
     uint32_t n_vals = 0;           // value slots (inputs are slots 0..n_inputs-1)
     uint64_t store_u64() const { return (uint64_t)val_base + 4ull * n_vals; }
     // eval program
-    std::vector<Op> ops;           // sorted by level
+    std::vector<Op> ops;           // [0, inv_begin) sorted by level, then the deferred OP_INV ops
+    uint32_t inv_begin = 0, inv_end = 0;   // IsZero inverses feed no other op: they run last, batch-inverted per thread
     std::vector<AbsorbOp> absorbs; // sorted by level
     std::vector<Level> levels;
     std::vector<Code> aux;         // PACK8 operand lists

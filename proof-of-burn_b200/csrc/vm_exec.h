@@ -73,9 +73,62 @@ POB_HD void vm_exec_op(const VmCtx &x, const Op &op) {
         for (int k = 0; k < 8; k++) { Fr v = vm_load(x, x.aux[op.a + k]); w |= (uint64_t)(v.l[0] & 0xffu) << (8 * k); }
         x.U[dst] = w;
         break; }
+    case OP_GTC: {
+        Fr a = vm_load(x, op.a);
+        bool gt = !fr_fits64(a) || fr_lo64(a) > (uint64_t)op.b;
+        vm_store_val(vd, fr_from_u64(gt ? 1 : 0));
+        break; }
+    case OP_SELSUM: {
+        Fr sel = vm_load(x, op.a), r = fr_zero();
+        if (fr_fits64(sel) && fr_lo64(sel) <= (uint64_t)op.c) r = vm_load(x, x.aux[op.b + (uint32_t)fr_lo64(sel)]);
+        vm_store_val(vd, r);
+        break; }
+    case OP_CHAIN: {
+        Fr acc = vm_load(x, op.c);
+        for (uint32_t k = 0; k < op.b; k++) {
+            Fr m = vm_load(x, x.aux[op.a + 2 * k]), ad = vm_load(x, x.aux[op.a + 2 * k + 1]);
+            acc = fr_add(fr_mul(acc, m), ad);
+            vm_store_val(vd + 4ull * k, acc);
+        }
+        break; }
     case OP_CHK_EQ: { Fr a = vm_load(x, op.a), b = vm_load(x, op.b); if (!fr_eq(a, b)) vm_fail(x, op.c); break; }
     case OP_CHK_RANGE: { Fr a = vm_load(x, op.a); if (!fr_lt_pow2(a, op.b)) vm_fail(x, op.c); break; }
     default: break;
+    }
+}
+
+// Deferred IsZero inverses (comparators.circom:30).  Thread `tid` of `nthr` owns ops begin+tid, +nthr, ...: zero and
+// table-sized inputs are answered directly, the rest share ONE field inversion per thread (Montgomery's trick:
+// prefix products parked in the destination slots, then unwound in reverse).
+POB_HD int vm_inv_class(const VmCtx &x, const Fr &a, Fr &direct) {
+    if (fr_is_zero(a)) { direct = a; return 0; }
+    if (fr_fits64(a) && fr_lo64(a) < INV_TABLE_N) { direct = x.invtab[fr_lo64(a)]; return 0; }
+    Fr n; fr_raw_sub(n, fr_p(), a);
+    if (fr_fits64(n) && fr_lo64(n) < INV_TABLE_N) { direct = fr_neg(x.invtab[fr_lo64(n)]); return 0; }
+    return 1;
+}
+POB_HD void vm_inv_batch(const VmCtx &x, const Op *ops, uint32_t begin, uint32_t end, uint32_t tid, uint32_t nthr) {
+    if (begin + tid >= end) return;
+    Fr acc = fr_from_u64(1); bool any = false;
+    uint32_t last = begin + tid;
+    for (uint32_t i = begin + tid; i < end; i += nthr) {
+        last = i;
+        Fr a = vm_load(x, ops[i].a), d;
+        uint64_t *vd = x.U + x.val_base + 4ull * op_dst(ops[i]);
+        if (vm_inv_class(x, a, d) == 0) vm_store_val(vd, d);
+        else { vm_store_val(vd, acc); acc = fr_mul(acc, a); any = true; }
+    }
+    if (!any) return;
+    Fr inv = fr_inv(acc);
+    for (uint32_t i = last;; i -= nthr) {
+        Fr a = vm_load(x, ops[i].a), d;
+        if (vm_inv_class(x, a, d) != 0) {
+            uint64_t *vd = x.U + x.val_base + 4ull * op_dst(ops[i]);
+            Fr pre = vm_load_val(vd);
+            vm_store_val(vd, fr_mul(inv, pre));
+            inv = fr_mul(inv, a);
+        }
+        if (i < begin + tid + nthr) break;
     }
 }
 

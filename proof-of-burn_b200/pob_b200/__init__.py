@@ -40,10 +40,10 @@ class Desc(ctypes.Structure):
     _fields_ = [("n_signals", ctypes.c_uint64), ("n_outputs", ctypes.c_uint32), ("n_inputs", ctypes.c_uint32),
                 ("witness_bytes", ctypes.c_uint64), ("wtns_file_bytes", ctypes.c_uint64), ("store_bytes", ctypes.c_uint64),
                 ("n_ops", ctypes.c_uint64), ("n_absorbs", ctypes.c_uint32), ("n_levels", ctypes.c_uint32),
-                ("n_tiles", ctypes.c_uint32), ("n_slots", ctypes.c_uint32), ("chunk", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("n_tiles", ctypes.c_uint32), ("n_slots", ctypes.c_uint32), ("chunk", ctypes.c_uint32), ("expand_group", ctypes.c_uint32)]
 
     def as_dict(self):
-        return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved"}
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
 class Timing(ctypes.Structure):

@@ -52,6 +52,7 @@ uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_
         for (uint32_t i = lv.t_begin; i < lv.t_end; i++) vm_exec_op(x, P.ops[i]);
         for (uint32_t i = lv.w_begin; i < lv.w_end; i++) vm_absorb_scalar(U.data(), P.absorbs[i]);
     }
+    for (uint32_t tid = 0; tid < 64; tid++) vm_inv_batch(x, P.ops.data(), P.inv_begin, P.inv_end, tid, 64);
     if (witness)
         for (const Tile &t : P.tiles)
             for (uint32_t k = 0; k < t.n; k++)
@@ -61,4 +62,17 @@ uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_
             vm_expand(P.codes[ROUND_SIGNALS + 1 + i], U.data(), 0, P.val_base, P.konst.data(), outputs + 4 * i);
     return status == STATUS_OK ? 0 : status;
 }
+}
+
+// level histogram for tuning: out[3*i+0..2] = thread ops, absorb ops, INV ops of level i (up to max_levels)
+extern "C" uint32_t pob_emu_level_hist(void *h, uint32_t *out, uint32_t max_levels) {
+    const Program &P = ((EmuProgram *)h)->P;
+    uint32_t n = (uint32_t)P.levels.size();
+    for (uint32_t i = 0; i < n && i < max_levels; i++) {
+        const Level &L = P.levels[i];
+        uint32_t inv = 0;
+        for (uint32_t k = L.t_begin; k < L.t_end; k++) if (op_opc(P.ops[k]) == OP_INV) inv++;
+        out[3 * i] = L.t_end - L.t_begin; out[3 * i + 1] = L.w_end - L.w_begin; out[3 * i + 2] = inv;
+    }
+    return n;
 }
