@@ -195,10 +195,11 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     t_wall = time.time()
-    dev_ms, exp_ms, exp_launches, launches, ok = 0.0, 0.0, 0, 0, 0
+    dev_ms, exp_ms, exp_launches, launches, ok, eval_ms, eval_launches = 0.0, 0.0, 0, 0, 0, 0.0, 0
     for _ in range(a.steps):
         r = step_resident()
         dev_ms += r.timing["total_ms"]; exp_ms += r.timing["expand_ms"]; exp_launches += r.timing["expand_launches"]
+        eval_ms += r.timing["eval_ms"]; eval_launches += r.timing["eval_launches"]
         launches += r.timing["expand_launches"] + r.timing["eval_launches"] + r.timing["other_launches"]
         ok += r.n_ok
     barrier()
@@ -242,7 +243,9 @@ def main():
                 "config": {"workload": workload, "circuit": expr, "n_signals": desc["n_signals"], "witness_bytes": desc["witness_bytes"],
                            "resident_slots": desc["n_slots"], "parallelism": "instances sharded by index, %d per GPU" % a.batch,
                            "l2": "each step writes %.1f GB per GPU, far beyond the 126 MB L2; no flush needed" % (a.batch * desc["witness_bytes"] / 1e9),
-                           "wall_ms_per_step": wall_ms_max / a.steps},
+                           "wall_ms_per_step": wall_ms_max / a.steps,
+                           "eval_kernel": {"ms_per_launch": eval_ms / max(1, eval_launches), "instances_per_launch": min(desc["chunk"], a.batch),
+                                           "note": "runs concurrently with k_expand on a higher-priority stream"}},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "witnesses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": "host pinned inputs -> pob_run_batch -> status + output signals on host; witnesses stay in the HBM slot ring for the on-GPU consumer"},

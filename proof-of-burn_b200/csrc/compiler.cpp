@@ -1403,7 +1403,7 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
         while (done < s.n) {
             uint32_t n = (uint32_t)std::min<uint64_t>(TILE_SIGNALS, s.n - done);
             Tile t; t.dst = s.dst + done; t.n = n; t.pad = 0;
-            if (s.round) { t.code_off = (uint32_t)done; t.ubase = s.ubase; }
+            if (s.round) { t.code_off = (uint32_t)done; t.ubase = s.ubase; t.pad = 1; }
             else { t.code_off = (uint32_t)(ROUND_SIGNALS + s.pos + done); t.ubase = 0; }
             P.tiles.push_back(t); done += n;
         }

@@ -78,7 +78,7 @@ POB_HD uint32_t rw_out(int l) { return RW_OUT + l; }
 struct Level { uint32_t t_begin, t_end, w_begin, w_end; };
 
 // ---- expand tiles: a contiguous run of witness entries and where its codes live -------------------------------
-struct Tile { uint64_t dst; uint32_t n, code_off, ubase, pad; };  // BIT codes are relative to ubase
+struct Tile { uint64_t dst; uint32_t n, code_off, ubase, pad; };  // BIT codes are relative to ubase; pad = 1: round tile (all BIT)
 static const uint32_t TILE_SIGNALS = 8192;
 
 // ---- circuit identity ---------------------------------------------------------------------------------------
