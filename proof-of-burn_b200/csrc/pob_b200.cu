@@ -125,29 +125,15 @@ struct ExpandArgs {
     uint64_t *const *wit;                         // per instance of the chunk: witness slot base
 };
 
-__device__ __forceinline__ void st256_cs(uint64_t *p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
-    asm volatile("st.global.cs.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
-}
-
 // grid = (n_tiles, instances in group); one CTA streams one tile (<= 8192 entries = 256 KiB) of one witness.
-// VARIANT (tuning knob, chosen once from measurements): 0 = generic decode, default stores; 1 = streaming (.cs) stores;
-// 2 = BIT-specialised fast path for round tiles + .cs; 3 = as 2 with default stores.
-template <int VARIANT>
+// Measured alternatives (profiles/r01_expand_sweep.md): streaming (.cs) stores and a BIT-only fast path for round tiles
+// were neutral / slower -- the kernel is DRAM-write bound, not issue bound -- so the single generic loop is kept.
 __global__ void __launch_bounds__(256) k_expand(const ExpandArgs a) {
     const Tile t = a.tiles[blockIdx.x];
     const uint64_t *U = a.stores + (uint64_t)blockIdx.y * a.store_stride;
     uint64_t *W = a.wit[blockIdx.y] + t.dst * 4;
     const Code *c = a.codes + t.code_off;
     const uint64_t *Ub = U + t.ubase;
-    if (VARIANT >= 2 && t.pad) {       // round tile: every code is BIT
-#pragma unroll 8
-        for (uint32_t k = threadIdx.x; k < t.n; k += 256) {
-            const uint32_t p = __ldg(c + k);
-            const uint64_t v0 = (Ub[(p >> 6) & 0xffffffu] >> (p & 63)) & 1ull;
-            if (VARIANT == 2) st256_cs(W + 4ull * k, v0, 0, 0, 0); else st256(W + 4ull * k, v0, 0, 0, 0);
-        }
-        return;
-    }
 #pragma unroll 4
     for (uint32_t k = threadIdx.x; k < t.n; k += 256) {
         const Code cd = __ldg(c + k);
@@ -157,7 +143,7 @@ __global__ void __launch_bounds__(256) k_expand(const ExpandArgs a) {
         else if (kind == K_CONST) v0 = p;
         else if (kind == K_VAL) { const uint64_t *s = U + a.val_base + 4ull * p; v0 = s[0]; v1 = s[1]; v2 = s[2]; v3 = s[3]; }
         else { const uint64_t *s = reinterpret_cast<const uint64_t *>(a.konst + p); v0 = s[0]; v1 = s[1]; v2 = s[2]; v3 = s[3]; }
-        if (VARIANT == 1 || VARIANT == 2) st256_cs(W + 4ull * k, v0, v1, v2, v3); else st256(W + 4ull * k, v0, v1, v2, v3);
+        st256(W + 4ull * k, v0, v1, v2, v3);
     }
 }
 
@@ -203,7 +189,6 @@ struct pob_handle {
     uint64_t **h_witptr = nullptr;
     uint64_t *d_staged = nullptr; uint32_t n_staged = 0;
     uint32_t xgroup = 0;                       // instances per expand launch (distinct witness slots)
-    int variant = 0;                           // k_expand tuning variant (POB_EXPAND_VARIANT, default chosen from measurements)
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
     cudaEvent_t ev_eval_done[RING] = {nullptr, nullptr}, ev_exp_done[RING] = {nullptr, nullptr}, ev_h2d[RING] = {nullptr, nullptr},
                 ev_start = nullptr, ev_end = nullptr;
@@ -312,7 +297,6 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (nslots > 4096) nslots = 4096;
         if (nslots == 0) throw std::runtime_error("not even one witness slot fits in free HBM");
         h->xgroup = (uint32_t)std::min<uint64_t>(16, nslots);
-        if (const char *v = getenv("POB_EXPAND_VARIANT")) h->variant = atoi(v);
         if (const char *v = getenv("POB_EXPAND_GROUP")) h->xgroup = (uint32_t)std::max(1, std::min<int>(atoi(v), (int)nslots));
         if (const char *v = getenv("POB_EVAL_CHUNK")) chunk = (uint32_t)std::max(1, atoi(v));
         h->chunk = chunk;
@@ -412,13 +396,7 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
                     const uint32_t gc = std::min(X, cnt - off);
                     ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, stores + (size_t)off * h->store_stride, h->store_stride, P.val_base, h->d_witptr + first + off};
                     CU(cudaEventRecord(ev[2 + 2 * g], h->s_exp));
-                    const dim3 grid((unsigned)P.tiles.size(), gc);
-                    switch (h->variant) {
-                    case 1: k_expand<1><<<grid, 256, 0, h->s_exp>>>(xa); break;
-                    case 2: k_expand<2><<<grid, 256, 0, h->s_exp>>>(xa); break;
-                    case 3: k_expand<3><<<grid, 256, 0, h->s_exp>>>(xa); break;
-                    default: k_expand<0><<<grid, 256, 0, h->s_exp>>>(xa); break;
-                    }
+                    k_expand<<<dim3((unsigned)P.tiles.size(), gc), 256, 0, h->s_exp>>>(xa);
                     CU(cudaEventRecord(ev[3 + 2 * g], h->s_exp));
                     T.expand_launches++;
                     if (digest) for (uint32_t j = 0; j < gc; j++) {
