@@ -234,7 +234,9 @@ def main():
         achieved = bytes_per_launch / (per_launch_ms / 1e3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "expand_traffic.json"))).get("dram_bytes_per_launch")
+            # ncu --set full capture of one 1-witness launch (profiles/), scaled to the witnesses per launch timed here
+            per_wit = json.load(open(os.path.join(ROOT, "profiles", "expand_traffic.json"))).get("dram_bytes_per_witness")
+            traffic = per_wit * (a.batch * a.steps / max(1, exp_launches)) if per_wit and a.layers == 16 else None
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": "witnesses/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
