@@ -110,6 +110,15 @@ int pob_write_wtns(pob_handle *h, uint32_t index, const char *path);
 /* device pointer of a resident witness (for an on-GPU consumer such as a prover's first stage) */
 int pob_witness_device_ptr(pob_handle *h, uint32_t index, void **dptr);
 
+/* ---- the step just before the path ------------------------------------------------------
+ * replaces: find_burn_key() of the reference input generator (tests/main.py:47-56): starting at start_key, find the
+ * first burnKey >= start_key whose keccak256(burnKey[32 BE] | revealAmount[32 BE] | burnExtraCommitment[32 BE] |
+ * "EIP-7503") begins with `zero_bytes` zero bytes (circuits/utils/proof_of_work.circom:54-81).  Searches at most
+ * max_tries consecutive keys on the GPU; *tries receives the number of keys up to and including the hit.
+ * Returns POB_E_RANGE when no key in the window satisfies the check. */
+int pob_pow_grind(int device, const uint64_t start_key[4], const uint64_t reveal_amount[4], const uint64_t burn_extra_commitment[4],
+                  uint32_t zero_bytes, uint64_t max_tries, uint64_t found_key[4], uint64_t *tries);
+
 const char *pob_last_error(void);
 const char *pob_version(void);
 

@@ -164,6 +164,45 @@ __global__ void __launch_bounds__(256) k_digest(const uint64_t *wit, uint64_t n_
     if (threadIdx.x == 0) { uint64_t s = 0; for (int w = 0; w < 8; w++) s += part[w]; atomicAdd(out, (unsigned long long)s); }
 }
 
+// ---- proof-of-work burn-key grinder (reference tests/main.py:47-56; circuits/utils/proof_of_work.circom:54-81) ----
+// One candidate key per thread: a single-block keccak256 of key|reveal|extra|"EIP-7503" held in 25 registers.
+struct GrindArgs { uint64_t start[4], lanes_tail[9]; uint64_t first, count; uint32_t zero_bytes; unsigned long long *hit; };
+__device__ __forceinline__ uint64_t bswap64(uint64_t x) { return __byte_perm((uint32_t)(x >> 32), 0, 0x0123) | ((uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32); }
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+__global__ void __launch_bounds__(256) k_pow_grind(const GrindArgs a) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.count) return;
+    // key = start + first + idx (256-bit add)
+    uint64_t k0 = a.start[0], k1 = a.start[1], k2 = a.start[2], k3 = a.start[3];
+    const uint64_t add = a.first + idx;
+    k0 += add; if (k0 < add) { if (++k1 == 0) { if (++k2 == 0) ++k3; } }
+    uint64_t s[25];
+    s[0] = bswap64(k3); s[1] = bswap64(k2); s[2] = bswap64(k1); s[3] = bswap64(k0);      // 32-byte big-endian key
+#pragma unroll
+    for (int i = 0; i < 9; i++) s[4 + i] = a.lanes_tail[i];                                // reveal | extra | "EIP-7503"
+    s[13] = 0x01; s[14] = 0; s[15] = 0; s[16] = 0x8000000000000000ull;                     // 0x01 ... 0x80 padding of a 104-byte message
+#pragma unroll
+    for (int i = 17; i < 25; i++) s[i] = 0;
+#pragma unroll 1
+    for (int r = 0; r < 24; r++) {
+        uint64_t c[5], d[5], b[25];
+#pragma unroll
+        for (int x = 0; x < 5; x++) c[x] = s[x] ^ s[x + 5] ^ s[x + 10] ^ s[x + 15] ^ s[x + 20];
+#pragma unroll
+        for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
+#pragma unroll
+        for (int i = 0; i < 25; i++) s[i] ^= d[i % 5];
+        b[0] = s[0];
+#pragma unroll
+        for (int i = 0; i < 24; i++) b[keccak_rot(i + 1)] = rotl64(s[keccak_rot(i)], keccak_shl(i));
+#pragma unroll
+        for (int i = 0; i < 25; i++) s[i] = b[i] ^ (~b[chi_b(i)] & b[chi_c(i)]);
+        s[0] ^= keccak_rc(r);
+    }
+    const uint64_t mask = a.zero_bytes >= 8 ? ~0ull : ((1ull << (8 * a.zero_bytes)) - 1);
+    if ((s[0] & mask) == 0) atomicMin(a.hit, (unsigned long long)idx);
+}
+
 }  // namespace
 
 // =============================================================================================================
@@ -434,6 +473,43 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
         h->timing = T; h->last_n = n; h->last_expanded = expand;
     } catch (const std::exception &e) { return fail(POB_E_CUDA, std::string("pob_run_batch: ") + e.what()); }
     return POB_OK;
+}
+
+int pob_pow_grind(int device, const uint64_t start_key[4], const uint64_t reveal_amount[4], const uint64_t burn_extra_commitment[4],
+                  uint32_t zero_bytes, uint64_t max_tries, uint64_t found_key[4], uint64_t *tries) {
+    if (!start_key || !reveal_amount || !burn_extra_commitment || !found_key || zero_bytes > 8 || max_tries == 0)
+        return fail(POB_E_BAD_ARG, "pob_pow_grind: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(POB_E_NO_DEVICE, "pob_pow_grind: no such CUDA device");
+    unsigned long long *d_hit = nullptr;
+    try {
+        CU(cudaSetDevice(device));
+        GrindArgs ga; memcpy(ga.start, start_key, 32); ga.zero_bytes = zero_bytes;
+        uint8_t msg[72];                                     // bytes 32..103 of the message
+        for (int i = 0; i < 32; i++) { msg[i] = (uint8_t)(reveal_amount[3 - i / 8] >> (8 * (7 - i % 8))); msg[32 + i] = (uint8_t)(burn_extra_commitment[3 - i / 8] >> (8 * (7 - i % 8))); }
+        memcpy(msg + 64, "EIP-7503", 8);
+        memcpy(ga.lanes_tail, msg, 72);                      // little-endian lanes of a little-endian host
+        CU(cudaMalloc(&d_hit, 8));
+        ga.hit = d_hit;
+        const uint64_t WINDOW = 1ull << 22;
+        for (uint64_t first = 0; first < max_tries; first += WINDOW) {
+            unsigned long long none = ~0ull, hit = ~0ull;
+            CU(cudaMemcpy(d_hit, &none, 8, cudaMemcpyHostToDevice));
+            ga.first = first; ga.count = std::min<uint64_t>(WINDOW, max_tries - first);
+            k_pow_grind<<<(unsigned)((ga.count + 255) / 256), 256>>>(ga);
+            CU(cudaGetLastError());
+            CU(cudaMemcpy(&hit, d_hit, 8, cudaMemcpyDeviceToHost));
+            if (hit != ~0ull) {
+                uint64_t add = first + hit, k[4] = {start_key[0], start_key[1], start_key[2], start_key[3]};
+                k[0] += add; if (k[0] < add) { if (++k[1] == 0) { if (++k[2] == 0) ++k[3]; } }
+                memcpy(found_key, k, 32); if (tries) *tries = add + 1;
+                cudaFree(d_hit); return POB_OK;
+            }
+        }
+        cudaFree(d_hit);
+    } catch (const std::exception &e) { if (d_hit) cudaFree(d_hit); return fail(POB_E_CUDA, std::string("pob_pow_grind: ") + e.what()); }
+    if (tries) *tries = max_tries;
+    return fail(POB_E_RANGE, "pob_pow_grind: no key in the search window satisfies the proof-of-work check");
 }
 
 int pob_last_timing(const pob_handle *h, pob_timing *out) {

@@ -91,6 +91,8 @@ def lib():
         L.pob_write_wtns.argtypes = [vp, u32, ctypes.c_char_p]
         L.pob_witness_device_ptr.restype = ci
         L.pob_witness_device_ptr.argtypes = [vp, u32, ctypes.POINTER(vp)]
+        L.pob_pow_grind.restype = ci
+        L.pob_pow_grind.argtypes = [ci, vp, vp, vp, u32, u64, vp, ctypes.POINTER(u64)]
         L.pob_last_error.restype = ctypes.c_char_p
         L.pob_version.restype = ctypes.c_char_p
         _LIB = L
@@ -294,6 +296,34 @@ class Circuit:
         p = ctypes.c_void_p()
         _check(lib().pob_witness_device_ptr(self._h, index, ctypes.byref(p)))
         return p.value
+
+
+def pow_grind(start_key, reveal_amount, burn_extra_commitment, zero_bytes=2, max_tries=1 << 32, device=0):
+    """GPU replacement of the reference's find_burn_key (tests/main.py:47-56): first burnKey >= start_key whose
+    keccak(burnKey | revealAmount | burnExtraCommitment | "EIP-7503") starts with `zero_bytes` zero bytes.
+    Returns (burn_key, tries)."""
+    a, b, c = (to_limbs([v]) for v in (start_key, reveal_amount, burn_extra_commitment))
+    out = np.zeros((1, 4), dtype=np.uint64)
+    tries = ctypes.c_uint64(0)
+    _check(lib().pob_pow_grind(int(device), a.ctypes.data, b.ctypes.data, c.ctypes.data, int(zero_bytes), int(max_tries), out.ctypes.data, ctypes.byref(tries)))
+    return from_limbs(out[0]), int(tries.value)
+
+
+def repad_pob_input(inp, max_layers, node_blocks, header_blocks):
+    """Re-pad a ProofOfBurn input JSON to a circuit shape: unused layers are zero with length 256 (the convention of
+    reference tests/main.py:148-150), the header is zero-extended.  The reference generator still pads to the (4,.,5)
+    test shape (tests/main.py:8-11) although main_proof_of_burn.circom:27 needs (16,4,16)."""
+    out = dict(inp)
+    nb, hb = node_blocks * 136, header_blocks * 136
+    layers = [list(l)[:nb] + [0] * (nb - len(l)) for l in inp["layers"]]
+    lens = list(inp["layerLens"])
+    while len(layers) < max_layers:
+        layers.append([0] * nb)
+        lens.append(256)
+    out["layers"], out["layerLens"] = layers[:max_layers], lens[:max_layers]
+    hdr = list(inp["blockHeader"])
+    out["blockHeader"] = hdr[:hb] + [0] * (hb - len(hdr))
+    return out
 
 
 CIRCUIT_ALIASES = {"main_proof_of_burn": MAIN_PROOF_OF_BURN, "main_spend": MAIN_SPEND}

@@ -1,0 +1,165 @@
+"""More GPU parity: fuzzed gadget inputs, ordering policy, slot ring / residency, staged inputs, synthetic batches at
+the full main shape, a second circuit shape, and the proof-of-work grinder.  All through the C-ABI."""
+import numpy as np
+import pytest
+
+from helpers import suite, pob_fixture, repad_pob
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fuzz_gadgets_match_oracle():
+    import pob_b200
+    from oracle import oracle
+    from fuzz_cases import cases
+    by_main = {}
+    for main, inp in cases():
+        by_main.setdefault(main, []).append(inp)
+    rejected = 0
+    for main, inps in by_main.items():
+        c = pob_b200.Circuit(main, max_slots=len(inps))
+        try:
+            res = c.run(inps, expand=True, digest=True)
+            for i, inp in enumerate(inps):
+                w = oracle.run(main, inp)
+                try:
+                    assert int(res.status[i]) == w.status, "%s %s: status %d vs oracle %d" % (main, inp, res.status[i], w.status)
+                    if w.ok:
+                        assert int(res.digests[i]) == w.digest()
+                        assert np.array_equal(c.witness(i), w.limbs), "%s %s" % (main, inp)
+                    else:
+                        rejected += 1
+                finally:
+                    w.free()
+        finally:
+            c.close()
+    assert rejected > 10
+
+
+def test_creation_order_policy_on_gpu():
+    import pob_b200
+    from oracle import oracle
+    s = suite("test_spend")
+    c = pob_b200.Circuit("Spend(31)", hcreate=True, max_slots=1)
+    try:
+        res = c.run([s["cases"][0]["input"]])
+        w = oracle.run("Spend(31)", s["cases"][0]["input"], hcreate=True)
+        w0 = oracle.run("Spend(31)", s["cases"][0]["input"], hcreate=False)
+        assert res.status[0] == 0 and np.array_equal(c.witness(0), w.limbs)
+        assert not np.array_equal(w.limbs, w0.limbs)
+        w.free(); w0.free()
+    finally:
+        c.close()
+
+
+def test_slot_ring_wraps_and_residency_is_enforced():
+    import pob_b200
+    from oracle import oracle
+    base = suite("test_spend")["cases"][0]["input"]
+    inps = [dict(base, extraCommitment=str(1000 + i)) for i in range(8)]
+    c = pob_b200.Circuit("Spend(31)", max_slots=3)
+    try:
+        assert c.desc["n_slots"] == 3
+        res = c.run(inps)
+        assert (res.status == 0).all() and len({o[0] for o in res.outputs}) == 8
+        for i in (5, 6, 7):                                   # the last three are resident
+            w = oracle.run("Spend(31)", inps[i])
+            assert np.array_equal(c.witness(i), w.limbs) and res.outputs[i] == w.outputs()
+            w.free()
+        for i in (0, 4):                                      # overwritten by later instances
+            with pytest.raises(pob_b200.PobError) as e:
+                c.witness(i)
+            assert e.value.code == -5
+        with pytest.raises(pob_b200.PobError):
+            c.witness(8)
+        res2 = c.run(inps[:2], expand=False)                  # status/outputs only: nothing resident afterwards
+        assert res2.outputs == res.outputs[:2]
+        with pytest.raises(pob_b200.PobError):
+            c.witness(0)
+    finally:
+        c.close()
+
+
+def test_staged_inputs_equal_host_inputs():
+    import pob_b200
+    base = suite("test_spend")["cases"][0]["input"]
+    inps = [dict(base, extraCommitment=str(7 + i)) for i in range(40)]     # > one eval chunk
+    c = pob_b200.Circuit("Spend(31)", max_slots=4)
+    try:
+        packed = c.pack(inps)
+        a = c.run_packed(packed, digest=True)
+        c.stage(packed)
+        b = c.run_packed(None, n=len(inps), staged=True, digest=True)
+        assert np.array_equal(a.status, b.status) and np.array_equal(a.outputs_limbs, b.outputs_limbs) and np.array_equal(a.digests, b.digests)
+        assert a.timing["h2d_bytes"] == 40 * 4 * 32 and b.timing["h2d_bytes"] == 0
+    finally:
+        c.close()
+
+
+def test_synthetic_batch_main_shape():
+    """BASELINE.json configs[2] in miniature: 40 synthetic valid main-shape inputs (more than the 21 resident slots, more
+    than one eval chunk): all accepted; three instances checked against the oracle by commitment + whole-witness digest."""
+    import pob_b200
+    from pob_b200 import synth
+    from oracle import oracle
+    shape = (16, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)
+    insts = synth.make_batch(40, shape, seed=99)
+    c = pob_b200.Circuit(pob_b200.MAIN_PROOF_OF_BURN)
+    try:
+        res = c.run_packed(synth.pack_instances(insts, shape), digest=True)
+        assert (res.status == 0).all()
+        for i in (0, 21, 39):
+            w = oracle.run(pob_b200.MAIN_PROOF_OF_BURN, synth.to_json(insts[i], shape))
+            try:
+                assert w.ok and res.outputs[i] == w.outputs() and int(res.digests[i]) == w.digest()
+            finally:
+                w.free()
+        first = 215907954 - 70000
+        w = oracle.run(pob_b200.MAIN_PROOF_OF_BURN, synth.to_json(insts[39], shape))
+        assert np.array_equal(c.witness(39, first, 70000), w.limbs[first:])
+        w.free()
+    finally:
+        c.close()
+
+
+def test_second_shape_eight_layers():
+    """config 5 point: ProofOfBurn(8,4,16,...) -- S(8) = 133,592,506 entries"""
+    import pob_b200
+    from pob_b200 import synth
+    from oracle import oracle
+    shape = (8, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)
+    expr = "ProofOfBurn(8, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)"
+    insts = synth.make_batch(2, shape, seed=5)
+    c = pob_b200.Circuit(expr, max_slots=2)
+    try:
+        assert c.n_signals == 51277058 + 10289431 * 8
+        res = c.run_packed(synth.pack_instances(insts, shape), digest=True)
+        w = oracle.run(expr, synth.to_json(insts[1], shape))
+        assert res.status[1] == 0 and w.ok and res.outputs[1] == w.outputs() and int(res.digests[1]) == w.digest()
+        w.free()
+    finally:
+        c.close()
+
+
+def test_pow_grinder_finds_the_first_key():
+    """reference tests/testcases/proof_of_work.py: (burnKey, 234, 345): 812 -> 1 zero byte, 47109 -> 2, neighbours 0"""
+    import pob_b200
+    from pob_b200 import synth
+    assert pob_b200.pow_grind(812, 234, 345, zero_bytes=1) == (812, 1)
+    assert pob_b200.pow_grind(47109, 234, 345, zero_bytes=2) == (47109, 1)
+
+    def cpu_first(start, zb):
+        k = start
+        post = (234).to_bytes(32, "big") + (345).to_bytes(32, "big") + b"EIP-7503"
+        while any(synth.keccak256(k.to_bytes(32, "big") + post)[:zb]):
+            k += 1
+        return k
+    k1, t1 = pob_b200.pow_grind(813, 234, 345, zero_bytes=1)
+    assert k1 == cpu_first(813, 1) and t1 == k1 - 813 + 1
+    k2, _ = pob_b200.pow_grind(40000, 234, 345, zero_bytes=2)
+    assert k2 == cpu_first(40000, 2)
+    big = (1 << 200) + 12345                                   # carries across limbs, random large key
+    k3, _ = pob_b200.pow_grind(big, 7, 9, zero_bytes=2)
+    assert k3 >= big and synth.keccak256(k3.to_bytes(32, "big") + (7).to_bytes(32, "big") + (9).to_bytes(32, "big") + b"EIP-7503")[:2] == b"\x00\x00"
+    with pytest.raises(pob_b200.PobError):
+        pob_b200.pow_grind(0, 1, 2, zero_bytes=8, max_tries=1 << 16)

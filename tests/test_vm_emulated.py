@@ -62,3 +62,27 @@ def test_round_table_is_shared():
     assert st["n_round_blocks"] == 48
     # codes = one shared 102,656-entry KeccakfRound table + the flat (non-round) signals
     assert st["n_codes"] == 102656 + st["n_signals"] - 48 * 102656
+
+
+def test_fuzz_programs_match_oracle():
+    """seeded random / boundary / out-of-range inputs: status codes and accepted witnesses must agree"""
+    import emu
+    from fuzz_cases import cases
+    progs = {}
+    rejected = 0
+    for main, inp in cases():
+        name, params = oracle.parse_main(main)
+        if main not in progs:
+            progs[main] = emu.EmuProgram(name, oracle.to_limbs(params) if params else np.zeros((1, 4), dtype=np.uint64), len(params))
+        flat = oracle.to_limbs(oracle.flatten_inputs(oracle.schema(name, params), inp))
+        w = oracle.run_flat(name, params, flat)
+        try:
+            st, wit, _ = progs[main].run(flat)
+            assert st == w.status, "%s %s: status %d vs oracle %d" % (main, inp, st, w.status)
+            if w.ok:
+                assert np.array_equal(wit, w.limbs), "%s %s" % (main, inp)
+            else:
+                rejected += 1
+        finally:
+            w.free()
+    assert rejected > 10
