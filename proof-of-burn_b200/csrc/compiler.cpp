@@ -1396,6 +1396,33 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     P.codes.resize(ROUND_SIGNALS);
     { LaneSink S{P.codes.data(), 0}; emit_round(S);
       if ((size_t)(S.p - P.codes.data()) != ROUND_SIGNALS) throw std::runtime_error("pob: internal: round table size mismatch"); }
+    // derive (and thereby verify) the 64-signal group descriptors of the round table
+    P.round_desc.resize(ROUND_SIGNALS / 64);
+    for (uint32_t g = 0; g < ROUND_SIGNALS / 64; g++) {
+        const Code *c = &P.codes[64 * g];
+        auto W = [&](int j) { return (code_payload(c[j]) >> 6); };
+        auto Bt = [&](int j) { return (code_payload(c[j]) & 63u); };
+        bool ok = true, lane = true;
+        for (int j = 0; j < 64; j++) { if (code_kind(c[j]) != K_BIT) ok = false; if (W(j) != W(0) || Bt(j) != (uint32_t)j) lane = false; }
+        uint64_t d = 0;
+        if (ok && lane) d = (uint64_t)W(0);
+        else if (ok) {
+            bool found = false;
+            for (uint32_t f = 0; f < 3 && !found; f++) {
+                uint32_t w[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}; bool m = true;
+                for (uint32_t j = 0; j < 64 && m; j++) {
+                    uint32_t sidx = 64 * f + j, gi = sidx / 3, mem = sidx % 3;
+                    if (Bt((int)j) != gi) m = false;
+                    else if (w[mem] == 0xffffffffu) w[mem] = W((int)j);
+                    else if (w[mem] != W((int)j)) m = false;
+                }
+                if (m) { d = (uint64_t)w[0] | ((uint64_t)w[1] << 16) | ((uint64_t)w[2] << 32) | ((uint64_t)(1 + f) << 48); found = true; }
+            }
+            ok = found;
+        }
+        if (!ok || (d & 0xffff) >= ROUND_WORDS_SPAN) throw std::runtime_error("pob: internal: round table group does not fit a descriptor");
+        P.round_desc[g] = d;
+    }
     P.codes.insert(P.codes.end(), B.flat, B.flat + B.flat_n);
     P.n_round_blocks = B.n_round_blocks; P.n_flat_signals = B.flat_n;
     for (auto &s : B.segs) {

@@ -115,35 +115,76 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval(const EvalArgs a) {
     }
 }
 
+// 256-bit store (STG.E.ENL2.256).  No "memory" clobber on purpose: the compiler must be free to hoist the next
+// entries' loads above it so that several loads are in flight per thread (the witness is written, never read, here).
 __device__ __forceinline__ void st256(uint64_t *p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
-    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d));
 }
 
 struct ExpandArgs {
-    const Tile *tiles; const Code *codes; const Fr *konst;
+    const Tile *tiles; const Code *codes; const Fr *konst; const uint2 *round_desc;
     const uint64_t *stores; uint64_t store_stride; uint32_t val_base;
-    uint64_t *const *wit;                         // per instance of the chunk: witness slot base
+    uint64_t *const *wit;                         // per instance of the group: witness slot base
 };
 
 // grid = (n_tiles, instances in group); one CTA streams one tile (<= 8192 entries = 256 KiB) of one witness.
-// Measured alternatives (profiles/r01_expand_sweep.md): streaming (.cs) stores and a BIT-only fast path for round tiles
-// were neutral / slower -- the kernel is DRAM-write bound, not issue bound -- so the single generic loop is kept.
-__global__ void __launch_bounds__(256) k_expand(const ExpandArgs a) {
+//  * KeccakfRound tiles (95.8 % of the witness): the source of every entry follows from a 8-byte descriptor per 64
+//    entries (12.8 KB table, L1-resident) and a lane word of the round (2 KB, L1-resident): no per-entry code stream.
+//  * all other tiles: one 32-bit code per entry.
+// Loads are issued U entries ahead of the stores; DRAM writes are the only traffic that reaches HBM.
+template <int UN, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_expand(const ExpandArgs a) {
     const Tile t = a.tiles[blockIdx.x];
     const uint64_t *U = a.stores + (uint64_t)blockIdx.y * a.store_stride;
     uint64_t *W = a.wit[blockIdx.y] + t.dst * 4;
-    const Code *c = a.codes + t.code_off;
     const uint64_t *Ub = U + t.ubase;
-#pragma unroll 4
-    for (uint32_t k = threadIdx.x; k < t.n; k += 256) {
-        const Code cd = __ldg(c + k);
-        const uint32_t kind = code_kind(cd), p = code_payload(cd);
-        uint64_t v0, v1 = 0, v2 = 0, v3 = 0;
-        if (kind == K_BIT) v0 = (Ub[p >> 6] >> (p & 63)) & 1ull;
-        else if (kind == K_CONST) v0 = p;
-        else if (kind == K_VAL) { const uint64_t *s = U + a.val_base + 4ull * p; v0 = s[0]; v1 = s[1]; v2 = s[2]; v3 = s[3]; }
-        else { const uint64_t *s = reinterpret_cast<const uint64_t *>(a.konst + p); v0 = s[0]; v1 = s[1]; v2 = s[2]; v3 = s[3]; }
-        st256(W + 4ull * k, v0, v1, v2, v3);
+    if (t.pad) {
+        const uint2 *D = a.round_desc + (t.code_off >> 6);
+        for (uint32_t base = threadIdx.x; base < t.n; base += 256 * UN) {
+            uint64_t word[UN]; uint32_t bit[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const uint32_t k = base + 256 * u;
+                word[u] = 0; bit[u] = 0;
+                if (k < t.n) {
+                    const uint2 d = __ldg(D + (k >> 6));
+                    const uint32_t tt = k & 63, mode = d.y >> 16;
+                    uint32_t w = d.x & 0xffffu, b = tt;
+                    if (mode) {
+                        const uint32_t sidx = (mode - 1) * 64 + tt, g = sidx / 3, m = sidx - 3 * g;
+                        b = g; w = (m == 0) ? (d.x & 0xffffu) : (m == 1) ? (d.x >> 16) : (d.y & 0xffffu);
+                    }
+                    word[u] = Ub[w]; bit[u] = b;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const uint32_t k = base + 256 * u;
+                if (k < t.n) st256(W + 4ull * k, (word[u] >> bit[u]) & 1ull, 0, 0, 0);
+            }
+        }
+        return;
+    }
+    const Code *c = a.codes + t.code_off;
+    constexpr int UG = 4;
+    for (uint32_t base = threadIdx.x; base < t.n; base += 256 * UG) {
+        Code cd[UG];
+#pragma unroll
+        for (int u = 0; u < UG; u++) { const uint32_t k = base + 256 * u; cd[u] = k < t.n ? __ldg(c + k) : 0u; }
+        uint64_t v[UG][4];
+#pragma unroll
+        for (int u = 0; u < UG; u++) {
+            const uint32_t kind = code_kind(cd[u]), p = code_payload(cd[u]);
+            v[u][1] = v[u][2] = v[u][3] = 0;
+            if (kind == K_BIT) v[u][0] = (Ub[p >> 6] >> (p & 63)) & 1ull;
+            else if (kind == K_CONST) v[u][0] = p;
+            else {
+                const uint64_t *s = (kind == K_VAL) ? U + a.val_base + 4ull * p : reinterpret_cast<const uint64_t *>(a.konst + p);
+                v[u][0] = s[0]; v[u][1] = s[1]; v[u][2] = s[2]; v[u][3] = s[3];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UG; u++) { const uint32_t k = base + 256 * u; if (k < t.n) st256(W + 4ull * k, v[u][0], v[u][1], v[u][2], v[u][3]); }
     }
 }
 
@@ -216,7 +257,7 @@ struct pob_handle {
     Program P; int device = 0;
     // device program
     Op *d_ops = nullptr; AbsorbOp *d_abs = nullptr; Level *d_levels = nullptr; Code *d_aux = nullptr; Fr *d_konst = nullptr;
-    Code *d_codes = nullptr; Tile *d_tiles = nullptr; Fr *d_invtab = nullptr;
+    Code *d_codes = nullptr; Tile *d_tiles = nullptr; Fr *d_invtab = nullptr; uint64_t *d_round_desc = nullptr;
     // stores (ring of RING chunks)
     static const uint32_t RING = 2;
     uint32_t chunk = 0; uint64_t store_stride = 0; uint64_t *d_stores = nullptr; uint64_t *d_inputs = nullptr;
@@ -228,6 +269,7 @@ struct pob_handle {
     uint64_t **h_witptr = nullptr;
     uint64_t *d_staged = nullptr; uint32_t n_staged = 0;
     uint32_t xgroup = 0;                       // instances per expand launch (distinct witness slots)
+    int variant = 0;                           // k_expand unroll/occupancy variant (POB_EXPAND_VARIANT), tuning only
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
     cudaEvent_t ev_eval_done[RING] = {nullptr, nullptr}, ev_exp_done[RING] = {nullptr, nullptr}, ev_h2d[RING] = {nullptr, nullptr},
                 ev_start = nullptr, ev_end = nullptr;
@@ -278,7 +320,7 @@ void pob_destroy(pob_handle *h) {
     if (h->s_eval) cudaStreamSynchronize(h->s_eval);
     if (h->s_exp) cudaStreamSynchronize(h->s_exp);
     for (void *p : {(void *)h->d_ops, (void *)h->d_abs, (void *)h->d_levels, (void *)h->d_aux, (void *)h->d_konst, (void *)h->d_codes,
-                    (void *)h->d_tiles, (void *)h->d_invtab, (void *)h->d_stores, (void *)h->d_inputs, (void *)h->d_status,
+                    (void *)h->d_tiles, (void *)h->d_invtab, (void *)h->d_round_desc, (void *)h->d_stores, (void *)h->d_inputs, (void *)h->d_status,
                     (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr, (void *)h->d_staged})
         if (p) cudaFree(p);
     for (uint64_t *s : h->slots) cudaFree(s);
@@ -312,6 +354,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         h->d_ops = upload(P.ops); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
         h->d_konst = upload(P.konst); h->d_codes = upload(P.codes); h->d_tiles = upload(P.tiles);
         h->d_invtab = upload(build_inverse_table());
+        h->d_round_desc = upload(P.round_desc);
         // the small eval grid must get SMs while the expand grid (hundreds of thousands of CTAs) is draining:
         // eval runs on the highest-priority stream, expand on the lowest
         int pr_least = 0, pr_greatest = 0; CU(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
@@ -336,6 +379,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (nslots > 4096) nslots = 4096;
         if (nslots == 0) throw std::runtime_error("not even one witness slot fits in free HBM");
         h->xgroup = (uint32_t)std::min<uint64_t>(16, nslots);
+        if (const char *v = getenv("POB_EXPAND_VARIANT")) h->variant = atoi(v);
         if (const char *v = getenv("POB_EXPAND_GROUP")) h->xgroup = (uint32_t)std::max(1, std::min<int>(atoi(v), (int)nslots));
         if (const char *v = getenv("POB_EVAL_CHUNK")) chunk = (uint32_t)std::max(1, atoi(v));
         h->chunk = chunk;
@@ -433,9 +477,16 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
                 uint32_t g = 0;
                 for (uint32_t off = 0; off < cnt; off += X, g++) {
                     const uint32_t gc = std::min(X, cnt - off);
-                    ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, stores + (size_t)off * h->store_stride, h->store_stride, P.val_base, h->d_witptr + first + off};
+                    ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, reinterpret_cast<const uint2 *>(h->d_round_desc), stores + (size_t)off * h->store_stride, h->store_stride, P.val_base, h->d_witptr + first + off};
                     CU(cudaEventRecord(ev[2 + 2 * g], h->s_exp));
-                    k_expand<<<dim3((unsigned)P.tiles.size(), gc), 256, 0, h->s_exp>>>(xa);
+                    const dim3 grid((unsigned)P.tiles.size(), gc);
+                    switch (h->variant) {
+                    case 1: k_expand<8, 8><<<grid, 256, 0, h->s_exp>>>(xa); break;
+                    case 2: k_expand<4, 8><<<grid, 256, 0, h->s_exp>>>(xa); break;
+                    case 3: k_expand<16, 4><<<grid, 256, 0, h->s_exp>>>(xa); break;
+                    case 4: k_expand<2, 8><<<grid, 256, 0, h->s_exp>>>(xa); break;
+                    default: k_expand<8, 5><<<grid, 256, 0, h->s_exp>>>(xa); break;
+                    }
                     CU(cudaEventRecord(ev[3 + 2 * g], h->s_exp));
                     T.expand_launches++;
                     if (digest) for (uint32_t j = 0; j < gc; j++) {

@@ -108,6 +108,11 @@ struct Program {
     // expand program
     std::vector<Code> codes;       // [0, ROUND_SIGNALS) = shared KeccakfRound table, then flat codes
     std::vector<Tile> tiles;
+    // compact form of the shared KeccakfRound table: one 8-byte descriptor per 64 consecutive signals
+    //   bits 0-15 w0, 16-31 w1, 32-47 w2 (lane words relative to the round base), 48-63 mode:
+    //   mode 0: a lane -- signal t is bit t of w0;  mode 1+f: 64-signal phase f of a 192-signal gate block
+    //   [out_i, a_i, b_i]_i -- signal s = 64 f + t is bit s/3 of w_{s%3}
+    std::vector<uint64_t> round_desc;
     // statistics
     uint64_t n_round_blocks = 0, n_flat_signals = 0;
 };

@@ -55,8 +55,15 @@ uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_
     for (uint32_t tid = 0; tid < 64; tid++) vm_inv_batch(x, P.ops.data(), P.inv_begin, P.inv_end, tid, 64);
     if (witness)
         for (const Tile &t : P.tiles)
-            for (uint32_t k = 0; k < t.n; k++)
-                vm_expand(P.codes[t.code_off + k], U.data(), t.ubase, P.val_base, P.konst.data(), witness + 4 * (t.dst + k));
+            for (uint32_t k = 0; k < t.n; k++) {
+                uint64_t *o = witness + 4 * (t.dst + k);
+                if (t.pad) {            // KeccakfRound tile: 64-signal group descriptors (same decode as k_expand)
+                    uint64_t d = P.round_desc[(t.code_off >> 6) + (k >> 6)];
+                    uint32_t tt = k & 63, mode = (uint32_t)(d >> 48), w = (uint32_t)(d & 0xffff), b = tt;
+                    if (mode) { uint32_t sidx = (mode - 1) * 64 + tt, g = sidx / 3, m = sidx - 3 * g; b = g; w = (uint32_t)((d >> (16 * m)) & 0xffff); }
+                    o[0] = (U[t.ubase + w] >> b) & 1ull; o[1] = o[2] = o[3] = 0;
+                } else vm_expand(P.codes[t.code_off + k], U.data(), t.ubase, P.val_base, P.konst.data(), o);
+            }
     if (outputs)
         for (uint32_t i = 0; i < P.n_outputs; i++)
             vm_expand(P.codes[ROUND_SIGNALS + 1 + i], U.data(), 0, P.val_base, P.konst.data(), outputs + 4 * i);
