@@ -89,8 +89,8 @@ struct EvalArgs {
     uint32_t *status; uint64_t *outputs;          // chunk base
 };
 
-static const int EVAL_THREADS = 1024;
-__global__ void __launch_bounds__(EVAL_THREADS) k_eval(const EvalArgs a) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     const uint32_t inst = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     uint64_t *U = a.stores + (uint64_t)inst * a.store_stride;
     __shared__ uint32_t s_status;
@@ -270,6 +270,8 @@ struct pob_handle {
     uint64_t *d_staged = nullptr; uint32_t n_staged = 0;
     uint32_t xgroup = 0;                       // instances per expand launch (distinct witness slots)
     int variant = 0;                           // k_expand unroll/occupancy variant (POB_EXPAND_VARIANT), tuning only
+    int eval_threads = 1024;                   // k_eval CTA size (POB_EVAL_THREADS), tuning only
+    bool serialize = false;                    // POB_SERIALIZE=1: eval and expand on one stream (no overlap), tuning only
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
     cudaEvent_t ev_eval_done[RING] = {nullptr, nullptr}, ev_exp_done[RING] = {nullptr, nullptr}, ev_h2d[RING] = {nullptr, nullptr},
                 ev_start = nullptr, ev_end = nullptr;
@@ -380,6 +382,8 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (nslots == 0) throw std::runtime_error("not even one witness slot fits in free HBM");
         h->xgroup = (uint32_t)std::min<uint64_t>(16, nslots);
         if (const char *v = getenv("POB_EXPAND_VARIANT")) h->variant = atoi(v);
+        if (const char *v = getenv("POB_EVAL_THREADS")) h->eval_threads = atoi(v);
+        if (const char *v = getenv("POB_SERIALIZE")) h->serialize = atoi(v) != 0;
         if (const char *v = getenv("POB_EXPAND_GROUP")) h->xgroup = (uint32_t)std::max(1, std::min<int>(atoi(v), (int)nslots));
         if (const char *v = getenv("POB_EVAL_CHUNK")) chunk = (uint32_t)std::max(1, atoi(v));
         h->chunk = chunk;
@@ -468,7 +472,11 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
                         h->d_codes + ROUND_SIGNALS + 1, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
                         h->d_status + first, h->d_outputs + (size_t)first * no * 4};
             CU(cudaEventRecord(ev[0], h->s_eval));
-            k_eval<<<cnt, EVAL_THREADS, 0, h->s_eval>>>(ea);
+            switch (h->eval_threads) {
+            case 256: k_eval<256><<<cnt, 256, 0, h->s_eval>>>(ea); break;
+            case 512: k_eval<512><<<cnt, 512, 0, h->s_eval>>>(ea); break;
+            default: k_eval<1024><<<cnt, 1024, 0, h->s_eval>>>(ea); break;
+            }
             CU(cudaEventRecord(ev[1], h->s_eval));
             CU(cudaEventRecord(h->ev_eval_done[r], h->s_eval));
             T.eval_launches++;
@@ -496,6 +504,7 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
                 }
                 group_count.push_back(g);
                 CU(cudaEventRecord(h->ev_exp_done[r], h->s_exp));
+                if (h->serialize) CU(cudaStreamWaitEvent(h->s_eval, h->ev_exp_done[r], 0));
             } else {
                 group_count.push_back(0);
                 CU(cudaEventRecord(h->ev_exp_done[r], h->s_eval));
