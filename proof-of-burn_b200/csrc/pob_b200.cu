@@ -354,7 +354,12 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         const Program &P = h->P;
         CU(cudaSetDevice(device));
         h->d_ops = upload(P.ops); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
-        h->d_konst = upload(P.konst); h->d_codes = upload(P.codes); h->d_tiles = upload(P.tiles);
+        h->d_konst = upload(P.konst); h->d_codes = upload(P.codes);
+        if (const char *v = getenv("POB_TILE_FILTER")) {      // tuning only: 1 = KeccakfRound tiles only, 2 = the others only (witness incomplete!)
+            std::vector<Tile> sub; for (const Tile &t : P.tiles) if ((atoi(v) == 1) == (t.pad != 0)) sub.push_back(t);
+            h->P.tiles = sub;
+        }
+        h->d_tiles = upload(h->P.tiles);
         h->d_invtab = upload(build_inverse_table());
         h->d_round_desc = upload(P.round_desc);
         // the small eval grid must get SMs while the expand grid (hundreds of thousands of CTAs) is draining:
