@@ -1435,6 +1435,10 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
             P.tiles.push_back(t); done += n;
         }
     }
+    // Tile order is free (every tile carries its own destination).  KeccakfRound tiles only read L1-resident tables, the
+    // other tiles read their code stream and store values through L2/DRAM; interleaving those reads with the write
+    // stream costs DRAM efficiency (profiles/r01_expand_sweep.md), so all round tiles go first, the rest last.
+    std::stable_sort(P.tiles.begin(), P.tiles.end(), [](const Tile &a, const Tile &b) { return a.pad > b.pad; });
     return P;
 }
 

@@ -359,6 +359,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
             std::vector<Tile> sub; for (const Tile &t : P.tiles) if ((atoi(v) == 1) == (t.pad != 0)) sub.push_back(t);
             h->P.tiles = sub;
         }
+        if (getenv("POB_FLAT_FIRST")) std::stable_sort(h->P.tiles.begin(), h->P.tiles.end(), [](const Tile &a, const Tile &b) { return a.pad < b.pad; });   // tuning only
         h->d_tiles = upload(h->P.tiles);
         h->d_invtab = upload(build_inverse_table());
         h->d_round_desc = upload(P.round_desc);
