@@ -71,7 +71,8 @@ class Builder {
         flat = (Code *)mmap(nullptr, flat_cap * sizeof(Code), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
         if (flat == MAP_FAILED) throw std::runtime_error("pob: cannot reserve code arena");
         Fr m1; Fr one = fr_from_u64(1); fr_raw_sub(m1, fr_p(), one);
-        MINUS1 = konst(m1);
+        MINUS1 = konst(m1);                             // must be konst index 0: vm_exec.h keys its negate fast path on it
+        if (MINUS1 != c_konst(0)) throw std::runtime_error("pob: internal: MINUS1 must be the first table constant");
         Blk b = alloc(1); flat[b.pos] = ONE;            // witness[0] = 1
     }
     ~Builder() { if (flat && flat != MAP_FAILED) munmap(flat, flat_cap * sizeof(Code)); }
@@ -155,6 +156,7 @@ class Builder {
             if (ka && fr_eq(fa, fr_from_u64(1))) return b;
             if (kb && fr_eq(fb, fr_from_u64(1))) return a;
         }
+        if (ka && !kb) { std::swap(a, b); std::swap(ka, kb); std::swap(fa, fb); }   // keep the constant factor in `b` (VM fast paths)
         uint32_t lv = 1 + std::max(level_of(a), std::max(level_of(b), level_of(c)));
         return emit_val(OP_FMA, a, b, c, lv);
     }

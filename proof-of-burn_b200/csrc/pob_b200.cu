@@ -375,6 +375,24 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
             CU(cudaEventCreateWithFlags(&h->ev_h2d[r], cudaEventDisableTiming));
         }
         CU(cudaEventCreate(&h->ev_start)); CU(cudaEventCreate(&h->ev_end));
+        // keep the non-round code stream (read once per instance by the code tiles) resident in L2 while 110 GB of
+        // witness per launch stream through it: persisting access-policy window on the expand stream
+        if (!getenv("POB_NO_L2_PERSIST")) {
+            int dev_max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&dev_max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+            size_t want = P.codes.size() * sizeof(Code);
+            size_t win = std::min<size_t>(want, (size_t)std::max(0, max_window));
+            if (dev_max_persist > 0 && win > 0) {
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)dev_max_persist, want));
+                cudaStreamAttrValue attr{};
+                attr.accessPolicyWindow.base_ptr = h->d_codes; attr.accessPolicyWindow.num_bytes = win;
+                attr.accessPolicyWindow.hitRatio = 1.0f; attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                cudaStreamSetAttribute(h->s_exp, cudaStreamAttributeAccessPolicyWindow, &attr);
+                cudaGetLastError();
+            }
+        }
         // witness slots: as many as fit in 80 % of free HBM after the store ring
         size_t free_b = 0, total_b = 0; CU(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t wbytes = 32ull * P.n_signals;

@@ -57,8 +57,13 @@ POB_HD void vm_exec_op(const VmCtx &x, const Op &op) {
     uint64_t *vd = x.U + x.val_base + 4ull * dst;
     switch (opc) {
     case OP_FMA: {
-        Fr a = vm_load(x, op.a), b = vm_load(x, op.b), c = vm_load(x, op.c);
-        vm_store_val(vd, fr_add(fr_mul(a, b), c));
+        // the two commonest multipliers never need a field multiplication: b == 1 (a + c) and b == -1 (c - a;
+        // konst[0] is p-1 by construction -- Builder::MINUS1)
+        Fr a = vm_load(x, op.a), c = vm_load(x, op.c), r;
+        if (op.b == c_const(1)) r = fr_add(a, c);
+        else if (op.b == c_konst(0)) r = fr_sub(c, a);
+        else { Fr b = vm_load(x, op.b); r = fr_add(fr_mul(a, b), c); }
+        vm_store_val(vd, r);
         break; }
     case OP_ISZ: { Fr a = vm_load(x, op.a); vm_store_val(vd, fr_from_u64(fr_is_zero(a) ? 1 : 0)); break; }
     case OP_INV: { Fr a = vm_load(x, op.a); vm_store_val(vd, vm_inverse(x, a)); break; }
