@@ -57,6 +57,8 @@ class Builder {
     // program
     struct OpRec { Op op; uint32_t level; };
     std::vector<OpRec> ops;
+    std::vector<Op> seq_ops;            // OP_SEQ bodies
+    bool in_seq = false; size_t seq_start = 0; uint32_t seq_first_val = 0;
     struct AbsRec { AbsorbOp op; uint32_t level; };
     std::vector<AbsRec> absorbs;
     std::vector<Code> aux;
@@ -144,8 +146,31 @@ class Builder {
         if (it != cse.end()) return it->second;
         uint32_t slot = new_val(level);
         if (slot >= (1u << 26)) throw std::runtime_error("pob: too many value slots");
-        ops.push_back({Op{(opc << 26) | slot, a, b, c}, level});
+        if (in_seq) seq_ops.push_back(Op{(opc << 26) | slot, a, b, c});
+        else ops.push_back({Op{(opc << 26) | slot, a, b, c}, level});
         Code r = c_val(slot); cse.emplace(key, r); return r;
+    }
+    // ---- sequential regions: everything emitted between begin_seq/end_seq runs on one thread as a single op ----
+    void begin_seq() {
+        if (in_seq) throw std::runtime_error("pob: internal: nested sequential region");
+        in_seq = true; seq_start = seq_ops.size(); seq_first_val = n_vals;
+    }
+    void end_seq() {
+        in_seq = false;
+        size_t cnt = seq_ops.size() - seq_start;
+        if (cnt == 0) return;
+        uint32_t lv = 0;
+        auto ext = [&](Code c) {
+            if (code_kind(c) == K_VAL && code_payload(c) >= seq_first_val) return;     // defined inside the region
+            lv = std::max(lv, level_of(c));
+        };
+        for (size_t i = seq_start; i < seq_ops.size(); i++) {
+            const Op &o = seq_ops[i];
+            if (op_opc(o) != OP_FMA) throw std::runtime_error("pob: internal: only FMA ops are supported in a sequential region");
+            ext(o.a); ext(o.b); ext(o.c);
+        }
+        for (uint32_t sl = seq_first_val; sl < n_vals; sl++) lvlV[sl] = lv + 1;
+        ops.push_back({Op{OP_SEQ << 26, (uint32_t)seq_start, (uint32_t)cnt, 0}, lv + 1});
     }
     Code fma(Code a, Code b, Code c) {              // a*b + c
         Fr fa, fb, fc; bool ka = const_val(a, fa), kb = const_val(b, fb), kc = const_val(c, fc);
@@ -446,6 +471,7 @@ static Blk T_MixS(Builder &B, const PoseidonK &k, int r, const Code *in) {
 static Blk T_PoseidonEx(Builder &B, int nInputs, const Code *inputs, Code initialState) {
     int t = nInputs + 1; PoseidonK k = poseidon_k(t);
     Blk o = B.alloc(2 + (size_t)nInputs); B.copy(o.pos + 1, inputs, (size_t)nInputs); B.at(o.pos + 1 + (size_t)nInputs) = initialState;
+    B.begin_seq();      // ~65 rounds of x^5 / affine mixes: inherently serial, run by one thread
     Code st[8], nx[8];
     st[0] = initialState; for (int j = 1; j < t; j++) st[j] = inputs[j - 1];
     auto take = [&](Blk b, Code *dst) { for (int j = 0; j < t; j++) dst[j] = B.at(b.pos + (size_t)j); };
@@ -470,6 +496,7 @@ static Blk T_PoseidonEx(Builder &B, int nInputs, const Code *inputs, Code initia
     }
     for (int j = 0; j < t; j++) nx[j] = B.at(T_Sigma(B, st[j]).pos);
     Blk ml = T_MixLast(B, t, k.M, 0, nx);
+    B.end_seq();
     B.at(o.pos) = B.at(ml.pos); return o;
 }
 // Poseidon(n) :198-208
@@ -1373,9 +1400,13 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
         if (opc == OP_FMA) bad = uses_inv(o.op.a) || uses_inv(o.op.b) || uses_inv(o.op.c);
         else if (opc == OP_CHK_EQ || opc == OP_DIV || opc == OP_MOD) bad = uses_inv(o.op.a) || uses_inv(o.op.b);
         else if (opc == OP_CHAIN) bad = uses_inv(o.op.c);
+        else if (opc == OP_SEQ) bad = false;
         else if (opc != OP_PACK8) bad = uses_inv(o.op.a);
         if (bad) throw std::runtime_error("pob: internal: an IsZero inverse is consumed by another op");
     }
+    for (auto &o : B.seq_ops) if (uses_inv(o.a) || uses_inv(o.b) || uses_inv(o.c)) throw std::runtime_error("pob: internal: an IsZero inverse is consumed inside a sequential region");
+    P.seq_ops = B.seq_ops;
+    if (P.seq_ops.empty()) P.seq_ops.push_back(Op{0, 0, 0, 0});
     for (Code c : B.aux) if (uses_inv(c)) throw std::runtime_error("pob: internal: an IsZero inverse is consumed by an operand list");
     uint32_t max_level = 0;
     for (auto &o : B.ops) if (op_opc(o.op) != OP_INV) max_level = std::max(max_level, o.level);
@@ -1390,8 +1421,19 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     { std::vector<uint32_t> tp = tstart, wp = wstart; uint32_t ip = P.inv_begin;
       for (auto &o : B.ops) { if (op_opc(o.op) == OP_INV) P.ops[ip++] = o.op; else P.ops[tp[o.level]++] = o.op; }
       for (auto &a : B.absorbs) P.absorbs[wp[a.level]++] = a.op; }
+    // inside a level: long sequential ops first, then grouped by opcode / operand class so that the 32 lanes of a
+    // warp run the same case of the interpreter switch (and the same fast or slow multiplication path)
+    auto op_key = [](const Op &o) -> uint32_t {
+        uint32_t opc = op_opc(o);
+        if (opc == OP_SEQ) return 0;
+        if (opc == OP_CHAIN) return 1;
+        uint32_t k = (opc + 2) << 4;
+        if (opc == OP_FMA) k |= (o.b == c_const(1)) ? 0u : (o.b == c_konst(0)) ? 1u : (code_kind(o.b) == K_KONST) ? 3u : 2u;
+        return k;
+    };
     for (uint32_t l = 1; l <= max_level; l++) {
         if (tcount[l] == 0 && wcount[l] == 0) continue;
+        std::stable_sort(P.ops.begin() + tstart[l], P.ops.begin() + tstart[l] + tcount[l], [&](const Op &x, const Op &y) { return op_key(x) < op_key(y); });
         P.levels.push_back(Level{tstart[l], tstart[l] + tcount[l], wstart[l], wstart[l] + wcount[l]});
     }
     // ---- codes + tiles ----

@@ -81,7 +81,7 @@ __device__ void absorb_warp(uint64_t *W, const AbsorbOp op) {
 }
 
 struct EvalArgs {
-    const Op *ops; const AbsorbOp *absorbs; const Level *levels; uint32_t n_levels, inv_begin, inv_end;
+    const Op *ops; const Op *seq_ops; const AbsorbOp *absorbs; const Level *levels; uint32_t n_levels, inv_begin, inv_end;
     const Code *aux; const Fr *konst; const Fr *invtab;
     const Code *out_codes; uint32_t n_outputs, n_inputs, val_base;
     uint64_t *stores; uint64_t store_stride;     // u64 units
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     const uint64_t *in = a.inputs + (uint64_t)inst * a.n_inputs * 4;
     for (uint32_t i = tid; i < a.n_inputs * 4; i += nthr) U[a.val_base + i] = in[i];
     __syncthreads();
-    VmCtx x{U, a.val_base, a.konst, a.aux, a.invtab, &s_status};
+    VmCtx x{U, a.val_base, a.konst, a.aux, a.invtab, &s_status, a.seq_ops};
     const uint32_t warp = tid >> 5, nwarp = nthr >> 5;
     for (uint32_t lv = 0; lv < a.n_levels; lv++) {
         const Level L = a.levels[lv];
@@ -256,7 +256,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 struct pob_handle {
     Program P; int device = 0;
     // device program
-    Op *d_ops = nullptr; AbsorbOp *d_abs = nullptr; Level *d_levels = nullptr; Code *d_aux = nullptr; Fr *d_konst = nullptr;
+    Op *d_ops = nullptr, *d_seq_ops = nullptr; AbsorbOp *d_abs = nullptr; Level *d_levels = nullptr; Code *d_aux = nullptr; Fr *d_konst = nullptr;
     Code *d_codes = nullptr; Tile *d_tiles = nullptr; Fr *d_invtab = nullptr; uint64_t *d_round_desc = nullptr;
     // stores (ring of RING chunks)
     static const uint32_t RING = 2;
@@ -321,7 +321,7 @@ void pob_destroy(pob_handle *h) {
     cudaSetDevice(h->device);
     if (h->s_eval) cudaStreamSynchronize(h->s_eval);
     if (h->s_exp) cudaStreamSynchronize(h->s_exp);
-    for (void *p : {(void *)h->d_ops, (void *)h->d_abs, (void *)h->d_levels, (void *)h->d_aux, (void *)h->d_konst, (void *)h->d_codes,
+    for (void *p : {(void *)h->d_ops, (void *)h->d_seq_ops, (void *)h->d_abs, (void *)h->d_levels, (void *)h->d_aux, (void *)h->d_konst, (void *)h->d_codes,
                     (void *)h->d_tiles, (void *)h->d_invtab, (void *)h->d_round_desc, (void *)h->d_stores, (void *)h->d_inputs, (void *)h->d_status,
                     (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr, (void *)h->d_staged})
         if (p) cudaFree(p);
@@ -353,7 +353,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
     try {
         const Program &P = h->P;
         CU(cudaSetDevice(device));
-        h->d_ops = upload(P.ops); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
+        h->d_ops = upload(P.ops); h->d_seq_ops = upload(P.seq_ops); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
         h->d_konst = upload(P.konst); h->d_codes = upload(P.codes);
         if (const char *v = getenv("POB_TILE_FILTER")) {      // tuning only: 1 = KeccakfRound tiles only, 2 = the others only (witness incomplete!)
             std::vector<Tile> sub; for (const Tile &t : P.tiles) if ((atoi(v) == 1) == (t.pad != 0)) sub.push_back(t);
@@ -375,24 +375,8 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
             CU(cudaEventCreateWithFlags(&h->ev_h2d[r], cudaEventDisableTiming));
         }
         CU(cudaEventCreate(&h->ev_start)); CU(cudaEventCreate(&h->ev_end));
-        // keep the non-round code stream (read once per instance by the code tiles) resident in L2 while 110 GB of
-        // witness per launch stream through it: persisting access-policy window on the expand stream
-        if (!getenv("POB_NO_L2_PERSIST")) {
-            int dev_max_persist = 0, max_window = 0;
-            cudaDeviceGetAttribute(&dev_max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
-            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
-            size_t want = P.codes.size() * sizeof(Code);
-            size_t win = std::min<size_t>(want, (size_t)std::max(0, max_window));
-            if (dev_max_persist > 0 && win > 0) {
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)dev_max_persist, want));
-                cudaStreamAttrValue attr{};
-                attr.accessPolicyWindow.base_ptr = h->d_codes; attr.accessPolicyWindow.num_bytes = win;
-                attr.accessPolicyWindow.hitRatio = 1.0f; attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                cudaStreamSetAttribute(h->s_exp, cudaStreamAttributeAccessPolicyWindow, &attr);
-                cudaGetLastError();
-            }
-        }
+        // (an L2 persisting access-policy window for the code stream was tried and REDUCED k_expand to 4.9 TB/s: the
+        // carve-out takes L2 away from write combining -- profiles/r01_expand_sweep.md)
         // witness slots: as many as fit in 80 % of free HBM after the store ring
         size_t free_b = 0, total_b = 0; CU(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t wbytes = 32ull * P.n_signals;
@@ -492,7 +476,7 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
             }
             if (c >= R) CU(cudaStreamWaitEvent(h->s_eval, h->ev_exp_done[r], 0));      // store ring slot r is free again
             uint64_t *stores = h->d_stores + (size_t)r * E * h->store_stride;
-            EvalArgs ea{h->d_ops, h->d_abs, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
+            EvalArgs ea{h->d_ops, h->d_seq_ops, h->d_abs, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
                         h->d_codes + ROUND_SIGNALS + 1, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
                         h->d_status + first, h->d_outputs + (size_t)first * no * 4};
             CU(cudaEventRecord(ev[0], h->s_eval));

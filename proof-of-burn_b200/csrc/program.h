@@ -48,6 +48,9 @@ enum Opc : uint32_t {
     OP_SELSUM = 10,    // V[dst] = (a <= c) ? aux[b + a] : 0, b/c raw.  sum_{j<=c} IsEqual(a, j)*vals[j]: selector.circom:31-41
     OP_CHAIN = 11,     // x = c; for k < b: x = x*aux[a+2k] + aux[a+2k+1]; V[dst+k] = x   (one thread walks an affine
                        //   recurrence whose every step is a signal: substring_check.circom:47-49, 95)
+    OP_SEQ = 12,       // run seq_ops[a .. a+b) in order on ONE thread, no barriers in between: a long inherently
+                       //   serial dependency chain (a whole Poseidon permutation, poseidon.circom:67-196) costs one
+                       //   level instead of ~600 CTA-wide barriers
 };
 struct Op { uint32_t opc_dst; Code a, b, c; };                    // opc in the top 6 bits, dst in the low 26
 POB_HD uint32_t op_opc(const Op &o) { return o.opc_dst >> 26; }
@@ -101,6 +104,7 @@ struct Program {
     // eval program
     std::vector<Op> ops;           // [0, inv_begin) sorted by level, then the deferred OP_INV ops
     uint32_t inv_begin = 0, inv_end = 0;   // IsZero inverses feed no other op: they run last, batch-inverted per thread
+    std::vector<Op> seq_ops;       // bodies of the OP_SEQ ops
     std::vector<AbsorbOp> absorbs; // sorted by level
     std::vector<Level> levels;
     std::vector<Code> aux;         // PACK8 operand lists

@@ -18,6 +18,7 @@ struct VmCtx {
     const Code *aux;
     const Fr *invtab;
     uint32_t *status;       // min over failing constraints of (component base + 1); STATUS_OK if none
+    const Op *seq_ops;      // bodies of OP_SEQ
 };
 
 POB_HD Fr vm_load_val(const uint64_t *p) {
@@ -52,7 +53,7 @@ POB_HD Fr vm_inverse(const VmCtx &x, const Fr &a) {
     return fr_inv(a);
 }
 
-POB_HD void vm_exec_op(const VmCtx &x, const Op &op) {
+POB_HD void vm_exec_basic(const VmCtx &x, const Op &op) {
     uint32_t opc = op_opc(op), dst = op_dst(op);
     uint64_t *vd = x.U + x.val_base + 4ull * dst;
     switch (opc) {
@@ -100,6 +101,11 @@ POB_HD void vm_exec_op(const VmCtx &x, const Op &op) {
     case OP_CHK_RANGE: { Fr a = vm_load(x, op.a); if (!fr_lt_pow2(a, op.b)) vm_fail(x, op.c); break; }
     default: break;
     }
+}
+
+POB_HD void vm_exec_op(const VmCtx &x, const Op &op) {
+    if (op_opc(op) == OP_SEQ) { for (uint32_t k = 0; k < op.b; k++) vm_exec_basic(x, x.seq_ops[op.a + k]); }
+    else vm_exec_basic(x, op);
 }
 
 // Deferred IsZero inverses (comparators.circom:30).  Thread `tid` of `nthr` owns ops begin+tid, +nthr, ...: zero and

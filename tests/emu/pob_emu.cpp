@@ -47,7 +47,7 @@ uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_
     std::vector<uint64_t> U(P.store_u64() + 4, 0);
     memcpy(U.data() + P.val_base, inputs, (size_t)P.n_inputs * 32);
     uint32_t status = STATUS_OK;
-    VmCtx x{U.data(), P.val_base, P.konst.data(), P.aux.data(), e->invtab.data(), &status};
+    VmCtx x{U.data(), P.val_base, P.konst.data(), P.aux.data(), e->invtab.data(), &status, P.seq_ops.data()};
     for (const Level &lv : P.levels) {
         for (uint32_t i = lv.t_begin; i < lv.t_end; i++) vm_exec_op(x, P.ops[i]);
         for (uint32_t i = lv.w_begin; i < lv.w_end; i++) vm_absorb_scalar(U.data(), P.absorbs[i]);

@@ -14,7 +14,4 @@ t = r.timing
 print("tiles %d  expand %.3f ms/launch (%d launches) = %.1f GB/s   total %.1f ms = %.1f wit/s  eval %.2f ms/launch" % (c.desc["n_tiles"], t["expand_ms"]/t["expand_launches"], t["expand_launches"], 32*c.n_signals*128/t["expand_ms"]/1e6, t["total_ms"], 128/t["total_ms"]*1e3, t["eval_ms"]/t["eval_launches"]))
 PY
 }
-run POB_SERIALIZE=1 POB_NO_L2_PERSIST=1
-run POB_SERIALIZE=1
-run A=1
-run POB_NO_L2_PERSIST=1
+run "$@"
