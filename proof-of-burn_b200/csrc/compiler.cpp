@@ -57,8 +57,9 @@ class Builder {
     // program
     struct OpRec { Op op; uint32_t level; };
     std::vector<OpRec> ops;
-    std::vector<Op> seq_ops;            // OP_SEQ bodies
-    bool in_seq = false; size_t seq_start = 0; uint32_t seq_first_val = 0;
+    struct PosRec { PoseidonOp op; uint32_t level; };
+    std::vector<PosRec> poseidons;
+    std::vector<Fr> pos_konst; uint32_t pos_koff[6] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
     struct AbsRec { AbsorbOp op; uint32_t level; };
     std::vector<AbsRec> absorbs;
     std::vector<Code> aux;
@@ -146,31 +147,8 @@ class Builder {
         if (it != cse.end()) return it->second;
         uint32_t slot = new_val(level);
         if (slot >= (1u << 26)) throw std::runtime_error("pob: too many value slots");
-        if (in_seq) seq_ops.push_back(Op{(opc << 26) | slot, a, b, c});
-        else ops.push_back({Op{(opc << 26) | slot, a, b, c}, level});
+        ops.push_back({Op{(opc << 26) | slot, a, b, c}, level});
         Code r = c_val(slot); cse.emplace(key, r); return r;
-    }
-    // ---- sequential regions: everything emitted between begin_seq/end_seq runs on one thread as a single op ----
-    void begin_seq() {
-        if (in_seq) throw std::runtime_error("pob: internal: nested sequential region");
-        in_seq = true; seq_start = seq_ops.size(); seq_first_val = n_vals;
-    }
-    void end_seq() {
-        in_seq = false;
-        size_t cnt = seq_ops.size() - seq_start;
-        if (cnt == 0) return;
-        uint32_t lv = 0;
-        auto ext = [&](Code c) {
-            if (code_kind(c) == K_VAL && code_payload(c) >= seq_first_val) return;     // defined inside the region
-            lv = std::max(lv, level_of(c));
-        };
-        for (size_t i = seq_start; i < seq_ops.size(); i++) {
-            const Op &o = seq_ops[i];
-            if (op_opc(o) != OP_FMA) throw std::runtime_error("pob: internal: only FMA ops are supported in a sequential region");
-            ext(o.a); ext(o.b); ext(o.c);
-        }
-        for (uint32_t sl = seq_first_val; sl < n_vals; sl++) lvlV[sl] = lv + 1;
-        ops.push_back({Op{OP_SEQ << 26, (uint32_t)seq_start, (uint32_t)cnt, 0}, lv + 1});
     }
     Code fma(Code a, Code b, Code c) {              // a*b + c
         Fr fa, fb, fc; bool ka = const_val(a, fa), kb = const_val(b, fb), kc = const_val(c, fc);
@@ -273,6 +251,26 @@ class Builder {
             ops.push_back({Op{(OP_PACK8 << 26) | (w0 + w), a0, 0, 0}, l + 1});
         }
         return w0;
+    }
+    // one Poseidon permutation as a warp op: returns the first slot of its value block (layout: program.h)
+    uint32_t poseidon(uint32_t t, const Code *in) {
+        if (t < 3 || t > 5) throw std::runtime_error("pob: Poseidon width outside this circuit's closure (t = 3, 4, 5)");
+        const PosLayout L = pos_layout(t);
+        if (pos_koff[t] == ~0u) {                       // C, S, M, P of this width, converted to Montgomery form once
+            pos_koff[t] = (uint32_t)pos_konst.size();
+            const uint64_t (*tabs[4])[4] = {t == 3 ? POSEIDON_C_T3 : t == 4 ? POSEIDON_C_T4 : POSEIDON_C_T5,
+                                            t == 3 ? POSEIDON_S_T3 : t == 4 ? POSEIDON_S_T4 : POSEIDON_S_T5,
+                                            t == 3 ? POSEIDON_M_T3 : t == 4 ? POSEIDON_M_T4 : POSEIDON_M_T5,
+                                            t == 3 ? POSEIDON_P_T3 : t == 4 ? POSEIDON_P_T4 : POSEIDON_P_T5};
+            const uint32_t cnt[4] = {t * 8 + L.rp, L.rp * (2 * t - 1), t * t, t * t};
+            for (int k = 0; k < 4; k++) for (uint32_t i = 0; i < cnt[k]; i++) { Fr f; memcpy(f.l, tabs[k][i], 32); pos_konst.push_back(fr_to_mont(f)); }
+        }
+        uint32_t lv = 0; for (uint32_t j = 0; j < t; j++) lv = std::max(lv, level_of(in[j]));
+        uint32_t a0 = (uint32_t)aux.size(); aux.insert(aux.end(), in, in + t);
+        uint32_t base = n_vals;
+        for (uint32_t i = 0; i < L.total; i++) new_val(lv + 1);
+        poseidons.push_back({PoseidonOp{t, a0, base, pos_koff[t]}, lv + 1});
+        return base;
     }
     // one Absorb: returns base word of its ABSORB_WORDS block
     uint32_t absorb(uint32_t s_idx, uint32_t blk_idx) {
@@ -422,82 +420,37 @@ static Blk T_Mux1(Builder &B, Code c0, Code c1, Code s) {
 // ============================================================================================================
 // circomlib/circuits/poseidon.circom
 // ============================================================================================================
-struct PoseidonK { int t, rp; const uint64_t (*C)[4], (*S)[4], (*M)[4], (*P)[4]; };
-static PoseidonK poseidon_k(int t) {
-    PoseidonK k; k.t = t;
-    if (t == 3) { k.rp = 57; k.C = POSEIDON_C_T3; k.S = POSEIDON_S_T3; k.M = POSEIDON_M_T3; k.P = POSEIDON_P_T3; }
-    else if (t == 4) { k.rp = 56; k.C = POSEIDON_C_T4; k.S = POSEIDON_S_T4; k.M = POSEIDON_M_T4; k.P = POSEIDON_P_T4; }
-    else if (t == 5) { k.rp = 60; k.C = POSEIDON_C_T5; k.S = POSEIDON_S_T5; k.M = POSEIDON_M_T5; k.P = POSEIDON_P_T5; }
-    else throw std::runtime_error("pob: Poseidon width outside this circuit's closure (t = 3, 4, 5)");
-    return k;
-}
-static Code KC(Builder &B, const uint64_t (*tab)[4], int i) { Fr f; memcpy(f.l, tab[i], 32); return B.konst(f); }
-// Sigma :5-16  own: out, in, in2, in4
-static Blk T_Sigma(Builder &B, Code in) {
-    Blk o = B.alloc(4); B.at(o.pos + 1) = in;
-    Code in2 = B.mul(in, in), in4 = B.mul(in2, in2);
-    B.at(o.pos + 2) = in2; B.at(o.pos + 3) = in4; B.at(o.pos) = B.mul(in4, in); return o;
-}
-// Ark(t,C,r) :18-25
-static Blk T_Ark(Builder &B, const PoseidonK &k, int r, const Code *in) {
-    size_t t = (size_t)k.t; Blk o = B.alloc(2 * t); B.copy(o.pos + t, in, t);
-    for (size_t i = 0; i < t; i++) B.at(o.pos + i) = B.add(in[i], KC(B, k.C, (int)i + r));
-    return o;
-}
-// Mix(t,M) :27-39
-static Blk T_Mix(Builder &B, int t_, const uint64_t (*M)[4], const Code *in) {
-    size_t t = (size_t)t_; Blk o = B.alloc(2 * t); B.copy(o.pos + t, in, t);
-    for (size_t i = 0; i < t; i++) {
-        Code lc = ZERO; for (size_t j = 0; j < t; j++) lc = B.fma(in[j], KC(B, M, (int)(j * t + i)), lc);
-        B.at(o.pos + i) = lc;
-    }
-    return o;
-}
-// MixLast(t,M,s) :41-50
-static Blk T_MixLast(Builder &B, int t_, const uint64_t (*M)[4], int s, const Code *in) {
-    size_t t = (size_t)t_; Blk o = B.alloc(1 + t); B.copy(o.pos + 1, in, t);
-    Code lc = ZERO; for (size_t j = 0; j < t; j++) lc = B.fma(in[j], KC(B, M, (int)(j * t) + s), lc);
-    B.at(o.pos) = lc; return o;
-}
-// MixS(t,S,r) :52-65
-static Blk T_MixS(Builder &B, const PoseidonK &k, int r, const Code *in) {
-    int t = k.t; Blk o = B.alloc(2 * (size_t)t); B.copy(o.pos + (size_t)t, in, (size_t)t);
-    Code lc = ZERO; for (int i = 0; i < t; i++) lc = B.fma(in[i], KC(B, k.S, (t * 2 - 1) * r + i), lc);
-    B.at(o.pos) = lc;
-    for (int i = 1; i < t; i++) B.at(o.pos + (size_t)i) = B.fma(in[0], KC(B, k.S, (t * 2 - 1) * r + t + i - 1), in[i]);
-    return o;
-}
-// PoseidonEx(nInputs,1) :67-196  own: out[1], inputs[n], initialState
+// PoseidonEx(nInputs,1) :67-196  own: out[1], inputs[n], initialState.  The arithmetic is one warp op (Builder::poseidon);
+// here only the circom numbering of its ~1100 signals is laid out over the op's value block.
 static Blk T_PoseidonEx(Builder &B, int nInputs, const Code *inputs, Code initialState) {
-    int t = nInputs + 1; PoseidonK k = poseidon_k(t);
+    const uint32_t t = (uint32_t)nInputs + 1; const PosLayout L = pos_layout(t);
     Blk o = B.alloc(2 + (size_t)nInputs); B.copy(o.pos + 1, inputs, (size_t)nInputs); B.at(o.pos + 1 + (size_t)nInputs) = initialState;
-    B.begin_seq();      // ~65 rounds of x^5 / affine mixes: inherently serial, run by one thread
-    Code st[8], nx[8];
-    st[0] = initialState; for (int j = 1; j < t; j++) st[j] = inputs[j - 1];
-    auto take = [&](Blk b, Code *dst) { for (int j = 0; j < t; j++) dst[j] = B.at(b.pos + (size_t)j); };
-    take(T_Ark(B, k, 0, st), st);
-    for (int r = 0; r < 3; r++) {
-        for (int j = 0; j < t; j++) nx[j] = B.at(T_Sigma(B, st[j]).pos);
-        take(T_Ark(B, k, (r + 1) * t, nx), nx);
-        take(T_Mix(B, t, k.M, nx), st);
+    Code st[8], cur[8];
+    st[0] = initialState; for (uint32_t j = 1; j < t; j++) st[j] = inputs[j - 1];
+    const uint32_t base = B.poseidon(t, st);
+    auto V = [&](uint32_t off) { return c_val(base + off); };
+    { Blk a = B.alloc(2 * t); for (uint32_t j = 0; j < t; j++) { B.at(a.pos + j) = V(j); B.at(a.pos + t + j) = st[j]; cur[j] = V(j); } }   // ark[0]
+    auto sigma = [&](Code in, uint32_t off) {            // Sigma :5-16  own: out, in, in2, in4
+        Blk s = B.alloc(4); B.at(s.pos) = V(off + 2); B.at(s.pos + 1) = in; B.at(s.pos + 2) = V(off); B.at(s.pos + 3) = V(off + 1);
+    };
+    auto full = [&](uint32_t F) {                        // t x Sigma, Ark :18-25, Mix :27-39
+        for (uint32_t j = 0; j < t; j++) sigma(cur[j], F + 3 * j);
+        Blk a = B.alloc(2 * t); for (uint32_t j = 0; j < t; j++) { B.at(a.pos + j) = V(F + 3 * t + j); B.at(a.pos + t + j) = V(F + 3 * j + 2); }
+        Blk m = B.alloc(2 * t); for (uint32_t j = 0; j < t; j++) { B.at(m.pos + j) = V(F + 4 * t + j); B.at(m.pos + t + j) = V(F + 3 * t + j); cur[j] = V(F + 4 * t + j); }
+    };
+    for (uint32_t f = 0; f < 4; f++) full(L.F1 + 5 * t * f);                        // :101-136 (the 4th mixes with P)
+    for (uint32_t r = 0; r < L.rp; r++) {                                            // :138-160
+        const uint32_t Bs = L.PB + r * (4 + t);
+        sigma(cur[0], Bs);
+        Blk m = B.alloc(2 * t);                                                      // MixS :52-65  own: out[t], in[t]
+        for (uint32_t j = 0; j < t; j++) { B.at(m.pos + j) = V(Bs + 4 + j); B.at(m.pos + t + j) = j == 0 ? V(Bs + 3) : cur[j]; }
+        for (uint32_t j = 0; j < t; j++) cur[j] = V(Bs + 4 + j);
     }
-    for (int j = 0; j < t; j++) nx[j] = B.at(T_Sigma(B, st[j]).pos);
-    take(T_Ark(B, k, 4 * t, nx), nx);
-    take(T_Mix(B, t, k.P, nx), st);
-    for (int r = 0; r < k.rp; r++) {
-        Blk s = T_Sigma(B, st[0]);
-        nx[0] = B.add(B.at(s.pos), KC(B, k.C, 5 * t + r)); for (int j = 1; j < t; j++) nx[j] = st[j];
-        take(T_MixS(B, k, r, nx), st);
-    }
-    for (int r = 0; r < 3; r++) {
-        for (int j = 0; j < t; j++) nx[j] = B.at(T_Sigma(B, st[j]).pos);
-        take(T_Ark(B, k, 5 * t + k.rp + r * t, nx), nx);
-        take(T_Mix(B, t, k.M, nx), st);
-    }
-    for (int j = 0; j < t; j++) nx[j] = B.at(T_Sigma(B, st[j]).pos);
-    Blk ml = T_MixLast(B, t, k.M, 0, nx);
-    B.end_seq();
-    B.at(o.pos) = B.at(ml.pos); return o;
+    for (uint32_t f = 0; f < 3; f++) full(L.SB + 5 * t * f);                        // :162-182
+    for (uint32_t j = 0; j < t; j++) sigma(cur[j], L.LB + 3 * j);                    // :184-187
+    Blk ml = B.alloc(1 + t);                                                         // MixLast :41-50  own: out, in[t]
+    B.at(ml.pos) = V(L.LB + 3 * t); for (uint32_t j = 0; j < t; j++) B.at(ml.pos + 1 + j) = V(L.LB + 3 * j + 2);
+    B.at(o.pos) = V(L.LB + 3 * t); return o;
 }
 // Poseidon(n) :198-208
 static Blk T_Poseidon(Builder &B, int n, const Code *inputs) {
@@ -1400,17 +1353,21 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
         if (opc == OP_FMA) bad = uses_inv(o.op.a) || uses_inv(o.op.b) || uses_inv(o.op.c);
         else if (opc == OP_CHK_EQ || opc == OP_DIV || opc == OP_MOD) bad = uses_inv(o.op.a) || uses_inv(o.op.b);
         else if (opc == OP_CHAIN) bad = uses_inv(o.op.c);
-        else if (opc == OP_SEQ) bad = false;
         else if (opc != OP_PACK8) bad = uses_inv(o.op.a);
         if (bad) throw std::runtime_error("pob: internal: an IsZero inverse is consumed by another op");
     }
-    for (auto &o : B.seq_ops) if (uses_inv(o.a) || uses_inv(o.b) || uses_inv(o.c)) throw std::runtime_error("pob: internal: an IsZero inverse is consumed inside a sequential region");
-    P.seq_ops = B.seq_ops;
-    if (P.seq_ops.empty()) P.seq_ops.push_back(Op{0, 0, 0, 0});
     for (Code c : B.aux) if (uses_inv(c)) throw std::runtime_error("pob: internal: an IsZero inverse is consumed by an operand list");
     uint32_t max_level = 0;
     for (auto &o : B.ops) if (op_opc(o.op) != OP_INV) max_level = std::max(max_level, o.level);
     for (auto &a : B.absorbs) max_level = std::max(max_level, a.level);
+    for (auto &q : B.poseidons) max_level = std::max(max_level, q.level);
+    std::vector<uint32_t> pcount(max_level + 2, 0), pstart(max_level + 2, 0);
+    for (auto &q : B.poseidons) pcount[q.level]++;
+    for (uint32_t l = 1; l <= max_level + 1; l++) pstart[l] = pstart[l - 1] + pcount[l - 1];
+    P.poseidons.resize(B.poseidons.size());
+    { std::vector<uint32_t> pp = pstart; for (auto &q : B.poseidons) P.poseidons[pp[q.level]++] = q.op; }
+    P.pos_konst = B.pos_konst; if (P.pos_konst.empty()) P.pos_konst.push_back(fr_zero());
+    for (auto &q : B.poseidons) for (uint32_t j = 0; j < q.op.t; j++) if (uses_inv(B.aux[q.op.in_aux + j])) throw std::runtime_error("pob: internal: an IsZero inverse feeds a Poseidon");
     std::vector<uint32_t> tcount(max_level + 2, 0), wcount(max_level + 2, 0);
     for (auto &o : B.ops) if (op_opc(o.op) != OP_INV) tcount[o.level]++;
     for (auto &a : B.absorbs) wcount[a.level]++;
@@ -1425,16 +1382,15 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     // warp run the same case of the interpreter switch (and the same fast or slow multiplication path)
     auto op_key = [](const Op &o) -> uint32_t {
         uint32_t opc = op_opc(o);
-        if (opc == OP_SEQ) return 0;
         if (opc == OP_CHAIN) return 1;
         uint32_t k = (opc + 2) << 4;
         if (opc == OP_FMA) k |= (o.b == c_const(1)) ? 0u : (o.b == c_konst(0)) ? 1u : (code_kind(o.b) == K_KONST) ? 3u : 2u;
         return k;
     };
     for (uint32_t l = 1; l <= max_level; l++) {
-        if (tcount[l] == 0 && wcount[l] == 0) continue;
+        if (tcount[l] == 0 && wcount[l] == 0 && pcount[l] == 0) continue;
         std::stable_sort(P.ops.begin() + tstart[l], P.ops.begin() + tstart[l] + tcount[l], [&](const Op &x, const Op &y) { return op_key(x) < op_key(y); });
-        P.levels.push_back(Level{tstart[l], tstart[l] + tcount[l], wstart[l], wstart[l] + wcount[l]});
+        P.levels.push_back(Level{tstart[l], tstart[l] + tcount[l], wstart[l], wstart[l] + wcount[l], pstart[l], pstart[l] + pcount[l]});
     }
     // ---- codes + tiles ----
     P.codes.resize(ROUND_SIGNALS);

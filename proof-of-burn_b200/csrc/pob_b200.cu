@@ -80,8 +80,61 @@ __device__ void absorb_warp(uint64_t *W, const AbsorbOp op) {
     }
 }
 
+// ---- one Poseidon permutation by one warp (circomlib/circuits/poseidon.circom:67-196) ---------------------------
+// Lane j < t owns state element j in Montgomery form; Mix / MixS exchange elements with warp shuffles; every
+// intermediate signal is converted back to canonical form and written to its slot (layout: program.h PosLayout).
+__device__ __forceinline__ Fr shfl_fr(const Fr &v, int src) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src);
+    return r;
+}
+__device__ void poseidon_warp(const VmCtx &x, const PoseidonOp op, const Fr *pk) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t t = op.t; const PosLayout L = pos_layout(t);
+    const bool act = (uint32_t)lane < t; const uint32_t j = act ? (uint32_t)lane : 0u;
+    const Fr *K = pk + op.koff;
+    uint64_t *V = x.U + x.val_base + 4ull * op.base;
+    auto put = [&](uint32_t off, const Fr &m) { if (act) vm_store_val(V + 4ull * off, fr_from_mont(m)); };
+    Fr s = fr_add(fr_to_mont(vm_load(x, x.aux[op.in_aux + j])), K[L.kC + j]);     // ark[0]
+    put(j, s);
+    auto full = [&](uint32_t F, uint32_t coff, uint32_t moff) {
+        Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);
+        put(F + 3 * j, x2); put(F + 3 * j + 1, x4); put(F + 3 * j + 2, x5);
+        Fr y = fr_add(x5, K[L.kC + coff + j]); put(F + 3 * t + j, y);
+        Fr acc = fr_zero();
+        for (uint32_t k = 0; k < t; k++) { Fr yk = shfl_fr(y, (int)k); acc = fr_add(acc, fr_mont(K[moff + k * t + j], yk)); }
+        put(F + 4 * t + j, acc); s = acc;
+    };
+    for (uint32_t f = 0; f < 4; f++) full(L.F1 + 5 * t * f, (f + 1) * t, f == 3 ? L.kP : L.kM);
+#pragma unroll 1
+    for (uint32_t r = 0; r < L.rp; r++) {
+        const uint32_t B = L.PB + r * (4 + t), so = (2 * t - 1) * r;
+        Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);                // meaningful on lane 0 only
+        Fr z0 = fr_add(x5, K[L.kC + 5 * t + r]);
+        if (lane == 0) { vm_store_val(V + 4ull * B, fr_from_mont(x2)); vm_store_val(V + 4ull * (B + 1), fr_from_mont(x4));
+                         vm_store_val(V + 4ull * (B + 2), fr_from_mont(x5)); vm_store_val(V + 4ull * (B + 3), fr_from_mont(z0)); }
+        z0 = shfl_fr(z0, 0);
+        const Fr in = (lane == 0) ? z0 : s;
+        Fr prod = fr_mont(K[L.kS + so + j], in);                                          // S[so + i] * in[i]
+        Fr o0 = fr_zero();
+        for (uint32_t k = 0; k < t; k++) o0 = fr_add(o0, shfl_fr(prod, (int)k));
+        Fr oj = fr_add(s, fr_mont(z0, K[L.kS + so + t + (j ? j : 1) - 1]));                // lanes 1..t-1
+        s = (lane == 0) ? o0 : oj;
+        put(B + 4 + j, s);
+    }
+    for (uint32_t f = 0; f < 3; f++) full(L.SB + 5 * t * f, 5 * t + L.rp + f * t, L.kM);
+    {
+        Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);
+        put(L.LB + 3 * j, x2); put(L.LB + 3 * j + 1, x4); put(L.LB + 3 * j + 2, x5);
+        Fr prod = fr_mont(K[L.kM + j * t], x5), out = fr_zero();
+        for (uint32_t k = 0; k < t; k++) out = fr_add(out, shfl_fr(prod, (int)k));
+        if (lane == 0) vm_store_val(V + 4ull * (L.LB + 3 * t), fr_from_mont(out));
+    }
+}
+
 struct EvalArgs {
-    const Op *ops; const Op *seq_ops; const AbsorbOp *absorbs; const Level *levels; uint32_t n_levels, inv_begin, inv_end;
+    const Op *ops; const AbsorbOp *absorbs; const PoseidonOp *poseidons; const Fr *pos_konst; const Level *levels; uint32_t n_levels, inv_begin, inv_end;
     const Code *aux; const Fr *konst; const Fr *invtab;
     const Code *out_codes; uint32_t n_outputs, n_inputs, val_base;
     uint64_t *stores; uint64_t store_stride;     // u64 units
@@ -98,12 +151,15 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     const uint64_t *in = a.inputs + (uint64_t)inst * a.n_inputs * 4;
     for (uint32_t i = tid; i < a.n_inputs * 4; i += nthr) U[a.val_base + i] = in[i];
     __syncthreads();
-    VmCtx x{U, a.val_base, a.konst, a.aux, a.invtab, &s_status, a.seq_ops};
+    VmCtx x{U, a.val_base, a.konst, a.aux, a.invtab, &s_status};
     const uint32_t warp = tid >> 5, nwarp = nthr >> 5;
     for (uint32_t lv = 0; lv < a.n_levels; lv++) {
         const Level L = a.levels[lv];
         for (uint32_t i = L.t_begin + tid; i < L.t_end; i += nthr) vm_exec_op(x, a.ops[i]);
-        for (uint32_t w = L.w_begin + warp; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]);
+        // warp ops: Poseidons take the first warps (long), Keccak absorbs the next ones
+        for (uint32_t q = L.p_begin + warp; q < L.p_end; q += nwarp) poseidon_warp(x, a.poseidons[q], a.pos_konst);
+        { const uint32_t np = (L.p_end - L.p_begin) % nwarp, wv = (warp + nwarp - np) % nwarp;
+          for (uint32_t w = L.w_begin + wv; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]); }
         __syncthreads();
     }
     vm_inv_batch(x, a.ops, a.inv_begin, a.inv_end, tid, nthr);     // IsZero inverse hints: no consumers, done last
@@ -256,7 +312,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 struct pob_handle {
     Program P; int device = 0;
     // device program
-    Op *d_ops = nullptr, *d_seq_ops = nullptr; AbsorbOp *d_abs = nullptr; Level *d_levels = nullptr; Code *d_aux = nullptr; Fr *d_konst = nullptr;
+    Op *d_ops = nullptr; PoseidonOp *d_pos = nullptr; Fr *d_pos_konst = nullptr; AbsorbOp *d_abs = nullptr; Level *d_levels = nullptr; Code *d_aux = nullptr; Fr *d_konst = nullptr;
     Code *d_codes = nullptr; Tile *d_tiles = nullptr; Fr *d_invtab = nullptr; uint64_t *d_round_desc = nullptr;
     // stores (ring of RING chunks)
     static const uint32_t RING = 2;
@@ -321,7 +377,7 @@ void pob_destroy(pob_handle *h) {
     cudaSetDevice(h->device);
     if (h->s_eval) cudaStreamSynchronize(h->s_eval);
     if (h->s_exp) cudaStreamSynchronize(h->s_exp);
-    for (void *p : {(void *)h->d_ops, (void *)h->d_seq_ops, (void *)h->d_abs, (void *)h->d_levels, (void *)h->d_aux, (void *)h->d_konst, (void *)h->d_codes,
+    for (void *p : {(void *)h->d_ops, (void *)h->d_pos, (void *)h->d_pos_konst, (void *)h->d_abs, (void *)h->d_levels, (void *)h->d_aux, (void *)h->d_konst, (void *)h->d_codes,
                     (void *)h->d_tiles, (void *)h->d_invtab, (void *)h->d_round_desc, (void *)h->d_stores, (void *)h->d_inputs, (void *)h->d_status,
                     (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr, (void *)h->d_staged})
         if (p) cudaFree(p);
@@ -353,7 +409,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
     try {
         const Program &P = h->P;
         CU(cudaSetDevice(device));
-        h->d_ops = upload(P.ops); h->d_seq_ops = upload(P.seq_ops); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
+        h->d_ops = upload(P.ops); h->d_pos = upload(P.poseidons); h->d_pos_konst = upload(P.pos_konst); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
         h->d_konst = upload(P.konst); h->d_codes = upload(P.codes);
         if (const char *v = getenv("POB_TILE_FILTER")) {      // tuning only: 1 = KeccakfRound tiles only, 2 = the others only (witness incomplete!)
             std::vector<Tile> sub; for (const Tile &t : P.tiles) if ((atoi(v) == 1) == (t.pad != 0)) sub.push_back(t);
@@ -476,7 +532,7 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
             }
             if (c >= R) CU(cudaStreamWaitEvent(h->s_eval, h->ev_exp_done[r], 0));      // store ring slot r is free again
             uint64_t *stores = h->d_stores + (size_t)r * E * h->store_stride;
-            EvalArgs ea{h->d_ops, h->d_seq_ops, h->d_abs, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
+            EvalArgs ea{h->d_ops, h->d_abs, h->d_pos, h->d_pos_konst, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
                         h->d_codes + ROUND_SIGNALS + 1, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
                         h->d_status + first, h->d_outputs + (size_t)first * no * 4};
             CU(cudaEventRecord(ev[0], h->s_eval));

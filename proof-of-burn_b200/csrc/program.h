@@ -48,9 +48,6 @@ enum Opc : uint32_t {
     OP_SELSUM = 10,    // V[dst] = (a <= c) ? aux[b + a] : 0, b/c raw.  sum_{j<=c} IsEqual(a, j)*vals[j]: selector.circom:31-41
     OP_CHAIN = 11,     // x = c; for k < b: x = x*aux[a+2k] + aux[a+2k+1]; V[dst+k] = x   (one thread walks an affine
                        //   recurrence whose every step is a signal: substring_check.circom:47-49, 95)
-    OP_SEQ = 12,       // run seq_ops[a .. a+b) in order on ONE thread, no barriers in between: a long inherently
-                       //   serial dependency chain (a whole Poseidon permutation, poseidon.circom:67-196) costs one
-                       //   level instead of ~600 CTA-wide barriers
 };
 struct Op { uint32_t opc_dst; Code a, b, c; };                    // opc in the top 6 bits, dst in the low 26
 POB_HD uint32_t op_opc(const Op &o) { return o.opc_dst >> 26; }
@@ -78,7 +75,24 @@ POB_HD uint32_t rw_rp(int i, int k) { return RW_RP + 3 * i + k; }
 POB_HD uint32_t rw_ch(int l, int k) { return RW_CH + 3 * l + k; }
 POB_HD uint32_t rw_out(int l) { return RW_OUT + l; }
 
-struct Level { uint32_t t_begin, t_end, w_begin, w_end; };
+// ---- warp op: one Poseidon permutation (circomlib/circuits/poseidon.circom:67-196, optimised schedule) ----------
+// Lane j < t owns state element j (Montgomery form); every intermediate signal the circuit exposes is written, in
+// canonical form, to a block of value slots laid out in computation order:
+//   0 .. t-1                         ark[0].out
+//   F1 + 5t*f, f = 0..3              first-half full round f: sigma j -> (in2, in4, out) at +3j ; ark.out at +3t ; mix.out at +4t
+//   PB + (4+t)*r, r = 0..RP-1        partial round r: sigma (in2, in4, out), mixS.in[0] (= out + C), mixS.out[t]
+//   SB + 5t*f, f = 0..2              second-half full rounds (same shape)
+//   LB                               last sigmas (3t), then mixLast.out
+struct PoseidonOp { uint32_t t, in_aux, base, koff; };          // inputs: aux[in_aux .. +t) = initialState, inputs[]
+struct PosLayout { uint32_t t, rp, F1, PB, SB, LB, total, kC, kS, kM, kP, ktotal; };
+POB_HD PosLayout pos_layout(uint32_t t) {
+    PosLayout L; L.t = t; L.rp = (t == 3) ? 57u : (t == 4) ? 56u : 60u;
+    L.F1 = t; L.PB = 21 * t; L.SB = L.PB + L.rp * (4 + t); L.LB = L.SB + 15 * t; L.total = L.LB + 3 * t + 1;
+    L.kC = 0; L.kS = t * 8 + L.rp; L.kM = L.kS + L.rp * (2 * t - 1); L.kP = L.kM + t * t; L.ktotal = L.kP + t * t;
+    return L;
+}
+
+struct Level { uint32_t t_begin, t_end, w_begin, w_end, p_begin, p_end; };
 
 // ---- expand tiles: a contiguous run of witness entries and where its codes live -------------------------------
 struct Tile { uint64_t dst; uint32_t n, code_off, ubase, pad; };  // BIT codes are relative to ubase; pad = 1: round tile (all BIT)
@@ -104,8 +118,9 @@ struct Program {
     // eval program
     std::vector<Op> ops;           // [0, inv_begin) sorted by level, then the deferred OP_INV ops
     uint32_t inv_begin = 0, inv_end = 0;   // IsZero inverses feed no other op: they run last, batch-inverted per thread
-    std::vector<Op> seq_ops;       // bodies of the OP_SEQ ops
     std::vector<AbsorbOp> absorbs; // sorted by level
+    std::vector<PoseidonOp> poseidons;   // sorted by level
+    std::vector<Fr> pos_konst;     // Poseidon C,S,M,P tables per width, MONTGOMERY form (PoseidonOp::koff)
     std::vector<Level> levels;
     std::vector<Code> aux;         // PACK8 operand lists
     std::vector<Fr> konst;         // big constants

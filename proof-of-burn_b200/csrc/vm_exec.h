@@ -18,7 +18,6 @@ struct VmCtx {
     const Code *aux;
     const Fr *invtab;
     uint32_t *status;       // min over failing constraints of (component base + 1); STATUS_OK if none
-    const Op *seq_ops;      // bodies of OP_SEQ
 };
 
 POB_HD Fr vm_load_val(const uint64_t *p) {
@@ -53,7 +52,7 @@ POB_HD Fr vm_inverse(const VmCtx &x, const Fr &a) {
     return fr_inv(a);
 }
 
-POB_HD void vm_exec_basic(const VmCtx &x, const Op &op) {
+POB_HD void vm_exec_op(const VmCtx &x, const Op &op) {
     uint32_t opc = op_opc(op), dst = op_dst(op);
     uint64_t *vd = x.U + x.val_base + 4ull * dst;
     switch (opc) {
@@ -101,11 +100,6 @@ POB_HD void vm_exec_basic(const VmCtx &x, const Op &op) {
     case OP_CHK_RANGE: { Fr a = vm_load(x, op.a); if (!fr_lt_pow2(a, op.b)) vm_fail(x, op.c); break; }
     default: break;
     }
-}
-
-POB_HD void vm_exec_op(const VmCtx &x, const Op &op) {
-    if (op_opc(op) == OP_SEQ) { for (uint32_t k = 0; k < op.b; k++) vm_exec_basic(x, x.seq_ops[op.a + k]); }
-    else vm_exec_basic(x, op);
 }
 
 // Deferred IsZero inverses (comparators.circom:30).  Thread `tid` of `nthr` owns ops begin+tid, +nthr, ...: zero and
@@ -199,6 +193,49 @@ inline void vm_absorb_scalar(uint64_t *W, const AbsorbOp &op) {
         ch[0] ^= keccak_rc(r);
         for (int l = 0; l < 25; l++) { B[rw_out(l)] = ch[l]; st[l] = ch[l]; }
     }
+}
+
+// Scalar reference of the Poseidon warp op (HOST ONLY users: tests/emu).  The device implementation is the
+// warp-cooperative poseidon_warp() in pob_b200.cu; both must fill the slot layout documented in program.h.
+inline void vm_poseidon_scalar(const VmCtx &x, const PoseidonOp &op, const Fr *pk) {
+    const PosLayout L = pos_layout(op.t); const uint32_t t = op.t;
+    const Fr *K = pk + op.koff;
+    auto C = [&](uint32_t i) { return fr_from_mont(K[L.kC + i]); };
+    auto S = [&](uint32_t i) { return fr_from_mont(K[L.kS + i]); };
+    auto put = [&](uint32_t off, const Fr &v) { vm_store_val(x.U + x.val_base + 4ull * (op.base + off), v); };
+    Fr st[5], y[5];
+    for (uint32_t j = 0; j < t; j++) { st[j] = fr_add(vm_load(x, x.aux[op.in_aux + j]), C(j)); put(j, st[j]); }
+    auto full = [&](uint32_t F, uint32_t coff, uint32_t moff) {
+        for (uint32_t j = 0; j < t; j++) {
+            Fr x2 = fr_mul(st[j], st[j]), x4 = fr_mul(x2, x2), x5 = fr_mul(x4, st[j]);
+            put(F + 3 * j, x2); put(F + 3 * j + 1, x4); put(F + 3 * j + 2, x5);
+            y[j] = fr_add(x5, C(coff + j)); put(F + 3 * t + j, y[j]);
+        }
+        for (uint32_t i = 0; i < t; i++) {
+            Fr acc = fr_zero(); for (uint32_t j = 0; j < t; j++) acc = fr_add(acc, fr_mul(fr_from_mont(K[moff + j * t + i]), y[j]));
+            put(F + 4 * t + i, acc);
+        }
+        for (uint32_t i = 0; i < t; i++) st[i] = vm_load_val(x.U + x.val_base + 4ull * (op.base + F + 4 * t + i));
+    };
+    for (uint32_t f = 0; f < 4; f++) full(L.F1 + 5 * t * f, (f + 1) * t, f == 3 ? L.kP : L.kM);
+    for (uint32_t r = 0; r < L.rp; r++) {
+        const uint32_t B = L.PB + r * (4 + t);
+        Fr x2 = fr_mul(st[0], st[0]), x4 = fr_mul(x2, x2), x5 = fr_mul(x4, st[0]);
+        put(B, x2); put(B + 1, x4); put(B + 2, x5);
+        Fr z0 = fr_add(x5, C(5 * t + r)); put(B + 3, z0);
+        Fr o0 = fr_mul(S((2 * t - 1) * r), z0);
+        for (uint32_t i = 1; i < t; i++) o0 = fr_add(o0, fr_mul(S((2 * t - 1) * r + i), st[i]));
+        for (uint32_t i = 1; i < t; i++) { st[i] = fr_add(st[i], fr_mul(z0, S((2 * t - 1) * r + t + i - 1))); put(B + 4 + i, st[i]); }
+        st[0] = o0; put(B + 4, o0);
+    }
+    for (uint32_t f = 0; f < 3; f++) full(L.SB + 5 * t * f, 5 * t + L.rp + f * t, L.kM);
+    Fr out = fr_zero();
+    for (uint32_t j = 0; j < t; j++) {
+        Fr x2 = fr_mul(st[j], st[j]), x4 = fr_mul(x2, x2), x5 = fr_mul(x4, st[j]);
+        put(L.LB + 3 * j, x2); put(L.LB + 3 * j + 1, x4); put(L.LB + 3 * j + 2, x5);
+        out = fr_add(out, fr_mul(fr_from_mont(K[L.kM + j * t]), x5));
+    }
+    put(L.LB + 3 * t, out);
 }
 
 // ---- expand: one witness code -> 32-byte little-endian field element (4 x u64) --------------------------------

@@ -47,10 +47,11 @@ uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_
     std::vector<uint64_t> U(P.store_u64() + 4, 0);
     memcpy(U.data() + P.val_base, inputs, (size_t)P.n_inputs * 32);
     uint32_t status = STATUS_OK;
-    VmCtx x{U.data(), P.val_base, P.konst.data(), P.aux.data(), e->invtab.data(), &status, P.seq_ops.data()};
+    VmCtx x{U.data(), P.val_base, P.konst.data(), P.aux.data(), e->invtab.data(), &status};
     for (const Level &lv : P.levels) {
         for (uint32_t i = lv.t_begin; i < lv.t_end; i++) vm_exec_op(x, P.ops[i]);
         for (uint32_t i = lv.w_begin; i < lv.w_end; i++) vm_absorb_scalar(U.data(), P.absorbs[i]);
+        for (uint32_t i = lv.p_begin; i < lv.p_end; i++) vm_poseidon_scalar(x, P.poseidons[i], P.pos_konst.data());
     }
     for (uint32_t tid = 0; tid < 64; tid++) vm_inv_batch(x, P.ops.data(), P.inv_begin, P.inv_end, tid, 64);
     if (witness)
