@@ -140,6 +140,7 @@ struct EvalArgs {
     uint64_t *stores; uint64_t store_stride;     // u64 units
     const uint64_t *inputs;                       // chunk base: instance j at inputs + j * n_inputs * 4
     uint32_t *status; uint64_t *outputs;          // chunk base
+    long long *prof;                              // tuning only: per-level clock64 stamps of instance 0 (or null)
 };
 
 template <int THREADS>
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     VmCtx x{U, a.val_base, a.konst, a.aux, a.invtab, &s_status};
     const uint32_t warp = tid >> 5, nwarp = nthr >> 5;
     for (uint32_t lv = 0; lv < a.n_levels; lv++) {
+        if (a.prof && inst == 0 && tid == 0) a.prof[lv] = clock64();
         const Level L = a.levels[lv];
         for (uint32_t i = L.t_begin + tid; i < L.t_end; i += nthr) vm_exec_op(x, a.ops[i]);
         // warp ops: Poseidons take the first warps (long), Keccak absorbs the next ones
@@ -162,7 +164,9 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
           for (uint32_t w = L.w_begin + wv; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]); }
         __syncthreads();
     }
+    if (a.prof && inst == 0 && tid == 0) a.prof[a.n_levels] = clock64();
     vm_inv_batch(x, a.ops, a.inv_begin, a.inv_end, tid, nthr);     // IsZero inverse hints: no consumers, done last
+    if (a.prof && inst == 0) { __syncthreads(); if (tid == 0) a.prof[a.n_levels + 1] = clock64(); }
     if (tid == 0) a.status[inst] = (s_status == STATUS_OK) ? 0u : s_status;
     for (uint32_t i = tid; i < a.n_outputs; i += nthr) {
         uint64_t v[4]; vm_expand(a.out_codes[i], U, 0, a.val_base, a.konst, v);
@@ -324,6 +328,7 @@ struct pob_handle {
     uint64_t **d_witptr = nullptr; uint32_t *h_status = nullptr; uint64_t *h_outputs = nullptr; uint64_t *h_digests = nullptr;
     uint64_t **h_witptr = nullptr;
     uint64_t *d_staged = nullptr; uint32_t n_staged = 0;
+    long long *d_prof = nullptr;               // POB_EVAL_PROFILE: per-level clock stamps (tuning only)
     uint32_t xgroup = 0;                       // instances per expand launch (distinct witness slots)
     int variant = 0;                           // k_expand unroll/occupancy variant (POB_EXPAND_VARIANT), tuning only
     int eval_threads = 1024;                   // k_eval CTA size (POB_EVAL_THREADS), tuning only
@@ -433,6 +438,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         CU(cudaEventCreate(&h->ev_start)); CU(cudaEventCreate(&h->ev_end));
         // (an L2 persisting access-policy window for the code stream was tried and REDUCED k_expand to 4.9 TB/s: the
         // carve-out takes L2 away from write combining -- profiles/r01_expand_sweep.md)
+        if (getenv("POB_EVAL_PROFILE")) CU(cudaMalloc(&h->d_prof, (P.levels.size() + 2) * sizeof(long long)));
         // witness slots: as many as fit in 80 % of free HBM after the store ring
         size_t free_b = 0, total_b = 0; CU(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t wbytes = 32ull * P.n_signals;
@@ -534,7 +540,7 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
             uint64_t *stores = h->d_stores + (size_t)r * E * h->store_stride;
             EvalArgs ea{h->d_ops, h->d_abs, h->d_pos, h->d_pos_konst, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
                         h->d_codes + ROUND_SIGNALS + 1, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
-                        h->d_status + first, h->d_outputs + (size_t)first * no * 4};
+                        h->d_status + first, h->d_outputs + (size_t)first * no * 4, (c == 0) ? h->d_prof : nullptr};
             CU(cudaEventRecord(ev[0], h->s_eval));
             switch (h->eval_threads) {
             case 256: k_eval<256><<<cnt, 256, 0, h->s_eval>>>(ea); break;
@@ -593,6 +599,18 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
             cudaEvent_t *ev = &h->ev_pool[(size_t)c * ev_per_chunk];
             float ms = 0; CU(cudaEventElapsedTime(&ms, ev[0], ev[1])); T.eval_ms += ms;
             for (uint32_t g = 0; g < group_count[c]; g++) { CU(cudaEventElapsedTime(&ms, ev[2 + 2 * g], ev[3 + 2 * g])); T.expand_ms += ms; }
+        }
+        if (h->d_prof) {
+            std::vector<long long> st(P.levels.size() + 2);
+            CU(cudaMemcpy(st.data(), h->d_prof, st.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            FILE *f = fopen(getenv("POB_EVAL_PROFILE"), "w");
+            if (f) {
+                for (size_t l = 0; l + 1 < st.size(); l++) {
+                    if (l < P.levels.size()) fprintf(f, "level %zu ops %u absorbs %u poseidons %u cycles %lld\n", l, P.levels[l].t_end - P.levels[l].t_begin, P.levels[l].w_end - P.levels[l].w_begin, P.levels[l].p_end - P.levels[l].p_begin, st[l + 1] - st[l]);
+                    else fprintf(f, "inverse-batch ops %u cycles %lld\n", P.inv_end - P.inv_begin, st[l + 1] - st[l]);
+                }
+                fclose(f);
+            }
         }
         h->timing = T; h->last_n = n; h->last_expanded = expand;
     } catch (const std::exception &e) { return fail(POB_E_CUDA, std::string("pob_run_batch: ") + e.what()); }
