@@ -57,6 +57,9 @@ class Builder {
     // program
     struct OpRec { Op op; uint32_t level; };
     std::vector<OpRec> ops;
+    struct PsumRec { PsumOp op; uint32_t level; };
+    std::vector<PsumRec> psums;
+    std::vector<uint8_t> inv_generic;   // per value slot: 1 = an IsZero inverse whose input is expected to be a large value
     struct PosRec { PoseidonOp op; uint32_t level; };
     std::vector<PosRec> poseidons;
     std::vector<Fr> pos_konst; uint32_t pos_koff[6] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
@@ -171,9 +174,11 @@ class Builder {
         Fr fa; if (const_val(a, fa)) return fr_is_zero(fa) ? ONE : ZERO;
         return emit_val(OP_ISZ, a, 0, 0, 1 + level_of(a));
     }
-    Code inv(Code a) {
+    Code inv(Code a, bool likely_large = false) {
         Fr fa; if (const_val(a, fa)) return fr_is_zero(fa) ? ZERO : konst(fr_inv(fa));
-        return emit_val(OP_INV, a, 0, 0, 1 + level_of(a));
+        Code r = emit_val(OP_INV, a, 0, 0, 1 + level_of(a));
+        if (likely_large) { inv_generic.resize(n_vals, 0); inv_generic[code_payload(r)] = 1; }
+        return r;
     }
     // (a > k) on canonical integers == prod_{j<=k} (1 - IsEqual(j, a))
     Code gtc(Code a, uint32_t k) {
@@ -192,15 +197,14 @@ class Builder {
             out[i] = c_val(slot);
         }
     }
-    // x_{k+1} = x_k * m[k] + ad[k], every x_k a signal: one thread walks the recurrence
-    void chain(Code x0, const Code *m, const Code *ad, size_t n, Code *out) {
+    // V[k] = x0 + sum_{i<=k} terms[i], every partial sum a signal: one warp-level prefix-sum op
+    void prefix_sum(Code x0, const Code *terms, size_t n, Code *out) {
         uint32_t lv = level_of(x0);
-        for (size_t i = 0; i < n; i++) lv = std::max(lv, std::max(level_of(m[i]), level_of(ad[i])));
-        uint32_t a0 = (uint32_t)aux.size();
-        for (size_t i = 0; i < n; i++) { aux.push_back(m[i]); aux.push_back(ad[i]); }
+        for (size_t i = 0; i < n; i++) lv = std::max(lv, level_of(terms[i]));
+        uint32_t a0 = (uint32_t)aux.size(); aux.insert(aux.end(), terms, terms + n);
         uint32_t first = n_vals;
         for (size_t i = 0; i < n; i++) { uint32_t slot = new_val(lv + 1); out[i] = c_val(slot); }
-        ops.push_back({Op{(OP_CHAIN << 26) | first, a0, (uint32_t)n, x0}, lv + 1});
+        psums.push_back({PsumOp{a0, (uint32_t)n, first, x0}, lv + 1});
     }
     // balanced sum of terms that are `var` accumulations in the circuit (only the total is a signal)
     Code sum_tree(std::vector<Code> v) {
@@ -385,13 +389,13 @@ static Blk T_Num2Bits_strict(Builder &B, Code in) {
 // circomlib/circuits/comparators.circom, mux1.circom
 // ============================================================================================================
 // IsZero :24-35  own: out, in, inv
-static Blk T_IsZero(Builder &B, Code in) {
-    Blk o = B.alloc(3); B.at(o.pos + 1) = in; B.at(o.pos + 2) = B.inv(in); B.at(o.pos) = B.isz(in); return o;
+static Blk T_IsZero(Builder &B, Code in, bool likely_large = false) {
+    Blk o = B.alloc(3); B.at(o.pos + 1) = in; B.at(o.pos + 2) = B.inv(in, likely_large); B.at(o.pos) = B.isz(in); return o;
 }
 // IsEqual :37-46  own: out, in[2] ; isz.in = in[1] - in[0]
-static Blk T_IsEqual(Builder &B, Code in0, Code in1) {
+static Blk T_IsEqual(Builder &B, Code in0, Code in1, bool likely_large = false) {
     Blk o = B.alloc(3); B.at(o.pos + 1) = in0; B.at(o.pos + 2) = in1;
-    Blk z = T_IsZero(B, B.sub(in1, in0)); B.at(o.pos) = B.at(z.pos); return o;
+    Blk z = T_IsZero(B, B.sub(in1, in0), likely_large); B.at(o.pos) = B.at(z.pos); return o;
 }
 // LessThan(n) :89-100
 static Blk T_LessThan(Builder &B, int n, Code in0, Code in1) {
@@ -695,23 +699,23 @@ static Blk T_SubstringCheck(Builder &B, int maxMainLen, int subLen, const Code *
     B.at(Mo) = ZERO;
     Fr pw = fr_from_u64(1), c256 = fr_from_u64(256);
     {   // M[i+1] = mainInput[i]*256^i + M[i]
-        std::vector<Code> ones(MM, ONE), terms(MM);
+        std::vector<Code> terms(MM);
         for (size_t i = 0; i < MM; i++) { terms[i] = B.mul(mainInput[i], B.konst(pw)); pw = fr_mul(pw, c256); }
-        B.chain(ZERO, ones.data(), terms.data(), MM, &B.at(Mo + 1));
+        B.prefix_sum(ZERO, terms.data(), MM, &B.at(Mo + 1));
     }
     B.at(allowed) = ONE; B.at(sums) = ZERO;
     pw = fr_from_u64(1);
     Code lastIdx = B.add(B.sub(mainLen, c_const((uint32_t)SL)), ONE);
-    std::vector<Code> sones(Kn, ONE), sterms(Kn);
+    std::vector<Code> sterms(Kn);
     for (size_t i = 0; i < Kn; i++) {
         Blk e1 = T_IsEqual(B, c_const((uint32_t)i), lastIdx); B.at(isLast + i) = B.at(e1.pos);
         B.at(allowed + i + 1) = B.gtc(lastIdx, (uint32_t)i);       // allowed[i]*(1 - isLastIndex[i]) == (lastIdx > i)
-        Blk e2 = T_IsEqual(B, B.mul(subN, B.konst(pw)), B.sub(B.at(Mo + i + SL), B.at(Mo + i)));
+        Blk e2 = T_IsEqual(B, B.mul(subN, B.konst(pw)), B.sub(B.at(Mo + i + SL), B.at(Mo + i)), /*likely_large=*/true);
         Code ex = B.at(e2.pos); B.at(exists + i) = ex;
         sterms[i] = B.mul(B.at(allowed + i + 1), ex);
         pw = fr_mul(pw, c256);
     }
-    B.chain(ZERO, sones.data(), sterms.data(), Kn, &B.at(sums + 1));   // sums[i+1] = sums[i] + allowed[i+1]*exists[i]
+    B.prefix_sum(ZERO, sterms.data(), Kn, &B.at(sums + 1));   // sums[i+1] = sums[i] + allowed[i+1]*exists[i]
     Blk z = T_IsZero(B, B.at(sums + Kn)); B.at(dne) = B.at(z.pos);
     B.at(o.pos) = B.not1(B.at(z.pos));
     return o;
@@ -1352,7 +1356,6 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
         bool bad = false;
         if (opc == OP_FMA) bad = uses_inv(o.op.a) || uses_inv(o.op.b) || uses_inv(o.op.c);
         else if (opc == OP_CHK_EQ || opc == OP_DIV || opc == OP_MOD) bad = uses_inv(o.op.a) || uses_inv(o.op.b);
-        else if (opc == OP_CHAIN) bad = uses_inv(o.op.c);
         else if (opc != OP_PACK8) bad = uses_inv(o.op.a);
         if (bad) throw std::runtime_error("pob: internal: an IsZero inverse is consumed by another op");
     }
@@ -1361,6 +1364,13 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     for (auto &o : B.ops) if (op_opc(o.op) != OP_INV) max_level = std::max(max_level, o.level);
     for (auto &a : B.absorbs) max_level = std::max(max_level, a.level);
     for (auto &q : B.poseidons) max_level = std::max(max_level, q.level);
+    for (auto &q : B.psums) max_level = std::max(max_level, q.level);
+    std::vector<uint32_t> scount(max_level + 2, 0), sstart(max_level + 2, 0);
+    for (auto &q : B.psums) scount[q.level]++;
+    for (uint32_t l = 1; l <= max_level + 1; l++) sstart[l] = sstart[l - 1] + scount[l - 1];
+    P.psums.resize(B.psums.size());
+    { std::vector<uint32_t> sp = sstart; for (auto &q : B.psums) P.psums[sp[q.level]++] = q.op; }
+    for (auto &q : B.psums) if (uses_inv(q.op.x0)) throw std::runtime_error("pob: internal: an IsZero inverse feeds a prefix sum");
     std::vector<uint32_t> pcount(max_level + 2, 0), pstart(max_level + 2, 0);
     for (auto &q : B.poseidons) pcount[q.level]++;
     for (uint32_t l = 1; l <= max_level + 1; l++) pstart[l] = pstart[l - 1] + pcount[l - 1];
@@ -1375,22 +1385,27 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     for (uint32_t l = 1; l <= max_level + 1; l++) { tstart[l] = tstart[l - 1] + tcount[l - 1]; wstart[l] = wstart[l - 1] + wcount[l - 1]; }
     P.ops.resize(B.ops.size()); P.absorbs.resize(B.absorbs.size());
     P.inv_begin = (uint32_t)(B.ops.size() - n_inv); P.inv_end = (uint32_t)B.ops.size();
-    { std::vector<uint32_t> tp = tstart, wp = wstart; uint32_t ip = P.inv_begin;
-      for (auto &o : B.ops) { if (op_opc(o.op) == OP_INV) P.ops[ip++] = o.op; else P.ops[tp[o.level]++] = o.op; }
+    B.inv_generic.resize(B.n_vals, 0);
+    size_t n_ginv = 0; for (auto &o : B.ops) if (op_opc(o.op) == OP_INV && B.inv_generic[op_dst(o.op)]) n_ginv++;
+    P.ginv_begin = (uint32_t)(P.inv_end - n_ginv);
+    { std::vector<uint32_t> tp = tstart, wp = wstart; uint32_t ip = P.inv_begin, gp = P.ginv_begin;
+      for (auto &o : B.ops) {
+          if (op_opc(o.op) == OP_INV) { if (B.inv_generic[op_dst(o.op)]) P.ops[gp++] = o.op; else P.ops[ip++] = o.op; }
+          else P.ops[tp[o.level]++] = o.op;
+      }
       for (auto &a : B.absorbs) P.absorbs[wp[a.level]++] = a.op; }
     // inside a level: long sequential ops first, then grouped by opcode / operand class so that the 32 lanes of a
     // warp run the same case of the interpreter switch (and the same fast or slow multiplication path)
     auto op_key = [](const Op &o) -> uint32_t {
         uint32_t opc = op_opc(o);
-        if (opc == OP_CHAIN) return 1;
         uint32_t k = (opc + 2) << 4;
         if (opc == OP_FMA) k |= (o.b == c_const(1)) ? 0u : (o.b == c_konst(0)) ? 1u : (code_kind(o.b) == K_KONST) ? 3u : 2u;
         return k;
     };
     for (uint32_t l = 1; l <= max_level; l++) {
-        if (tcount[l] == 0 && wcount[l] == 0 && pcount[l] == 0) continue;
+        if (tcount[l] == 0 && wcount[l] == 0 && pcount[l] == 0 && scount[l] == 0) continue;
         std::stable_sort(P.ops.begin() + tstart[l], P.ops.begin() + tstart[l] + tcount[l], [&](const Op &x, const Op &y) { return op_key(x) < op_key(y); });
-        P.levels.push_back(Level{tstart[l], tstart[l] + tcount[l], wstart[l], wstart[l] + wcount[l], pstart[l], pstart[l] + pcount[l]});
+        P.levels.push_back(Level{tstart[l], tstart[l] + tcount[l], wstart[l], wstart[l] + wcount[l], pstart[l], pstart[l] + pcount[l], sstart[l], sstart[l] + scount[l]});
     }
     // ---- codes + tiles ----
     P.codes.resize(ROUND_SIGNALS);

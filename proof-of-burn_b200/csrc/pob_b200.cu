@@ -95,7 +95,9 @@ __device__ void poseidon_warp(const VmCtx &x, const PoseidonOp op, const Fr *pk)
     const bool act = (uint32_t)lane < t; const uint32_t j = act ? (uint32_t)lane : 0u;
     const Fr *K = pk + op.koff;
     uint64_t *V = x.U + x.val_base + 4ull * op.base;
-    auto put = [&](uint32_t off, const Fr &m) { if (act) vm_store_val(V + 4ull * off, fr_from_mont(m)); };
+    // values are parked in their slots in MONTGOMERY form (nothing but this warp reads them before the sweep below):
+    // no conversion sits on the dependency chain of the 65 rounds
+    auto put = [&](uint32_t off, const Fr &m) { if (act) vm_store_val(V + 4ull * off, m); };
     Fr s = fr_add(fr_to_mont(vm_load(x, x.aux[op.in_aux + j])), K[L.kC + j]);     // ark[0]
     put(j, s);
     auto full = [&](uint32_t F, uint32_t coff, uint32_t moff) {
@@ -112,8 +114,7 @@ __device__ void poseidon_warp(const VmCtx &x, const PoseidonOp op, const Fr *pk)
         const uint32_t B = L.PB + r * (4 + t), so = (2 * t - 1) * r;
         Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);                // meaningful on lane 0 only
         Fr z0 = fr_add(x5, K[L.kC + 5 * t + r]);
-        if (lane == 0) { vm_store_val(V + 4ull * B, fr_from_mont(x2)); vm_store_val(V + 4ull * (B + 1), fr_from_mont(x4));
-                         vm_store_val(V + 4ull * (B + 2), fr_from_mont(x5)); vm_store_val(V + 4ull * (B + 3), fr_from_mont(z0)); }
+        if (lane == 0) { vm_store_val(V + 4ull * B, x2); vm_store_val(V + 4ull * (B + 1), x4); vm_store_val(V + 4ull * (B + 2), x5); vm_store_val(V + 4ull * (B + 3), z0); }
         z0 = shfl_fr(z0, 0);
         const Fr in = (lane == 0) ? z0 : s;
         Fr prod = fr_mont(K[L.kS + so + j], in);                                          // S[so + i] * in[i]
@@ -129,12 +130,37 @@ __device__ void poseidon_warp(const VmCtx &x, const PoseidonOp op, const Fr *pk)
         put(L.LB + 3 * j, x2); put(L.LB + 3 * j + 1, x4); put(L.LB + 3 * j + 2, x5);
         Fr prod = fr_mont(K[L.kM + j * t], x5), out = fr_zero();
         for (uint32_t k = 0; k < t; k++) out = fr_add(out, shfl_fr(prod, (int)k));
-        if (lane == 0) vm_store_val(V + 4ull * (L.LB + 3 * t), fr_from_mont(out));
+        if (lane == 0) vm_store_val(V + 4ull * (L.LB + 3 * t), out);
+    }
+    __syncwarp();
+    for (uint32_t i = (uint32_t)lane; i < L.total; i += 32) {         // all 32 lanes: Montgomery -> canonical, in place
+        uint64_t *p = V + 4ull * i;
+        vm_store_val(p, fr_from_mont(vm_load_val(p)));
     }
 }
 
+// ---- prefix sum with every partial sum a signal (substring_check.circom:47-49, :95) by one warp -----------------
+__device__ void psum_warp(const VmCtx &x, const PsumOp op) {
+    const uint32_t lane = threadIdx.x & 31, per = (op.n + 31) / 32;
+    const uint32_t lo = min(op.n, lane * per), hi = min(op.n, lo + per);
+    Fr acc = fr_zero();
+    for (uint32_t k = lo; k < hi; k++) acc = fr_add(acc, vm_load(x, x.aux[op.aux0 + k]));
+    Fr incl = acc;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        Fr o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.l[i] = __shfl_up_sync(0xffffffffu, incl.l[i], off);
+        if ((int)lane >= off) incl = fr_add(incl, o);
+    }
+    Fr run = fr_add(vm_load(x, op.x0), fr_sub(incl, acc));            // x0 + sum of all earlier lanes
+    uint64_t *V = x.U + x.val_base + 4ull * op.dst;
+    for (uint32_t k = lo; k < hi; k++) { run = fr_add(run, vm_load(x, x.aux[op.aux0 + k])); vm_store_val(V + 4ull * k, run); }
+}
+
 struct EvalArgs {
-    const Op *ops; const AbsorbOp *absorbs; const PoseidonOp *poseidons; const Fr *pos_konst; const Level *levels; uint32_t n_levels, inv_begin, inv_end;
+    const Op *ops; const AbsorbOp *absorbs; const PoseidonOp *poseidons; const Fr *pos_konst; const PsumOp *psums;
+    const Level *levels; uint32_t n_levels, inv_begin, ginv_begin, inv_end;
     const Code *aux; const Fr *konst; const Fr *invtab;
     const Code *out_codes; uint32_t n_outputs, n_inputs, val_base;
     uint64_t *stores; uint64_t store_stride;     // u64 units
@@ -161,11 +187,16 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
         // warp ops: Poseidons take the first warps (long), Keccak absorbs the next ones
         for (uint32_t q = L.p_begin + warp; q < L.p_end; q += nwarp) poseidon_warp(x, a.poseidons[q], a.pos_konst);
         { const uint32_t np = (L.p_end - L.p_begin) % nwarp, wv = (warp + nwarp - np) % nwarp;
-          for (uint32_t w = L.w_begin + wv; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]); }
+          for (uint32_t w = L.w_begin + wv; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]);
+          const uint32_t nw2 = (np + (L.w_end - L.w_begin)) % nwarp, sv = (warp + nwarp - nw2) % nwarp;
+          for (uint32_t q = L.s_begin + sv; q < L.s_end; q += nwarp) psum_warp(x, a.psums[q]); }
         __syncthreads();
     }
     if (a.prof && inst == 0 && tid == 0) a.prof[a.n_levels] = clock64();
-    vm_inv_batch(x, a.ops, a.inv_begin, a.inv_end, tid, nthr);     // IsZero inverse hints: no consumers, done last
+    // IsZero inverse hints: no consumers, done last.  Table-sized inputs are spread over all threads; the ones expected
+    // to need a real inversion go to 256 threads so that only 8 warps pay for a Fermat ladder (one per thread).
+    vm_inv_batch(x, a.ops, a.inv_begin, a.ginv_begin, tid, nthr);
+    if (tid < 256) vm_inv_batch(x, a.ops, a.ginv_begin, a.inv_end, tid, 256);
     if (a.prof && inst == 0) { __syncthreads(); if (tid == 0) a.prof[a.n_levels + 1] = clock64(); }
     if (tid == 0) a.status[inst] = (s_status == STATUS_OK) ? 0u : s_status;
     for (uint32_t i = tid; i < a.n_outputs; i += nthr) {
@@ -316,7 +347,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 struct pob_handle {
     Program P; int device = 0;
     // device program
-    Op *d_ops = nullptr; PoseidonOp *d_pos = nullptr; Fr *d_pos_konst = nullptr; AbsorbOp *d_abs = nullptr; Level *d_levels = nullptr; Code *d_aux = nullptr; Fr *d_konst = nullptr;
+    Op *d_ops = nullptr; PsumOp *d_psums = nullptr; PoseidonOp *d_pos = nullptr; Fr *d_pos_konst = nullptr; AbsorbOp *d_abs = nullptr; Level *d_levels = nullptr; Code *d_aux = nullptr; Fr *d_konst = nullptr;
     Code *d_codes = nullptr; Tile *d_tiles = nullptr; Fr *d_invtab = nullptr; uint64_t *d_round_desc = nullptr;
     // stores (ring of RING chunks)
     static const uint32_t RING = 2;
@@ -382,7 +413,7 @@ void pob_destroy(pob_handle *h) {
     cudaSetDevice(h->device);
     if (h->s_eval) cudaStreamSynchronize(h->s_eval);
     if (h->s_exp) cudaStreamSynchronize(h->s_exp);
-    for (void *p : {(void *)h->d_ops, (void *)h->d_pos, (void *)h->d_pos_konst, (void *)h->d_abs, (void *)h->d_levels, (void *)h->d_aux, (void *)h->d_konst, (void *)h->d_codes,
+    for (void *p : {(void *)h->d_ops, (void *)h->d_psums, (void *)h->d_pos, (void *)h->d_pos_konst, (void *)h->d_abs, (void *)h->d_levels, (void *)h->d_aux, (void *)h->d_konst, (void *)h->d_codes,
                     (void *)h->d_tiles, (void *)h->d_invtab, (void *)h->d_round_desc, (void *)h->d_stores, (void *)h->d_inputs, (void *)h->d_status,
                     (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr, (void *)h->d_staged})
         if (p) cudaFree(p);
@@ -414,7 +445,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
     try {
         const Program &P = h->P;
         CU(cudaSetDevice(device));
-        h->d_ops = upload(P.ops); h->d_pos = upload(P.poseidons); h->d_pos_konst = upload(P.pos_konst); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
+        h->d_ops = upload(P.ops); h->d_psums = upload(P.psums); h->d_pos = upload(P.poseidons); h->d_pos_konst = upload(P.pos_konst); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
         h->d_konst = upload(P.konst); h->d_codes = upload(P.codes);
         if (const char *v = getenv("POB_TILE_FILTER")) {      // tuning only: 1 = KeccakfRound tiles only, 2 = the others only (witness incomplete!)
             std::vector<Tile> sub; for (const Tile &t : P.tiles) if ((atoi(v) == 1) == (t.pad != 0)) sub.push_back(t);
@@ -538,7 +569,7 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
             }
             if (c >= R) CU(cudaStreamWaitEvent(h->s_eval, h->ev_exp_done[r], 0));      // store ring slot r is free again
             uint64_t *stores = h->d_stores + (size_t)r * E * h->store_stride;
-            EvalArgs ea{h->d_ops, h->d_abs, h->d_pos, h->d_pos_konst, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
+            EvalArgs ea{h->d_ops, h->d_abs, h->d_pos, h->d_pos_konst, h->d_psums, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.ginv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
                         h->d_codes + ROUND_SIGNALS + 1, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
                         h->d_status + first, h->d_outputs + (size_t)first * no * 4, (c == 0) ? h->d_prof : nullptr};
             CU(cudaEventRecord(ev[0], h->s_eval));

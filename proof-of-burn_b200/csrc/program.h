@@ -46,8 +46,6 @@ enum Opc : uint32_t {
     OP_GTC = 9,        // V[dst] = (a > b) as canonical integers, b raw u32.  prod_{j<=i}(1 - IsEqual(j, a)) == (a > i):
                        //   utils/keccak.circom:427-433 (Pad filter), array.circom:26-40 (Filter), substring_check.circom:87-88
     OP_SELSUM = 10,    // V[dst] = (a <= c) ? aux[b + a] : 0, b/c raw.  sum_{j<=c} IsEqual(a, j)*vals[j]: selector.circom:31-41
-    OP_CHAIN = 11,     // x = c; for k < b: x = x*aux[a+2k] + aux[a+2k+1]; V[dst+k] = x   (one thread walks an affine
-                       //   recurrence whose every step is a signal: substring_check.circom:47-49, 95)
 };
 struct Op { uint32_t opc_dst; Code a, b, c; };                    // opc in the top 6 bits, dst in the low 26
 POB_HD uint32_t op_opc(const Op &o) { return o.opc_dst >> 26; }
@@ -92,7 +90,11 @@ POB_HD PosLayout pos_layout(uint32_t t) {
     return L;
 }
 
-struct Level { uint32_t t_begin, t_end, w_begin, w_end, p_begin, p_end; };
+// ---- warp op: prefix sum whose every partial sum is a signal (substring_check.circom:47-49 M[], :95 sums[]) -------
+//   V[dst + k] = x0 + sum_{i <= k} aux[aux0 + i]      (k < n); lanes own contiguous ranges, totals combined by a warp scan
+struct PsumOp { uint32_t aux0, n, dst; Code x0; };
+
+struct Level { uint32_t t_begin, t_end, w_begin, w_end, p_begin, p_end, s_begin, s_end; };
 
 // ---- expand tiles: a contiguous run of witness entries and where its codes live -------------------------------
 struct Tile { uint64_t dst; uint32_t n, code_off, ubase, pad; };  // BIT codes are relative to ubase; pad = 1: round tile (all BIT)
@@ -117,9 +119,11 @@ struct Program {
     uint64_t store_u64() const { return (uint64_t)val_base + 4ull * n_vals; }
     // eval program
     std::vector<Op> ops;           // [0, inv_begin) sorted by level, then the deferred OP_INV ops
-    uint32_t inv_begin = 0, inv_end = 0;   // IsZero inverses feed no other op: they run last, batch-inverted per thread
+    uint32_t inv_begin = 0, ginv_begin = 0, inv_end = 0;   // IsZero inverses feed no other op: they run last, batch-inverted
+                                   // per thread; [ginv_begin, inv_end) are the ones expected to miss the small-value table
     std::vector<AbsorbOp> absorbs; // sorted by level
     std::vector<PoseidonOp> poseidons;   // sorted by level
+    std::vector<PsumOp> psums;     // sorted by level
     std::vector<Fr> pos_konst;     // Poseidon C,S,M,P tables per width, MONTGOMERY form (PoseidonOp::koff)
     std::vector<Level> levels;
     std::vector<Code> aux;         // PACK8 operand lists

@@ -88,14 +88,6 @@ POB_HD void vm_exec_op(const VmCtx &x, const Op &op) {
         if (fr_fits64(sel) && fr_lo64(sel) <= (uint64_t)op.c) r = vm_load(x, x.aux[op.b + (uint32_t)fr_lo64(sel)]);
         vm_store_val(vd, r);
         break; }
-    case OP_CHAIN: {
-        Fr acc = vm_load(x, op.c);
-        for (uint32_t k = 0; k < op.b; k++) {
-            Fr m = vm_load(x, x.aux[op.a + 2 * k]), ad = vm_load(x, x.aux[op.a + 2 * k + 1]);
-            acc = fr_add(fr_mul(acc, m), ad);
-            vm_store_val(vd + 4ull * k, acc);
-        }
-        break; }
     case OP_CHK_EQ: { Fr a = vm_load(x, op.a), b = vm_load(x, op.b); if (!fr_eq(a, b)) vm_fail(x, op.c); break; }
     case OP_CHK_RANGE: { Fr a = vm_load(x, op.a); if (!fr_lt_pow2(a, op.b)) vm_fail(x, op.c); break; }
     default: break;
@@ -193,6 +185,12 @@ inline void vm_absorb_scalar(uint64_t *W, const AbsorbOp &op) {
         ch[0] ^= keccak_rc(r);
         for (int l = 0; l < 25; l++) { B[rw_out(l)] = ch[l]; st[l] = ch[l]; }
     }
+}
+
+// Scalar reference of the prefix-sum warp op (HOST ONLY users: tests/emu); device: psum_warp() in pob_b200.cu.
+inline void vm_psum_scalar(const VmCtx &x, const PsumOp &op) {
+    Fr acc = vm_load(x, op.x0);
+    for (uint32_t k = 0; k < op.n; k++) { acc = fr_add(acc, vm_load(x, x.aux[op.aux0 + k])); vm_store_val(x.U + x.val_base + 4ull * (op.dst + k), acc); }
 }
 
 // Scalar reference of the Poseidon warp op (HOST ONLY users: tests/emu).  The device implementation is the

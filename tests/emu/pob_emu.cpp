@@ -52,8 +52,10 @@ uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_
         for (uint32_t i = lv.t_begin; i < lv.t_end; i++) vm_exec_op(x, P.ops[i]);
         for (uint32_t i = lv.w_begin; i < lv.w_end; i++) vm_absorb_scalar(U.data(), P.absorbs[i]);
         for (uint32_t i = lv.p_begin; i < lv.p_end; i++) vm_poseidon_scalar(x, P.poseidons[i], P.pos_konst.data());
+        for (uint32_t i = lv.s_begin; i < lv.s_end; i++) vm_psum_scalar(x, P.psums[i]);
     }
-    for (uint32_t tid = 0; tid < 64; tid++) vm_inv_batch(x, P.ops.data(), P.inv_begin, P.inv_end, tid, 64);
+    for (uint32_t tid = 0; tid < 64; tid++) vm_inv_batch(x, P.ops.data(), P.inv_begin, P.ginv_begin, tid, 64);
+    for (uint32_t tid = 0; tid < 8; tid++) vm_inv_batch(x, P.ops.data(), P.ginv_begin, P.inv_end, tid, 8);
     if (witness)
         for (const Tile &t : P.tiles)
             for (uint32_t k = 0; k < t.n; k++) {
