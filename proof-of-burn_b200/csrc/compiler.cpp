@@ -1440,72 +1440,20 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     }
     P.codes.insert(P.codes.end(), B.flat, B.flat + B.flat_n);
     P.n_round_blocks = B.n_round_blocks; P.n_flat_signals = B.flat_n;
-    // lane / gate-array group starting at c (absolute lane words): returns signals consumed (64 or 192) and appends descriptors
-    auto try_group = [&](const Code *c, uint64_t avail, std::vector<Program::FlatDesc> &out) -> uint32_t {
-        if (avail < 64) return 0;
-        auto lane_word = [&](const Code *q, uint32_t &w) -> bool {          // 64 codes = bits 0..63 of one word (or all CONST 0)
-            if (q[0] == ZERO) { for (int j = 1; j < 64; j++) if (q[j] != ZERO) return false; w = FLAT_ZERO_WORD; return true; }
-            if (code_kind(q[0]) != K_BIT || (code_payload(q[0]) & 63u)) return false;
-            w = code_payload(q[0]) >> 6;
-            for (uint32_t j = 1; j < 64; j++) if (q[j] != c_bit(w, j)) return false;
-            return true;
-        };
-        uint32_t w;
-        if (lane_word(c, w)) { out.push_back({w, 0, 0, 0}); return 64; }
-        if (avail < 192) return 0;
-        uint32_t ws[3];
-        for (uint32_t m = 0; m < 3; m++) {                                   // gate block [out_i, a_i, b_i]_i
-            const Code q = c[m];
-            if (q == ZERO) ws[m] = FLAT_ZERO_WORD;
-            else if (code_kind(q) == K_BIT && (code_payload(q) & 63u) == 0) ws[m] = code_payload(q) >> 6;
-            else return 0;
-        }
-        for (uint32_t sidx = 0; sidx < 192; sidx++) {
-            const uint32_t m = sidx % 3, g = sidx / 3;
-            const Code want = ws[m] == FLAT_ZERO_WORD ? ZERO : c_bit(ws[m], g);
-            if (c[sidx] != want) return 0;
-        }
-        for (uint32_t f = 0; f < 3; f++) out.push_back({ws[0], ws[1], ws[2], 1 + f});
-        return 192;
-    };
-    auto emit_code_tiles = [&](uint64_t dst, size_t pos, uint64_t n) {
-        for (uint64_t done = 0; done < n;) {
-            uint32_t k = (uint32_t)std::min<uint64_t>(TILE_SIGNALS, n - done);
-            P.tiles.push_back(Tile{dst + done, k, (uint32_t)(ROUND_SIGNALS + pos + done), 0, 0}); done += k;
-        }
-    };
     for (auto &s : B.segs) {
-        if (s.round) {
-            for (uint64_t done = 0; done < s.n;) {
-                uint32_t k = (uint32_t)std::min<uint64_t>(TILE_SIGNALS, s.n - done);
-                P.tiles.push_back(Tile{s.dst + done, k, (uint32_t)done, s.ubase, 1}); done += k;
-            }
-            continue;
+        uint64_t done = 0;
+        while (done < s.n) {
+            uint32_t n = (uint32_t)std::min<uint64_t>(TILE_SIGNALS, s.n - done);
+            Tile t; t.dst = s.dst + done; t.n = n; t.pad = 0;
+            if (s.round) { t.code_off = (uint32_t)done; t.ubase = s.ubase; t.pad = 1; }
+            else { t.code_off = (uint32_t)(ROUND_SIGNALS + s.pos + done); t.ubase = 0; }
+            P.tiles.push_back(t); done += n;
         }
-        const Code *c = B.flat + s.pos;
-        uint64_t i = 0, pending = 0;
-        std::vector<Program::FlatDesc> run;
-        while (i < s.n) {
-            run.clear();
-            uint64_t j = i; uint32_t g;
-            while ((g = try_group(c + j, s.n - j, run)) != 0) j += g;
-            if (j - i >= MIN_DESC_RUN) {
-                emit_code_tiles(s.dst + pending, s.pos + pending, i - pending);
-                size_t d0 = P.flat_desc.size(); P.flat_desc.insert(P.flat_desc.end(), run.begin(), run.end());
-                for (uint64_t done = 0; done < j - i;) {
-                    uint32_t k = (uint32_t)std::min<uint64_t>(TILE_SIGNALS, j - i - done);
-                    P.tiles.push_back(Tile{s.dst + i + done, k, (uint32_t)(d0 + done / 64), 0, 2}); done += k;
-                }
-                pending = j; i = j;
-            } else i = (j > i) ? j : i + 1;
-        }
-        emit_code_tiles(s.dst + pending, s.pos + pending, s.n - pending);
     }
-    if (P.flat_desc.empty()) P.flat_desc.push_back({0, 0, 0, 0});
     // Tile order is free (every tile carries its own destination).  KeccakfRound tiles only read L1-resident tables, the
     // other tiles read their code stream and store values through L2/DRAM; interleaving those reads with the write
     // stream costs DRAM efficiency (profiles/r01_expand_sweep.md), so all round tiles go first, the rest last.
-    std::stable_sort(P.tiles.begin(), P.tiles.end(), [](const Tile &a, const Tile &b) { return (a.pad == 0) < (b.pad == 0); });
+    std::stable_sort(P.tiles.begin(), P.tiles.end(), [](const Tile &a, const Tile &b) { return a.pad > b.pad; });
     return P;
 }
 

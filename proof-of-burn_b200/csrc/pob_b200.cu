@@ -213,7 +213,7 @@ __device__ __forceinline__ void st256(uint64_t *p, uint64_t a, uint64_t b, uint6
 }
 
 struct ExpandArgs {
-    const Tile *tiles; const Code *codes; const Fr *konst; const uint2 *round_desc; const uint4 *flat_desc;
+    const Tile *tiles; const Code *codes; const Fr *konst; const uint2 *round_desc;
     const uint64_t *stores; uint64_t store_stride; uint32_t val_base;
     uint64_t *const *wit;                         // per instance of the group: witness slot base
 };
@@ -229,31 +229,6 @@ __global__ void __launch_bounds__(256, MINB) k_expand(const ExpandArgs a) {
     const uint64_t *U = a.stores + (uint64_t)blockIdx.y * a.store_stride;
     uint64_t *W = a.wit[blockIdx.y] + t.dst * 4;
     const uint64_t *Ub = U + t.ubase;
-    if (t.pad == 2) {                   // lane-run tile outside the round blocks: 16-byte descriptors, absolute lane words
-        const uint4 *D = a.flat_desc + t.code_off;
-        for (uint32_t base = threadIdx.x; base < t.n; base += 256 * UN) {
-            uint64_t word[UN]; uint32_t bit[UN];
-#pragma unroll
-            for (int u = 0; u < UN; u++) {
-                const uint32_t k = base + 256 * u;
-                word[u] = 0; bit[u] = 0;
-                if (k < t.n) {
-                    const uint4 d = __ldg(D + (k >> 6));
-                    const uint32_t tt = k & 63;
-                    uint32_t w = d.x, b = tt;
-                    if (d.w) { const uint32_t sidx = (d.w - 1) * 64 + tt, g = sidx / 3, m = sidx - 3 * g; b = g; w = (m == 0) ? d.x : (m == 1) ? d.y : d.z; }
-                    if (w != FLAT_ZERO_WORD) word[u] = U[w];
-                    bit[u] = b;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UN; u++) {
-                const uint32_t k = base + 256 * u;
-                if (k < t.n) st256(W + 4ull * k, (word[u] >> bit[u]) & 1ull, 0, 0, 0);
-            }
-        }
-        return;
-    }
     if (t.pad) {
         const uint2 *D = a.round_desc + (t.code_off >> 6);
         for (uint32_t base = threadIdx.x; base < t.n; base += 256 * UN) {
@@ -373,7 +348,7 @@ struct pob_handle {
     Program P; int device = 0;
     // device program
     Op *d_ops = nullptr; PsumOp *d_psums = nullptr; PoseidonOp *d_pos = nullptr; Fr *d_pos_konst = nullptr; AbsorbOp *d_abs = nullptr; Level *d_levels = nullptr; Code *d_aux = nullptr; Fr *d_konst = nullptr;
-    Code *d_codes = nullptr; Tile *d_tiles = nullptr; Fr *d_invtab = nullptr; uint64_t *d_round_desc = nullptr; Program::FlatDesc *d_flat_desc = nullptr;
+    Code *d_codes = nullptr; Tile *d_tiles = nullptr; Fr *d_invtab = nullptr; uint64_t *d_round_desc = nullptr;
     // stores (ring of RING chunks)
     static const uint32_t RING = 2;
     uint32_t chunk = 0; uint64_t store_stride = 0; uint64_t *d_stores = nullptr; uint64_t *d_inputs = nullptr;
@@ -439,7 +414,7 @@ void pob_destroy(pob_handle *h) {
     if (h->s_eval) cudaStreamSynchronize(h->s_eval);
     if (h->s_exp) cudaStreamSynchronize(h->s_exp);
     for (void *p : {(void *)h->d_ops, (void *)h->d_psums, (void *)h->d_pos, (void *)h->d_pos_konst, (void *)h->d_abs, (void *)h->d_levels, (void *)h->d_aux, (void *)h->d_konst, (void *)h->d_codes,
-                    (void *)h->d_tiles, (void *)h->d_invtab, (void *)h->d_round_desc, (void *)h->d_flat_desc, (void *)h->d_stores, (void *)h->d_inputs, (void *)h->d_status,
+                    (void *)h->d_tiles, (void *)h->d_invtab, (void *)h->d_round_desc, (void *)h->d_stores, (void *)h->d_inputs, (void *)h->d_status,
                     (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr, (void *)h->d_staged})
         if (p) cudaFree(p);
     for (uint64_t *s : h->slots) cudaFree(s);
@@ -473,12 +448,13 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         h->d_ops = upload(P.ops); h->d_psums = upload(P.psums); h->d_pos = upload(P.poseidons); h->d_pos_konst = upload(P.pos_konst); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
         h->d_konst = upload(P.konst); h->d_codes = upload(P.codes);
         if (const char *v = getenv("POB_TILE_FILTER")) {      // tuning only: 1 = KeccakfRound tiles only, 2 = the others only (witness incomplete!)
-            std::vector<Tile> sub; for (const Tile &t : P.tiles) if ((uint32_t)atoi(v) == t.pad + 1) sub.push_back(t);   // 1 code, 2 round, 3 lane-run
+            std::vector<Tile> sub; for (const Tile &t : P.tiles) if ((atoi(v) == 1) == (t.pad != 0)) sub.push_back(t);
             h->P.tiles = sub;
         }
+        if (getenv("POB_FLAT_FIRST")) std::stable_sort(h->P.tiles.begin(), h->P.tiles.end(), [](const Tile &a, const Tile &b) { return a.pad < b.pad; });   // tuning only
         h->d_tiles = upload(h->P.tiles);
         h->d_invtab = upload(build_inverse_table());
-        h->d_round_desc = upload(P.round_desc); h->d_flat_desc = upload(P.flat_desc);
+        h->d_round_desc = upload(P.round_desc);
         // the small eval grid must get SMs while the expand grid (hundreds of thousands of CTAs) is draining:
         // eval runs on the highest-priority stream, expand on the lowest
         int pr_least = 0, pr_greatest = 0; CU(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
@@ -610,7 +586,7 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
                 uint32_t g = 0;
                 for (uint32_t off = 0; off < cnt; off += X, g++) {
                     const uint32_t gc = std::min(X, cnt - off);
-                    ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, reinterpret_cast<const uint2 *>(h->d_round_desc), reinterpret_cast<const uint4 *>(h->d_flat_desc), stores + (size_t)off * h->store_stride, h->store_stride, P.val_base, h->d_witptr + first + off};
+                    ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, reinterpret_cast<const uint2 *>(h->d_round_desc), stores + (size_t)off * h->store_stride, h->store_stride, P.val_base, h->d_witptr + first + off};
                     CU(cudaEventRecord(ev[2 + 2 * g], h->s_exp));
                     const dim3 grid((unsigned)P.tiles.size(), gc);
                     switch (h->variant) {

@@ -97,11 +97,8 @@ struct PsumOp { uint32_t aux0, n, dst; Code x0; };
 struct Level { uint32_t t_begin, t_end, w_begin, w_end, p_begin, p_end, s_begin, s_end; };
 
 // ---- expand tiles: a contiguous run of witness entries and where its codes live -------------------------------
-struct Tile { uint64_t dst; uint32_t n, code_off, ubase, pad; };  // pad 0: code tile (BIT codes relative to ubase); 1: KeccakfRound tile
-                                                                  // (round_desc); 2: lane-run tile (flat_desc)
+struct Tile { uint64_t dst; uint32_t n, code_off, ubase, pad; };  // BIT codes are relative to ubase; pad = 1: round tile (all BIT)
 static const uint32_t TILE_SIGNALS = 8192;
-static const uint32_t FLAT_ZERO_WORD = 0xffffffffu;
-static const uint32_t MIN_DESC_RUN = 1024;      // shorter lane runs stay in the per-entry code stream
 
 // ---- circuit identity ---------------------------------------------------------------------------------------
 enum CircuitKind : int32_t { CIRCUIT_SPEND = 0, CIRCUIT_PROOF_OF_BURN = 1, CIRCUIT_GADGET = 2 };
@@ -139,11 +136,6 @@ struct Program {
     //   mode 0: a lane -- signal t is bit t of w0;  mode 1+f: 64-signal phase f of a 192-signal gate block
     //   [out_i, a_i, b_i]_i -- signal s = 64 f + t is bit s/3 of w_{s%3}
     std::vector<uint64_t> round_desc;
-    // the same idea for lane-structured runs OUTSIDE the round blocks (Absorb / Keccakf / Final / KeccakBytes own lane
-    // arrays and gate arrays, keccak.circom:304-385,454-489): 16-byte descriptors with absolute 32-bit lane words
-    // (FLAT_ZERO_WORD = an all-zero lane), used by tiles with pad == 2 (Tile::code_off indexes this array)
-    struct FlatDesc { uint32_t w0, w1, w2, mode; };
-    std::vector<FlatDesc> flat_desc;
     // statistics
     uint64_t n_round_blocks = 0, n_flat_signals = 0;
 };

@@ -34,7 +34,7 @@ def lib():
 
 
 STAT_NAMES = ["n_signals", "n_outputs", "n_inputs", "n_words", "n_vals", "n_ops", "n_absorbs", "n_levels", "n_tiles",
-              "n_codes", "n_konst", "n_round_blocks", "n_code_tile_signals", "n_lane_tile_signals"]
+              "n_codes", "n_konst", "n_round_blocks"]
 
 
 class EmuProgram:
@@ -43,7 +43,7 @@ class EmuProgram:
         self.h = lib().pob_emu_compile(name.encode(), params_limbs.ctypes.data, nparams, int(hcreate), err, 512)
         if not self.h:
             raise RuntimeError(err.value.decode())
-        st = np.zeros(14, dtype=np.uint64)
+        st = np.zeros(12, dtype=np.uint64)
         lib().pob_emu_stats(self.h, st.ctypes.data)
         self.stats = dict(zip(STAT_NAMES, (int(v) for v in st)))
         self.schema = lib().pob_emu_schema(self.h).decode()

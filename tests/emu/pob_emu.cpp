@@ -37,7 +37,6 @@ void pob_emu_stats(void *h, uint64_t *out) {
     out[0] = P.n_signals; out[1] = P.n_outputs; out[2] = P.n_inputs; out[3] = P.n_words; out[4] = P.n_vals;
     out[5] = P.ops.size(); out[6] = P.absorbs.size(); out[7] = P.levels.size(); out[8] = P.tiles.size();
     out[9] = P.codes.size(); out[10] = P.konst.size(); out[11] = P.n_round_blocks;
-    { uint64_t c0 = 0, c2 = 0; for (const Tile &t : P.tiles) { if (t.pad == 0) c0 += t.n; else if (t.pad == 2) c2 += t.n; } out[12] = c0; out[13] = c2; }
 }
 const char *pob_emu_schema(void *h) { return ((EmuProgram *)h)->P.input_schema.c_str(); }
 
@@ -61,12 +60,7 @@ uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_
         for (const Tile &t : P.tiles)
             for (uint32_t k = 0; k < t.n; k++) {
                 uint64_t *o = witness + 4 * (t.dst + k);
-                if (t.pad == 2) {       // lane-run tile: 16-byte descriptors with absolute lane words
-                    const Program::FlatDesc &d = P.flat_desc[t.code_off + (k >> 6)];
-                    uint32_t tt = k & 63, w = d.w0, b = tt;
-                    if (d.mode) { uint32_t sidx = (d.mode - 1) * 64 + tt, g = sidx / 3, m = sidx - 3 * g; b = g; w = m == 0 ? d.w0 : m == 1 ? d.w1 : d.w2; }
-                    o[0] = w == FLAT_ZERO_WORD ? 0 : ((U[w] >> b) & 1ull); o[1] = o[2] = o[3] = 0;
-                } else if (t.pad) {     // KeccakfRound tile: 64-signal group descriptors (same decode as k_expand)
+                if (t.pad) {            // KeccakfRound tile: 64-signal group descriptors (same decode as k_expand)
                     uint64_t d = P.round_desc[(t.code_off >> 6) + (k >> 6)];
                     uint32_t tt = k & 63, mode = (uint32_t)(d >> 48), w = (uint32_t)(d & 0xffff), b = tt;
                     if (mode) { uint32_t sidx = (mode - 1) * 64 + tt, g = sidx / 3, m = sidx - 3 * g; b = g; w = (uint32_t)((d >> (16 * m)) & 0xffff); }
