@@ -83,9 +83,9 @@ def _oracle_worker(args):
     from oracle import oracle
     t = time.time()
     w = oracle.run_flat(*oracle.parse_main(expr), flat)
-    ok, n = w.ok, w.n_signals
+    ok, n, dig = w.ok, w.n_signals, w.digest()
     w.free()
-    return ok, n, time.time() - t
+    return ok, n, time.time() - t, dig
 
 
 def cpu_baseline_run(expr, packed, procs, rounds=1):
@@ -95,13 +95,14 @@ def cpu_baseline_run(expr, packed, procs, rounds=1):
     oracle.build()
     jobs = [(expr, packed[i % len(packed)][:, :].copy()) for i in range(procs)]
     t0 = time.time()
-    done = 0
+    done, digests = 0, []
     with mp.get_context("fork").Pool(procs) as pool:
         for _ in range(rounds):
             res = pool.map(_oracle_worker, jobs)
             assert all(r[0] for r in res), "oracle rejected a synthetic instance"
-            done += len(res)
+            done += len(res); digests = [r[3] for r in res]
     dt = time.time() - t0
+    cpu_baseline_run.last_digests = digests        # whole-witness digests of jobs 0..procs-1 (parity check in the B200 arm)
     return done / dt, dt, done
 
 
@@ -275,6 +276,12 @@ def main():
             v, dt, done = cpu_baseline_run(expr, pinned.array[: min(a.batch, procs)], procs)
             line["cpu_baseline"] = {"value": v, "unit": "witnesses/s", "cores": procs, "kind": "port",
                                     "sample": "%d single-threaded oracle processes x 1 witness of the same workload (%.1f s)" % (procs, dt)}
+            # the oracle runs above double as an in-run parity check: whole-witness digests of the same instances on the GPU
+            k = min(a.batch, procs)
+            rg = circuit.run_packed(pinned.array[:k], digest=True)
+            match = [int(rg.digests[i]) == int(cpu_baseline_run.last_digests[i]) for i in range(k)]
+            line["parity"] = {"instances": k, "digest_match": all(match), "what": "64-bit digest of all %d witness entries, GPU vs oracle" % desc["n_signals"]}
+            assert all(match), "GPU witness digest differs from the oracle"
         print(json.dumps(line))
     circuit.close()
     if dist is not None:

@@ -163,3 +163,22 @@ def test_pow_grinder_finds_the_first_key():
     assert k3 >= big and synth.keccak256(k3.to_bytes(32, "big") + (7).to_bytes(32, "big") + (9).to_bytes(32, "big") + b"EIP-7503")[:2] == b"\x00\x00"
     with pytest.raises(pob_b200.PobError):
         pob_b200.pow_grind(0, 1, 2, zero_bytes=8, max_tries=1 << 16)
+
+
+def test_cli_matches_reference_argv(tmp_path):
+    """`python -m pob_b200 main_spend input.json witness.wtns` == the reference `./main_spend input.json witness.wtns`
+    (Makefile:6): same file the oracle writes; a failing input exits non-zero and writes nothing."""
+    import json, subprocess, sys, os
+    from oracle import oracle
+    s = suite("test_spend")
+    inp, out = str(tmp_path / "input.json"), str(tmp_path / "witness.wtns")
+    json.dump(s["cases"][0]["input"], open(inp, "w"))
+    env = dict(os.environ, PYTHONPATH=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "proof-of-burn_b200"))
+    r = subprocess.run([sys.executable, "-m", "pob_b200", "main_spend", inp, out], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    w = oracle.run("Spend(31)", s["cases"][0]["input"]); ref = str(tmp_path / "ref.wtns"); w.write_wtns(ref); w.free()
+    assert open(out, "rb").read() == open(ref, "rb").read()
+    bad, out2 = str(tmp_path / "bad.json"), str(tmp_path / "bad.wtns")
+    json.dump(s["cases"][1]["input"], open(bad, "w"))
+    r = subprocess.run([sys.executable, "-m", "pob_b200", "main_spend", bad, out2], env=env, capture_output=True, text=True)
+    assert r.returncode != 0 and r.stderr and not os.path.exists(out2)
