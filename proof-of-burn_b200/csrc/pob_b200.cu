@@ -216,6 +216,7 @@ struct ExpandArgs {
     const Tile *tiles; const Code *codes; const Fr *konst; const uint2 *round_desc;
     const uint64_t *stores; uint64_t store_stride; uint32_t val_base;
     uint64_t *const *wit;                         // per instance of the group: witness slot base
+    uint32_t tile0, swap_xy;                      // first tile of this launch; swap_xy: blockIdx.x = instance, .y = tile
 };
 
 // grid = (n_tiles, instances in group); one CTA streams one tile (<= 8192 entries = 256 KiB) of one witness.
@@ -225,9 +226,10 @@ struct ExpandArgs {
 // Loads are issued U entries ahead of the stores; DRAM writes are the only traffic that reaches HBM.
 template <int UN, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_expand(const ExpandArgs a) {
-    const Tile t = a.tiles[blockIdx.x];
-    const uint64_t *U = a.stores + (uint64_t)blockIdx.y * a.store_stride;
-    uint64_t *W = a.wit[blockIdx.y] + t.dst * 4;
+    const uint32_t inst = a.swap_xy ? blockIdx.x : blockIdx.y;
+    const Tile t = a.tiles[a.tile0 + (a.swap_xy ? blockIdx.y : blockIdx.x)];
+    const uint64_t *U = a.stores + (uint64_t)inst * a.store_stride;
+    uint64_t *W = a.wit[inst] + t.dst * 4;
     const uint64_t *Ub = U + t.ubase;
     if (t.pad) {
         const uint2 *D = a.round_desc + (t.code_off >> 6);
@@ -361,7 +363,8 @@ struct pob_handle {
     uint64_t *d_staged = nullptr; uint32_t n_staged = 0;
     long long *d_prof = nullptr;               // POB_EVAL_PROFILE: per-level clock stamps (tuning only)
     uint32_t xgroup = 0;                       // instances per expand launch (distinct witness slots)
-    int variant = 0;                           // k_expand unroll/occupancy variant (POB_EXPAND_VARIANT), tuning only
+    int variant = 0;                           // POB_EXPAND_VARIANT=1: single expand launch per group (tuning only)
+    uint32_t n_round_tiles = 0;                // tiles [0, n_round_tiles) are KeccakfRound tiles, the rest code tiles
     int eval_threads = 1024;                   // k_eval CTA size (POB_EVAL_THREADS), tuning only
     bool serialize = false;                    // POB_SERIALIZE=1: eval and expand on one stream (no overlap), tuning only
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
@@ -453,6 +456,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         }
         if (getenv("POB_FLAT_FIRST")) std::stable_sort(h->P.tiles.begin(), h->P.tiles.end(), [](const Tile &a, const Tile &b) { return a.pad < b.pad; });   // tuning only
         h->d_tiles = upload(h->P.tiles);
+        for (const Tile &t : h->P.tiles) if (t.pad) h->n_round_tiles++;
         h->d_invtab = upload(build_inverse_table());
         h->d_round_desc = upload(P.round_desc);
         // the small eval grid must get SMs while the expand grid (hundreds of thousands of CTAs) is draining:
@@ -586,15 +590,16 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
                 uint32_t g = 0;
                 for (uint32_t off = 0; off < cnt; off += X, g++) {
                     const uint32_t gc = std::min(X, cnt - off);
-                    ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, reinterpret_cast<const uint2 *>(h->d_round_desc), stores + (size_t)off * h->store_stride, h->store_stride, P.val_base, h->d_witptr + first + off};
+                    ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, reinterpret_cast<const uint2 *>(h->d_round_desc), stores + (size_t)off * h->store_stride, h->store_stride, P.val_base, h->d_witptr + first + off, 0, 0};
                     CU(cudaEventRecord(ev[2 + 2 * g], h->s_exp));
-                    const dim3 grid((unsigned)P.tiles.size(), gc);
-                    switch (h->variant) {
-                    case 1: k_expand<8, 8><<<grid, 256, 0, h->s_exp>>>(xa); break;
-                    case 2: k_expand<4, 8><<<grid, 256, 0, h->s_exp>>>(xa); break;
-                    case 3: k_expand<16, 4><<<grid, 256, 0, h->s_exp>>>(xa); break;
-                    case 4: k_expand<2, 8><<<grid, 256, 0, h->s_exp>>>(xa); break;
-                    default: k_expand<8, 5><<<grid, 256, 0, h->s_exp>>>(xa); break;
+                    // launch 1: KeccakfRound tiles, tile-major (each CTA's tables are L1-resident);
+                    // launch 2: code tiles, INSTANCE-major, so that a tile's code stream is fetched from DRAM once and
+                    // served from L2 to the other witnesses of the group
+                    const uint32_t n_round = h->n_round_tiles, n_code = (uint32_t)P.tiles.size() - n_round;
+                    if (h->variant == 1) { xa.tile0 = 0; xa.swap_xy = 0; k_expand<8, 5><<<dim3((unsigned)P.tiles.size(), gc), 256, 0, h->s_exp>>>(xa); }
+                    else {
+                        if (n_round) { xa.tile0 = 0; xa.swap_xy = 0; k_expand<8, 5><<<dim3(n_round, gc), 256, 0, h->s_exp>>>(xa); }
+                        if (n_code) { xa.tile0 = n_round; xa.swap_xy = 1; k_expand<8, 5><<<dim3(gc, n_code), 256, 0, h->s_exp>>>(xa); T.other_launches++; }
                     }
                     CU(cudaEventRecord(ev[3 + 2 * g], h->s_exp));
                     T.expand_launches++;
