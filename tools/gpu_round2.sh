@@ -10,7 +10,7 @@ if [ "$NG" -gt 1 ]; then
 fi
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee $OUT/pytest_gpu_$TAG.log
 echo "== bench b1024"; timeout 900 python bench.py --batch 1024 2>$OUT/bench_$TAG.err | tee $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err
-echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 | tee $OUT/bench_ref_$TAG.json; timeout 600 python bench.py --impl reference --steps 1 --warmup 0 --cpu-procs 64 | tee $OUT/bench_ref64_$TAG.json
+echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 | tee $OUT/bench_ref_$TAG.json
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --batch 64 --steps 1 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu_$TAG.log 2>&1
