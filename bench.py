@@ -124,7 +124,7 @@ def mem_limited_procs(want, bytes_per_proc):
             pass
     if not avail:
         return min(want, 4)
-    return max(1, min(want, int(avail * 0.4 // bytes_per_proc)))
+    return max(1, min(want, int(avail * 0.5 // bytes_per_proc)))
 
 
 def host_cores():
@@ -163,7 +163,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        procs = mem_limited_procs(a.cpu_procs or max(1, min(cores // 2, 32)), 40 * (51277058 + 10289431 * a.layers))
+        procs = mem_limited_procs(a.cpu_procs or max(1, min(cores // 2, 32)), 34 * (51277058 + 10289431 * a.layers))
         insts = synth.make_batch(procs, shape, seed=a.seed)
         packed = synth.pack_instances(insts, shape)
         for _ in range(min(a.warmup, 1)):
@@ -293,7 +293,7 @@ def main():
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "expand_share_of_step": exp_ms / dev_ms}}
         if world == 1 and not a.no_cpu_baseline:
-            procs = mem_limited_procs(a.cpu_procs or max(1, min(cores // 2, 32)), 40 * desc["n_signals"])
+            procs = mem_limited_procs(a.cpu_procs or max(1, min(cores // 2, 32)), 34 * desc["n_signals"])
             v, dt, done = cpu_baseline_run(expr, pinned.array[: min(a.batch, procs)], procs)
             line["cpu_baseline"] = {"value": v, "unit": "witnesses/s", "cores": procs, "kind": "port",
                                     "sample": "%d single-threaded oracle processes x 1 witness of the same workload (%.1f s)" % (procs, dt)}

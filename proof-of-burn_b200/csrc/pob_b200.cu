@@ -224,13 +224,29 @@ struct ExpandArgs {
 //    entries (12.8 KB table, L1-resident) and a lane word of the round (2 KB, L1-resident): no per-entry code stream.
 //  * all other tiles: one 32-bit code per entry.
 // Loads are issued U entries ahead of the stores; DRAM writes are the only traffic that reaches HBM.
-template <int UN, int MINB>
+template <int UN, int MINB, int SMEM>
 __global__ void __launch_bounds__(256, MINB) k_expand(const ExpandArgs a) {
     const uint32_t inst = a.swap_xy ? blockIdx.x : blockIdx.y;
     const Tile t = a.tiles[a.tile0 + (a.swap_xy ? blockIdx.y : blockIdx.x)];
     const uint64_t *U = a.stores + (uint64_t)inst * a.store_stride;
     uint64_t *W = a.wit[inst] + t.dst * 4;
     const uint64_t *Ub = U + t.ubase;
+    if (SMEM && t.pad) {                // tuning variant: tables of the tile staged in shared memory in one burst
+        __shared__ uint2 sD[128]; __shared__ uint64_t sW[ROUND_WORDS_SPAN + 1];
+        const uint2 *D = a.round_desc + (t.code_off >> 6);
+        if (threadIdx.x < ((t.n + 63) >> 6)) sD[threadIdx.x] = __ldg(D + threadIdx.x);
+        for (uint32_t i = threadIdx.x; i < ROUND_WORDS_SPAN; i += 256) sW[i] = Ub[i];
+        __syncthreads();
+#pragma unroll 8
+        for (uint32_t k = threadIdx.x; k < t.n; k += 256) {
+            const uint2 d = sD[k >> 6];
+            const uint32_t tt = k & 63, mode = d.y >> 16;
+            uint32_t w = d.x & 0xffffu, b = tt;
+            if (mode) { const uint32_t sidx = (mode - 1) * 64 + tt, g = sidx / 3, m = sidx - 3 * g; b = g; w = (m == 0) ? (d.x & 0xffffu) : (m == 1) ? (d.x >> 16) : (d.y & 0xffffu); }
+            st256(W + 4ull * k, (sW[w] >> b) & 1ull, 0, 0, 0);
+        }
+        return;
+    }
     if (t.pad) {
         const uint2 *D = a.round_desc + (t.code_off >> 6);
         for (uint32_t base = threadIdx.x; base < t.n; base += 256 * UN) {
@@ -596,10 +612,12 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
                     // launch 2: code tiles, INSTANCE-major, so that a tile's code stream is fetched from DRAM once and
                     // served from L2 to the other witnesses of the group
                     const uint32_t n_round = h->n_round_tiles, n_code = (uint32_t)P.tiles.size() - n_round;
-                    if (h->variant == 1) { xa.tile0 = 0; xa.swap_xy = 0; k_expand<8, 5><<<dim3((unsigned)P.tiles.size(), gc), 256, 0, h->s_exp>>>(xa); }
+                    if (h->variant == 1) { xa.tile0 = 0; xa.swap_xy = 0; k_expand<8, 5, 0><<<dim3((unsigned)P.tiles.size(), gc), 256, 0, h->s_exp>>>(xa); }
                     else {
-                        if (n_round) { xa.tile0 = 0; xa.swap_xy = 0; k_expand<8, 5><<<dim3(n_round, gc), 256, 0, h->s_exp>>>(xa); }
-                        if (n_code) { xa.tile0 = n_round; xa.swap_xy = 1; k_expand<8, 5><<<dim3(gc, n_code), 256, 0, h->s_exp>>>(xa); T.other_launches++; }
+                        if (n_round) { xa.tile0 = 0; xa.swap_xy = 0;
+                            if (h->variant == 2) k_expand<8, 5, 1><<<dim3(n_round, gc), 256, 0, h->s_exp>>>(xa);
+                            else k_expand<8, 5, 0><<<dim3(n_round, gc), 256, 0, h->s_exp>>>(xa); }
+                        if (n_code) { xa.tile0 = n_round; xa.swap_xy = 1; k_expand<8, 5, 0><<<dim3(gc, n_code), 256, 0, h->s_exp>>>(xa); T.other_launches++; }
                     }
                     CU(cudaEventRecord(ev[3 + 2 * g], h->s_exp));
                     T.expand_launches++;
@@ -728,15 +746,27 @@ int pob_write_wtns(pob_handle *h, uint32_t index, const char *path) {
     u32 = 1; ok &= fwrite(&u32, 4, 1, f) == 1; u64 = 40; ok &= fwrite(&u64, 8, 1, f) == 1;
     u32 = 32; ok &= fwrite(&u32, 4, 1, f) == 1; ok &= fwrite(p.l, 4, 8, f) == 8; u32 = (uint32_t)n; ok &= fwrite(&u32, 4, 1, f) == 1;
     u32 = 2; ok &= fwrite(&u32, 4, 1, f) == 1; u64 = 32ull * n; ok &= fwrite(&u64, 8, 1, f) == 1;
+    // double-buffered: the D2H copy of chunk i+1 (pinned, own stream) overlaps the fwrite of chunk i
     const uint64_t CH = 1ull << 21;     // 2 Mi entries = 64 MiB per hop
-    void *buf = nullptr;
-    if (cudaSetDevice(h->device) != cudaSuccess || cudaMallocHost(&buf, CH * 32) != cudaSuccess) { fclose(f); return fail(POB_E_CUDA, "pob_write_wtns: cudaMallocHost failed"); }
-    for (uint64_t off = 0; ok && off < n; off += CH) {
-        uint64_t cnt = std::min(CH, n - off);
-        if (cudaMemcpy(buf, s + 4 * off, (size_t)cnt * 32, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaFreeHost(buf); fclose(f); return fail(POB_E_CUDA, "pob_write_wtns: cudaMemcpy failed"); }
-        ok &= fwrite(buf, 32, (size_t)cnt, f) == cnt;
+    void *buf[2] = {nullptr, nullptr}; cudaStream_t cs = nullptr; cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool cuda_ok = cudaSetDevice(h->device) == cudaSuccess && cudaMallocHost(&buf[0], CH * 32) == cudaSuccess && cudaMallocHost(&buf[1], CH * 32) == cudaSuccess &&
+                   cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreate(&ev[0]) == cudaSuccess && cudaEventCreate(&ev[1]) == cudaSuccess;
+    const uint64_t nchunk = (n + CH - 1) / CH;
+    auto issue = [&](uint64_t c) {
+        const uint64_t off = c * CH, cnt = std::min(CH, n - off);
+        return cudaMemcpyAsync(buf[c & 1], s + 4 * off, (size_t)cnt * 32, cudaMemcpyDeviceToHost, cs) == cudaSuccess && cudaEventRecord(ev[c & 1], cs) == cudaSuccess;
+    };
+    if (cuda_ok && nchunk) cuda_ok = issue(0);
+    for (uint64_t c = 0; cuda_ok && ok && c < nchunk; c++) {
+        cuda_ok = cudaEventSynchronize(ev[c & 1]) == cudaSuccess;
+        if (cuda_ok && c + 1 < nchunk) cuda_ok = issue(c + 1);
+        const uint64_t cnt = std::min(CH, n - c * CH);
+        if (cuda_ok) ok &= fwrite(buf[c & 1], 32, (size_t)cnt, f) == cnt;
     }
-    cudaFreeHost(buf);
+    if (cs) cudaStreamSynchronize(cs);
+    for (int i = 0; i < 2; i++) { if (buf[i]) cudaFreeHost(buf[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+    if (cs) cudaStreamDestroy(cs);
+    if (!cuda_ok) { fclose(f); return fail(POB_E_CUDA, "pob_write_wtns: CUDA copy failed"); }
     ok &= fclose(f) == 0;
     return ok ? POB_OK : fail(POB_E_IO, std::string("short write to ") + path);
 }

@@ -49,7 +49,7 @@ POB_HD Fr vm_inverse(const VmCtx &x, const Fr &a) {
     if (fr_fits64(a) && fr_lo64(a) < INV_TABLE_N) return x.invtab[fr_lo64(a)];
     Fr n; fr_raw_sub(n, fr_p(), a);
     if (fr_fits64(n) && fr_lo64(n) < INV_TABLE_N) return fr_neg(x.invtab[fr_lo64(n)]);
-    return fr_inv(a);
+    return fr_inv_eea(a);
 }
 
 POB_HD void vm_exec_op(const VmCtx &x, const Op &op) {
@@ -116,7 +116,7 @@ POB_HD void vm_inv_batch(const VmCtx &x, const Op *ops, uint32_t begin, uint32_t
         else { vm_store_val(vd, acc); acc = fr_mul(acc, a); any = true; }
     }
     if (!any) return;
-    Fr inv = fr_inv(acc);
+    Fr inv = fr_inv_eea(acc);
     for (uint32_t i = last;; i -= nthr) {
         Fr a = vm_load(x, ops[i].a), d;
         if (vm_inv_class(x, a, d) != 0) {

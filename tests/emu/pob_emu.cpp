@@ -86,3 +86,19 @@ extern "C" uint32_t pob_emu_level_hist(void *h, uint32_t *out, uint32_t max_leve
     }
     return n;
 }
+
+// self-test of the binary-EEA inversion against the Fermat ladder on n pseudo-random field elements; returns mismatches
+extern "C" uint32_t pob_emu_inv_selftest(uint32_t n) {
+    uint32_t bad = 0; uint64_t st = 0x9E3779B97F4A7C15ull;
+    for (uint32_t i = 0; i < n; i++) {
+        Fr a;
+        for (int k = 0; k < 8; k++) { st ^= st << 13; st ^= st >> 7; st ^= st << 17; a.l[k] = (uint32_t)(st >> 16); }
+        a.l[7] &= 0x0fffffffu;                                       // < 2^252 < p
+        if (i % 7 == 0) { a = fr_from_u64(i + 1); }                  // small values too
+        if (i % 11 == 0) { Fr t; fr_raw_sub(t, fr_p(), fr_from_u64(i + 1)); a = t; }   // p - small
+        if (fr_is_zero(a)) continue;
+        Fr x = fr_inv_eea(a), y = fr_inv(a);
+        if (!fr_eq(x, y) || !fr_eq(fr_mul(x, a), fr_from_u64(1))) bad++;
+    }
+    return bad;
+}

@@ -86,3 +86,11 @@ def test_fuzz_programs_match_oracle():
         finally:
             w.free()
     assert rejected > 10
+
+
+def test_binary_eea_inverse_equals_fermat():
+    """the VM's inversion routine (fr_inv_eea, csrc/fr_hd.h) against the Fermat ladder on 3000 field elements"""
+    import ctypes, emu
+    L = emu.lib()
+    L.pob_emu_inv_selftest.restype = ctypes.c_uint32
+    assert L.pob_emu_inv_selftest(ctypes.c_uint32(3000)) == 0
