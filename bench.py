@@ -289,7 +289,7 @@ def main():
                         "note": "host pinned inputs -> pob_run_batch -> status + output signals on host; witnesses stay in the HBM slot ring for the on-GPU consumer"},
                 "gpu_launches": launches_total,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "kernel": "k_expand", "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
+                             "kernel": "k_expand_round + k_expand_codes (one pair per 16 witnesses)", "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "expand_share_of_step": exp_ms / dev_ms}}
         if world == 1 and not a.no_cpu_baseline:

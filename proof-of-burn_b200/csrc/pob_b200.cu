@@ -7,9 +7,10 @@
 //             column parities / D, RhoPi lane walk and Chi neighbours exchanged with warp shuffles; every
 //             intermediate lane word the bit-level circuit exposes (utils/keccak.circom:58-297) is written
 //             to the store (238 words per round).
-//   k_expand  the HBM-bound kernel: turns 32-bit witness codes into 32-byte little-endian field elements and
-//             streams them with 256-bit stores (STG.E.ENL2.256).  Algorithmic bytes = 32 * n_signals per
-//             instance (6.909 GB for main_proof_of_burn); reads are ~4 B of L2-resident code per entry.
+//   k_expand_round / k_expand_codes  the HBM-bound kernels: materialise every witness entry as a 32-byte little-endian
+//             field element with one 256-bit store (STG.E.ENL2.256).  Algorithmic bytes = 32 * n_signals per instance
+//             (6.909 GB for main_proof_of_burn).  KeccakfRound blocks (95.8 %) are driven by 8-byte group descriptors
+//             and the round's lane words staged in shared memory; everything else by one 32-bit code per entry.
 //   k_digest  optional 64-bit digest of a materialised witness (parity tests at full size).
 // There is no host execution path for any of this: without a device pob_create fails.
 #include <cuda_runtime.h>
@@ -216,64 +217,44 @@ struct ExpandArgs {
     const Tile *tiles; const Code *codes; const Fr *konst; const uint2 *round_desc;
     const uint64_t *stores; uint64_t store_stride; uint32_t val_base;
     uint64_t *const *wit;                         // per instance of the group: witness slot base
-    uint32_t tile0, swap_xy;                      // first tile of this launch; swap_xy: blockIdx.x = instance, .y = tile
+    uint32_t tile0;                               // first tile of this launch (k_expand_codes)
 };
 
-// grid = (n_tiles, instances in group); one CTA streams one tile (<= 8192 entries = 256 KiB) of one witness.
-//  * KeccakfRound tiles (95.8 % of the witness): the source of every entry follows from a 8-byte descriptor per 64
-//    entries (12.8 KB table, L1-resident) and a lane word of the round (2 KB, L1-resident): no per-entry code stream.
-//  * all other tiles: one 32-bit code per entry.
-// Loads are issued U entries ahead of the stores; DRAM writes are the only traffic that reaches HBM.
-template <int UN, int MINB, int SMEM>
-__global__ void __launch_bounds__(256, MINB) k_expand(const ExpandArgs a) {
-    const uint32_t inst = a.swap_xy ? blockIdx.x : blockIdx.y;
-    const Tile t = a.tiles[a.tile0 + (a.swap_xy ? blockIdx.y : blockIdx.x)];
+// k_expand_round: grid = (KeccakfRound tiles, instances in the group) -- 95.8 % of the witness.  One CTA streams one
+// tile (<= 8192 entries = 256 KiB) with one 256-bit store per entry.  The source of every entry follows from an 8-byte
+// descriptor per 64 entries and a lane word of the round; the tile's <= 128 descriptors and the round's 263 words are
+// staged in shared memory in one burst, so the streaming loop touches no global memory but the witness itself.
+__global__ void __launch_bounds__(256) k_expand_round(const ExpandArgs a) {
+    const Tile t = a.tiles[blockIdx.x];
+    const uint64_t *Ub = a.stores + (uint64_t)blockIdx.y * a.store_stride + t.ubase;
+    uint64_t *W = a.wit[blockIdx.y] + t.dst * 4;
+    __shared__ uint2 sD[TILE_SIGNALS / 64]; __shared__ uint64_t sW[ROUND_WORDS_SPAN + 1];
+    const uint2 *D = a.round_desc + (t.code_off >> 6);
+    if (threadIdx.x < ((t.n + 63) >> 6)) sD[threadIdx.x] = __ldg(D + threadIdx.x);
+    for (uint32_t i = threadIdx.x; i < ROUND_WORDS_SPAN; i += 256) sW[i] = Ub[i];
+    __syncthreads();
+#pragma unroll 8
+    for (uint32_t k = threadIdx.x; k < t.n; k += 256) {
+        const uint2 d = sD[k >> 6];
+        const uint32_t tt = k & 63, mode = d.y >> 16;
+        uint32_t w = d.x & 0xffffu, b = tt;
+        if (mode) {                          // phase (mode-1) of a gate block [out_i, a_i, b_i]_i
+            const uint32_t sidx = (mode - 1) * 64 + tt, g = sidx / 3, m = sidx - 3 * g;
+            b = g; w = (m == 0) ? (d.x & 0xffffu) : (m == 1) ? (d.x >> 16) : (d.y & 0xffffu);
+        }
+        st256(W + 4ull * k, (sW[w] >> b) & 1ull, 0, 0, 0);
+    }
+}
+
+// k_expand_codes: grid = (instances in the group, code tiles) -- INSTANCE-major, so that a tile's code stream is fetched
+// from DRAM once and served from L2 to the other witnesses of the group.  One 32-bit code per entry, loads issued 4
+// entries ahead of the stores.
+__global__ void __launch_bounds__(256, 5) k_expand_codes(const ExpandArgs a) {
+    const uint32_t inst = blockIdx.x;
+    const Tile t = a.tiles[a.tile0 + blockIdx.y];
     const uint64_t *U = a.stores + (uint64_t)inst * a.store_stride;
     uint64_t *W = a.wit[inst] + t.dst * 4;
     const uint64_t *Ub = U + t.ubase;
-    if (SMEM && t.pad) {                // tuning variant: tables of the tile staged in shared memory in one burst
-        __shared__ uint2 sD[128]; __shared__ uint64_t sW[ROUND_WORDS_SPAN + 1];
-        const uint2 *D = a.round_desc + (t.code_off >> 6);
-        if (threadIdx.x < ((t.n + 63) >> 6)) sD[threadIdx.x] = __ldg(D + threadIdx.x);
-        for (uint32_t i = threadIdx.x; i < ROUND_WORDS_SPAN; i += 256) sW[i] = Ub[i];
-        __syncthreads();
-#pragma unroll 8
-        for (uint32_t k = threadIdx.x; k < t.n; k += 256) {
-            const uint2 d = sD[k >> 6];
-            const uint32_t tt = k & 63, mode = d.y >> 16;
-            uint32_t w = d.x & 0xffffu, b = tt;
-            if (mode) { const uint32_t sidx = (mode - 1) * 64 + tt, g = sidx / 3, m = sidx - 3 * g; b = g; w = (m == 0) ? (d.x & 0xffffu) : (m == 1) ? (d.x >> 16) : (d.y & 0xffffu); }
-            st256(W + 4ull * k, (sW[w] >> b) & 1ull, 0, 0, 0);
-        }
-        return;
-    }
-    if (t.pad) {
-        const uint2 *D = a.round_desc + (t.code_off >> 6);
-        for (uint32_t base = threadIdx.x; base < t.n; base += 256 * UN) {
-            uint64_t word[UN]; uint32_t bit[UN];
-#pragma unroll
-            for (int u = 0; u < UN; u++) {
-                const uint32_t k = base + 256 * u;
-                word[u] = 0; bit[u] = 0;
-                if (k < t.n) {
-                    const uint2 d = __ldg(D + (k >> 6));
-                    const uint32_t tt = k & 63, mode = d.y >> 16;
-                    uint32_t w = d.x & 0xffffu, b = tt;
-                    if (mode) {
-                        const uint32_t sidx = (mode - 1) * 64 + tt, g = sidx / 3, m = sidx - 3 * g;
-                        b = g; w = (m == 0) ? (d.x & 0xffffu) : (m == 1) ? (d.x >> 16) : (d.y & 0xffffu);
-                    }
-                    word[u] = Ub[w]; bit[u] = b;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UN; u++) {
-                const uint32_t k = base + 256 * u;
-                if (k < t.n) st256(W + 4ull * k, (word[u] >> bit[u]) & 1ull, 0, 0, 0);
-            }
-        }
-        return;
-    }
     const Code *c = a.codes + t.code_off;
     constexpr int UG = 4;
     for (uint32_t base = threadIdx.x; base < t.n; base += 256 * UG) {
@@ -379,7 +360,6 @@ struct pob_handle {
     uint64_t *d_staged = nullptr; uint32_t n_staged = 0;
     long long *d_prof = nullptr;               // POB_EVAL_PROFILE: per-level clock stamps (tuning only)
     uint32_t xgroup = 0;                       // instances per expand launch (distinct witness slots)
-    int variant = 0;                           // POB_EXPAND_VARIANT=1: single expand launch per group (tuning only)
     uint32_t n_round_tiles = 0;                // tiles [0, n_round_tiles) are KeccakfRound tiles, the rest code tiles
     int eval_threads = 1024;                   // k_eval CTA size (POB_EVAL_THREADS), tuning only
     bool serialize = false;                    // POB_SERIALIZE=1: eval and expand on one stream (no overlap), tuning only
@@ -502,7 +482,6 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (nslots > 4096) nslots = 4096;
         if (nslots == 0) throw std::runtime_error("not even one witness slot fits in free HBM");
         h->xgroup = (uint32_t)std::min<uint64_t>(16, nslots);
-        if (const char *v = getenv("POB_EXPAND_VARIANT")) h->variant = atoi(v);
         if (const char *v = getenv("POB_EVAL_THREADS")) h->eval_threads = atoi(v);
         if (const char *v = getenv("POB_SERIALIZE")) h->serialize = atoi(v) != 0;
         if (const char *v = getenv("POB_EXPAND_GROUP")) h->xgroup = (uint32_t)std::max(1, std::min<int>(atoi(v), (int)nslots));
@@ -606,19 +585,14 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
                 uint32_t g = 0;
                 for (uint32_t off = 0; off < cnt; off += X, g++) {
                     const uint32_t gc = std::min(X, cnt - off);
-                    ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, reinterpret_cast<const uint2 *>(h->d_round_desc), stores + (size_t)off * h->store_stride, h->store_stride, P.val_base, h->d_witptr + first + off, 0, 0};
+                    ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, reinterpret_cast<const uint2 *>(h->d_round_desc), stores + (size_t)off * h->store_stride, h->store_stride, P.val_base, h->d_witptr + first + off, 0};
                     CU(cudaEventRecord(ev[2 + 2 * g], h->s_exp));
                     // launch 1: KeccakfRound tiles, tile-major (each CTA's tables are L1-resident);
                     // launch 2: code tiles, INSTANCE-major, so that a tile's code stream is fetched from DRAM once and
                     // served from L2 to the other witnesses of the group
                     const uint32_t n_round = h->n_round_tiles, n_code = (uint32_t)P.tiles.size() - n_round;
-                    if (h->variant == 1) { xa.tile0 = 0; xa.swap_xy = 0; k_expand<8, 5, 0><<<dim3((unsigned)P.tiles.size(), gc), 256, 0, h->s_exp>>>(xa); }
-                    else {
-                        if (n_round) { xa.tile0 = 0; xa.swap_xy = 0;
-                            if (h->variant == 2) k_expand<8, 5, 1><<<dim3(n_round, gc), 256, 0, h->s_exp>>>(xa);
-                            else k_expand<8, 5, 0><<<dim3(n_round, gc), 256, 0, h->s_exp>>>(xa); }
-                        if (n_code) { xa.tile0 = n_round; xa.swap_xy = 1; k_expand<8, 5, 0><<<dim3(gc, n_code), 256, 0, h->s_exp>>>(xa); T.other_launches++; }
-                    }
+                    if (n_round) { xa.tile0 = 0; k_expand_round<<<dim3(n_round, gc), 256, 0, h->s_exp>>>(xa); }
+                    if (n_code) { xa.tile0 = n_round; k_expand_codes<<<dim3(gc, n_code), 256, 0, h->s_exp>>>(xa); T.other_launches++; }
                     CU(cudaEventRecord(ev[3 + 2 * g], h->s_exp));
                     T.expand_launches++;
                     if (digest) for (uint32_t j = 0; j < gc; j++) {

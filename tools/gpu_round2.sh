@@ -16,7 +16,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --cs
     python bench.py --batch 64 --steps 1 --warmup 1 --no-cpu-baseline > $OUT/bench_under_ncu_$TAG.log 2>&1
 tail -4 $OUT/launches_$TAG.csv
 echo "== ncu full k_expand (1 witness per launch)"
-POB_EXPAND_GROUP=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_expand -s 2 -c 1 -o $OUT/prof_expand_$TAG -f \
+POB_EXPAND_GROUP=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_expand_round -s 1 -c 1 -o $OUT/prof_expand_$TAG -f \
     python bench.py --batch 1 --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_expand_$TAG.log 2>&1; tail -2 $OUT/ncu_expand_$TAG.log
 echo "== ncu full k_eval (32 instances)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_eval -s 1 -c 1 -o $OUT/prof_eval_$TAG -f \
