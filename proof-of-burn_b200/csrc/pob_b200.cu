@@ -361,6 +361,7 @@ struct pob_handle {
     long long *d_prof = nullptr;               // POB_EVAL_PROFILE: per-level clock stamps (tuning only)
     uint32_t xgroup = 0;                       // instances per expand launch (distinct witness slots)
     uint32_t n_round_tiles = 0;                // tiles [0, n_round_tiles) are KeccakfRound tiles, the rest code tiles
+    uint32_t round_dyn_smem = 0;               // unused dynamic shared memory of k_expand_round: caps resident CTAs per SM
     int eval_threads = 1024;                   // k_eval CTA size (POB_EVAL_THREADS), tuning only
     bool serialize = false;                    // POB_SERIALIZE=1: eval and expand on one stream (no overlap), tuning only
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
@@ -484,6 +485,8 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         h->xgroup = (uint32_t)std::min<uint64_t>(16, nslots);
         if (const char *v = getenv("POB_EVAL_THREADS")) h->eval_threads = atoi(v);
         if (const char *v = getenv("POB_SERIALIZE")) h->serialize = atoi(v) != 0;
+        if (const char *v = getenv("POB_EXPAND_SMEM_KB")) h->round_dyn_smem = (uint32_t)atoi(v) * 1024u;
+        if (h->round_dyn_smem > 48 * 1024) CU(cudaFuncSetAttribute(k_expand_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
         if (const char *v = getenv("POB_EXPAND_GROUP")) h->xgroup = (uint32_t)std::max(1, std::min<int>(atoi(v), (int)nslots));
         if (const char *v = getenv("POB_EVAL_CHUNK")) chunk = (uint32_t)std::max(1, atoi(v));
         h->chunk = chunk;
@@ -591,7 +594,7 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
                     // launch 2: code tiles, INSTANCE-major, so that a tile's code stream is fetched from DRAM once and
                     // served from L2 to the other witnesses of the group
                     const uint32_t n_round = h->n_round_tiles, n_code = (uint32_t)P.tiles.size() - n_round;
-                    if (n_round) { xa.tile0 = 0; k_expand_round<<<dim3(n_round, gc), 256, 0, h->s_exp>>>(xa); }
+                    if (n_round) { xa.tile0 = 0; k_expand_round<<<dim3(n_round, gc), 256, h->round_dyn_smem, h->s_exp>>>(xa); }
                     if (n_code) { xa.tile0 = n_round; k_expand_codes<<<dim3(gc, n_code), 256, 0, h->s_exp>>>(xa); T.other_launches++; }
                     CU(cudaEventRecord(ev[3 + 2 * g], h->s_exp));
                     T.expand_launches++;
