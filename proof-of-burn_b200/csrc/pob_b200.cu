@@ -224,17 +224,18 @@ struct ExpandArgs {
 // tile (<= 8192 entries = 256 KiB) with one 256-bit store per entry.  The source of every entry follows from an 8-byte
 // descriptor per 64 entries and a lane word of the round; the tile's <= 128 descriptors and the round's 263 words are
 // staged in shared memory in one burst, so the streaming loop touches no global memory but the witness itself.
-__global__ void __launch_bounds__(256) k_expand_round(const ExpandArgs a) {
+template <int T>
+__global__ void __launch_bounds__(T) k_expand_round(const ExpandArgs a) {
     const Tile t = a.tiles[blockIdx.x];
     const uint64_t *Ub = a.stores + (uint64_t)blockIdx.y * a.store_stride + t.ubase;
     uint64_t *W = a.wit[blockIdx.y] + t.dst * 4;
     __shared__ uint2 sD[TILE_SIGNALS / 64]; __shared__ uint64_t sW[ROUND_WORDS_SPAN + 1];
     const uint2 *D = a.round_desc + (t.code_off >> 6);
     if (threadIdx.x < ((t.n + 63) >> 6)) sD[threadIdx.x] = __ldg(D + threadIdx.x);
-    for (uint32_t i = threadIdx.x; i < ROUND_WORDS_SPAN; i += 256) sW[i] = Ub[i];
+    for (uint32_t i = threadIdx.x; i < ROUND_WORDS_SPAN; i += T) sW[i] = Ub[i];
     __syncthreads();
 #pragma unroll 8
-    for (uint32_t k = threadIdx.x; k < t.n; k += 256) {
+    for (uint32_t k = threadIdx.x; k < t.n; k += T) {
         const uint2 d = sD[k >> 6];
         const uint32_t tt = k & 63, mode = d.y >> 16;
         uint32_t w = d.x & 0xffffu, b = tt;
@@ -362,6 +363,7 @@ struct pob_handle {
     uint32_t xgroup = 0;                       // instances per expand launch (distinct witness slots)
     uint32_t n_round_tiles = 0;                // tiles [0, n_round_tiles) are KeccakfRound tiles, the rest code tiles
     uint32_t round_dyn_smem = 0;               // unused dynamic shared memory of k_expand_round: caps resident CTAs per SM
+    uint32_t round_threads = 256;              // CTA size of k_expand_round (POB_EXPAND_THREADS), tuning only
     int eval_threads = 1024;                   // k_eval CTA size (POB_EVAL_THREADS), tuning only
     bool serialize = false;                    // POB_SERIALIZE=1: eval and expand on one stream (no overlap), tuning only
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
@@ -486,7 +488,12 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (const char *v = getenv("POB_EVAL_THREADS")) h->eval_threads = atoi(v);
         if (const char *v = getenv("POB_SERIALIZE")) h->serialize = atoi(v) != 0;
         if (const char *v = getenv("POB_EXPAND_SMEM_KB")) h->round_dyn_smem = (uint32_t)atoi(v) * 1024u;
-        if (h->round_dyn_smem > 48 * 1024) CU(cudaFuncSetAttribute(k_expand_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
+        if (const char *v = getenv("POB_EXPAND_THREADS")) h->round_threads = (uint32_t)atoi(v);
+        if (h->round_dyn_smem > 48 * 1024) {
+            CU(cudaFuncSetAttribute(k_expand_round<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
+            CU(cudaFuncSetAttribute(k_expand_round<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
+            CU(cudaFuncSetAttribute(k_expand_round<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
+        }
         if (const char *v = getenv("POB_EXPAND_GROUP")) h->xgroup = (uint32_t)std::max(1, std::min<int>(atoi(v), (int)nslots));
         if (const char *v = getenv("POB_EVAL_CHUNK")) chunk = (uint32_t)std::max(1, atoi(v));
         h->chunk = chunk;
@@ -594,7 +601,12 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
                     // launch 2: code tiles, INSTANCE-major, so that a tile's code stream is fetched from DRAM once and
                     // served from L2 to the other witnesses of the group
                     const uint32_t n_round = h->n_round_tiles, n_code = (uint32_t)P.tiles.size() - n_round;
-                    if (n_round) { xa.tile0 = 0; k_expand_round<<<dim3(n_round, gc), 256, h->round_dyn_smem, h->s_exp>>>(xa); }
+                    if (n_round) {
+                        xa.tile0 = 0;
+                        if (h->round_threads == 512) k_expand_round<512><<<dim3(n_round, gc), 512, h->round_dyn_smem, h->s_exp>>>(xa);
+                        else if (h->round_threads == 1024) k_expand_round<1024><<<dim3(n_round, gc), 1024, h->round_dyn_smem, h->s_exp>>>(xa);
+                        else k_expand_round<256><<<dim3(n_round, gc), 256, h->round_dyn_smem, h->s_exp>>>(xa);
+                    }
                     if (n_code) { xa.tile0 = n_round; k_expand_codes<<<dim3(gc, n_code), 256, 0, h->s_exp>>>(xa); T.other_launches++; }
                     CU(cudaEventRecord(ev[3 + 2 * g], h->s_exp));
                     T.expand_launches++;
