@@ -362,7 +362,10 @@ struct pob_handle {
     long long *d_prof = nullptr;               // POB_EVAL_PROFILE: per-level clock stamps (tuning only)
     uint32_t xgroup = 0;                       // instances per expand launch (distinct witness slots)
     uint32_t n_round_tiles = 0;                // tiles [0, n_round_tiles) are KeccakfRound tiles, the rest code tiles
-    uint32_t round_dyn_smem = 0;               // unused dynamic shared memory of k_expand_round: caps resident CTAs per SM
+    // k_expand_round is launched with 85 KiB of (unused) dynamic shared memory so that only TWO of its CTAs are resident
+    // per SM: fewer concurrent write streams give the DRAM controllers longer same-row bursts -- measured 7.35 TB/s with
+    // 2 CTAs/SM vs 7.26 / 7.19 / 7.09 / 6.97 TB/s with 3 / 4 / 5 / 8, and 5.96 TB/s with 1 (profiles/r01_expand_sweep.md)
+    uint32_t round_dyn_smem = 85 * 1024;
     uint32_t round_threads = 256;              // CTA size of k_expand_round (POB_EXPAND_THREADS), tuning only
     int eval_threads = 1024;                   // k_eval CTA size (POB_EVAL_THREADS), tuning only
     bool serialize = false;                    // POB_SERIALIZE=1: eval and expand on one stream (no overlap), tuning only
