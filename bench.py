@@ -283,7 +283,7 @@ def main():
                            "wall_ms_per_step": wall_ms_max / a.steps,
                            "witness_export_d2h_gbs": export_gbs,
                            "eval_kernel": {"ms_per_launch": eval_ms / max(1, eval_launches), "instances_per_launch": min(desc["chunk"], a.batch),
-                                           "note": "runs concurrently with k_expand on a higher-priority stream"}},
+                                           "note": "runs concurrently with the expand kernels on a higher-priority stream"}},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "witnesses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": "host pinned inputs -> pob_run_batch -> status + output signals on host; witnesses stay in the HBM slot ring for the on-GPU consumer"},
