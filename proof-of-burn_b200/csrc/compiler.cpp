@@ -13,6 +13,7 @@
 #include <sys/mman.h>
 #include <algorithm>
 #include <array>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <unordered_map>
@@ -1440,10 +1441,12 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     }
     P.codes.insert(P.codes.end(), B.flat, B.flat + B.flat_n);
     P.n_round_blocks = B.n_round_blocks; P.n_flat_signals = B.flat_n;
+    uint32_t tile_signals = TILE_SIGNALS;
+    if (const char *v = getenv("POB_TILE_SIGNALS")) { uint32_t t = (uint32_t)atoi(v); if (t >= 64 && t <= TILE_SIGNALS && t % 64 == 0) tile_signals = t; }   // tuning only
     for (auto &s : B.segs) {
         uint64_t done = 0;
         while (done < s.n) {
-            uint32_t n = (uint32_t)std::min<uint64_t>(TILE_SIGNALS, s.n - done);
+            uint32_t n = (uint32_t)std::min<uint64_t>(tile_signals, s.n - done);
             Tile t; t.dst = s.dst + done; t.n = n; t.pad = 0;
             if (s.round) { t.code_off = (uint32_t)done; t.ubase = s.ubase; t.pad = 1; }
             else { t.code_off = (uint32_t)(ROUND_SIGNALS + s.pos + done); t.ubase = 0; }

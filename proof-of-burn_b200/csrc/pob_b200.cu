@@ -367,6 +367,7 @@ struct pob_handle {
     // 2 CTAs/SM vs 7.26 / 7.19 / 7.09 / 6.97 TB/s with 3 / 4 / 5 / 8, and 5.96 TB/s with 1 (profiles/r01_expand_sweep.md)
     uint32_t round_dyn_smem = 85 * 1024;
     uint32_t round_threads = 256;              // CTA size of k_expand_round (POB_EXPAND_THREADS), tuning only
+    uint32_t codes_dyn_smem = 0;               // same occupancy cap for k_expand_codes (POB_CODES_SMEM_KB), tuning only
     int eval_threads = 1024;                   // k_eval CTA size (POB_EVAL_THREADS), tuning only
     bool serialize = false;                    // POB_SERIALIZE=1: eval and expand on one stream (no overlap), tuning only
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
@@ -492,6 +493,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (const char *v = getenv("POB_SERIALIZE")) h->serialize = atoi(v) != 0;
         if (const char *v = getenv("POB_EXPAND_SMEM_KB")) h->round_dyn_smem = (uint32_t)atoi(v) * 1024u;
         if (const char *v = getenv("POB_EXPAND_THREADS")) h->round_threads = (uint32_t)atoi(v);
+        if (const char *v = getenv("POB_CODES_SMEM_KB")) { h->codes_dyn_smem = (uint32_t)atoi(v) * 1024u; if (h->codes_dyn_smem > 48 * 1024) CU(cudaFuncSetAttribute(k_expand_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->codes_dyn_smem)); }
         if (h->round_dyn_smem > 48 * 1024) {
             CU(cudaFuncSetAttribute(k_expand_round<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
             CU(cudaFuncSetAttribute(k_expand_round<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
@@ -612,7 +614,7 @@ int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t fl
                         else if (h->round_threads == 1024) k_expand_round<1024><<<dim3(n_round, gc), 1024, h->round_dyn_smem, h->s_exp>>>(xa);
                         else k_expand_round<256><<<dim3(n_round, gc), 256, h->round_dyn_smem, h->s_exp>>>(xa);
                     }
-                    if (n_code) { xa.tile0 = n_round; k_expand_codes<<<dim3(gc, n_code), 256, 0, h->s_exp>>>(xa); T.other_launches++; }
+                    if (n_code) { xa.tile0 = n_round; k_expand_codes<<<dim3(gc, n_code), 256, h->codes_dyn_smem, h->s_exp>>>(xa); T.other_launches++; }
                     CU(cudaEventRecord(ev[3 + 2 * g], h->s_exp));
                     T.expand_launches++;
                     if (digest) for (uint32_t j = 0; j < gc; j++) {
