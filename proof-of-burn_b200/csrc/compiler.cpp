@@ -1442,7 +1442,7 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     P.codes.insert(P.codes.end(), B.flat, B.flat + B.flat_n);
     P.n_round_blocks = B.n_round_blocks; P.n_flat_signals = B.flat_n;
     uint32_t tile_signals = TILE_SIGNALS;
-    if (const char *v = getenv("POB_TILE_SIGNALS")) { uint32_t t = (uint32_t)atoi(v); if (t >= 64 && t <= TILE_SIGNALS && t % 64 == 0) tile_signals = t; }   // tuning only
+    if (const char *v = getenv("POB_TILE_SIGNALS")) { uint32_t t = (uint32_t)atoi(v); if (t >= 64 && t <= MAX_TILE_SIGNALS && t % 64 == 0) tile_signals = t; }   // tuning only
     for (auto &s : B.segs) {
         uint64_t done = 0;
         while (done < s.n) {

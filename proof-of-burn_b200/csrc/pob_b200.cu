@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(T) k_expand_round(const ExpandArgs a) {
     const Tile t = a.tiles[blockIdx.x];
     const uint64_t *Ub = a.stores + (uint64_t)blockIdx.y * a.store_stride + t.ubase;
     uint64_t *W = a.wit[blockIdx.y] + t.dst * 4;
-    __shared__ uint2 sD[TILE_SIGNALS / 64]; __shared__ uint64_t sW[ROUND_WORDS_SPAN + 1];
+    __shared__ uint2 sD[MAX_TILE_SIGNALS / 64]; __shared__ uint64_t sW[ROUND_WORDS_SPAN + 1];
     const uint2 *D = a.round_desc + (t.code_off >> 6);
     for (uint32_t i = threadIdx.x; i < ((t.n + 63) >> 6); i += T) sD[i] = __ldg(D + i);
     for (uint32_t i = threadIdx.x; i < ROUND_WORDS_SPAN; i += T) sW[i] = Ub[i];

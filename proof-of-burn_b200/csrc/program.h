@@ -99,6 +99,7 @@ struct Level { uint32_t t_begin, t_end, w_begin, w_end, p_begin, p_end, s_begin,
 // ---- expand tiles: a contiguous run of witness entries and where its codes live -------------------------------
 struct Tile { uint64_t dst; uint32_t n, code_off, ubase, pad; };  // BIT codes are relative to ubase; pad = 1: round tile (all BIT)
 static const uint32_t TILE_SIGNALS = 8192;
+static const uint32_t MAX_TILE_SIGNALS = 32768;  // upper bound for the POB_TILE_SIGNALS tuning knob
 
 // ---- circuit identity ---------------------------------------------------------------------------------------
 enum CircuitKind : int32_t { CIRCUIT_SPEND = 0, CIRCUIT_PROOF_OF_BURN = 1, CIRCUIT_GADGET = 2 };
