@@ -421,7 +421,7 @@ void pob_destroy(pob_handle *h) {
     if (h->s_exp) cudaStreamSynchronize(h->s_exp);
     for (void *p : {(void *)h->d_ops, (void *)h->d_psums, (void *)h->d_pos, (void *)h->d_pos_konst, (void *)h->d_abs, (void *)h->d_levels, (void *)h->d_aux, (void *)h->d_konst, (void *)h->d_codes,
                     (void *)h->d_tiles, (void *)h->d_invtab, (void *)h->d_round_desc, (void *)h->d_stores, (void *)h->d_inputs, (void *)h->d_status,
-                    (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr, (void *)h->d_staged})
+                    (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr, (void *)h->d_staged, (void *)h->d_prof})
         if (p) cudaFree(p);
     for (uint64_t *s : h->slots) cudaFree(s);
     for (void *p : {(void *)h->h_status, (void *)h->h_outputs, (void *)h->h_digests, (void *)h->h_witptr}) if (p) cudaFreeHost(p);
