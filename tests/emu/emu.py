@@ -9,11 +9,11 @@ _LIB = None
 
 def build():
     so = os.path.join(_HERE, "libpob_emu.so")
-    srcs = [os.path.join(_HERE, "pob_emu.cpp")] + [os.path.join(_CSRC, f) for f in
+    srcs = [os.path.join(_HERE, "pob_emu.cpp"), os.path.join(_HERE, "host_ref.h")] + [os.path.join(_CSRC, f) for f in
             ("compiler.cpp", "compiler.h", "program.h", "vm_exec.h", "fr_hd.h", "poseidon_constants_data.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I", _CSRC,
-                               "-o", so, srcs[0], srcs[1]])
+                               "-I", _HERE, "-o", so, srcs[0], srcs[2]])
     return so
 
 

@@ -12,6 +12,7 @@
 #include <vector>
 #include "compiler.h"
 #include "vm_exec.h"
+#include "host_ref.h"
 
 using namespace pob;
 
