@@ -177,7 +177,12 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     __shared__ uint32_t s_status;
     if (tid == 0) s_status = STATUS_OK;
     const uint64_t *in = a.inputs + (uint64_t)inst * a.n_inputs * 4;
-    for (uint32_t i = tid; i < a.n_inputs * 4; i += nthr) U[a.val_base + i] = in[i];
+    // inputs -> first value slots, reduced mod p like the circom loader does (a caller may hand over limbs >= p)
+    for (uint32_t i = tid; i < a.n_inputs; i += nthr) {
+        Fr v = vm_load_val(in + 4ull * i);
+        while (fr_geq_p(v)) { Fr t; fr_raw_sub(t, v, fr_p()); v = t; }
+        vm_store_val(U + a.val_base + 4ull * i, v);
+    }
     __syncthreads();
     VmCtx x{U, a.val_base, a.konst, a.aux, a.invtab, &s_status};
     const uint32_t warp = tid >> 5, nwarp = nthr >> 5;

@@ -46,7 +46,11 @@ const char *pob_emu_schema(void *h) { return ((EmuProgram *)h)->P.input_schema.c
 uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_t *outputs) {
     EmuProgram *e = (EmuProgram *)h; const Program &P = e->P;
     std::vector<uint64_t> U(P.store_u64() + 4, 0);
-    memcpy(U.data() + P.val_base, inputs, (size_t)P.n_inputs * 32);
+    for (uint32_t i = 0; i < P.n_inputs; i++) {         // same input reduction as k_eval
+        Fr v = vm_load_val(inputs + 4ull * i);
+        while (fr_geq_p(v)) { Fr t; fr_raw_sub(t, v, fr_p()); v = t; }
+        vm_store_val(U.data() + P.val_base + 4ull * i, v);
+    }
     uint32_t status = STATUS_OK;
     VmCtx x{U.data(), P.val_base, P.konst.data(), P.aux.data(), e->invtab.data(), &status};
     for (const Level &lv : P.levels) {

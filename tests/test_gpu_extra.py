@@ -182,3 +182,18 @@ def test_cli_matches_reference_argv(tmp_path):
     json.dump(s["cases"][1]["input"], open(bad, "w"))
     r = subprocess.run([sys.executable, "-m", "pob_b200", "main_spend", bad, out2], env=env, capture_output=True, text=True)
     assert r.returncode != 0 and r.stderr and not os.path.exists(out2)
+
+
+def test_non_canonical_input_limbs_are_reduced():
+    """limbs >= p handed straight to the C-ABI are reduced mod p (circom's loader semantics): p + x behaves as x"""
+    import pob_b200
+    s = suite("test_spend")
+    c = pob_b200.Circuit("Spend(31)", max_slots=2)
+    try:
+        packed = c.pack([s["cases"][0]["input"], s["cases"][0]["input"]])
+        v = pob_b200.from_limbs(packed[1, 3]) + pob_b200.P          # extraCommitment + p, still < 2^256
+        packed[1, 3] = [(v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)]
+        res = c.run_packed(packed, digest=True)
+        assert (res.status == 0).all() and res.outputs[0] == res.outputs[1] and res.digests[0] == res.digests[1]
+    finally:
+        c.close()
