@@ -6,7 +6,10 @@
 //             (vm_exec.h).  Warp ops: one Keccak absorb per warp, state lane l held by thread l, Theta
 //             column parities / D, RhoPi lane walk and Chi neighbours exchanged with warp shuffles; every
 //             intermediate lane word the bit-level circuit exposes (utils/keccak.circom:58-297) is written
-//             to the store (238 words per round).
+//             to the store (238 words per round).  One Poseidon permutation per warp (state element j in
+//             Montgomery form on lane j, Mix/MixS via shuffles).  Prefix sums by warp scan.  IsZero inverse
+//             hints batch-inverted at the end (table for small inputs, one binary-EEA inversion per thread).
+//   k_pow_grind  proof-of-work burn-key search (the step before the path): one candidate key per thread.
 //   k_expand_round / k_expand_codes  the HBM-bound kernels: materialise every witness entry as a 32-byte little-endian
 //             field element with one 256-bit store (STG.E.ENL2.256).  Algorithmic bytes = 32 * n_signals per instance
 //             (6.909 GB for main_proof_of_burn).  KeccakfRound blocks (95.8 %) are driven by 8-byte group descriptors
@@ -479,7 +482,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
             CU(cudaEventCreateWithFlags(&h->ev_h2d[r], cudaEventDisableTiming));
         }
         CU(cudaEventCreate(&h->ev_start)); CU(cudaEventCreate(&h->ev_end));
-        // (an L2 persisting access-policy window for the code stream was tried and REDUCED k_expand to 4.9 TB/s: the
+        // (an L2 persisting access-policy window for the code stream was tried and REDUCED the expand kernel to 4.9 TB/s: the
         // carve-out takes L2 away from write combining -- profiles/r01_expand_sweep.md)
         if (getenv("POB_EVAL_PROFILE")) CU(cudaMalloc(&h->d_prof, (P.levels.size() + 2) * sizeof(long long)));
         // witness slots: as many as fit in 80 % of free HBM after the store ring

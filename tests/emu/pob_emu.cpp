@@ -65,7 +65,7 @@ uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_
         for (const Tile &t : P.tiles)
             for (uint32_t k = 0; k < t.n; k++) {
                 uint64_t *o = witness + 4 * (t.dst + k);
-                if (t.pad) {            // KeccakfRound tile: 64-signal group descriptors (same decode as k_expand)
+                if (t.pad) {            // KeccakfRound tile: 64-signal group descriptors (same decode as k_expand_round)
                     uint64_t d = P.round_desc[(t.code_off >> 6) + (k >> 6)];
                     uint32_t tt = k & 63, mode = (uint32_t)(d >> 48), w = (uint32_t)(d & 0xffff), b = tt;
                     if (mode) { uint32_t sidx = (mode - 1) * 64 + tt, g = sidx / 3, m = sidx - 3 * g; b = g; w = (uint32_t)((d >> (16 * m)) & 0xffff); }
