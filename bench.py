@@ -134,6 +134,59 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def bench_spend(a, rank, local_rank, world):
+    """main_spend = Spend(31) (circuits/main_spend.circom:6), 2,603,360 entries = 83.3 MB per witness.  Informational:
+    same timing rules as the headline run, single process."""
+    import numpy as np
+    import torch
+    import pob_b200
+    assert world == 1, "--circuit spend is a single-GPU informational run"
+    torch.cuda.set_device(local_rank)
+    rng = np.random.default_rng(a.seed)
+    P = pob_b200.P
+    insts = []
+    for _ in range(a.batch):
+        bal = int(rng.integers(1, 1 << 62))
+        insts.append({"burnKey": str(int.from_bytes(rng.bytes(31), "big") % P), "balance": str(bal),
+                      "withdrawnBalance": str(int(rng.integers(0, bal + 1))), "extraCommitment": int(rng.integers(0, 1 << 62))})
+    c = pob_b200.Circuit("Spend(31)", device=local_rank)
+    pinned = pob_b200.PinnedArray((a.batch, c.n_inputs, 4), np.uint64)
+    pinned.array[...] = c.pack(insts)
+    c.stage(pinned.array)
+    for _ in range(a.warmup):
+        c.run_packed(None, n=a.batch, staged=True)
+    torch.cuda.synchronize()
+    dev_ms = exp_ms = e2e_ms = 0.0
+    launches = ok = 0
+    for _ in range(a.steps):
+        r = c.run_packed(None, n=a.batch, staged=True)
+        dev_ms += r.timing["total_ms"]; exp_ms += r.timing["expand_ms"]; ok += r.n_ok
+        launches += r.timing["expand_launches"] + r.timing["eval_launches"] + r.timing["other_launches"]
+    for _ in range(a.steps):
+        r2 = c.run_packed(pinned.array)
+        e2e_ms += r2.timing["total_ms"]
+    assert ok == a.batch * a.steps
+    n = a.batch * a.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = 32.0 * c.n_signals * n / (exp_ms / 1e3) / 1e9
+    print(json.dumps({"metric": "main_spend witnesses/sec", "value": n / (dev_ms / 1e3), "unit": "witnesses/s", "n_gpus": 1, "steps": a.steps,
+                      "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "u256 (BN254-Fr integer)", "data": "synthetic",
+                      "config": {"workload": "main_spend Spend(31), batch %d synthetic valid inputs" % a.batch, "n_signals": c.n_signals,
+                                 "witness_bytes": c.desc["witness_bytes"], "resident_slots": c.desc["n_slots"], "chunk": c.desc["chunk"], "expand_group": c.desc["expand_group"]},
+                      "e2e": {"value": n / (e2e_ms / 1e3), "unit": "witnesses/s", "h2d_bytes_per_step": r2.timing["h2d_bytes"], "d2h_bytes_per_step": r2.timing["d2h_bytes"]},
+                      "gpu_launches": launches,
+                      "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                                   "kernel": "k_expand_round + k_expand_codes", "expand_share_of_step": exp_ms / dev_ms}}))
+    c.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -142,6 +195,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="instances per GPU per step (BASELINE.json configs[2]: 1024)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--layers", type=int, default=16, help="maxNumLayers of the circuit shape (config 5 sweep)")
+    ap.add_argument("--circuit", default="pob", choices=["pob", "spend"], help="pob = main_proof_of_burn (the headline metric); spend = main_spend (Spend(31), informational)")
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=7503)
@@ -153,6 +207,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     shape = (a.layers,) + MAIN_SHAPE[1:]
     expr = shape_expr(shape)
+    if a.circuit == "spend":
+        return bench_spend(a, rank, local_rank, world)
     workload = "main_proof_of_burn %s, batch %d synthetic valid test_pob_input.json-shaped inputs per GPU per step (trie depth %d-%d)" % (
         expr.replace(" ", ""), a.batch, min(8, a.layers), min(10, a.layers))
 

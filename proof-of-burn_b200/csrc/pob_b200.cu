@@ -489,14 +489,19 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         size_t free_b = 0, total_b = 0; CU(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t wbytes = 32ull * P.n_signals;
         h->store_stride = (P.store_u64() + 31) & ~31ull;
-        uint32_t chunk = 32;
+        // eval chunk: enough instances per launch to keep the SMs busy on small circuits, bounded by a ~0.5 GB store ring
+        // half (main_proof_of_burn: 32; Spend: 1024)
+        uint32_t chunk = (uint32_t)std::min<uint64_t>(1024, std::max<uint64_t>(32, (512ull << 20) / (h->store_stride * 8)));
+        chunk -= chunk % 32;
+        if (const char *v = getenv("POB_EVAL_CHUNK")) chunk = (uint32_t)std::max(1, atoi(v));
         const uint64_t ring_bytes_per_inst = pob_handle::RING * (h->store_stride * 8 + (uint64_t)P.n_inputs * 32);
         uint64_t budget = (uint64_t)(free_b * 0.8);
         uint64_t nslots = budget > chunk * ring_bytes_per_inst ? (budget - chunk * ring_bytes_per_inst) / wbytes : 0;
         if (max_slots && nslots > max_slots) nslots = max_slots;
         if (nslots > 4096) nslots = 4096;
         if (nslots == 0) throw std::runtime_error("not even one witness slot fits in free HBM");
-        h->xgroup = (uint32_t)std::min<uint64_t>(16, nslots);
+        // expand group: ~100 GB of witness per launch pair (main_proof_of_burn: 16 witnesses; Spend: up to the whole chunk)
+        h->xgroup = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(nslots, chunk), std::max<uint64_t>(16, (100ull << 30) / wbytes));
         if (const char *v = getenv("POB_EVAL_THREADS")) h->eval_threads = atoi(v);
         if (const char *v = getenv("POB_SERIALIZE")) h->serialize = atoi(v) != 0;
         if (const char *v = getenv("POB_EXPAND_SMEM_KB")) h->round_dyn_smem = (uint32_t)atoi(v) * 1024u;
@@ -508,8 +513,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
             CU(cudaFuncSetAttribute(k_expand_round<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
             CU(cudaFuncSetAttribute(k_expand_round<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
         }
-        if (const char *v = getenv("POB_EXPAND_GROUP")) h->xgroup = (uint32_t)std::max(1, std::min<int>(atoi(v), (int)nslots));
-        if (const char *v = getenv("POB_EVAL_CHUNK")) chunk = (uint32_t)std::max(1, atoi(v));
+        if (const char *v = getenv("POB_EXPAND_GROUP")) h->xgroup = (uint32_t)std::max(1, std::min<int>(atoi(v), (int)std::min<uint64_t>(nslots, chunk)));
         h->chunk = chunk;
         CU(cudaMalloc(&h->d_stores, (size_t)pob_handle::RING * chunk * h->store_stride * 8));
         CU(cudaMalloc(&h->d_inputs, std::max<size_t>(32, (size_t)pob_handle::RING * chunk * P.n_inputs * 32)));
