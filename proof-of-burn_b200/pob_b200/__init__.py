@@ -331,11 +331,31 @@ CIRCUIT_ALIASES = {"main_proof_of_burn": MAIN_PROOF_OF_BURN, "main_spend": MAIN_
 
 def main(argv=None):
     """CLI shim with the reference calculator's argv: `python -m pob_b200 <circuit> input.json witness.wtns`
-    (reference Makefile:5-6); <circuit> is main_proof_of_burn, main_spend or a `Template(params)` expression."""
+    (reference Makefile:5-6); <circuit> is main_proof_of_burn, main_spend or a `Template(params)` expression.
+    Batch form: `python -m pob_b200 <circuit> --batch in1.json in2.json ... --out DIR` evaluates all inputs in one
+    pob_run_batch and writes DIR/<name>.wtns for every accepted instance."""
     import sys
     argv = sys.argv[1:] if argv is None else argv
+    if len(argv) >= 4 and argv[1] == "--batch" and "--out" in argv:
+        k = argv.index("--out")
+        files, outdir = argv[2:k], argv[k + 1]
+        os.makedirs(outdir, exist_ok=True)
+        c = Circuit(CIRCUIT_ALIASES.get(argv[0], argv[0]))
+        rc = 0
+        slots = c.desc["n_slots"]
+        for lo in range(0, len(files), slots):          # at most n_slots witnesses are resident at a time
+            part = files[lo: lo + slots]
+            res = c.run([json.load(open(f)) for f in part])
+            for i, f in enumerate(part):
+                if res.status[i] != 0:
+                    print("%s: constraint failed in the component at witness index %d" % (f, int(res.status[i]) - 1), file=sys.stderr)
+                    rc = 1
+                else:
+                    c.write_wtns(i, os.path.join(outdir, os.path.splitext(os.path.basename(f))[0] + ".wtns"))
+        return rc
     if len(argv) != 3:
-        print("usage: python -m pob_b200 <main_proof_of_burn|main_spend|Template(params)> input.json witness.wtns", file=sys.stderr)
+        print("usage: python -m pob_b200 <main_proof_of_burn|main_spend|Template(params)> input.json witness.wtns\n"
+              "       python -m pob_b200 <circuit> --batch in1.json in2.json ... --out DIR", file=sys.stderr)
         return 2
     c = Circuit(CIRCUIT_ALIASES.get(argv[0], argv[0]), max_slots=1)
     res = c.run([json.load(open(argv[1]))])

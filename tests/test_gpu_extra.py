@@ -197,3 +197,19 @@ def test_non_canonical_input_limbs_are_reduced():
         assert (res.status == 0).all() and res.outputs[0] == res.outputs[1] and res.digests[0] == res.digests[1]
     finally:
         c.close()
+
+
+def test_cli_batch_mode(tmp_path):
+    import json, subprocess, sys, os
+    from oracle import oracle
+    s = suite("test_spend")
+    files = []
+    for i in (0, 3, 1):                       # two accepted inputs and one that must be rejected
+        f = str(tmp_path / ("case%d.json" % i)); json.dump(s["cases"][i]["input"], open(f, "w")); files.append(f)
+    out = str(tmp_path / "out")
+    env = dict(os.environ, PYTHONPATH=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "proof-of-burn_b200"))
+    r = subprocess.run([sys.executable, "-m", "pob_b200", "main_spend", "--batch"] + files + ["--out", out], env=env, capture_output=True, text=True)
+    assert r.returncode == 1 and "case1.json" in r.stderr
+    assert sorted(os.listdir(out)) == ["case0.wtns", "case3.wtns"]
+    w = oracle.run("Spend(31)", s["cases"][3]["input"]); ref = str(tmp_path / "ref.wtns"); w.write_wtns(ref); w.free()
+    assert open(os.path.join(out, "case3.wtns"), "rb").read() == open(ref, "rb").read()

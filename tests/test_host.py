@@ -76,3 +76,22 @@ def test_two_rank_reduction_over_gloo():
     times, counts = q.get(timeout=120)
     [p.join(timeout=60) for p in procs]
     assert times == [11.0, 5.0] and counts == [100, 1]
+
+
+def test_build_pob_input_packages_a_proof_like_the_reference_generator():
+    """pob_b200.inputs mirrors tests/main.py:65-178 after eth_getProof: nibble count from the leaf, shape-correct padding.
+    Checked on a synthetic world (the packaged JSON must equal the generator's own JSON and be accepted by the oracle)."""
+    from pob_b200 import synth, inputs
+    shape = (4, 4, 5, 20, 31, 2, 10 ** 18, 10 ** 19)
+    inst = synth.make_batch(1, shape, seed=21)[0]
+    j = inputs.build_pob_input(inst["layers"], inst["blockHeader"], inst["actualBalance"], inst["burnKey"], inst["revealAmount"],
+                               inst["burnExtraCommitment"], shape=shape[:3], proof_extra_commitment=inst["_proofExtraCommitment"])
+    ref = synth.to_json(inst, shape)
+    assert int(j["numLeafAddressNibbles"]) == inst["numLeafAddressNibbles"]
+    for k in ref:
+        assert [int(v) for v in np.ravel(j[k])] == [int(v) for v in np.ravel(ref[k])], k
+    w = oracle.run("ProofOfBurn(4, 4, 5, 20, 31, 2, 10 ** 18, 10 ** 19)", j)
+    assert w.ok
+    w.free()
+    with pytest.raises(ValueError):
+        inputs.build_pob_input(inst["layers"] * 3, inst["blockHeader"], 1, 1, 1, 1, shape=shape[:3])
