@@ -213,3 +213,32 @@ def test_cli_batch_mode(tmp_path):
     assert sorted(os.listdir(out)) == ["case0.wtns", "case3.wtns"]
     w = oracle.run("Spend(31)", s["cases"][3]["input"]); ref = str(tmp_path / "ref.wtns"); w.write_wtns(ref); w.free()
     assert open(os.path.join(out, "case3.wtns"), "rb").read() == open(ref, "rb").read()
+
+
+def test_commitments_of_a_batch_match_the_formula_independently_of_the_oracle():
+    """Size-independent property at the full main shape: for every instance of a 48-instance synthetic batch the output
+    signal equals keccak(blockRoot | nullifier | remainingCoin | revealAmount | burnExtraCommitment |
+    _proofExtraCommitment) >> 8 (reference tests/testcases/proof_of_burn.py:18-36), computed with the pure-Python
+    keccak / Poseidon of pob_b200.synth -- no oracle involved.  Also witness[0] = 1 and the input section of a resident
+    witness equals the packed inputs (circuits/proof_of_burn.circom:43-72 order)."""
+    import pob_b200
+    from pob_b200 import synth
+    shape = (16, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)
+    insts = synth.make_batch(48, shape, seed=4242)
+    packed = synth.pack_instances(insts, shape)
+    c = pob_b200.Circuit(pob_b200.MAIN_PROOF_OF_BURN)
+    try:
+        res = c.run_packed(packed)
+        assert (res.status == 0).all()
+        for i, it in enumerate(insts):
+            block_root = synth.keccak256(it["blockHeader"])
+            nullifier = synth.poseidon([synth.POSEIDON_PREFIX + 1, it["burnKey"]])
+            coin = synth.poseidon([synth.POSEIDON_PREFIX + 2, it["burnKey"], it["intendedBalance"] - it["revealAmount"]])
+            msg = block_root + b"".join(int(v).to_bytes(32, "big") for v in
+                                        (nullifier, coin, it["revealAmount"], it["burnExtraCommitment"], it["_proofExtraCommitment"]))
+            assert res.outputs[i] == [int.from_bytes(synth.keccak256(msg)[:31], "big")], "instance %d" % i
+        head = c.witness(47, 0, 2 + c.n_inputs)
+        assert pob_b200.from_limbs(head[0]) == 1 and res.outputs[47] == [pob_b200.from_limbs(head[1])]
+        assert np.array_equal(head[2:], packed[47])
+    finally:
+        c.close()
