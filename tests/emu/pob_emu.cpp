@@ -107,3 +107,10 @@ extern "C" uint32_t pob_emu_inv_selftest(uint32_t n) {
     }
     return bad;
 }
+
+// histogram of code kinds in the code tiles (tuning aid): out[0..3] = CONST, BIT, VAL, KONST entries
+extern "C" void pob_emu_code_hist(void *h, uint64_t *out) {
+    const Program &P = ((EmuProgram *)h)->P;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (const Tile &t : P.tiles) if (!t.pad) for (uint32_t k = 0; k < t.n; k++) out[code_kind(P.codes[t.code_off + k])]++;
+}
