@@ -110,6 +110,14 @@ int pob_write_wtns(pob_handle *h, uint32_t index, const char *path);
 /* device pointer of a resident witness (for an on-GPU consumer such as a prover's first stage) */
 int pob_witness_device_ptr(pob_handle *h, uint32_t index, void **dptr);
 
+/* ---- on-GPU self-check of a resident witness (Keccak part) -----------------------------------
+ * Independent of the layout tables that produced the witness: for every KeccakfRound component (95.8 % of the entries)
+ * the kernel reads the component's own `in[25][64]` and `out[25][64]` signals straight from the witness (positions fixed
+ * by circuits/utils/keccak.circom:290-297: out first, then in), recomputes one textbook Keccak-f round (theta, rho-pi,
+ * chi, iota with the round index the block has inside its Keccakf) and compares; it also checks that all 3200 entries
+ * are 0 or 1.  *n_blocks = blocks examined, *n_bad = blocks that fail. */
+int pob_selfcheck_keccak(pob_handle *h, uint32_t index, uint64_t *n_blocks, uint64_t *n_bad);
+
 /* ---- the step just before the path ------------------------------------------------------
  * replaces: find_burn_key() of the reference input generator (tests/main.py:47-56): starting at start_key, find the
  * first burnKey >= start_key whose keccak256(burnKey[32 BE] | revealAmount[32 BE] | burnExtraCommitment[32 BE] |

@@ -343,6 +343,47 @@ __global__ void __launch_bounds__(256) k_pow_grind(const GrindArgs a) {
     if ((s[0] & mask) == 0) atomicMin(a.hit, (unsigned long long)idx);
 }
 
+// ---- self-check: every KeccakfRound block of a materialised witness satisfies out == KeccakRound_r(in) -------------
+// One warp per block.  Lane l < 25 assembles lane word l of `in` (witness entries base+1600+64l .. +63) and of `out`
+// (base+64l ..) from the 32-byte entries, lane 0 gathers the 25 input words and runs one textbook round.
+__global__ void __launch_bounds__(256) k_check_rounds(const uint64_t *wit, const uint64_t *block_base, uint32_t n_blocks, unsigned long long *n_bad) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_blocks) return;
+    const uint64_t base = block_base[warp];
+    const int r = (int)(warp % 24);                       // round blocks are emitted 24 per Keccakf, in order
+    uint64_t win = 0, wout = 0; bool bad = false;
+    if (lane < 25) {
+        for (uint32_t k = 0; k < 64; k++) {
+            const ulonglong4 a = *reinterpret_cast<const ulonglong4 *>(wit + 4 * (base + 1600 + 64 * lane + k));
+            const ulonglong4 b = *reinterpret_cast<const ulonglong4 *>(wit + 4 * (base + 64 * lane + k));
+            bad |= (a.x > 1) | (b.x > 1) | ((a.y | a.z | a.w | b.y | b.z | b.w) != 0);
+            win |= (a.x & 1ull) << k; wout |= (b.x & 1ull) << k;
+        }
+    }
+    uint64_t s[25], o[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) { s[i] = __shfl_sync(0xffffffffu, win, i); o[i] = __shfl_sync(0xffffffffu, wout, i); }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        uint64_t c[5], d[5], b[25];
+#pragma unroll
+        for (int x = 0; x < 5; x++) c[x] = s[x] ^ s[x + 5] ^ s[x + 10] ^ s[x + 15] ^ s[x + 20];
+#pragma unroll
+        for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
+#pragma unroll
+        for (int i = 0; i < 25; i++) s[i] ^= d[i % 5];
+        b[0] = s[0];
+#pragma unroll
+        for (int i = 0; i < 24; i++) b[keccak_rot(i + 1)] = rotl64(s[keccak_rot(i)], keccak_shl(i));
+#pragma unroll
+        for (int i = 0; i < 25; i++) s[i] = b[i] ^ (~b[chi_b(i)] & b[chi_c(i)]);
+        s[0] ^= keccak_rc(r);
+#pragma unroll
+        for (int i = 0; i < 25; i++) bad |= (s[i] != o[i]);
+        if (bad) atomicAdd(n_bad, 1ull);
+    }
+}
+
 }  // namespace
 
 // =============================================================================================================
@@ -370,6 +411,7 @@ struct pob_handle {
     long long *d_prof = nullptr;               // POB_EVAL_PROFILE: per-level clock stamps (tuning only)
     uint32_t xgroup = 0;                       // instances per expand launch (distinct witness slots)
     uint32_t n_round_tiles = 0;                // tiles [0, n_round_tiles) are KeccakfRound tiles, the rest code tiles
+    uint64_t *d_block_base = nullptr; uint32_t n_blocks = 0;   // witness index of every KeccakfRound block (self-check)
     // k_expand_round is launched with 85 KiB of (unused) dynamic shared memory so that only TWO of its CTAs are resident
     // per SM: fewer concurrent write streams give the DRAM controllers longer same-row bursts -- measured 7.35 TB/s with
     // 2 CTAs/SM vs 7.26 / 7.19 / 7.09 / 6.97 TB/s with 3 / 4 / 5 / 8, and 5.96 TB/s with 1 (profiles/r01_expand_sweep.md)
@@ -429,7 +471,7 @@ void pob_destroy(pob_handle *h) {
     if (h->s_exp) cudaStreamSynchronize(h->s_exp);
     for (void *p : {(void *)h->d_ops, (void *)h->d_psums, (void *)h->d_pos, (void *)h->d_pos_konst, (void *)h->d_abs, (void *)h->d_levels, (void *)h->d_aux, (void *)h->d_konst, (void *)h->d_codes,
                     (void *)h->d_tiles, (void *)h->d_invtab, (void *)h->d_round_desc, (void *)h->d_stores, (void *)h->d_inputs, (void *)h->d_status,
-                    (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr, (void *)h->d_staged, (void *)h->d_prof})
+                    (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr, (void *)h->d_staged, (void *)h->d_prof, (void *)h->d_block_base})
         if (p) cudaFree(p);
     for (uint64_t *s : h->slots) cudaFree(s);
     for (void *p : {(void *)h->h_status, (void *)h->h_outputs, (void *)h->h_digests, (void *)h->h_witptr}) if (p) cudaFreeHost(p);
@@ -468,6 +510,8 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (getenv("POB_FLAT_FIRST")) std::stable_sort(h->P.tiles.begin(), h->P.tiles.end(), [](const Tile &a, const Tile &b) { return a.pad < b.pad; });   // tuning only
         h->d_tiles = upload(h->P.tiles);
         for (const Tile &t : h->P.tiles) if (t.pad) h->n_round_tiles++;
+        { std::vector<uint64_t> bases; for (const Tile &t : P.tiles) if (t.pad && t.code_off == 0) bases.push_back(t.dst);
+          std::sort(bases.begin(), bases.end()); h->n_blocks = (uint32_t)bases.size(); h->d_block_base = upload(bases); }
         h->d_invtab = upload(build_inverse_table());
         h->d_round_desc = upload(P.round_desc);
         // the small eval grid must get SMs while the expand grid (hundreds of thousands of CTAs) is draining:
@@ -726,6 +770,22 @@ static int resident_slot(pob_handle *h, uint32_t index, uint64_t **slot) {
     const uint32_t nslots = (uint32_t)h->slots.size();
     if ((uint64_t)index + nslots < h->last_n) return fail(POB_E_RANGE, "witness slot already overwritten by a later instance");
     *slot = h->slots[index % nslots]; return POB_OK;
+}
+
+int pob_selfcheck_keccak(pob_handle *h, uint32_t index, uint64_t *n_blocks, uint64_t *n_bad) {
+    if (!h || !n_blocks || !n_bad) return fail(POB_E_BAD_ARG, "pob_selfcheck_keccak: null argument");
+    uint64_t *s = nullptr; int rc = resident_slot(h, index, &s); if (rc) return rc;
+    unsigned long long *d_bad = nullptr, bad = 0;
+    try {
+        CU(cudaSetDevice(h->device));
+        CU(cudaMalloc(&d_bad, 8)); CU(cudaMemset(d_bad, 0, 8));
+        if (h->n_blocks) k_check_rounds<<<(h->n_blocks * 32 + 255) / 256, 256>>>(s, h->d_block_base, h->n_blocks, d_bad);
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(&bad, d_bad, 8, cudaMemcpyDeviceToHost));
+        cudaFree(d_bad);
+    } catch (const std::exception &e) { if (d_bad) cudaFree(d_bad); return fail(POB_E_CUDA, std::string("pob_selfcheck_keccak: ") + e.what()); }
+    *n_blocks = h->n_blocks; *n_bad = bad;
+    return POB_OK;
 }
 
 int pob_witness_device_ptr(pob_handle *h, uint32_t index, void **dptr) {

@@ -91,6 +91,8 @@ def lib():
         L.pob_write_wtns.argtypes = [vp, u32, ctypes.c_char_p]
         L.pob_witness_device_ptr.restype = ci
         L.pob_witness_device_ptr.argtypes = [vp, u32, ctypes.POINTER(vp)]
+        L.pob_selfcheck_keccak.restype = ci
+        L.pob_selfcheck_keccak.argtypes = [vp, u32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
         L.pob_pow_grind.restype = ci
         L.pob_pow_grind.argtypes = [ci, vp, vp, vp, u32, u64, vp, ctypes.POINTER(u64)]
         L.pob_last_error.restype = ctypes.c_char_p
@@ -291,6 +293,13 @@ class Circuit:
 
     def write_wtns(self, index, path):
         _check(lib().pob_write_wtns(self._h, index, path.encode()))
+
+    def selfcheck_keccak(self, index):
+        """on-GPU check that every KeccakfRound block of resident witness `index` satisfies out == KeccakRound(in);
+        returns (blocks examined, blocks failing)"""
+        nb, bad = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _check(lib().pob_selfcheck_keccak(self._h, index, ctypes.byref(nb), ctypes.byref(bad)))
+        return int(nb.value), int(bad.value)
 
     def witness_device_ptr(self, index):
         p = ctypes.c_void_p()
