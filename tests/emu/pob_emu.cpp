@@ -114,3 +114,25 @@ extern "C" void pob_emu_code_hist(void *h, uint64_t *out) {
     out[0] = out[1] = out[2] = out[3] = 0;
     for (const Tile &t : P.tiles) if (!t.pad) for (uint32_t k = 0; k < t.n; k++) out[code_kind(P.codes[t.code_off + k])]++;
 }
+
+// self-test of fr_mont / fr_mul against 512-bit schoolbook arithmetic done with unsigned __int128 on the host
+extern "C" uint32_t pob_emu_mul_selftest(uint32_t n) {
+    typedef unsigned __int128 u128;
+    uint32_t bad = 0; uint64_t st = 0x2545F4914F6CDD1Dull;
+    auto rnd = [&](Fr &a, uint32_t i) {
+        for (int k = 0; k < 8; k++) { st ^= st << 13; st ^= st >> 7; st ^= st << 17; a.l[k] = (uint32_t)(st >> 11); }
+        a.l[7] &= 0x0fffffffu;
+        if (i % 5 == 0) { Fr t; fr_raw_sub(t, fr_p(), fr_from_u64(i + 1)); a = t; }      // p - small
+        if (i % 9 == 0) a = fr_from_u64(st);
+    };
+    // reference: (a*b) mod p by shift-and-add
+    auto mulmod = [&](const Fr &a, const Fr &b) { Fr r = fr_zero(); for (int i = 255; i >= 0; i--) { r = fr_add(r, r); if (fr_bit(b, (unsigned)i)) r = fr_add(r, a); } return r; };
+    for (uint32_t i = 0; i < n; i++) {
+        Fr a, b; rnd(a, i); rnd(b, i + 3);
+        Fr want = mulmod(a, b);
+        if (!fr_eq(fr_mul(a, b), want)) bad++;
+        if (!fr_eq(fr_from_mont(fr_mont(fr_to_mont(a), fr_to_mont(b))), want)) bad++;
+    }
+    (void)sizeof(u128);
+    return bad;
+}

@@ -94,3 +94,11 @@ def test_binary_eea_inverse_equals_fermat():
     L = emu.lib()
     L.pob_emu_inv_selftest.restype = ctypes.c_uint32
     assert L.pob_emu_inv_selftest(ctypes.c_uint32(3000)) == 0
+
+
+def test_montgomery_multiplication_against_shift_and_add():
+    """fr_mont / fr_mul (csrc/fr_hd.h, column-wise Montgomery) against a bit-serial (a*b) mod p on 2000 pairs incl. p-k"""
+    import ctypes, emu
+    L = emu.lib()
+    L.pob_emu_mul_selftest.restype = ctypes.c_uint32
+    assert L.pob_emu_mul_selftest(ctypes.c_uint32(2000)) == 0
