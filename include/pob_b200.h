@@ -117,6 +117,8 @@ int pob_witness_device_ptr(pob_handle *h, uint32_t index, void **dptr);
  * chi, iota with the round index the block has inside its Keccakf) and compares; it also checks that all 3200 entries
  * are 0 or 1.  *n_blocks = blocks examined, *n_bad = blocks that fail. */
 int pob_selfcheck_keccak(pob_handle *h, uint32_t index, uint64_t *n_blocks, uint64_t *n_bad);
+/* test hook for the self-check: overwrite ONE entry of a resident witness (fault injection) */
+int pob_debug_poke_witness(pob_handle *h, uint32_t index, uint64_t signal, const uint64_t value[4]);
 
 /* ---- the step just before the path ------------------------------------------------------
  * replaces: find_burn_key() of the reference input generator (tests/main.py:47-56): starting at start_key, find the

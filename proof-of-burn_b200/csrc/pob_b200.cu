@@ -788,6 +788,15 @@ int pob_selfcheck_keccak(pob_handle *h, uint32_t index, uint64_t *n_blocks, uint
     return POB_OK;
 }
 
+int pob_debug_poke_witness(pob_handle *h, uint32_t index, uint64_t signal, const uint64_t value[4]) {
+    if (!h || !value) return fail(POB_E_BAD_ARG, "pob_debug_poke_witness: null argument");
+    uint64_t *s = nullptr; int rc = resident_slot(h, index, &s); if (rc) return rc;
+    if (signal >= h->P.n_signals) return fail(POB_E_RANGE, "pob_debug_poke_witness: signal index out of range");
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaMemcpy(s + 4 * signal, value, 32, cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(POB_E_CUDA, "pob_debug_poke_witness: cudaMemcpy failed");
+    return POB_OK;
+}
+
 int pob_witness_device_ptr(pob_handle *h, uint32_t index, void **dptr) {
     if (!h || !dptr) return fail(POB_E_BAD_ARG, "pob_witness_device_ptr: null argument");
     uint64_t *s = nullptr; int rc = resident_slot(h, index, &s); if (rc) return rc;

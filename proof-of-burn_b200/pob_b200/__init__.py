@@ -93,6 +93,8 @@ def lib():
         L.pob_witness_device_ptr.argtypes = [vp, u32, ctypes.POINTER(vp)]
         L.pob_selfcheck_keccak.restype = ci
         L.pob_selfcheck_keccak.argtypes = [vp, u32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+        L.pob_debug_poke_witness.restype = ci
+        L.pob_debug_poke_witness.argtypes = [vp, u32, u64, vp]
         L.pob_pow_grind.restype = ci
         L.pob_pow_grind.argtypes = [ci, vp, vp, vp, u32, u64, vp, ctypes.POINTER(u64)]
         L.pob_last_error.restype = ctypes.c_char_p
@@ -300,6 +302,11 @@ class Circuit:
         nb, bad = ctypes.c_uint64(0), ctypes.c_uint64(0)
         _check(lib().pob_selfcheck_keccak(self._h, index, ctypes.byref(nb), ctypes.byref(bad)))
         return int(nb.value), int(bad.value)
+
+    def poke_witness(self, index, signal, value):
+        """test hook (fault injection for the self-check): overwrite one entry of a resident witness"""
+        v = to_limbs([value])
+        _check(lib().pob_debug_poke_witness(self._h, index, signal, v.ctypes.data))
 
     def witness_device_ptr(self, index):
         p = ctypes.c_void_p()

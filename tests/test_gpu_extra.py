@@ -246,42 +246,27 @@ def test_commitments_of_a_batch_match_the_formula_independently_of_the_oracle():
 
 def test_on_gpu_keccak_selfcheck_detects_corruption():
     """pob_selfcheck_keccak: every KeccakfRound block of a materialised witness satisfies out == KeccakRound(in); a single
-    flipped bit inside one block is detected (and only that block fails)."""
+    flipped bit inside the in/out signals of one block is detected, and only that block fails."""
     import pob_b200
-    pytest.importorskip("cuda")
-    import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        from cuda import cudart
     s = suite("test_keccak_2")
     c = pob_b200.Circuit("KeccakBytes(2)", max_slots=2)
     try:
         res = c.run([s["cases"][3]["input"]])
         assert res.status[0] == 0
-        nb, bad = c.selfcheck_keccak(0)
-        assert (nb, bad) == (48, 0)
+        assert c.selfcheck_keccak(0) == (48, 0)
         w = c.witness(0)
-        # find the first KeccakfRound block: own signals out[1600], in[1600] are bits and Theta follows; locate via the
-        # library's own report of blocks is not exposed, so corrupt an entry known to be inside round block 0:
-        # KeccakBytes(2) layout puts the first Keccakf after the byte-level gadgets; take the last block instead:
-        last_block_start = c.n_signals
-        # walk back over the tail: Reshape(32,8) 512 + 32 x Bits2Num(8) 288 and the Keccak/Final selectors precede the end;
-        # simpler and robust: flip an `out` bit of EVERY candidate by scanning for the self-check to react
-        dptr = c.witness_device_ptr(0)
-        target = None
-        for idx in range(c.n_signals - 1, 0, -4099):
-            one = np.array([int(w[idx, 0]) ^ 1, 0, 0, 0], dtype=np.uint64)
+        detected = 0
+        for idx in range(c.n_signals - 1, 0, -4001):        # ~1280 probes; 3 % of the entries are in/out of a round block
             if w[idx, 1:].any() or w[idx, 0] > 1:
                 continue
-            cudart.cudaMemcpy(dptr + 32 * idx, one.ctypes.data, 32, cudart.cudaMemcpyKind.cudaMemcpyHostToDevice)
-            nb2, bad2 = c.selfcheck_keccak(0)
-            orig = np.array([int(w[idx, 0]), 0, 0, 0], dtype=np.uint64)
-            cudart.cudaMemcpy(dptr + 32 * idx, orig.ctypes.data, 32, cudart.cudaMemcpyKind.cudaMemcpyHostToDevice)
-            if bad2:
-                target = (idx, bad2)
-                break
-        assert target is not None and target[1] == 1, "no corruption was detected: %r" % (target,)
+            c.poke_witness(0, idx, int(w[idx, 0]) ^ 1)
+            nb, bad = c.selfcheck_keccak(0)
+            c.poke_witness(0, idx, int(w[idx, 0]))
+            assert nb == 48 and bad in (0, 1)
+            detected += bad
+        assert detected >= 1, "no injected fault was detected"
         assert c.selfcheck_keccak(0) == (48, 0)
+        assert np.array_equal(c.witness(0), w)
     finally:
         c.close()
 
