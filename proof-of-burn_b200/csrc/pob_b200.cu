@@ -532,7 +532,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         // witness slots: as many as fit in 80 % of free HBM after the store ring
         size_t free_b = 0, total_b = 0; CU(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t wbytes = 32ull * P.n_signals;
-        h->store_stride = (P.store_u64() + 31) & ~31ull;
+        h->store_stride = std::max<uint64_t>(32, (P.store_u64() + 31) & ~31ull);     // never 0 (constant-only gadgets such as EIP7503())
         // eval chunk: enough instances per launch to keep the SMs busy on small circuits, bounded by a ~0.5 GB store ring
         // half (main_proof_of_burn: 32; Spend: 1024)
         uint32_t chunk = (uint32_t)std::min<uint64_t>(1024, std::max<uint64_t>(32, (512ull << 20) / (h->store_stride * 8)));
