@@ -1,4 +1,4 @@
-// fr_hd.h -- BN254-Fr arithmetic for the B200 witness VM: 8 x 32-bit limbs, Montgomery (CIOS) multiply.
+// fr_hd.h -- BN254-Fr arithmetic for the B200 witness VM: 8 x 32-bit limbs, column-wise Montgomery multiply.
 //
 // Every signal of the proof-of-burn circuits is an element of this field (reference: the implicit field
 // ops under every `<==` -- circomlib/circuits/gates.circom:26,34,42, comparators.circom:30-33,
@@ -71,9 +71,9 @@ POB_HD Fr fr_neg(const Fr &a) { if (fr_is_zero(a)) return a; Fr t; fr_raw_sub(t,
 
 // Montgomery product a*b*2^-256 mod p, column-wise (product scanning): the 64 limb products of the 512-bit product are
 // mutually independent (each column keeps a split lo/hi accumulator, so no carry chain links them), and the reduction
-// needs only the 8-step chain m_k = column_k * n0'.  On a GPU this is what matters when one warp walks a long
-// dependency chain (Poseidon rounds, inverse batch): latency drops ~4x versus the word-serial CIOS form, with the same
-// number of IMAD.WIDE instructions.  Result < p (one conditional subtraction; inputs < p).
+// needs only the 8-step chain m_k = column_k * n0'.  Same number of IMAD.WIDE instructions as the word-serial CIOS
+// form; measured on B200 it is neither faster nor slower inside k_eval (a lone warp is bound by in-order issue, and the
+// 64-register cap spills the limb arrays -- ROADMAP.md).  Result < p (one conditional subtraction; inputs < p).
 POB_HD Fr fr_mont(const Fr &a, const Fr &b) {
     uint32_t T[16];
     uint64_t c = 0;
