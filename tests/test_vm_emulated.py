@@ -102,3 +102,13 @@ def test_montgomery_multiplication_against_shift_and_add():
     L = emu.lib()
     L.pob_emu_mul_selftest.restype = ctypes.c_uint32
     assert L.pob_emu_mul_selftest(ctypes.c_uint32(2000)) == 0
+
+
+def test_main_shape_program_matches_oracle_entry_by_entry():
+    """BASELINE.json configs[1] on the CPU: the compiled program of main_proof_of_burn = ProofOfBurn(16,4,16,50,31,2,
+    10^19,10^20), run by the test-only emulator on the reference fixture re-padded to the main shape, equals the oracle on
+    all 215,907,954 witness entries (needs ~14 GB of RAM, ~70 s)."""
+    from helpers import repad_pob
+    expr = "ProofOfBurn(16, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)"
+    prog = _compare(expr, [repad_pob(pob_fixture(), 16, 4, 16)])
+    assert prog.stats["n_signals"] == 215907954 and prog.stats["n_absorbs"] == 84 and prog.stats["n_round_blocks"] == 2016
