@@ -101,9 +101,6 @@ struct Tile { uint64_t dst; uint32_t n, code_off, ubase, pad; };  // BIT codes a
 static const uint32_t TILE_SIGNALS = 8192;
 static const uint32_t MAX_TILE_SIGNALS = 32768;  // upper bound for the POB_TILE_SIGNALS tuning knob
 
-// ---- circuit identity ---------------------------------------------------------------------------------------
-enum CircuitKind : int32_t { CIRCUIT_SPEND = 0, CIRCUIT_PROOF_OF_BURN = 1, CIRCUIT_GADGET = 2 };
-
 struct Program {
     // identity
     std::string main_name;
