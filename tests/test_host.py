@@ -95,3 +95,18 @@ def test_build_pob_input_packages_a_proof_like_the_reference_generator():
     w.free()
     with pytest.raises(ValueError):
         inputs.build_pob_input(inst["layers"] * 3, inst["blockHeader"], 1, 1, 1, 1, shape=shape[:3])
+
+
+def test_bench_helpers():
+    """bench.py host logic: shape expression round-trips through the layout compiler; the CPU-baseline process count is
+    bounded by available memory (a witness is 6.9 GB per oracle process)."""
+    import importlib.util, pob_b200
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    expr = bench.shape_expr((8,) + bench.MAIN_SHAPE[1:])
+    assert pob_b200.parse_main(expr) == ("ProofOfBurn", [8, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20])
+    assert bench.shape_expr(bench.MAIN_SHAPE).replace(" ", "") == bench.MAIN_EXPR.replace(" ", "").replace("10**19", str(10 ** 19)).replace("10**20", str(10 ** 20))
+    assert bench.N_SIGNALS_MAIN == pob_b200.layout_info(bench.MAIN_EXPR)["n_signals"]
+    assert 1 <= bench.mem_limited_procs(64, 34 * bench.N_SIGNALS_MAIN) <= 64
+    assert bench.mem_limited_procs(64, 1 << 60) == 1            # nothing fits: still one process
