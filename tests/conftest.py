@@ -19,6 +19,9 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         has_gpu = False
     skip_gpu = pytest.mark.skip(reason="no CUDA device")
+    skip_slow = pytest.mark.skip(reason="multi-GB extra shape; set POB_SLOW=1 to run")
     for it in items:
         if "gpu" in it.keywords and not has_gpu:
             it.add_marker(skip_gpu)
+        if "slow" in it.keywords and os.environ.get("POB_SLOW") != "1":
+            it.add_marker(skip_slow)

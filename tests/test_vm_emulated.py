@@ -112,3 +112,15 @@ def test_main_shape_program_matches_oracle_entry_by_entry():
     expr = "ProofOfBurn(16, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)"
     prog = _compare(expr, [repad_pob(pob_fixture(), 16, 4, 16)])
     assert prog.stats["n_signals"] == 215907954 and prog.stats["n_absorbs"] == 84 and prog.stats["n_round_blocks"] == 2016
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("layers", [8, 12])
+def test_config5_shapes_program_matches_oracle(layers):
+    """BASELINE.json configs[4] shapes ProofOfBurn(L,4,16,...) on a synthetic valid instance, all S(L) entries (POB_SLOW=1)"""
+    from pob_b200 import synth
+    shape = (layers, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)
+    inst = synth.make_batch(1, shape, seed=layers)[0]
+    expr = "ProofOfBurn(%d, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)" % layers
+    prog = _compare(expr, [synth.to_json(inst, shape)])
+    assert prog.stats["n_signals"] == 51277058 + 10289431 * layers
