@@ -11,6 +11,11 @@ instance is evaluated and its complete 215,907,954-entry witness vector (6.909 G
   e2e   : the same through the public call with HOST (pinned) input buffers: H2D of every step's inputs and
           D2H of its per-instance status + output signals inside the timed region.
   roofline : expand kernel, algorithmic bytes (32 B x n_signals x instances per launch) / CUDA-event duration.
+  handoff  : the same batch with every witness CONSUMED on the GPU (the digest kernel reads all of it before its slot is
+          reused) and a sample with every witness EXPORTED to host memory through the consumer-paced path
+          (pob_export_batch): nothing is overwritten unread in either mode.  The headline `value` itself is the
+          generation-only run (POB_RUN_DISCARD): BASELINE.json's metric counts witnesses written to HBM.
+  latency  : one main-shape witness alone on the GPU (BASELINE.json configs[1]), input on the host -> witness in HBM.
   cpu_baseline : the CPU oracle (a restatement of the reference calculator -- "port"), P processes on host cores.
 Instances shard by index across ranks with no data-path collective; NCCL is used only for the barrier, the
 max-over-ranks time and the final ok-count reduction (weak scaling: B per GPU is fixed).
@@ -127,6 +132,16 @@ def mem_limited_procs(want, bytes_per_proc):
     return max(1, min(want, int(avail * 0.5 // bytes_per_proc)))
 
 
+def shared_config(a, expr, world):
+    """identical in the B200 arm and the reference arm (the driver compares the two `config` objects)"""
+    n_sig = 51277058 + 10289431 * a.layers
+    return {"workload": "main_proof_of_burn %s, batch %d synthetic valid test_pob_input.json-shaped inputs per GPU per step (trie depth %d-%d)" % (
+                expr.replace(" ", ""), a.batch, min(8, a.layers), min(10, a.layers)),
+            "circuit": expr, "n_signals": n_sig, "witness_bytes": 32 * n_sig, "batch_per_gpu": a.batch,
+            "parallelism": "instances sharded by index, %d per GPU" % a.batch,
+            "l2": "each step writes %.1f GB per GPU, far beyond the 126 MB L2; no flush needed" % (a.batch * 32 * n_sig / 1e9)}
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -154,16 +169,16 @@ def bench_spend(a, rank, local_rank, world):
     pinned.array[...] = c.pack(insts)
     c.stage(pinned.array)
     for _ in range(a.warmup):
-        c.run_packed(None, n=a.batch, staged=True)
+        c.run_packed(None, n=a.batch, staged=True, discard=True)
     torch.cuda.synchronize()
     dev_ms = exp_ms = e2e_ms = 0.0
     launches = ok = 0
     for _ in range(a.steps):
-        r = c.run_packed(None, n=a.batch, staged=True)
+        r = c.run_packed(None, n=a.batch, staged=True, discard=True)
         dev_ms += r.timing["total_ms"]; exp_ms += r.timing["expand_ms"]; ok += r.n_ok
         launches += r.timing["expand_launches"] + r.timing["eval_launches"] + r.timing["other_launches"]
     for _ in range(a.steps):
-        r2 = c.run_packed(pinned.array)
+        r2 = c.run_packed(pinned.array, discard=True)
         e2e_ms += r2.timing["total_ms"]
     assert ok == a.batch * a.steps
     n = a.batch * a.steps
@@ -197,7 +212,10 @@ def main():
     ap.add_argument("--layers", type=int, default=16, help="maxNumLayers of the circuit shape (config 5 sweep)")
     ap.add_argument("--circuit", default="pob", choices=["pob", "spend"], help="pob = main_proof_of_burn (the headline metric); spend = main_spend (Spend(31), informational)")
     ap.add_argument("--cpu-procs", type=int, default=0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the timed oracle leg (the in-run digest parity check still runs: --parity)")
+    ap.add_argument("--parity", type=int, default=2, help="instances whose whole-witness digest is compared with the oracle when the cpu baseline is skipped (0 = none)")
+    ap.add_argument("--consume-batch", type=int, default=256, help="instances of the 'every witness consumed on the GPU' figure (0 = skip)")
+    ap.add_argument("--export-sample", type=int, default=24, help="instances of the 'every witness exported to the host' figure (0 = skip)")
     ap.add_argument("--seed", type=int, default=7503)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
@@ -209,8 +227,6 @@ def main():
     expr = shape_expr(shape)
     if a.circuit == "spend":
         return bench_spend(a, rank, local_rank, world)
-    workload = "main_proof_of_burn %s, batch %d synthetic valid test_pob_input.json-shaped inputs per GPU per step (trie depth %d-%d)" % (
-        expr.replace(" ", ""), a.batch, min(8, a.layers), min(10, a.layers))
 
     from pob_b200 import synth
     cores = host_cores()
@@ -222,15 +238,14 @@ def main():
         procs = mem_limited_procs(a.cpu_procs or max(1, min(cores // 2, 32)), 34 * (51277058 + 10289431 * a.layers))
         insts = synth.make_batch(procs, shape, seed=a.seed)
         packed = synth.pack_instances(insts, shape)
-        for _ in range(min(a.warmup, 1)):
+        for _ in range(a.warmup):
             cpu_baseline_run(expr, packed, procs)
-        t0 = time.time()
         v, dt, done = cpu_baseline_run(expr, packed, procs, rounds=a.steps)
-        line = {"metric": METRIC, "value": v, "unit": "witnesses/s", "impl": "reference", "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
+        line = {"metric": METRIC, "value": v, "unit": "witnesses/s", "impl": "reference", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u256 (BN254-Fr integer)",
-                "data": "synthetic", "config": {"workload": workload, "sample": "%d instances per step" % procs},
+                "data": "synthetic", "config": shared_config(a, expr, world),
                 "cpu_baseline": {"value": v, "unit": "witnesses/s", "cores": procs, "kind": "port",
-                                 "sample": "%d steps x %d single-threaded oracle processes, one full %d-entry witness each (circom is absent: the oracle is a restatement of the reference calculator)" % (a.steps, procs, 51277058 + 10289431 * a.layers)},
+                                 "sample": "each step = %d single-threaded oracle processes x one full %d-entry witness of the workload (a bounded sample of the %d-instance batch; circom is absent: the oracle is a restatement of the reference calculator)" % (procs, 51277058 + 10289431 * a.layers, a.batch)},
                 "e2e": {"value": v, "unit": "witnesses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return 0
@@ -252,20 +267,20 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    circuit = pob_b200.Circuit(expr, device=local_rank)
-    desc = circuit.desc
-    # this rank's shard: instances [rank*B, (rank+1)*B) of the global batch
+    # this rank's shard: instances [rank*B, (rank+1)*B) of the global batch (generated by a fork pool, before CUDA is touched)
     from pob_b200 import shard
     insts = synth.make_batch(a.batch, shape, seed=shard.shard_seed(a.seed, rank, a.batch))
+    circuit = pob_b200.Circuit(expr, device=local_rank)
+    desc = circuit.desc
     pinned = pob_b200.PinnedArray((a.batch, circuit.n_inputs, 4), np.uint64)
     synth.pack_instances(insts, shape, out=pinned.array)
     circuit.stage(pinned.array)
 
     def step_resident():
-        return circuit.run_packed(None, n=a.batch, expand=True, staged=True)
+        return circuit.run_packed(None, n=a.batch, expand=True, staged=True, discard=True)
 
     def step_e2e():
-        return circuit.run_packed(pinned.array, expand=True)
+        return circuit.run_packed(pinned.array, expand=True, discard=True)
 
     for _ in range(a.warmup):
         r = step_resident()
@@ -293,19 +308,27 @@ def main():
         e2e_ms += r2.timing["total_ms"]; h2d, d2h = r2.timing["h2d_bytes"], r2.timing["d2h_bytes"]
     barrier()
 
-    # witness hand-off over PCIe, informational: 1 GiB window of the last resident witness -> pinned host
-    export_gbs = None
+    # ---- consumer-paced figures: nothing is overwritten unread ------------------------------------
+    handoff, latency = {}, None
+    if a.consume_batch > 0:
+        nb = min(a.batch, a.consume_batch)
+        circuit.run_packed(None, n=min(nb, 32), staged=True, digest=True)
+        rc = circuit.run_packed(None, n=nb, staged=True, digest=True)      # the digest kernel reads every entry of every witness
+        handoff["consumed_on_gpu"] = {"value": nb / (rc.timing["total_ms"] / 1e3), "unit": "witnesses/s", "instances": nb,
+                                      "consumer": "k_digest reads all %d entries of each witness before its slot is reused (adds 1 x witness bytes of HBM reads)" % desc["n_signals"]}
+    if a.export_sample > 0 and rank == 0:
+        ne = min(a.batch, a.export_sample)
+        circuit.export_batch(None, n=min(ne, 2), staged=True)
+        rx, st = circuit.export_batch(None, n=ne, staged=True)
+        handoff["exported_to_host"] = {"value": st["witnesses"] / (st["total_ms"] / 1e3), "unit": "witnesses/s", "instances": int(st["witnesses"]), "d2h_gbs": st["d2h_gbs"],
+                                       "sink": "pinned host staging ring over 2 copy streams (pob_export_batch, paths=NULL); PCIe-bound"}
     if rank == 0:
-        try:
-            nwin = min(circuit.n_signals, 1 << 25)
-            win = pob_b200.PinnedArray((nwin, 4), np.uint64)
-            pob_b200._check(pob_b200.lib().pob_copy_witness(circuit._h, a.batch - 1, 0, nwin, win.ptr))
-            t0 = time.time()
-            pob_b200._check(pob_b200.lib().pob_copy_witness(circuit._h, a.batch - 1, 0, nwin, win.ptr))
-            export_gbs = nwin * 32 / (time.time() - t0) / 1e9
-            win.free()
-        except Exception:
-            export_gbs = None
+        one = pinned.array[:1]
+        circuit.run_packed(one)
+        ms = sorted(circuit.run_packed(one).timing["total_ms"] for _ in range(5))
+        tl = circuit.run_packed(one).timing
+        latency = {"single_witness_ms": ms[len(ms) // 2], "eval_ms": tl["eval_ms"], "expand_ms": tl["expand_ms"],
+                   "what": "one main-shape instance alone on the GPU (BASELINE.json configs[1]): host input -> status + outputs on host, witness complete in HBM"}
     (dev_ms_max, e2e_ms_max, wall_ms_max), (ok_total, launches_total) = shard.reduce_timing_and_counts(
         dist, "cuda", [dev_ms, e2e_ms, wall_ms], [ok, launches])     # time = max over ranks; counts summed over NCCL
     total_instances = world * a.batch * a.steps
@@ -323,38 +346,44 @@ def main():
         bytes_per_launch = 32.0 * desc["n_signals"] * a.batch * a.steps / max(1, exp_launches)
         per_launch_ms = exp_ms / max(1, exp_launches)
         achieved = bytes_per_launch / (per_launch_ms / 1e3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         try:
-            # ncu --set full capture of one 1-witness launch (profiles/), scaled to the witnesses per launch timed here
-            per_wit = json.load(open(os.path.join(ROOT, "profiles", "expand_traffic.json"))).get("dram_bytes_per_witness")
-            traffic = per_wit * (a.batch * a.steps / max(1, exp_launches)) if per_wit and a.layers == 16 else None
+            # ncu --set full captures of ONE-witness launches of both shipped expand kernels (profiles/), scaled to the
+            # witnesses per launch pair timed here
+            tj = json.load(open(os.path.join(ROOT, "profiles", "expand_traffic.json")))
+            per_wit = tj.get("dram_bytes_per_witness")
+            if per_wit and a.layers == 16:
+                traffic = per_wit * (a.batch * a.steps / max(1, exp_launches)); traffic_src = tj.get("source")
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": "witnesses/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u256 (BN254-Fr integer)", "data": "synthetic",
-                "config": {"workload": workload, "circuit": expr, "n_signals": desc["n_signals"], "witness_bytes": desc["witness_bytes"],
-                           "resident_slots": desc["n_slots"], "parallelism": "instances sharded by index, %d per GPU" % a.batch,
-                           "l2": "each step writes %.1f GB per GPU, far beyond the 126 MB L2; no flush needed" % (a.batch * desc["witness_bytes"] / 1e9),
-                           "wall_ms_per_step": wall_ms_max / a.steps,
-                           "witness_export_d2h_gbs": export_gbs,
-                           "eval_kernel": {"ms_per_launch": eval_ms / max(1, eval_launches), "instances_per_launch": min(desc["chunk"], a.batch),
-                                           "note": "runs concurrently with the expand kernels on a higher-priority stream"}},
+                "config": shared_config(a, expr, world),
+                "details": {"resident_slots": desc["n_slots"], "wall_ms_per_step": wall_ms_max / a.steps, "eval_chunk": desc["chunk"], "expand_group": desc["expand_group"],
+                            "eval_kernel": {"ms_per_launch": eval_ms / max(1, eval_launches), "instances_per_launch": min(desc["chunk"], a.batch),
+                                            "note": "runs concurrently with the expand kernels on a higher-priority stream"}},
+                "handoff": handoff, "latency": latency,
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "witnesses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "note": "host pinned inputs -> pob_run_batch -> status + output signals on host; witnesses stay in the HBM slot ring for the on-GPU consumer"},
+                        "note": "host pinned inputs -> pob_run_batch(POB_RUN_DISCARD) -> status + output signals on host; generation-only: see `handoff` for the runs in which every witness is consumed / exported"},
                 "gpu_launches": launches_total,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "kernel": "k_expand_round + k_expand_codes (one pair per 16 witnesses)", "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                             "kernel": "k_expand_round + k_expand_codes (one pair per %d witnesses)" % desc["expand_group"], "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "expand_share_of_step": exp_ms / dev_ms}}
-        if world == 1 and not a.no_cpu_baseline:
+        k = 0
+        if not a.no_cpu_baseline:
             procs = mem_limited_procs(a.cpu_procs or max(1, min(cores // 2, 32)), 34 * desc["n_signals"])
             v, dt, done = cpu_baseline_run(expr, pinned.array[: min(a.batch, procs)], procs)
             line["cpu_baseline"] = {"value": v, "unit": "witnesses/s", "cores": procs, "kind": "port",
                                     "sample": "%d single-threaded oracle processes x 1 witness of the same workload (%.1f s)" % (procs, dt)}
-            # the oracle runs above double as an in-run parity check: whole-witness digests of the same instances on the GPU
             k = min(a.batch, procs)
+        elif a.parity > 0:
+            k = min(a.batch, mem_limited_procs(a.parity, 34 * desc["n_signals"]))
+            cpu_baseline_run(expr, pinned.array[:k], k)
+        if k:
+            # the oracle runs above double as an in-run parity check: whole-witness digests of the same instances on the GPU
             rg = circuit.run_packed(pinned.array[:k], digest=True)
             match = [int(rg.digests[i]) == int(cpu_baseline_run.last_digests[i]) for i in range(k)]
             line["parity"] = {"instances": k, "digest_match": all(match), "what": "64-bit digest of all %d witness entries, GPU vs oracle" % desc["n_signals"]}

@@ -35,14 +35,20 @@ enum {
     POB_E_NO_MEMORY = -4,     /* not even one witness slot fits in free HBM */
     POB_E_RANGE = -5,         /* instance index not resident / offset out of range */
     POB_E_IO = -6,            /* file write failed */
-    POB_E_COMPILE = -7        /* the layout compiler rejected the circuit shape */
+    POB_E_COMPILE = -7,       /* the layout compiler rejected the circuit shape */
+    POB_E_REJECTED = -8,      /* the instance failed a circuit constraint: it has no witness (reference tests/test.py:65-68) */
+    POB_E_BUSY = -9,          /* every witness slot is held by the consumer: release one first / a batch is in flight */
+    POB_DONE = 1              /* pob_acquire: no further witness in this batch (not an error) */
 };
 
 /* flags for pob_run_batch */
 enum {
     POB_RUN_EXPAND = 1u,          /* materialise every instance's full witness vector in its HBM slot */
     POB_RUN_DIGEST = 2u,          /* also compute a 64-bit digest of each materialised witness (reads it back once) */
-    POB_RUN_INPUTS_STAGED = 4u    /* ignore `inputs`, use the device-resident batch set by pob_stage_inputs */
+    POB_RUN_INPUTS_STAGED = 4u,   /* ignore `inputs`, use the device-resident batch set by pob_stage_inputs */
+    POB_RUN_DISCARD = 8u          /* generation-only run: with n > n_slots earlier witnesses are overwritten UNREAD by later
+                                     ones (throughput measurement of the path itself).  Without this flag, a digest or a
+                                     retain list, pob_run_batch refuses n > n_slots: use pob_submit/pob_acquire/pob_release. */
 };
 
 typedef struct {
@@ -88,10 +94,51 @@ int pob_stage_inputs(pob_handle *h, const uint64_t *inputs, uint32_t n);
  * status : n x uint32 out; 0 = every constraint holds, else 1 + witness index of the first signal of the
  *          lowest-numbered component that owns a failing constraint.
  * outputs: n x n_outputs x 4 limbs out (may be NULL).
- * digests: n x uint64 out, only with POB_RUN_DIGEST (may be NULL otherwise).
- * Instance i's witness lives in slot i % n_slots until overwritten by a later instance or batch. */
+ * digests: n x uint64 out, only with POB_RUN_DIGEST (may be NULL otherwise); 0 for a rejected instance.
+ * A rejected instance (status != 0) contributes NO witness: its slot is not written and every accessor below
+ * answers POB_E_REJECTED for it (the reference calculator aborts without a usable witness, tests/test.py:65-68).
+ * With POB_RUN_EXPAND instance i lives in slot i % n_slots.  n > n_slots is only accepted together with
+ * POB_RUN_DIGEST (every witness is consumed by the digest kernel before its slot is reused) or POB_RUN_DISCARD;
+ * afterwards the last n_slots instances are resident. */
 int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t flags,
                   uint32_t *status, uint64_t *outputs, uint64_t *digests);
+/* the same, but only the instances retain[0..n_retain) (strictly ascending, n_retain <= n_slots) are materialised:
+ * all n instances are evaluated (status, outputs), the retained ones stay resident, the others cost no HBM traffic
+ * (SURVEY.md 8(b) "which indices to retain"). */
+int pob_run_batch_retain(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t flags,
+                         const uint32_t *retain, uint32_t n_retain,
+                         uint32_t *status, uint64_t *outputs, uint64_t *digests);
+
+/* ---- consumer-paced hand-off: no witness is ever overwritten unread ----------------------
+ * The reference's contract is one run -> one witness.wtns the prover reads (Makefile:5-6).  Here the consumer (an
+ * on-GPU prover stage, an exporter) takes the witnesses of a batch one by one, in instance order, and hands each
+ * slot back when it is done; generation stalls -- on the GPU, stream-ordered -- while all slots are held.
+ *   pob_submit   start a batch (POB_RUN_EXPAND implied); returns at once, work is queued as slots allow.
+ *   pob_acquire  next instance: POB_OK (*index, *dptr = its resident witness), POB_E_REJECTED (*index set, no witness,
+ *                nothing to release), POB_DONE (batch exhausted), POB_E_BUSY (release a slot first).
+ *                consumer_stream == NULL: returns when the witness is complete in HBM (host wait);
+ *                else (a cudaStream_t): returns at once and makes that stream wait for the witness on the GPU.
+ *   pob_release  the consumer is done with instance `index`; consumer_stream (or NULL = already finished on the
+ *                host) orders the reuse of the slot after the consumer's queued work.
+ *   pob_finish   drain the batch (instances never acquired are generated and dropped), return status/outputs/digests.
+ * One batch at a time per handle; the last n_slots non-released instances stay resident after pob_finish. */
+int pob_submit(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t flags);
+int pob_acquire(pob_handle *h, uint32_t *index, void **dptr, void *consumer_stream);
+int pob_release(pob_handle *h, uint32_t index, void *consumer_stream);
+int pob_finish(pob_handle *h, uint32_t *status, uint64_t *outputs, uint64_t *digests);
+
+/* replaces: n runs of `./<circuit> input_i.json witness_i.wtns` INCLUDING the files: every accepted instance is
+ * exported through the consumer-paced path above -- D2H over several copy streams into a pinned staging ring, a writer
+ * thread per batch doing the file I/O -- so generation, PCIe transfer and disk writes overlap and no witness is dropped.
+ * paths: n entries; NULL entry (or paths == NULL) = transfer to host memory only (PCIe line-rate measurement). */
+typedef struct {
+    uint64_t witnesses;        /* exported instances */
+    uint64_t bytes;            /* .wtns bytes moved to the host */
+    float total_ms;            /* wall time of the call */
+    float d2h_gbs;             /* bytes / total time */
+} pob_export_stats;
+int pob_export_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t flags, const char *const *paths,
+                     uint32_t *status, uint64_t *outputs, pob_export_stats *stats);
 
 /* device timings of the last pob_run_batch (CUDA events on the library's own streams), and kernel count */
 typedef struct {
@@ -117,8 +164,6 @@ int pob_witness_device_ptr(pob_handle *h, uint32_t index, void **dptr);
  * chi, iota with the round index the block has inside its Keccakf) and compares; it also checks that all 3200 entries
  * are 0 or 1.  *n_blocks = blocks examined, *n_bad = blocks that fail. */
 int pob_selfcheck_keccak(pob_handle *h, uint32_t index, uint64_t *n_blocks, uint64_t *n_bad);
-/* test hook for the self-check: overwrite ONE entry of a resident witness (fault injection) */
-int pob_debug_poke_witness(pob_handle *h, uint32_t index, uint64_t signal, const uint64_t value[4]);
 
 /* ---- the step just before the path ------------------------------------------------------
  * replaces: find_burn_key() of the reference input generator (tests/main.py:47-56): starting at start_key, find the

@@ -41,11 +41,34 @@ def lib():
     return _LIB
 
 
+def _int_expr(text, env=None):
+    """integer expressions of template parameters / schema dims (`10 ** 19`, `p1*136`): whitelisted AST walk"""
+    import ast, operator
+    ops = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, ast.FloorDiv: operator.floordiv, ast.Pow: operator.pow}
+
+    def ev(n):
+        if isinstance(n, ast.Expression):
+            return ev(n.body)
+        if isinstance(n, ast.Constant) and type(n.value) is int:
+            return n.value
+        if isinstance(n, ast.Name) and env and n.id in env:
+            return int(env[n.id])
+        if isinstance(n, ast.UnaryOp) and isinstance(n.op, ast.USub):
+            return -ev(n.operand)
+        if isinstance(n, ast.BinOp) and type(n.op) in ops:
+            a, b = ev(n.left), ev(n.right)
+            if isinstance(n.op, ast.Pow) and not 0 <= b <= 4096:
+                raise ValueError(text)
+            return ops[type(n.op)](a, b)
+        raise ValueError("unsupported expression %r" % text)
+    return int(ev(ast.parse(text.strip(), mode="eval")))
+
+
 def parse_main(expr):
     """'ProofOfBurn(4, 4, 5, 20, 31, 2, 10 ** 18, 10 ** 19)' -> ('ProofOfBurn', [4,4,5,20,31,2,10**18,10**19])"""
     m = re.match(r"\s*(\w+)\s*\((.*)\)\s*$", expr, re.S)
     name, args = m.group(1), m.group(2).strip()
-    params = [int(eval(a, {"__builtins__": {}})) for a in args.split(",")] if args else []
+    params = [_int_expr(a) for a in args.split(",")] if args else []
     return name, params
 
 
@@ -76,7 +99,7 @@ def schema(name, params):
     out = []
     for item in [x for x in s.decode().split(",") if x]:
         m = re.match(r"(\w+)((?:\[[^\]]+\])*)$", item)
-        dims = [int(eval(d, {"__builtins__": {}}, env)) for d in re.findall(r"\[([^\]]+)\]", m.group(2))]
+        dims = [_int_expr(d, env) for d in re.findall(r"\[([^\]]+)\]", m.group(2))]
         out.append((m.group(1), dims))
     return out
 

@@ -1258,8 +1258,12 @@ static uint32_t run_main(Builder &B, const std::string &name, const std::vector<
     if (IS("ProofOfBurn")) {
         if (p.size() < 8) throw std::runtime_error("pob: ProofOfBurn needs 8 parameters");
         PobParams P{PI(p, 0), PI(p, 1), PI(p, 2), PI(p, 3), PI(p, 4), PI(p, 5), p[6], p[7]};
-        if (P.maxNumLayers < 1 || P.maxNodeBlocks < 1 || P.maxHeaderBlocks < 1 || P.amountBytes > 31 || (size_t)P.maxHeaderBlocks * 136 < 123)
-            throw std::runtime_error("pob: unsupported ProofOfBurn shape");
+        // proof_of_burn.circom:195-204 hard-codes maxLeafLen = 139 = the output length of RlpMerklePatriciaTrieLeaf(32, 31)
+        // (108 + amountBytes) and compares 139 bytes of lastLayer: any other amountBytes, or layers shorter than 139
+        // bytes, do not compile in the reference either
+        if (P.maxNumLayers < 1 || P.maxNodeBlocks < 1 || P.maxHeaderBlocks < 1 || P.amountBytes != 31 || (size_t)P.maxNodeBlocks * 136 < 139 ||
+            (size_t)P.maxHeaderBlocks * 136 < 123)
+            throw std::runtime_error("pob: unsupported ProofOfBurn shape (needs amountBytes == 31, maxNodeBlocks*136 >= 139, maxHeaderBlocks*136 >= 123)");
         T_ProofOfBurn(B, P, in); return 1;
     }
     if (IS("EIP7503")) { T_EIP7503(B); return 8; }
@@ -1436,13 +1440,17 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
             }
             ok = found;
         }
-        if (!ok || (d & 0xffff) >= ROUND_WORDS_SPAN) throw std::runtime_error("pob: internal: round table group does not fit a descriptor");
+        // k_expand_round indexes its shared-memory word table with all three descriptor words
+        if (!ok || (d & 0xffff) >= ROUND_WORDS_SPAN || ((d >> 48) && (((d >> 16) & 0xffff) >= ROUND_WORDS_SPAN || ((d >> 32) & 0xffff) >= ROUND_WORDS_SPAN)))
+            throw std::runtime_error("pob: internal: round table group does not fit a descriptor");
         P.round_desc[g] = d;
     }
     P.codes.insert(P.codes.end(), B.flat, B.flat + B.flat_n);
     P.n_round_blocks = B.n_round_blocks; P.n_flat_signals = B.flat_n;
     uint32_t tile_signals = TILE_SIGNALS;
-    if (const char *v = getenv("POB_TILE_SIGNALS")) { uint32_t t = (uint32_t)atoi(v); if (t >= 64 && t <= MAX_TILE_SIGNALS && t % 64 == 0) tile_signals = t; }   // tuning only
+#ifdef POB_TUNING
+    if (const char *v = getenv("POB_TILE_SIGNALS")) { uint32_t t = (uint32_t)atoi(v); if (t >= 64 && t <= MAX_TILE_SIGNALS && t % 64 == 0) tile_signals = t; }
+#endif
     for (auto &s : B.segs) {
         uint64_t done = 0;
         while (done < s.n) {

@@ -1,0 +1,381 @@
+// kernels.cuh -- device code (sm_100a) of the batched witness generator; included by pob_b200.cu only.
+//
+//   k_eval    one CTA per proof instance: runs the levelised witness program over the instance store.
+//             Thread ops: BN254-Fr FMA / IsZero / inverse / div-mod / byte packing / constraint checks
+//             (vm_exec.h).  Warp ops: one Keccak absorb per warp, state lane l held by thread l, Theta
+//             column parities / D, RhoPi lane walk and Chi neighbours exchanged with warp shuffles; every
+//             intermediate lane word the bit-level circuit exposes (utils/keccak.circom:58-297) is written
+//             to the store (238 words per round).  One Poseidon permutation per warp (state element j in
+//             Montgomery form on lane j, Mix/MixS via shuffles).  Prefix sums by warp scan.  IsZero inverse
+//             hints batch-inverted at the end (table for small inputs, one binary-EEA inversion per thread).
+//   k_pow_grind  proof-of-work burn-key search (the step before the path): one candidate key per thread.
+//   k_expand_round / k_expand_codes  the HBM-bound kernels: materialise every witness entry as a 32-byte little-endian
+//             field element with one 256-bit store (STG.E.ENL2.256).  Algorithmic bytes = 32 * n_signals per instance
+//             (6.909 GB for main_proof_of_burn).  KeccakfRound blocks (95.8 %) are driven by 8-byte group descriptors
+//             and the round's lane words staged in shared memory; everything else by one 32-bit code per entry.
+//   k_digest  64-bit digest of a materialised witness (parity tests at full size; the built-in on-GPU consumer).
+#pragma once
+#include <cuda_runtime.h>
+#include "vm_exec.h"
+
+using namespace pob;
+
+namespace {
+
+__device__ __forceinline__ int inv_rot(int L) {      // i such that rot[i + 1] == L  (L = 1..24)
+    constexpr int INV[25] = {0, 23, 17, 5, 11, 6, 22, 1, 8, 21, 0, 2, 16, 15, 19, 12, 7, 3, 4, 14, 18, 9, 20, 13, 10};
+    return INV[L];
+}
+
+// One Absorb (utils/keccak.circom:304-323) by one warp; lane l < 25 owns state lane l.
+__device__ void absorb_warp(uint64_t *W, const AbsorbOp op) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool act = lane < 25;
+    const int l = act ? lane : 0;
+    uint64_t st = (act && op.s_idx != NONE_IDX) ? W[op.s_idx + l] : 0ull;
+    if (lane < 17) st ^= W[op.blk_idx + lane];
+    if (act) W[op.out_idx + l] = st;
+    const int col = l % 5;
+#pragma unroll 1
+    for (int r = 0; r < 24; r++) {
+        uint64_t *B = W + op.out_idx + RW * r;
+        // Theta: Xor5 chain of my column (all lanes of a column compute it redundantly; lanes 0..4 store it)
+        uint64_t v0 = __shfl_sync(FULL, st, col), v1 = __shfl_sync(FULL, st, col + 5), v2 = __shfl_sync(FULL, st, col + 10),
+                 v3 = __shfl_sync(FULL, st, col + 15), v4 = __shfl_sync(FULL, st, col + 20);
+        uint64_t x0 = v0 ^ v1, x1 = x0 ^ v2, x2 = x1 ^ v3, c = x2 ^ v4;
+        if (lane < 5) { B[rw_x5(lane, 0)] = x0; B[rw_x5(lane, 1)] = x1; B[rw_x5(lane, 2)] = x2; B[rw_x5(lane, 3)] = c; }
+        // D(i) = c[(i+4)%5] ^ rotl(c[(i+1)%5], 1)
+        uint64_t ca = __shfl_sync(FULL, c, (col + 1) % 5), cb = __shfl_sync(FULL, c, (col + 4) % 5);
+        uint64_t s0 = ca << 1, s1 = ca >> 63, so = s0 | s1, d = cb ^ so;
+        if (lane < 5) { B[rw_dd(lane, 0)] = s0; B[rw_dd(lane, 1)] = s1; B[rw_dd(lane, 2)] = so; B[rw_dd(lane, 3)] = d; }
+        uint64_t th = st ^ d;
+        if (act) B[rw_th(l)] = th;
+        // RhoPi: lane i < 24 performs step i on theta[rot[i]], the result belongs to lane rot[i+1]
+        const int i = lane < 24 ? lane : 0;
+        uint64_t a = __shfl_sync(FULL, th, keccak_rot(i));
+        const int shl = keccak_shl(i);
+        uint64_t a0 = a >> (64 - shl), a1 = a << shl, ro = a0 | a1;
+        if (lane < 24) { B[rw_rp(lane, 0)] = a0; B[rw_rp(lane, 1)] = a1; B[rw_rp(lane, 2)] = ro; }
+        uint64_t rp = __shfl_sync(FULL, ro, inv_rot(l));
+        if (lane == 0) rp = th;
+        // Chi
+        uint64_t vb = __shfl_sync(FULL, rp, chi_b(l)), vc = __shfl_sync(FULL, rp, chi_c(l));
+        uint64_t nb = ~vb, bc = nb & vc, ch = rp ^ bc;
+        if (act) { B[rw_ch(l, 0)] = nb; B[rw_ch(l, 1)] = bc; B[rw_ch(l, 2)] = ch; }
+        // Iota
+        const uint64_t rc = keccak_rc(r);
+        if (lane == 0) { B[RW_RC] = rc; ch ^= rc; }
+        if (act) B[rw_out(l)] = ch;
+        st = ch;
+    }
+}
+
+// ---- one Poseidon permutation by one warp (circomlib/circuits/poseidon.circom:67-196) ---------------------------
+// Lane j < t owns state element j in Montgomery form; Mix / MixS exchange elements with warp shuffles; every
+// intermediate signal is converted back to canonical form and written to its slot (layout: program.h PosLayout).
+__device__ __forceinline__ Fr shfl_fr(const Fr &v, int src) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src);
+    return r;
+}
+__device__ void poseidon_warp(const VmCtx &x, const PoseidonOp op, const Fr *pk) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t t = op.t; const PosLayout L = pos_layout(t);
+    const bool act = (uint32_t)lane < t; const uint32_t j = act ? (uint32_t)lane : 0u;
+    const Fr *K = pk + op.koff;
+    uint64_t *V = x.U + x.val_base + 4ull * op.base;
+    // values are parked in their slots in MONTGOMERY form (nothing but this warp reads them before the sweep below):
+    // no conversion sits on the dependency chain of the 65 rounds
+    auto put = [&](uint32_t off, const Fr &m) { if (act) vm_store_val(V + 4ull * off, m); };
+    Fr s = fr_add(fr_to_mont(vm_load(x, x.aux[op.in_aux + j])), K[L.kC + j]);     // ark[0]
+    put(j, s);
+    auto full = [&](uint32_t F, uint32_t coff, uint32_t moff) {
+        Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);
+        put(F + 3 * j, x2); put(F + 3 * j + 1, x4); put(F + 3 * j + 2, x5);
+        Fr y = fr_add(x5, K[L.kC + coff + j]); put(F + 3 * t + j, y);
+        Fr acc = fr_zero();
+        for (uint32_t k = 0; k < t; k++) { Fr yk = shfl_fr(y, (int)k); acc = fr_add(acc, fr_mont(K[moff + k * t + j], yk)); }
+        put(F + 4 * t + j, acc); s = acc;
+    };
+    for (uint32_t f = 0; f < 4; f++) full(L.F1 + 5 * t * f, (f + 1) * t, f == 3 ? L.kP : L.kM);
+#pragma unroll 1
+    for (uint32_t r = 0; r < L.rp; r++) {
+        const uint32_t B = L.PB + r * (4 + t), so = (2 * t - 1) * r;
+        Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);                // meaningful on lane 0 only
+        Fr z0 = fr_add(x5, K[L.kC + 5 * t + r]);
+        if (lane == 0) { vm_store_val(V + 4ull * B, x2); vm_store_val(V + 4ull * (B + 1), x4); vm_store_val(V + 4ull * (B + 2), x5); vm_store_val(V + 4ull * (B + 3), z0); }
+        z0 = shfl_fr(z0, 0);
+        const Fr in = (lane == 0) ? z0 : s;
+        Fr prod = fr_mont(K[L.kS + so + j], in);                                          // S[so + i] * in[i]
+        Fr o0 = fr_zero();
+        for (uint32_t k = 0; k < t; k++) o0 = fr_add(o0, shfl_fr(prod, (int)k));
+        Fr oj = fr_add(s, fr_mont(z0, K[L.kS + so + t + (j ? j : 1) - 1]));                // lanes 1..t-1
+        s = (lane == 0) ? o0 : oj;
+        put(B + 4 + j, s);
+    }
+    for (uint32_t f = 0; f < 3; f++) full(L.SB + 5 * t * f, 5 * t + L.rp + f * t, L.kM);
+    {
+        Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);
+        put(L.LB + 3 * j, x2); put(L.LB + 3 * j + 1, x4); put(L.LB + 3 * j + 2, x5);
+        Fr prod = fr_mont(K[L.kM + j * t], x5), out = fr_zero();
+        for (uint32_t k = 0; k < t; k++) out = fr_add(out, shfl_fr(prod, (int)k));
+        if (lane == 0) vm_store_val(V + 4ull * (L.LB + 3 * t), out);
+    }
+    __syncwarp();
+    for (uint32_t i = (uint32_t)lane; i < L.total; i += 32) {         // all 32 lanes: Montgomery -> canonical, in place
+        uint64_t *p = V + 4ull * i;
+        vm_store_val(p, fr_from_mont(vm_load_val(p)));
+    }
+}
+
+// ---- prefix sum with every partial sum a signal (substring_check.circom:47-49, :95) by one warp -----------------
+__device__ void psum_warp(const VmCtx &x, const PsumOp op) {
+    const uint32_t lane = threadIdx.x & 31, per = (op.n + 31) / 32;
+    const uint32_t lo = min(op.n, lane * per), hi = min(op.n, lo + per);
+    Fr acc = fr_zero();
+    for (uint32_t k = lo; k < hi; k++) acc = fr_add(acc, vm_load(x, x.aux[op.aux0 + k]));
+    Fr incl = acc;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        Fr o;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.l[i] = __shfl_up_sync(0xffffffffu, incl.l[i], off);
+        if ((int)lane >= off) incl = fr_add(incl, o);
+    }
+    Fr run = fr_add(vm_load(x, op.x0), fr_sub(incl, acc));            // x0 + sum of all earlier lanes
+    uint64_t *V = x.U + x.val_base + 4ull * op.dst;
+    for (uint32_t k = lo; k < hi; k++) { run = fr_add(run, vm_load(x, x.aux[op.aux0 + k])); vm_store_val(V + 4ull * k, run); }
+}
+
+struct EvalArgs {
+    const Op *ops; const AbsorbOp *absorbs; const PoseidonOp *poseidons; const Fr *pos_konst; const PsumOp *psums;
+    const Level *levels; uint32_t n_levels, inv_begin, ginv_begin, inv_end;
+    const Code *aux; const Fr *konst; const Fr *invtab;
+    const Code *out_codes; uint32_t n_outputs, n_inputs, val_base;
+    uint64_t *stores; uint64_t store_stride;     // u64 units
+    const uint64_t *inputs;                       // chunk base: instance j at inputs + j * n_inputs * 4
+    uint32_t *status; uint64_t *outputs;          // chunk base
+    long long *prof;                              // tuning only: per-level clock64 stamps of instance 0 (or null)
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
+    const uint32_t inst = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    uint64_t *U = a.stores + (uint64_t)inst * a.store_stride;
+    __shared__ uint32_t s_status;
+    if (tid == 0) s_status = STATUS_OK;
+    const uint64_t *in = a.inputs + (uint64_t)inst * a.n_inputs * 4;
+    // inputs -> first value slots, reduced mod p like the circom loader does (a caller may hand over limbs >= p)
+    for (uint32_t i = tid; i < a.n_inputs; i += nthr) {
+        Fr v = vm_load_val(in + 4ull * i);
+        while (fr_geq_p(v)) { Fr t; fr_raw_sub(t, v, fr_p()); v = t; }
+        vm_store_val(U + a.val_base + 4ull * i, v);
+    }
+    __syncthreads();
+    VmCtx x{U, a.val_base, a.konst, a.aux, a.invtab, &s_status};
+    const uint32_t warp = tid >> 5, nwarp = nthr >> 5;
+    for (uint32_t lv = 0; lv < a.n_levels; lv++) {
+        if (a.prof && inst == 0 && tid == 0) a.prof[lv] = clock64();
+        const Level L = a.levels[lv];
+        for (uint32_t i = L.t_begin + tid; i < L.t_end; i += nthr) vm_exec_op(x, a.ops[i]);
+        // warp ops: Poseidons take the first warps (long), Keccak absorbs the next ones
+        for (uint32_t q = L.p_begin + warp; q < L.p_end; q += nwarp) poseidon_warp(x, a.poseidons[q], a.pos_konst);
+        { const uint32_t np = (L.p_end - L.p_begin) % nwarp, wv = (warp + nwarp - np) % nwarp;
+          for (uint32_t w = L.w_begin + wv; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]);
+          const uint32_t nw2 = (np + (L.w_end - L.w_begin)) % nwarp, sv = (warp + nwarp - nw2) % nwarp;
+          for (uint32_t q = L.s_begin + sv; q < L.s_end; q += nwarp) psum_warp(x, a.psums[q]); }
+        __syncthreads();
+    }
+    if (a.prof && inst == 0 && tid == 0) a.prof[a.n_levels] = clock64();
+    // IsZero inverse hints: no consumers, done last.  Table-sized inputs are spread over all threads; the ones expected
+    // to need a real inversion go to 256 threads so that only 8 warps pay for a Fermat ladder (one per thread).
+    vm_inv_batch(x, a.ops, a.inv_begin, a.ginv_begin, tid, nthr);
+    if (tid < 256) vm_inv_batch(x, a.ops, a.ginv_begin, a.inv_end, tid, 256);
+    if (a.prof && inst == 0) { __syncthreads(); if (tid == 0) a.prof[a.n_levels + 1] = clock64(); }
+    if (tid == 0) a.status[inst] = (s_status == STATUS_OK) ? 0u : s_status;
+    for (uint32_t i = tid; i < a.n_outputs; i += nthr) {
+        uint64_t v[4]; vm_expand(a.out_codes[i], U, 0, a.val_base, a.konst, v);
+        uint64_t *o = a.outputs + ((uint64_t)inst * a.n_outputs + i) * 4;
+        o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3];
+    }
+}
+
+// 256-bit store (STG.E.ENL2.256).  No "memory" clobber on purpose: the compiler must be free to hoist the next
+// entries' loads above it so that several loads are in flight per thread (the witness is written, never read, here).
+__device__ __forceinline__ void st256(uint64_t *p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d));
+}
+
+struct ExpandArgs {
+    const Tile *tiles; const Code *codes; const Fr *konst; const uint2 *round_desc;
+    const uint64_t *stores; uint64_t store_stride; uint32_t val_base;   // store of chunk-local instance 0
+    uint64_t *const *wit;                         // per materialised instance of the group: witness slot base
+    const uint32_t *inst;                         // per materialised instance of the group: instance index within the batch
+    const uint32_t *status;                       // per instance of the batch; a rejected instance contributes no witness
+    uint32_t chunk_first;                         // batch index of the chunk's first instance (store = inst - chunk_first)
+    uint32_t tile0;                               // first tile of this launch (k_expand_codes)
+};
+
+// k_expand_round: grid = (KeccakfRound tiles, instances in the group) -- 95.8 % of the witness.  One CTA streams one
+// tile (<= 8192 entries = 256 KiB) with one 256-bit store per entry.  The source of every entry follows from an 8-byte
+// descriptor per 64 entries and a lane word of the round; the tile's <= 128 descriptors and the round's 263 words are
+// staged in shared memory in one burst, so the streaming loop touches no global memory but the witness itself.
+template <int T>
+__global__ void __launch_bounds__(T) k_expand_round(const ExpandArgs a) {
+    const uint32_t gi = a.inst[blockIdx.y];
+    if (a.status[gi] != 0) return;                // reference: a failed assert leaves no witness (tests/test.py:65-68)
+    const Tile t = a.tiles[blockIdx.x];
+    const uint64_t *Ub = a.stores + (uint64_t)(gi - a.chunk_first) * a.store_stride + t.ubase;
+    uint64_t *W = a.wit[blockIdx.y] + t.dst * 4;
+    __shared__ uint2 sD[MAX_TILE_SIGNALS / 64]; __shared__ uint64_t sW[ROUND_WORDS_SPAN + 1];
+    const uint2 *D = a.round_desc + (t.code_off >> 6);
+    for (uint32_t i = threadIdx.x; i < ((t.n + 63) >> 6); i += T) sD[i] = __ldg(D + i);
+    for (uint32_t i = threadIdx.x; i < ROUND_WORDS_SPAN; i += T) sW[i] = Ub[i];
+    __syncthreads();
+#pragma unroll 8
+    for (uint32_t k = threadIdx.x; k < t.n; k += T) {
+        const uint2 d = sD[k >> 6];
+        const uint32_t tt = k & 63, mode = d.y >> 16;
+        uint32_t w = d.x & 0xffffu, b = tt;
+        if (mode) {                          // phase (mode-1) of a gate block [out_i, a_i, b_i]_i
+            const uint32_t sidx = (mode - 1) * 64 + tt, g = sidx / 3, m = sidx - 3 * g;
+            b = g; w = (m == 0) ? (d.x & 0xffffu) : (m == 1) ? (d.x >> 16) : (d.y & 0xffffu);
+        }
+        st256(W + 4ull * k, (sW[w] >> b) & 1ull, 0, 0, 0);
+    }
+}
+
+// k_expand_codes: grid = (instances in the group, code tiles) -- INSTANCE-major, so that a tile's code stream is fetched
+// from DRAM once and served from L2 to the other witnesses of the group.  One 32-bit code per entry, loads issued 4
+// entries ahead of the stores.
+__global__ void __launch_bounds__(256, 5) k_expand_codes(const ExpandArgs a) {
+    const uint32_t gi = a.inst[blockIdx.x];
+    if (a.status[gi] != 0) return;
+    const Tile t = a.tiles[a.tile0 + blockIdx.y];
+    const uint64_t *U = a.stores + (uint64_t)(gi - a.chunk_first) * a.store_stride;
+    uint64_t *W = a.wit[blockIdx.x] + t.dst * 4;
+    const uint64_t *Ub = U + t.ubase;
+    const Code *c = a.codes + t.code_off;
+    constexpr int UG = 4;
+    for (uint32_t base = threadIdx.x; base < t.n; base += 256 * UG) {
+        Code cd[UG];
+#pragma unroll
+        for (int u = 0; u < UG; u++) { const uint32_t k = base + 256 * u; cd[u] = k < t.n ? __ldg(c + k) : 0u; }
+        uint64_t v[UG][4];
+#pragma unroll
+        for (int u = 0; u < UG; u++) {
+            const uint32_t kind = code_kind(cd[u]), p = code_payload(cd[u]);
+            v[u][1] = v[u][2] = v[u][3] = 0;
+            if (kind == K_BIT) v[u][0] = (Ub[p >> 6] >> (p & 63)) & 1ull;
+            else if (kind == K_CONST) v[u][0] = p;
+            else {
+                const uint64_t *s = (kind == K_VAL) ? U + a.val_base + 4ull * p : reinterpret_cast<const uint64_t *>(a.konst + p);
+                v[u][0] = s[0]; v[u][1] = s[1]; v[u][2] = s[2]; v[u][3] = s[3];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UG; u++) { const uint32_t k = base + 256 * u; if (k < t.n) st256(W + 4ull * k, v[u][0], v[u][1], v[u][2], v[u][3]); }
+    }
+}
+
+// digest = sum_i mix(i, limbs) mod 2^64 -- must equal oracle/pob_oracle.c:pob_oracle_digest
+__global__ void __launch_bounds__(256) k_digest(const uint64_t *wit, uint64_t n_signals, unsigned long long *out, const uint32_t *status) {
+    if (status && *status != 0) return;           // rejected instance: no witness, digest stays 0
+    uint64_t acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_signals; i += (uint64_t)gridDim.x * blockDim.x) {
+        const ulonglong4 v = *reinterpret_cast<const ulonglong4 *>(wit + 4 * i);
+        uint64_t h = (i + 1) * 0x9E3779B97F4A7C15ULL;
+        h ^= v.x * 0xBF58476D1CE4E5B9ULL + v.y * 0x94D049BB133111EBULL + v.z * 0xD6E8FEB86659FD93ULL + v.w * 0xA0761D6478BD642FULL;
+        h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 32;
+        acc += h;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    __shared__ uint64_t part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint64_t s = 0; for (int w = 0; w < 8; w++) s += part[w]; atomicAdd(out, (unsigned long long)s); }
+}
+
+// ---- proof-of-work burn-key grinder (reference tests/main.py:47-56; circuits/utils/proof_of_work.circom:54-81) ----
+// One candidate key per thread: a single-block keccak256 of key|reveal|extra|"EIP-7503" held in 25 registers.
+struct GrindArgs { uint64_t start[4], lanes_tail[9]; uint64_t first, count; uint32_t zero_bytes; unsigned long long *hit; };
+__device__ __forceinline__ uint64_t bswap64(uint64_t x) { return __byte_perm((uint32_t)(x >> 32), 0, 0x0123) | ((uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32); }
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+__global__ void __launch_bounds__(256) k_pow_grind(const GrindArgs a) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.count) return;
+    // key = start + first + idx (256-bit add)
+    uint64_t k0 = a.start[0], k1 = a.start[1], k2 = a.start[2], k3 = a.start[3];
+    const uint64_t add = a.first + idx;
+    k0 += add; if (k0 < add) { if (++k1 == 0) { if (++k2 == 0) ++k3; } }
+    uint64_t s[25];
+    s[0] = bswap64(k3); s[1] = bswap64(k2); s[2] = bswap64(k1); s[3] = bswap64(k0);      // 32-byte big-endian key
+#pragma unroll
+    for (int i = 0; i < 9; i++) s[4 + i] = a.lanes_tail[i];                                // reveal | extra | "EIP-7503"
+    s[13] = 0x01; s[14] = 0; s[15] = 0; s[16] = 0x8000000000000000ull;                     // 0x01 ... 0x80 padding of a 104-byte message
+#pragma unroll
+    for (int i = 17; i < 25; i++) s[i] = 0;
+#pragma unroll 1
+    for (int r = 0; r < 24; r++) {
+        uint64_t c[5], d[5], b[25];
+#pragma unroll
+        for (int x = 0; x < 5; x++) c[x] = s[x] ^ s[x + 5] ^ s[x + 10] ^ s[x + 15] ^ s[x + 20];
+#pragma unroll
+        for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
+#pragma unroll
+        for (int i = 0; i < 25; i++) s[i] ^= d[i % 5];
+        b[0] = s[0];
+#pragma unroll
+        for (int i = 0; i < 24; i++) b[keccak_rot(i + 1)] = rotl64(s[keccak_rot(i)], keccak_shl(i));
+#pragma unroll
+        for (int i = 0; i < 25; i++) s[i] = b[i] ^ (~b[chi_b(i)] & b[chi_c(i)]);
+        s[0] ^= keccak_rc(r);
+    }
+    const uint64_t mask = a.zero_bytes >= 8 ? ~0ull : ((1ull << (8 * a.zero_bytes)) - 1);
+    if ((s[0] & mask) == 0) atomicMin(a.hit, (unsigned long long)idx);
+}
+
+// ---- self-check: every KeccakfRound block of a materialised witness satisfies out == KeccakRound_r(in) -------------
+// One warp per block.  Lane l < 25 assembles lane word l of `in` (witness entries base+1600+64l .. +63) and of `out`
+// (base+64l ..) from the 32-byte entries, lane 0 gathers the 25 input words and runs one textbook round.
+__global__ void __launch_bounds__(256) k_check_rounds(const uint64_t *wit, const uint64_t *block_base, uint32_t n_blocks, unsigned long long *n_bad) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_blocks) return;
+    const uint64_t base = block_base[warp];
+    const int r = (int)(warp % 24);                       // round blocks are emitted 24 per Keccakf, in order
+    uint64_t win = 0, wout = 0; bool bad = false;
+    if (lane < 25) {
+        for (uint32_t k = 0; k < 64; k++) {
+            const ulonglong4 a = *reinterpret_cast<const ulonglong4 *>(wit + 4 * (base + 1600 + 64 * lane + k));
+            const ulonglong4 b = *reinterpret_cast<const ulonglong4 *>(wit + 4 * (base + 64 * lane + k));
+            bad |= (a.x > 1) | (b.x > 1) | ((a.y | a.z | a.w | b.y | b.z | b.w) != 0);
+            win |= (a.x & 1ull) << k; wout |= (b.x & 1ull) << k;
+        }
+    }
+    uint64_t s[25], o[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) { s[i] = __shfl_sync(0xffffffffu, win, i); o[i] = __shfl_sync(0xffffffffu, wout, i); }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        uint64_t c[5], d[5], b[25];
+#pragma unroll
+        for (int x = 0; x < 5; x++) c[x] = s[x] ^ s[x + 5] ^ s[x + 10] ^ s[x + 15] ^ s[x + 20];
+#pragma unroll
+        for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
+#pragma unroll
+        for (int i = 0; i < 25; i++) s[i] ^= d[i % 5];
+        b[0] = s[0];
+#pragma unroll
+        for (int i = 0; i < 24; i++) b[keccak_rot(i + 1)] = rotl64(s[keccak_rot(i)], keccak_shl(i));
+#pragma unroll
+        for (int i = 0; i < 25; i++) s[i] = b[i] ^ (~b[chi_b(i)] & b[chi_c(i)]);
+        s[0] ^= keccak_rc(r);
+#pragma unroll
+        for (int i = 0; i < 25; i++) bad |= (s[i] != o[i]);
+        if (bad) atomicAdd(n_bad, 1ull);
+    }
+}
+
+}  // namespace

@@ -1,398 +1,134 @@
-// pob_b200.cu -- CUDA kernels (sm_100a) and the C-ABI of the batched witness generator (include/pob_b200.h).
+// pob_b200.cu -- host side of the C-ABI (include/pob_b200.h) of the batched witness generator; the CUDA kernels
+// (sm_100a) live in kernels.cuh.  There is no host execution path for any witness value: without a device pob_create fails.
 //
-// Kernels
-//   k_eval    one CTA per proof instance: runs the levelised witness program over the instance store.
-//             Thread ops: BN254-Fr FMA / IsZero / inverse / div-mod / byte packing / constraint checks
-//             (vm_exec.h).  Warp ops: one Keccak absorb per warp, state lane l held by thread l, Theta
-//             column parities / D, RhoPi lane walk and Chi neighbours exchanged with warp shuffles; every
-//             intermediate lane word the bit-level circuit exposes (utils/keccak.circom:58-297) is written
-//             to the store (238 words per round).  One Poseidon permutation per warp (state element j in
-//             Montgomery form on lane j, Mix/MixS via shuffles).  Prefix sums by warp scan.  IsZero inverse
-//             hints batch-inverted at the end (table for small inputs, one binary-EEA inversion per thread).
-//   k_pow_grind  proof-of-work burn-key search (the step before the path): one candidate key per thread.
-//   k_expand_round / k_expand_codes  the HBM-bound kernels: materialise every witness entry as a 32-byte little-endian
-//             field element with one 256-bit store (STG.E.ENL2.256).  Algorithmic bytes = 32 * n_signals per instance
-//             (6.909 GB for main_proof_of_burn).  KeccakfRound blocks (95.8 %) are driven by 8-byte group descriptors
-//             and the round's lane words staged in shared memory; everything else by one 32-bit code per entry.
-//   k_digest  optional 64-bit digest of a materialised witness (parity tests at full size).
-// There is no host execution path for any of this: without a device pob_create fails.
+// Scheduling model.  A batch is cut into eval CHUNKS (instances per k_eval launch; the compact stores of two chunks are
+// resident) and expand GROUPS (witnesses materialised per k_expand_round / k_expand_codes launch pair, each into its own
+// HBM slot).  A small pump (advance()) queues work as far as resources allow: eval(c) once the store ring half it
+// overwrites has been expanded, group g once every slot it writes is free.  Three streams: inputs H2D one chunk ahead,
+// k_eval on the highest-priority stream (its 32-CTA grid must get SMs while the expand grid of hundreds of thousands of
+// CTAs drains), expand on the lowest.  Slots are freed by the consumer (pob_release; stream-ordered, so the stall happens
+// on the GPU), by the built-in digest consumer, or -- only when the caller says POB_RUN_DISCARD -- at once.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/pob_b200.h"
 #include "compiler.h"
-#include "vm_exec.h"
+#include "kernels.cuh"
 
 using namespace pob;
 
-// =============================================================================================================
-// device code
-// =============================================================================================================
-namespace {
-
-__device__ __forceinline__ int inv_rot(int L) {      // i such that rot[i + 1] == L  (L = 1..24)
-    constexpr int INV[25] = {0, 23, 17, 5, 11, 6, 22, 1, 8, 21, 0, 2, 16, 15, 19, 12, 7, 3, 4, 14, 18, 9, 20, 13, 10};
-    return INV[L];
-}
-
-// One Absorb (utils/keccak.circom:304-323) by one warp; lane l < 25 owns state lane l.
-__device__ void absorb_warp(uint64_t *W, const AbsorbOp op) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const bool act = lane < 25;
-    const int l = act ? lane : 0;
-    uint64_t st = (act && op.s_idx != NONE_IDX) ? W[op.s_idx + l] : 0ull;
-    if (lane < 17) st ^= W[op.blk_idx + lane];
-    if (act) W[op.out_idx + l] = st;
-    const int col = l % 5;
-#pragma unroll 1
-    for (int r = 0; r < 24; r++) {
-        uint64_t *B = W + op.out_idx + RW * r;
-        // Theta: Xor5 chain of my column (all lanes of a column compute it redundantly; lanes 0..4 store it)
-        uint64_t v0 = __shfl_sync(FULL, st, col), v1 = __shfl_sync(FULL, st, col + 5), v2 = __shfl_sync(FULL, st, col + 10),
-                 v3 = __shfl_sync(FULL, st, col + 15), v4 = __shfl_sync(FULL, st, col + 20);
-        uint64_t x0 = v0 ^ v1, x1 = x0 ^ v2, x2 = x1 ^ v3, c = x2 ^ v4;
-        if (lane < 5) { B[rw_x5(lane, 0)] = x0; B[rw_x5(lane, 1)] = x1; B[rw_x5(lane, 2)] = x2; B[rw_x5(lane, 3)] = c; }
-        // D(i) = c[(i+4)%5] ^ rotl(c[(i+1)%5], 1)
-        uint64_t ca = __shfl_sync(FULL, c, (col + 1) % 5), cb = __shfl_sync(FULL, c, (col + 4) % 5);
-        uint64_t s0 = ca << 1, s1 = ca >> 63, so = s0 | s1, d = cb ^ so;
-        if (lane < 5) { B[rw_dd(lane, 0)] = s0; B[rw_dd(lane, 1)] = s1; B[rw_dd(lane, 2)] = so; B[rw_dd(lane, 3)] = d; }
-        uint64_t th = st ^ d;
-        if (act) B[rw_th(l)] = th;
-        // RhoPi: lane i < 24 performs step i on theta[rot[i]], the result belongs to lane rot[i+1]
-        const int i = lane < 24 ? lane : 0;
-        uint64_t a = __shfl_sync(FULL, th, keccak_rot(i));
-        const int shl = keccak_shl(i);
-        uint64_t a0 = a >> (64 - shl), a1 = a << shl, ro = a0 | a1;
-        if (lane < 24) { B[rw_rp(lane, 0)] = a0; B[rw_rp(lane, 1)] = a1; B[rw_rp(lane, 2)] = ro; }
-        uint64_t rp = __shfl_sync(FULL, ro, inv_rot(l));
-        if (lane == 0) rp = th;
-        // Chi
-        uint64_t vb = __shfl_sync(FULL, rp, chi_b(l)), vc = __shfl_sync(FULL, rp, chi_c(l));
-        uint64_t nb = ~vb, bc = nb & vc, ch = rp ^ bc;
-        if (act) { B[rw_ch(l, 0)] = nb; B[rw_ch(l, 1)] = bc; B[rw_ch(l, 2)] = ch; }
-        // Iota
-        const uint64_t rc = keccak_rc(r);
-        if (lane == 0) { B[RW_RC] = rc; ch ^= rc; }
-        if (act) B[rw_out(l)] = ch;
-        st = ch;
-    }
-}
-
-// ---- one Poseidon permutation by one warp (circomlib/circuits/poseidon.circom:67-196) ---------------------------
-// Lane j < t owns state element j in Montgomery form; Mix / MixS exchange elements with warp shuffles; every
-// intermediate signal is converted back to canonical form and written to its slot (layout: program.h PosLayout).
-__device__ __forceinline__ Fr shfl_fr(const Fr &v, int src) {
-    Fr r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src);
-    return r;
-}
-__device__ void poseidon_warp(const VmCtx &x, const PoseidonOp op, const Fr *pk) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t t = op.t; const PosLayout L = pos_layout(t);
-    const bool act = (uint32_t)lane < t; const uint32_t j = act ? (uint32_t)lane : 0u;
-    const Fr *K = pk + op.koff;
-    uint64_t *V = x.U + x.val_base + 4ull * op.base;
-    // values are parked in their slots in MONTGOMERY form (nothing but this warp reads them before the sweep below):
-    // no conversion sits on the dependency chain of the 65 rounds
-    auto put = [&](uint32_t off, const Fr &m) { if (act) vm_store_val(V + 4ull * off, m); };
-    Fr s = fr_add(fr_to_mont(vm_load(x, x.aux[op.in_aux + j])), K[L.kC + j]);     // ark[0]
-    put(j, s);
-    auto full = [&](uint32_t F, uint32_t coff, uint32_t moff) {
-        Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);
-        put(F + 3 * j, x2); put(F + 3 * j + 1, x4); put(F + 3 * j + 2, x5);
-        Fr y = fr_add(x5, K[L.kC + coff + j]); put(F + 3 * t + j, y);
-        Fr acc = fr_zero();
-        for (uint32_t k = 0; k < t; k++) { Fr yk = shfl_fr(y, (int)k); acc = fr_add(acc, fr_mont(K[moff + k * t + j], yk)); }
-        put(F + 4 * t + j, acc); s = acc;
-    };
-    for (uint32_t f = 0; f < 4; f++) full(L.F1 + 5 * t * f, (f + 1) * t, f == 3 ? L.kP : L.kM);
-#pragma unroll 1
-    for (uint32_t r = 0; r < L.rp; r++) {
-        const uint32_t B = L.PB + r * (4 + t), so = (2 * t - 1) * r;
-        Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);                // meaningful on lane 0 only
-        Fr z0 = fr_add(x5, K[L.kC + 5 * t + r]);
-        if (lane == 0) { vm_store_val(V + 4ull * B, x2); vm_store_val(V + 4ull * (B + 1), x4); vm_store_val(V + 4ull * (B + 2), x5); vm_store_val(V + 4ull * (B + 3), z0); }
-        z0 = shfl_fr(z0, 0);
-        const Fr in = (lane == 0) ? z0 : s;
-        Fr prod = fr_mont(K[L.kS + so + j], in);                                          // S[so + i] * in[i]
-        Fr o0 = fr_zero();
-        for (uint32_t k = 0; k < t; k++) o0 = fr_add(o0, shfl_fr(prod, (int)k));
-        Fr oj = fr_add(s, fr_mont(z0, K[L.kS + so + t + (j ? j : 1) - 1]));                // lanes 1..t-1
-        s = (lane == 0) ? o0 : oj;
-        put(B + 4 + j, s);
-    }
-    for (uint32_t f = 0; f < 3; f++) full(L.SB + 5 * t * f, 5 * t + L.rp + f * t, L.kM);
-    {
-        Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);
-        put(L.LB + 3 * j, x2); put(L.LB + 3 * j + 1, x4); put(L.LB + 3 * j + 2, x5);
-        Fr prod = fr_mont(K[L.kM + j * t], x5), out = fr_zero();
-        for (uint32_t k = 0; k < t; k++) out = fr_add(out, shfl_fr(prod, (int)k));
-        if (lane == 0) vm_store_val(V + 4ull * (L.LB + 3 * t), out);
-    }
-    __syncwarp();
-    for (uint32_t i = (uint32_t)lane; i < L.total; i += 32) {         // all 32 lanes: Montgomery -> canonical, in place
-        uint64_t *p = V + 4ull * i;
-        vm_store_val(p, fr_from_mont(vm_load_val(p)));
-    }
-}
-
-// ---- prefix sum with every partial sum a signal (substring_check.circom:47-49, :95) by one warp -----------------
-__device__ void psum_warp(const VmCtx &x, const PsumOp op) {
-    const uint32_t lane = threadIdx.x & 31, per = (op.n + 31) / 32;
-    const uint32_t lo = min(op.n, lane * per), hi = min(op.n, lo + per);
-    Fr acc = fr_zero();
-    for (uint32_t k = lo; k < hi; k++) acc = fr_add(acc, vm_load(x, x.aux[op.aux0 + k]));
-    Fr incl = acc;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        Fr o;
-#pragma unroll
-        for (int i = 0; i < 8; i++) o.l[i] = __shfl_up_sync(0xffffffffu, incl.l[i], off);
-        if ((int)lane >= off) incl = fr_add(incl, o);
-    }
-    Fr run = fr_add(vm_load(x, op.x0), fr_sub(incl, acc));            // x0 + sum of all earlier lanes
-    uint64_t *V = x.U + x.val_base + 4ull * op.dst;
-    for (uint32_t k = lo; k < hi; k++) { run = fr_add(run, vm_load(x, x.aux[op.aux0 + k])); vm_store_val(V + 4ull * k, run); }
-}
-
-struct EvalArgs {
-    const Op *ops; const AbsorbOp *absorbs; const PoseidonOp *poseidons; const Fr *pos_konst; const PsumOp *psums;
-    const Level *levels; uint32_t n_levels, inv_begin, ginv_begin, inv_end;
-    const Code *aux; const Fr *konst; const Fr *invtab;
-    const Code *out_codes; uint32_t n_outputs, n_inputs, val_base;
-    uint64_t *stores; uint64_t store_stride;     // u64 units
-    const uint64_t *inputs;                       // chunk base: instance j at inputs + j * n_inputs * 4
-    uint32_t *status; uint64_t *outputs;          // chunk base
-    long long *prof;                              // tuning only: per-level clock64 stamps of instance 0 (or null)
-};
-
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
-    const uint32_t inst = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
-    uint64_t *U = a.stores + (uint64_t)inst * a.store_stride;
-    __shared__ uint32_t s_status;
-    if (tid == 0) s_status = STATUS_OK;
-    const uint64_t *in = a.inputs + (uint64_t)inst * a.n_inputs * 4;
-    // inputs -> first value slots, reduced mod p like the circom loader does (a caller may hand over limbs >= p)
-    for (uint32_t i = tid; i < a.n_inputs; i += nthr) {
-        Fr v = vm_load_val(in + 4ull * i);
-        while (fr_geq_p(v)) { Fr t; fr_raw_sub(t, v, fr_p()); v = t; }
-        vm_store_val(U + a.val_base + 4ull * i, v);
-    }
-    __syncthreads();
-    VmCtx x{U, a.val_base, a.konst, a.aux, a.invtab, &s_status};
-    const uint32_t warp = tid >> 5, nwarp = nthr >> 5;
-    for (uint32_t lv = 0; lv < a.n_levels; lv++) {
-        if (a.prof && inst == 0 && tid == 0) a.prof[lv] = clock64();
-        const Level L = a.levels[lv];
-        for (uint32_t i = L.t_begin + tid; i < L.t_end; i += nthr) vm_exec_op(x, a.ops[i]);
-        // warp ops: Poseidons take the first warps (long), Keccak absorbs the next ones
-        for (uint32_t q = L.p_begin + warp; q < L.p_end; q += nwarp) poseidon_warp(x, a.poseidons[q], a.pos_konst);
-        { const uint32_t np = (L.p_end - L.p_begin) % nwarp, wv = (warp + nwarp - np) % nwarp;
-          for (uint32_t w = L.w_begin + wv; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]);
-          const uint32_t nw2 = (np + (L.w_end - L.w_begin)) % nwarp, sv = (warp + nwarp - nw2) % nwarp;
-          for (uint32_t q = L.s_begin + sv; q < L.s_end; q += nwarp) psum_warp(x, a.psums[q]); }
-        __syncthreads();
-    }
-    if (a.prof && inst == 0 && tid == 0) a.prof[a.n_levels] = clock64();
-    // IsZero inverse hints: no consumers, done last.  Table-sized inputs are spread over all threads; the ones expected
-    // to need a real inversion go to 256 threads so that only 8 warps pay for a Fermat ladder (one per thread).
-    vm_inv_batch(x, a.ops, a.inv_begin, a.ginv_begin, tid, nthr);
-    if (tid < 256) vm_inv_batch(x, a.ops, a.ginv_begin, a.inv_end, tid, 256);
-    if (a.prof && inst == 0) { __syncthreads(); if (tid == 0) a.prof[a.n_levels + 1] = clock64(); }
-    if (tid == 0) a.status[inst] = (s_status == STATUS_OK) ? 0u : s_status;
-    for (uint32_t i = tid; i < a.n_outputs; i += nthr) {
-        uint64_t v[4]; vm_expand(a.out_codes[i], U, 0, a.val_base, a.konst, v);
-        uint64_t *o = a.outputs + ((uint64_t)inst * a.n_outputs + i) * 4;
-        o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3];
-    }
-}
-
-// 256-bit store (STG.E.ENL2.256).  No "memory" clobber on purpose: the compiler must be free to hoist the next
-// entries' loads above it so that several loads are in flight per thread (the witness is written, never read, here).
-__device__ __forceinline__ void st256(uint64_t *p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
-    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d));
-}
-
-struct ExpandArgs {
-    const Tile *tiles; const Code *codes; const Fr *konst; const uint2 *round_desc;
-    const uint64_t *stores; uint64_t store_stride; uint32_t val_base;
-    uint64_t *const *wit;                         // per instance of the group: witness slot base
-    uint32_t tile0;                               // first tile of this launch (k_expand_codes)
-};
-
-// k_expand_round: grid = (KeccakfRound tiles, instances in the group) -- 95.8 % of the witness.  One CTA streams one
-// tile (<= 8192 entries = 256 KiB) with one 256-bit store per entry.  The source of every entry follows from an 8-byte
-// descriptor per 64 entries and a lane word of the round; the tile's <= 128 descriptors and the round's 263 words are
-// staged in shared memory in one burst, so the streaming loop touches no global memory but the witness itself.
-template <int T>
-__global__ void __launch_bounds__(T) k_expand_round(const ExpandArgs a) {
-    const Tile t = a.tiles[blockIdx.x];
-    const uint64_t *Ub = a.stores + (uint64_t)blockIdx.y * a.store_stride + t.ubase;
-    uint64_t *W = a.wit[blockIdx.y] + t.dst * 4;
-    __shared__ uint2 sD[MAX_TILE_SIGNALS / 64]; __shared__ uint64_t sW[ROUND_WORDS_SPAN + 1];
-    const uint2 *D = a.round_desc + (t.code_off >> 6);
-    for (uint32_t i = threadIdx.x; i < ((t.n + 63) >> 6); i += T) sD[i] = __ldg(D + i);
-    for (uint32_t i = threadIdx.x; i < ROUND_WORDS_SPAN; i += T) sW[i] = Ub[i];
-    __syncthreads();
-#pragma unroll 8
-    for (uint32_t k = threadIdx.x; k < t.n; k += T) {
-        const uint2 d = sD[k >> 6];
-        const uint32_t tt = k & 63, mode = d.y >> 16;
-        uint32_t w = d.x & 0xffffu, b = tt;
-        if (mode) {                          // phase (mode-1) of a gate block [out_i, a_i, b_i]_i
-            const uint32_t sidx = (mode - 1) * 64 + tt, g = sidx / 3, m = sidx - 3 * g;
-            b = g; w = (m == 0) ? (d.x & 0xffffu) : (m == 1) ? (d.x >> 16) : (d.y & 0xffffu);
-        }
-        st256(W + 4ull * k, (sW[w] >> b) & 1ull, 0, 0, 0);
-    }
-}
-
-// k_expand_codes: grid = (instances in the group, code tiles) -- INSTANCE-major, so that a tile's code stream is fetched
-// from DRAM once and served from L2 to the other witnesses of the group.  One 32-bit code per entry, loads issued 4
-// entries ahead of the stores.
-__global__ void __launch_bounds__(256, 5) k_expand_codes(const ExpandArgs a) {
-    const uint32_t inst = blockIdx.x;
-    const Tile t = a.tiles[a.tile0 + blockIdx.y];
-    const uint64_t *U = a.stores + (uint64_t)inst * a.store_stride;
-    uint64_t *W = a.wit[inst] + t.dst * 4;
-    const uint64_t *Ub = U + t.ubase;
-    const Code *c = a.codes + t.code_off;
-    constexpr int UG = 4;
-    for (uint32_t base = threadIdx.x; base < t.n; base += 256 * UG) {
-        Code cd[UG];
-#pragma unroll
-        for (int u = 0; u < UG; u++) { const uint32_t k = base + 256 * u; cd[u] = k < t.n ? __ldg(c + k) : 0u; }
-        uint64_t v[UG][4];
-#pragma unroll
-        for (int u = 0; u < UG; u++) {
-            const uint32_t kind = code_kind(cd[u]), p = code_payload(cd[u]);
-            v[u][1] = v[u][2] = v[u][3] = 0;
-            if (kind == K_BIT) v[u][0] = (Ub[p >> 6] >> (p & 63)) & 1ull;
-            else if (kind == K_CONST) v[u][0] = p;
-            else {
-                const uint64_t *s = (kind == K_VAL) ? U + a.val_base + 4ull * p : reinterpret_cast<const uint64_t *>(a.konst + p);
-                v[u][0] = s[0]; v[u][1] = s[1]; v[u][2] = s[2]; v[u][3] = s[3];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UG; u++) { const uint32_t k = base + 256 * u; if (k < t.n) st256(W + 4ull * k, v[u][0], v[u][1], v[u][2], v[u][3]); }
-    }
-}
-
-// digest = sum_i mix(i, limbs) mod 2^64 -- must equal oracle/pob_oracle.c:pob_oracle_digest
-__global__ void __launch_bounds__(256) k_digest(const uint64_t *wit, uint64_t n_signals, unsigned long long *out) {
-    uint64_t acc = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_signals; i += (uint64_t)gridDim.x * blockDim.x) {
-        const ulonglong4 v = *reinterpret_cast<const ulonglong4 *>(wit + 4 * i);
-        uint64_t h = (i + 1) * 0x9E3779B97F4A7C15ULL;
-        h ^= v.x * 0xBF58476D1CE4E5B9ULL + v.y * 0x94D049BB133111EBULL + v.z * 0xD6E8FEB86659FD93ULL + v.w * 0xA0761D6478BD642FULL;
-        h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 32;
-        acc += h;
-    }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    __shared__ uint64_t part[8];
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) { uint64_t s = 0; for (int w = 0; w < 8; w++) s += part[w]; atomicAdd(out, (unsigned long long)s); }
-}
-
-// ---- proof-of-work burn-key grinder (reference tests/main.py:47-56; circuits/utils/proof_of_work.circom:54-81) ----
-// One candidate key per thread: a single-block keccak256 of key|reveal|extra|"EIP-7503" held in 25 registers.
-struct GrindArgs { uint64_t start[4], lanes_tail[9]; uint64_t first, count; uint32_t zero_bytes; unsigned long long *hit; };
-__device__ __forceinline__ uint64_t bswap64(uint64_t x) { return __byte_perm((uint32_t)(x >> 32), 0, 0x0123) | ((uint64_t)__byte_perm((uint32_t)x, 0, 0x0123) << 32); }
-__device__ __forceinline__ uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
-__global__ void __launch_bounds__(256) k_pow_grind(const GrindArgs a) {
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.count) return;
-    // key = start + first + idx (256-bit add)
-    uint64_t k0 = a.start[0], k1 = a.start[1], k2 = a.start[2], k3 = a.start[3];
-    const uint64_t add = a.first + idx;
-    k0 += add; if (k0 < add) { if (++k1 == 0) { if (++k2 == 0) ++k3; } }
-    uint64_t s[25];
-    s[0] = bswap64(k3); s[1] = bswap64(k2); s[2] = bswap64(k1); s[3] = bswap64(k0);      // 32-byte big-endian key
-#pragma unroll
-    for (int i = 0; i < 9; i++) s[4 + i] = a.lanes_tail[i];                                // reveal | extra | "EIP-7503"
-    s[13] = 0x01; s[14] = 0; s[15] = 0; s[16] = 0x8000000000000000ull;                     // 0x01 ... 0x80 padding of a 104-byte message
-#pragma unroll
-    for (int i = 17; i < 25; i++) s[i] = 0;
-#pragma unroll 1
-    for (int r = 0; r < 24; r++) {
-        uint64_t c[5], d[5], b[25];
-#pragma unroll
-        for (int x = 0; x < 5; x++) c[x] = s[x] ^ s[x + 5] ^ s[x + 10] ^ s[x + 15] ^ s[x + 20];
-#pragma unroll
-        for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
-#pragma unroll
-        for (int i = 0; i < 25; i++) s[i] ^= d[i % 5];
-        b[0] = s[0];
-#pragma unroll
-        for (int i = 0; i < 24; i++) b[keccak_rot(i + 1)] = rotl64(s[keccak_rot(i)], keccak_shl(i));
-#pragma unroll
-        for (int i = 0; i < 25; i++) s[i] = b[i] ^ (~b[chi_b(i)] & b[chi_c(i)]);
-        s[0] ^= keccak_rc(r);
-    }
-    const uint64_t mask = a.zero_bytes >= 8 ? ~0ull : ((1ull << (8 * a.zero_bytes)) - 1);
-    if ((s[0] & mask) == 0) atomicMin(a.hit, (unsigned long long)idx);
-}
-
-// ---- self-check: every KeccakfRound block of a materialised witness satisfies out == KeccakRound_r(in) -------------
-// One warp per block.  Lane l < 25 assembles lane word l of `in` (witness entries base+1600+64l .. +63) and of `out`
-// (base+64l ..) from the 32-byte entries, lane 0 gathers the 25 input words and runs one textbook round.
-__global__ void __launch_bounds__(256) k_check_rounds(const uint64_t *wit, const uint64_t *block_base, uint32_t n_blocks, unsigned long long *n_bad) {
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= n_blocks) return;
-    const uint64_t base = block_base[warp];
-    const int r = (int)(warp % 24);                       // round blocks are emitted 24 per Keccakf, in order
-    uint64_t win = 0, wout = 0; bool bad = false;
-    if (lane < 25) {
-        for (uint32_t k = 0; k < 64; k++) {
-            const ulonglong4 a = *reinterpret_cast<const ulonglong4 *>(wit + 4 * (base + 1600 + 64 * lane + k));
-            const ulonglong4 b = *reinterpret_cast<const ulonglong4 *>(wit + 4 * (base + 64 * lane + k));
-            bad |= (a.x > 1) | (b.x > 1) | ((a.y | a.z | a.w | b.y | b.z | b.w) != 0);
-            win |= (a.x & 1ull) << k; wout |= (b.x & 1ull) << k;
-        }
-    }
-    uint64_t s[25], o[25];
-#pragma unroll
-    for (int i = 0; i < 25; i++) { s[i] = __shfl_sync(0xffffffffu, win, i); o[i] = __shfl_sync(0xffffffffu, wout, i); }
-    bad = __any_sync(0xffffffffu, bad);
-    if (lane == 0) {
-        uint64_t c[5], d[5], b[25];
-#pragma unroll
-        for (int x = 0; x < 5; x++) c[x] = s[x] ^ s[x + 5] ^ s[x + 10] ^ s[x + 15] ^ s[x + 20];
-#pragma unroll
-        for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
-#pragma unroll
-        for (int i = 0; i < 25; i++) s[i] ^= d[i % 5];
-        b[0] = s[0];
-#pragma unroll
-        for (int i = 0; i < 24; i++) b[keccak_rot(i + 1)] = rotl64(s[keccak_rot(i)], keccak_shl(i));
-#pragma unroll
-        for (int i = 0; i < 25; i++) s[i] = b[i] ^ (~b[chi_b(i)] & b[chi_c(i)]);
-        s[0] ^= keccak_rc(r);
-#pragma unroll
-        for (int i = 0; i < 25; i++) bad |= (s[i] != o[i]);
-        if (bad) atomicAdd(n_bad, 1ull);
-    }
-}
-
-}  // namespace
-
-// =============================================================================================================
-// host side of the C-ABI
-// =============================================================================================================
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
+// Tuning / profiling knobs (POB_* environment variables) exist only in the -DPOB_TUNING build (`make tuning`, used by
+// tools/gpu_sweep3.sh); the shipped library reads no environment variable.
+static const char *tune_env(const char *name) {
+#ifdef POB_TUNING
+    return getenv(name);
+#else
+    (void)name; return nullptr;
+#endif
+}
+
+// =============================================================================================================
+// exporter: resident witness -> host (.wtns image), several copy streams into a pinned staging ring, file I/O on a
+// writer thread so that D2H DMA and disk writes overlap
+// =============================================================================================================
+namespace {
+
+struct Exporter {
+    static const int NB = 8, NS = 2;
+    const size_t bb = 32u << 20;                       // 32 MiB per hop
+    int device; void *buf[NB] = {}; cudaEvent_t ev[NB] = {}; cudaStream_t cs[NS] = {}; cudaEvent_t ev_join = nullptr;
+    struct Job { int b; int fd; uint64_t off; size_t bytes; bool close_fd; };
+    std::deque<Job> q; bool busy[NB] = {}; bool stop = false, io_err = false;
+    std::mutex m; std::condition_variable cv; std::thread th;
+    int next_b = 0; unsigned rr = 0; uint64_t bytes_moved = 0;
+
+    explicit Exporter(int dev) : device(dev) {
+        CU(cudaSetDevice(device));
+        for (int i = 0; i < NB; i++) { CU(cudaMallocHost(&buf[i], bb)); CU(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); }
+        for (int i = 0; i < NS; i++) CU(cudaStreamCreateWithFlags(&cs[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        th = std::thread([this] { run(); });
+    }
+    ~Exporter() {
+        { std::lock_guard<std::mutex> l(m); stop = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+        cudaSetDevice(device);
+        for (int i = 0; i < NS; i++) if (cs[i]) { cudaStreamSynchronize(cs[i]); cudaStreamDestroy(cs[i]); }
+        for (int i = 0; i < NB; i++) { if (buf[i]) cudaFreeHost(buf[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+        if (ev_join) cudaEventDestroy(ev_join);
+    }
+    void run() {                                       // writer thread
+        cudaSetDevice(device);
+        for (;;) {
+            Job j;
+            { std::unique_lock<std::mutex> l(m); cv.wait(l, [this] { return stop || !q.empty(); }); if (q.empty()) return; j = q.front(); q.pop_front(); }
+            bool ok = cudaEventSynchronize(ev[j.b]) == cudaSuccess;
+            if (ok && j.fd >= 0) {
+                const char *p = (const char *)buf[j.b]; size_t left = j.bytes; uint64_t off = j.off;
+                while (left) { ssize_t w = pwrite(j.fd, p, left, (off_t)off); if (w <= 0) { ok = false; break; } p += w; left -= (size_t)w; off += (uint64_t)w; }
+            }
+            if (j.close_fd && j.fd >= 0 && close(j.fd) != 0) ok = false;
+            { std::lock_guard<std::mutex> l(m); busy[j.b] = false; if (!ok) io_err = true; }
+            cv.notify_all();
+        }
+    }
+    int grab() {                                       // staging buffers are used strictly round-robin
+        std::unique_lock<std::mutex> l(m);
+        const int b = next_b; cv.wait(l, [&] { return !busy[b]; });
+        busy[b] = true; next_b = (b + 1) % NB; return b;
+    }
+    void drain() { std::unique_lock<std::mutex> l(m); cv.wait(l, [this] { if (!q.empty()) return false; for (int i = 0; i < NB; i++) if (busy[i]) return false; return true; }); }
+    // iden3 binary witness format, version 2 (what the circom runtime's writeBinWitness emits; SURVEY.md Appendix B)
+    static size_t header(uint8_t *o, uint64_t n) {
+        uint32_t u32; uint64_t u64; Fr p = fr_p(); size_t k = 0;
+        auto put = [&](const void *s, size_t b) { memcpy(o + k, s, b); k += b; };
+        put("wtns", 4); u32 = 2; put(&u32, 4); u32 = 2; put(&u32, 4);
+        u32 = 1; put(&u32, 4); u64 = 40; put(&u64, 8); u32 = 32; put(&u32, 4); put(p.l, 32); u32 = (uint32_t)n; put(&u32, 4);
+        u32 = 2; put(&u32, 4); u64 = 32ull * n; put(&u64, 8);
+        return k;                                      // 76
+    }
+    // queue the transfer of one resident witness; fd < 0: host memory only.  On return every D2H copy has been issued;
+    // stream cs[0] is ordered after all of them (the caller releases the slot on cs[0]).
+    void send(const uint64_t *dwit, uint64_t n_signals, int fd) {
+        CU(cudaSetDevice(device));
+        if (fd >= 0) { uint8_t hd[80]; size_t hb = header(hd, n_signals); if (pwrite(fd, hd, hb, 0) != (ssize_t)hb) { std::lock_guard<std::mutex> l(m); io_err = true; } }
+        const uint64_t total = 32ull * n_signals; const uint64_t nch = (total + bb - 1) / bb;
+        for (uint64_t c = 0; c < nch; c++) {
+            const uint64_t off = c * bb; const size_t bytes = (size_t)std::min<uint64_t>(bb, total - off);
+            const int b = grab(); cudaStream_t s = cs[rr++ % NS];
+            CU(cudaMemcpyAsync(buf[b], (const char *)dwit + off, bytes, cudaMemcpyDeviceToHost, s));
+            CU(cudaEventRecord(ev[b], s));
+            { std::lock_guard<std::mutex> l(m); q.push_back(Job{b, fd, 76 + off, bytes, c + 1 == nch}); }
+            cv.notify_all();
+            bytes_moved += bytes;
+        }
+        if (nch == 0 && fd >= 0) close(fd);
+        for (int i = 1; i < NS; i++) { CU(cudaEventRecord(ev_join, cs[i])); CU(cudaStreamWaitEvent(cs[0], ev_join, 0)); }
+    }
+};
+
+}  // namespace
+
+// =============================================================================================================
+// handle
+// =============================================================================================================
 struct pob_handle {
     Program P; int device = 0;
     // device program
@@ -403,12 +139,15 @@ struct pob_handle {
     uint32_t chunk = 0; uint64_t store_stride = 0; uint64_t *d_stores = nullptr; uint64_t *d_inputs = nullptr;
     // witness slots
     std::vector<uint64_t *> slots;
+    std::vector<int64_t> slot_owner;              // instance (of the current / last batch) whose witness the slot holds, -1 = none
+    std::vector<cudaEvent_t> slot_rel_ev; std::vector<uint8_t> slot_rel_pending;   // stream-ordered release by the consumer
+    std::vector<uint32_t> last_status; uint32_t last_n = 0;
     // per-batch buffers
     uint32_t cap_n = 0; uint32_t *d_status = nullptr; uint64_t *d_outputs = nullptr; unsigned long long *d_digests = nullptr;
-    uint64_t **d_witptr = nullptr; uint32_t *h_status = nullptr; uint64_t *h_outputs = nullptr; uint64_t *h_digests = nullptr;
-    uint64_t **h_witptr = nullptr;
+    uint64_t **d_witptr = nullptr; uint32_t *d_planinst = nullptr;
+    uint32_t *h_status = nullptr; uint64_t *h_outputs = nullptr; uint64_t *h_digests = nullptr; uint64_t **h_witptr = nullptr; uint32_t *h_planinst = nullptr;
     uint64_t *d_staged = nullptr; uint32_t n_staged = 0;
-    long long *d_prof = nullptr;               // POB_EVAL_PROFILE: per-level clock stamps (tuning only)
+    long long *d_prof = nullptr; std::string prof_path;   // POB_TUNING: per-level clock stamps
     uint32_t xgroup = 0;                       // instances per expand launch (distinct witness slots)
     uint32_t n_round_tiles = 0;                // tiles [0, n_round_tiles) are KeccakfRound tiles, the rest code tiles
     uint64_t *d_block_base = nullptr; uint32_t n_blocks = 0;   // witness index of every KeccakfRound block (self-check)
@@ -416,15 +155,24 @@ struct pob_handle {
     // per SM: fewer concurrent write streams give the DRAM controllers longer same-row bursts -- measured 7.35 TB/s with
     // 2 CTAs/SM vs 7.26 / 7.19 / 7.09 / 6.97 TB/s with 3 / 4 / 5 / 8, and 5.96 TB/s with 1 (profiles/r01_expand_sweep.md)
     uint32_t round_dyn_smem = 85 * 1024;
-    uint32_t round_threads = 256;              // CTA size of k_expand_round (POB_EXPAND_THREADS), tuning only
-    uint32_t codes_dyn_smem = 0;               // same occupancy cap for k_expand_codes (POB_CODES_SMEM_KB), tuning only
-    int eval_threads = 1024;                   // k_eval CTA size (POB_EVAL_THREADS), tuning only
-    bool serialize = false;                    // POB_SERIALIZE=1: eval and expand on one stream (no overlap), tuning only
+    uint32_t round_threads = 256, codes_dyn_smem = 0; int eval_threads = 1024; bool serialize = false;   // changed by POB_TUNING knobs only
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
     cudaEvent_t ev_eval_done[RING] = {nullptr, nullptr}, ev_exp_done[RING] = {nullptr, nullptr}, ev_h2d[RING] = {nullptr, nullptr},
-                ev_start = nullptr, ev_end = nullptr;
-    std::vector<cudaEvent_t> ev_pool;
-    uint32_t last_n = 0; bool last_expanded = false;
+                ev_start = nullptr, ev_end = nullptr, ev_tmp = nullptr;
+    std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+    // the batch in flight
+    struct Group { uint32_t begin, end, chunk; cudaEvent_t t0, t1; };
+    struct Batch {
+        bool active = false, async = false, staged = false, expand = false, digest = false;
+        const uint64_t *inputs = nullptr; uint32_t n = 0, nchunks = 0, next_eval = 0, next_group = 0, acq_pos = 0;
+        std::vector<uint32_t> plan, slot;         // instances to materialise (ascending) and their slots
+        std::vector<uint8_t> st;                  // per plan entry: 0 = not handed out yet, 1 = held by the consumer, 2 = released / dropped
+        std::vector<uint32_t> group_of;           // per plan entry
+        std::vector<Group> groups; std::vector<uint32_t> chunk_gend;   // groups sorted by chunk; chunk_gend[c] = one past the last group of chunks <= c
+        std::vector<cudaEvent_t> e0, e1, est;     // per chunk: eval begin / end, status+outputs on the host
+        pob_timing T{};
+    } B;
+    Exporter *exporter = nullptr;
     pob_timing timing{};
 };
 
@@ -446,11 +194,228 @@ template <class T> static T *upload(const std::vector<T> &v) {
     if (!v.empty()) CU(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return d;
 }
+static cudaEvent_t pool_event(pob_handle *h) {
+    if (h->ev_used == h->ev_pool.size()) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
+    return h->ev_pool[h->ev_used++];
+}
+
+// ---- batch machinery ------------------------------------------------------------------------------------------
+static void ensure_batch_buffers(pob_handle *h, uint32_t n) {
+    if (n <= h->cap_n) return;
+    const Program &P = h->P;
+    for (void *p : {(void *)h->d_status, (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr, (void *)h->d_planinst}) if (p) cudaFree(p);
+    for (void *p : {(void *)h->h_status, (void *)h->h_outputs, (void *)h->h_digests, (void *)h->h_witptr, (void *)h->h_planinst}) if (p) cudaFreeHost(p);
+    h->d_status = nullptr; h->d_outputs = nullptr; h->d_digests = nullptr; h->d_witptr = nullptr; h->d_planinst = nullptr;
+    h->h_status = nullptr; h->h_outputs = nullptr; h->h_digests = nullptr; h->h_witptr = nullptr; h->h_planinst = nullptr; h->cap_n = 0;
+    const size_t no = std::max<uint32_t>(1, P.n_outputs);
+    CU(cudaMalloc(&h->d_status, (size_t)n * 4)); CU(cudaMalloc(&h->d_outputs, (size_t)n * no * 32));
+    CU(cudaMalloc(&h->d_digests, (size_t)n * 8)); CU(cudaMalloc(&h->d_witptr, (size_t)n * sizeof(uint64_t *))); CU(cudaMalloc(&h->d_planinst, (size_t)n * 4));
+    CU(cudaMallocHost(&h->h_status, (size_t)n * 4)); CU(cudaMallocHost(&h->h_outputs, (size_t)n * no * 32));
+    CU(cudaMallocHost(&h->h_digests, (size_t)n * 8)); CU(cudaMallocHost(&h->h_witptr, (size_t)n * sizeof(uint64_t *))); CU(cudaMallocHost(&h->h_planinst, (size_t)n * 4));
+    h->cap_n = n;
+}
+
+static void enqueue_eval(pob_handle *h, uint32_t c) {
+    pob_handle::Batch &B = h->B; const Program &P = h->P;
+    const uint32_t E = h->chunk, R = pob_handle::RING, r = c % R, first = c * E, cnt = std::min(E, B.n - first);
+    const size_t in_stride = (size_t)P.n_inputs * 4, no = std::max<uint32_t>(1, P.n_outputs);
+    const uint64_t *d_in;
+    if (B.staged) d_in = h->d_staged + (size_t)first * in_stride;
+    else {
+        // inputs travel on their own stream, one chunk ahead of the eval kernel that consumes them
+        uint64_t *dst = h->d_inputs + (size_t)r * E * in_stride;
+        if (c >= R) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_eval_done[r], 0));
+        if (in_stride) { CU(cudaMemcpyAsync(dst, B.inputs + (size_t)first * in_stride, (size_t)cnt * in_stride * 8, cudaMemcpyHostToDevice, h->s_h2d)); B.T.h2d_bytes += (uint64_t)cnt * in_stride * 8; }
+        CU(cudaEventRecord(h->ev_h2d[r], h->s_h2d));
+        CU(cudaStreamWaitEvent(h->s_eval, h->ev_h2d[r], 0));
+        d_in = dst;
+    }
+    if (c >= R) CU(cudaStreamWaitEvent(h->s_eval, h->ev_exp_done[r], 0));      // store ring half r is free again
+    uint64_t *stores = h->d_stores + (size_t)r * E * h->store_stride;
+    EvalArgs ea{h->d_ops, h->d_abs, h->d_pos, h->d_pos_konst, h->d_psums, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.ginv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
+                h->d_codes + ROUND_SIGNALS + 1, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
+                h->d_status + first, h->d_outputs + (size_t)first * no * 4, (c == 0) ? h->d_prof : nullptr};
+    CU(cudaEventRecord(B.e0[c], h->s_eval));
+    switch (h->eval_threads) {
+    case 256: k_eval<256><<<cnt, 256, 0, h->s_eval>>>(ea); break;
+    case 512: k_eval<512><<<cnt, 512, 0, h->s_eval>>>(ea); break;
+    default: k_eval<1024><<<cnt, 1024, 0, h->s_eval>>>(ea); break;
+    }
+    CU(cudaEventRecord(B.e1[c], h->s_eval));
+    CU(cudaEventRecord(h->ev_eval_done[r], h->s_eval));
+    B.T.eval_launches++;
+    // accept/reject and the output signals of this chunk go to the host right away (the consumer needs the status)
+    CU(cudaMemcpyAsync(h->h_status + first, h->d_status + first, (size_t)cnt * 4, cudaMemcpyDeviceToHost, h->s_eval));
+    B.T.d2h_bytes += (uint64_t)cnt * 4;
+    if (P.n_outputs) { CU(cudaMemcpyAsync(h->h_outputs + (size_t)first * no * 4, h->d_outputs + (size_t)first * no * 4, (size_t)cnt * no * 32, cudaMemcpyDeviceToHost, h->s_eval)); B.T.d2h_bytes += (uint64_t)cnt * no * 32; }
+    CU(cudaEventRecord(B.est[c], h->s_eval));
+    const uint32_t g0 = c ? B.chunk_gend[c - 1] : 0;
+    if (B.chunk_gend[c] == g0) CU(cudaEventRecord(h->ev_exp_done[r], h->s_eval));   // nothing of this chunk is materialised
+}
+
+static void enqueue_group(pob_handle *h, uint32_t g) {
+    pob_handle::Batch &B = h->B; const Program &P = h->P;
+    const pob_handle::Group &G = B.groups[g];
+    const uint32_t E = h->chunk, R = pob_handle::RING, r = G.chunk % R, gc = G.end - G.begin;
+    CU(cudaStreamWaitEvent(h->s_exp, h->ev_eval_done[r], 0));
+    for (uint32_t k = G.begin; k < G.end; k++) {
+        const uint32_t s = B.slot[k];
+        if (h->slot_rel_pending[s]) { CU(cudaStreamWaitEvent(h->s_exp, h->slot_rel_ev[s], 0)); h->slot_rel_pending[s] = 0; }
+        h->slot_owner[s] = (int64_t)B.plan[k];
+    }
+    ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, reinterpret_cast<const uint2 *>(h->d_round_desc), h->d_stores + (size_t)r * E * h->store_stride, h->store_stride, P.val_base,
+                  h->d_witptr + G.begin, h->d_planinst + G.begin, h->d_status, G.chunk * E, 0};
+    CU(cudaEventRecord(G.t0, h->s_exp));
+    // launch 1: KeccakfRound tiles, tile-major (each CTA's tables are staged in shared memory);
+    // launch 2: code tiles, INSTANCE-major, so that a tile's code stream is fetched from DRAM once and
+    // served from L2 to the other witnesses of the group
+    const uint32_t n_round = h->n_round_tiles, n_code = (uint32_t)P.tiles.size() - n_round;
+    if (n_round) {
+        xa.tile0 = 0;
+        if (h->round_threads == 128) k_expand_round<128><<<dim3(n_round, gc), 128, h->round_dyn_smem, h->s_exp>>>(xa);
+        else if (h->round_threads == 512) k_expand_round<512><<<dim3(n_round, gc), 512, h->round_dyn_smem, h->s_exp>>>(xa);
+        else if (h->round_threads == 1024) k_expand_round<1024><<<dim3(n_round, gc), 1024, h->round_dyn_smem, h->s_exp>>>(xa);
+        else k_expand_round<256><<<dim3(n_round, gc), 256, h->round_dyn_smem, h->s_exp>>>(xa);
+    }
+    if (n_code) { xa.tile0 = n_round; k_expand_codes<<<dim3(gc, n_code), 256, h->codes_dyn_smem, h->s_exp>>>(xa); B.T.other_launches++; }
+    CU(cudaEventRecord(G.t1, h->s_exp));
+    B.T.expand_launches++;
+    if (B.digest) for (uint32_t k = G.begin; k < G.end; k++) {     // built-in on-GPU consumer: reads every entry of the witness once
+        k_digest<<<1184, 256, 0, h->s_exp>>>(h->slots[B.slot[k]], P.n_signals, h->d_digests + B.plan[k], h->d_status + B.plan[k]);
+        B.T.other_launches++;
+    }
+    if (!B.async) for (uint32_t k = G.begin; k < G.end; k++) B.st[k] = 2;   // synchronous batch: consumed by the digest (same stream) or dropped on request
+    if (g + 1 == B.chunk_gend[G.chunk]) {
+        CU(cudaEventRecord(h->ev_exp_done[r], h->s_exp));
+        if (h->serialize) CU(cudaStreamWaitEvent(h->s_eval, h->ev_exp_done[r], 0));
+    }
+}
+
+static bool group_slots_free(const pob_handle *h, uint32_t g) {
+    const pob_handle::Batch &B = h->B; const uint32_t ns = (uint32_t)h->slots.size();
+    for (uint32_t k = B.groups[g].begin; k < B.groups[g].end; k++) if (k >= ns && B.st[k - ns] != 2) return false;
+    return true;
+}
+// queue as much work as the store ring and the witness slots allow
+static void advance(pob_handle *h) {
+    pob_handle::Batch &B = h->B; const uint32_t R = pob_handle::RING, ng = (uint32_t)B.groups.size();
+    for (;;) {
+        bool progressed = false;
+        if (B.next_eval < B.nchunks && (B.next_eval < R || B.next_group >= B.chunk_gend[B.next_eval - R])) { enqueue_eval(h, B.next_eval++); progressed = true; }
+        if (B.next_group < ng && B.groups[B.next_group].chunk < B.next_eval && group_slots_free(h, B.next_group)) { enqueue_group(h, B.next_group++); progressed = true; }
+        if (!progressed) break;
+    }
+    CU(cudaGetLastError());
+}
+
+static int begin_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t flags, const uint32_t *retain, uint32_t n_retain, bool async, const char *who) {
+    const bool staged = (flags & POB_RUN_INPUTS_STAGED) != 0, digest = (flags & POB_RUN_DIGEST) != 0;
+    const bool expand = async || (flags & (POB_RUN_EXPAND | POB_RUN_DIGEST)) != 0 || retain != nullptr;
+    if (h->B.active) return fail(POB_E_BUSY, std::string(who) + ": a batch is in flight on this handle (pob_finish it first)");
+    if (staged ? (h->n_staged < n) : (inputs == nullptr && h->P.n_inputs)) return fail(POB_E_BAD_ARG, std::string(who) + ": no inputs");
+    const uint32_t ns = (uint32_t)h->slots.size();
+    if (retain) {
+        if (n_retain > ns) return fail(POB_E_RANGE, std::string(who) + ": more retained instances than witness slots");
+        for (uint32_t k = 0; k < n_retain; k++) if (retain[k] >= n || (k && retain[k] <= retain[k - 1])) return fail(POB_E_BAD_ARG, std::string(who) + ": retain[] must be strictly ascending instance indices");
+    } else if (expand && !async && n > ns && !(flags & (POB_RUN_DIGEST | POB_RUN_DISCARD)))
+        return fail(POB_E_RANGE, std::string(who) + ": n exceeds the resident witness slots; earlier witnesses would be overwritten unread -- use pob_submit/pob_acquire/pob_release, a retain list, POB_RUN_DIGEST or POB_RUN_DISCARD");
+    CU(cudaSetDevice(h->device));
+    ensure_batch_buffers(h, n);
+    pob_handle::Batch &B = h->B;
+    B = pob_handle::Batch();
+    B.async = async; B.staged = staged; B.expand = expand; B.digest = digest; B.inputs = inputs; B.n = n;
+    const uint32_t E = h->chunk;
+    B.nchunks = (n + E - 1) / E;
+    // with a consumer in the loop two groups must fit the slot ring, else generation and consumption cannot overlap
+    const uint32_t X = async ? std::max<uint32_t>(1, std::min(h->xgroup, ns / 2 ? ns / 2 : 1)) : h->xgroup;
+    if (expand) {
+        if (retain) B.plan.assign(retain, retain + n_retain);
+        else { B.plan.resize(n); for (uint32_t i = 0; i < n; i++) B.plan[i] = i; }
+    }
+    const uint32_t np = (uint32_t)B.plan.size();
+    B.slot.resize(np); B.st.assign(np, 0); B.group_of.resize(np);
+    for (uint32_t k = 0; k < np; k++) { B.slot[k] = k % ns; h->h_witptr[k] = h->slots[B.slot[k]]; h->h_planinst[k] = B.plan[k]; }
+    h->ev_used = 0;
+    B.chunk_gend.assign(B.nchunks, 0);
+    for (uint32_t k = 0; k < np;) {
+        const uint32_t c = B.plan[k] / E; uint32_t e = k;
+        while (e < np && e - k < X && B.plan[e] / E == c) e++;
+        for (uint32_t j = k; j < e; j++) B.group_of[j] = (uint32_t)B.groups.size();
+        B.groups.push_back(pob_handle::Group{k, e, c, pool_event(h), pool_event(h)});
+        B.chunk_gend[c] = (uint32_t)B.groups.size();
+        k = e;
+    }
+    for (uint32_t c = 1; c < B.nchunks; c++) B.chunk_gend[c] = std::max(B.chunk_gend[c], B.chunk_gend[c - 1]);
+    B.e0.resize(B.nchunks); B.e1.resize(B.nchunks); B.est.resize(B.nchunks);
+    for (uint32_t c = 0; c < B.nchunks; c++) { B.e0[c] = pool_event(h); B.e1[c] = pool_event(h); B.est[c] = pool_event(h); }
+    // the previous batch's residency ends here: its slots are about to be reused
+    std::fill(h->slot_owner.begin(), h->slot_owner.end(), (int64_t)-1);
+    std::fill(h->slot_rel_pending.begin(), h->slot_rel_pending.end(), (uint8_t)0);
+    h->last_n = 0; h->last_status.clear();
+    CU(cudaEventRecord(h->ev_start, h->s_eval));
+    if (np) {
+        CU(cudaMemcpyAsync(h->d_witptr, h->h_witptr, (size_t)np * sizeof(uint64_t *), cudaMemcpyHostToDevice, h->s_eval));
+        CU(cudaMemcpyAsync(h->d_planinst, h->h_planinst, (size_t)np * 4, cudaMemcpyHostToDevice, h->s_eval));
+    }
+    if (digest) CU(cudaMemsetAsync(h->d_digests, 0, (size_t)n * 8, h->s_eval));
+    CU(cudaEventRecord(h->ev_tmp, h->s_eval));
+    CU(cudaStreamWaitEvent(h->s_h2d, h->ev_tmp, 0));
+    B.active = true;
+    advance(h);
+    return POB_OK;
+}
+
+static int finish_batch(pob_handle *h, uint32_t *status, uint64_t *outputs, uint64_t *digests) {
+    pob_handle::Batch &B = h->B; const Program &P = h->P;
+    const uint32_t n = B.n; const size_t no = std::max<uint32_t>(1, P.n_outputs);
+    for (auto &s : B.st) s = 2;                            // whatever the consumer did not take is generated and dropped
+    advance(h);
+    if (B.next_eval != B.nchunks || B.next_group != B.groups.size()) throw std::runtime_error("internal: batch did not drain");
+    CU(cudaEventRecord(h->ev_tmp, h->s_eval));
+    CU(cudaStreamWaitEvent(h->s_exp, h->ev_tmp, 0));
+    if (B.digest) { CU(cudaMemcpyAsync(h->h_digests, h->d_digests, (size_t)n * 8, cudaMemcpyDeviceToHost, h->s_exp)); B.T.d2h_bytes += (uint64_t)n * 8; }
+    CU(cudaEventRecord(h->ev_end, h->s_exp));
+    CU(cudaStreamSynchronize(h->s_exp)); CU(cudaStreamSynchronize(h->s_eval)); CU(cudaStreamSynchronize(h->s_h2d));
+    CU(cudaGetLastError());
+    if (status) memcpy(status, h->h_status, (size_t)n * 4);
+    if (outputs && P.n_outputs) memcpy(outputs, h->h_outputs, (size_t)n * no * 32);
+    if (B.digest && digests) memcpy(digests, h->h_digests, (size_t)n * 8);
+    pob_timing &T = B.T;
+    CU(cudaEventElapsedTime(&T.total_ms, h->ev_start, h->ev_end));
+    for (uint32_t c = 0; c < B.nchunks; c++) { float ms = 0; CU(cudaEventElapsedTime(&ms, B.e0[c], B.e1[c])); T.eval_ms += ms; }
+    for (auto &G : B.groups) { float ms = 0; CU(cudaEventElapsedTime(&ms, G.t0, G.t1)); T.expand_ms += ms; }
+    if (h->d_prof) {
+        std::vector<long long> st(P.levels.size() + 2);
+        CU(cudaMemcpy(st.data(), h->d_prof, st.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(h->prof_path.c_str(), "w")) {
+            for (size_t l = 0; l + 1 < st.size(); l++) {
+                if (l < P.levels.size()) fprintf(f, "level %zu ops %u absorbs %u poseidons %u cycles %lld\n", l, P.levels[l].t_end - P.levels[l].t_begin, P.levels[l].w_end - P.levels[l].w_begin, P.levels[l].p_end - P.levels[l].p_begin, st[l + 1] - st[l]);
+                else fprintf(f, "inverse-batch ops %u cycles %lld\n", P.inv_end - P.inv_begin, st[l + 1] - st[l]);
+            }
+            fclose(f);
+        }
+    }
+    h->timing = T; h->last_n = n; h->last_status.assign(h->h_status, h->h_status + n);
+    B.active = false;
+    return POB_OK;
+}
+// a failure inside a batch leaves streams in an unknown state: drop the batch, keep the handle usable
+static void abort_batch(pob_handle *h) {
+    cudaDeviceSynchronize(); cudaGetLastError();
+    h->B.active = false; h->last_n = 0; h->last_status.clear();
+    std::fill(h->slot_owner.begin(), h->slot_owner.end(), (int64_t)-1);
+}
 
 extern "C" {
 
 const char *pob_last_error(void) { return g_err.c_str(); }
-const char *pob_version(void) { return "pob_b200 0.1 (sm_100a)"; }
+const char *pob_version(void) {
+#ifdef POB_TUNING
+    return "pob_b200 0.2 (sm_100a, TUNING build)";
+#else
+    return "pob_b200 0.2 (sm_100a)";
+#endif
+}
 
 const char *pob_input_schema(const char *main_name, int *nparams) {
     if (!main_name) return nullptr;
@@ -467,25 +432,25 @@ int pob_layout_info(const char *main_name, const uint64_t *params, int nparams, 
 void pob_destroy(pob_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    delete h->exporter; h->exporter = nullptr;
     if (h->s_eval) cudaStreamSynchronize(h->s_eval);
     if (h->s_exp) cudaStreamSynchronize(h->s_exp);
+    if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
     for (void *p : {(void *)h->d_ops, (void *)h->d_psums, (void *)h->d_pos, (void *)h->d_pos_konst, (void *)h->d_abs, (void *)h->d_levels, (void *)h->d_aux, (void *)h->d_konst, (void *)h->d_codes,
                     (void *)h->d_tiles, (void *)h->d_invtab, (void *)h->d_round_desc, (void *)h->d_stores, (void *)h->d_inputs, (void *)h->d_status,
-                    (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr, (void *)h->d_staged, (void *)h->d_prof, (void *)h->d_block_base})
+                    (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr, (void *)h->d_planinst, (void *)h->d_staged, (void *)h->d_prof, (void *)h->d_block_base})
         if (p) cudaFree(p);
     for (uint64_t *s : h->slots) cudaFree(s);
-    for (void *p : {(void *)h->h_status, (void *)h->h_outputs, (void *)h->h_digests, (void *)h->h_witptr}) if (p) cudaFreeHost(p);
+    for (void *p : {(void *)h->h_status, (void *)h->h_outputs, (void *)h->h_digests, (void *)h->h_witptr, (void *)h->h_planinst}) if (p) cudaFreeHost(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->slot_rel_ev) cudaEventDestroy(e);
     for (uint32_t r = 0; r < pob_handle::RING; r++) {
         if (h->ev_eval_done[r]) cudaEventDestroy(h->ev_eval_done[r]);
         if (h->ev_exp_done[r]) cudaEventDestroy(h->ev_exp_done[r]);
         if (h->ev_h2d[r]) cudaEventDestroy(h->ev_h2d[r]);
     }
-    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
-    if (h->ev_start) cudaEventDestroy(h->ev_start);
-    if (h->ev_end) cudaEventDestroy(h->ev_end);
-    if (h->s_eval) cudaStreamDestroy(h->s_eval);
-    if (h->s_exp) cudaStreamDestroy(h->s_exp);
+    for (cudaEvent_t e : {h->ev_start, h->ev_end, h->ev_tmp}) if (e) cudaEventDestroy(e);
+    for (cudaStream_t s : {h->s_h2d, h->s_eval, h->s_exp}) if (s) cudaStreamDestroy(s);
     delete h;
 }
 
@@ -503,11 +468,10 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         CU(cudaSetDevice(device));
         h->d_ops = upload(P.ops); h->d_psums = upload(P.psums); h->d_pos = upload(P.poseidons); h->d_pos_konst = upload(P.pos_konst); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
         h->d_konst = upload(P.konst); h->d_codes = upload(P.codes);
-        if (const char *v = getenv("POB_TILE_FILTER")) {      // tuning only: 1 = KeccakfRound tiles only, 2 = the others only (witness incomplete!)
+        if (const char *v = tune_env("POB_TILE_FILTER")) {      // TUNING build only: 1 = KeccakfRound tiles only, 2 = the others only (witness incomplete!)
             std::vector<Tile> sub; for (const Tile &t : P.tiles) if ((atoi(v) == 1) == (t.pad != 0)) sub.push_back(t);
             h->P.tiles = sub;
         }
-        if (getenv("POB_FLAT_FIRST")) std::stable_sort(h->P.tiles.begin(), h->P.tiles.end(), [](const Tile &a, const Tile &b) { return a.pad < b.pad; });   // tuning only
         h->d_tiles = upload(h->P.tiles);
         for (const Tile &t : h->P.tiles) if (t.pad) h->n_round_tiles++;
         { std::vector<uint64_t> bases; for (const Tile &t : P.tiles) if (t.pad && t.code_off == 0) bases.push_back(t.dst);
@@ -525,10 +489,10 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
             CU(cudaEventCreateWithFlags(&h->ev_exp_done[r], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&h->ev_h2d[r], cudaEventDisableTiming));
         }
-        CU(cudaEventCreate(&h->ev_start)); CU(cudaEventCreate(&h->ev_end));
+        CU(cudaEventCreate(&h->ev_start)); CU(cudaEventCreate(&h->ev_end)); CU(cudaEventCreateWithFlags(&h->ev_tmp, cudaEventDisableTiming));
         // (an L2 persisting access-policy window for the code stream was tried and REDUCED the expand kernel to 4.9 TB/s: the
         // carve-out takes L2 away from write combining -- profiles/r01_expand_sweep.md)
-        if (getenv("POB_EVAL_PROFILE")) CU(cudaMalloc(&h->d_prof, (P.levels.size() + 2) * sizeof(long long)));
+        if (const char *v = tune_env("POB_EVAL_PROFILE")) { h->prof_path = v; CU(cudaMalloc(&h->d_prof, (P.levels.size() + 2) * sizeof(long long))); }
         // witness slots: as many as fit in 80 % of free HBM after the store ring
         size_t free_b = 0, total_b = 0; CU(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t wbytes = 32ull * P.n_signals;
@@ -537,7 +501,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         // half (main_proof_of_burn: 32; Spend: 1024)
         uint32_t chunk = (uint32_t)std::min<uint64_t>(1024, std::max<uint64_t>(32, (512ull << 20) / (h->store_stride * 8)));
         chunk -= chunk % 32;
-        if (const char *v = getenv("POB_EVAL_CHUNK")) chunk = (uint32_t)std::max(1, atoi(v));
+        if (const char *v = tune_env("POB_EVAL_CHUNK")) chunk = (uint32_t)std::max(1, atoi(v));
         const uint64_t ring_bytes_per_inst = pob_handle::RING * (h->store_stride * 8 + (uint64_t)P.n_inputs * 32);
         uint64_t budget = (uint64_t)(free_b * 0.8);
         uint64_t nslots = budget > chunk * ring_bytes_per_inst ? (budget - chunk * ring_bytes_per_inst) / wbytes : 0;
@@ -546,22 +510,24 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (nslots == 0) throw std::runtime_error("not even one witness slot fits in free HBM");
         // expand group: ~100 GB of witness per launch pair (main_proof_of_burn: 16 witnesses; Spend: up to the whole chunk)
         h->xgroup = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(nslots, chunk), std::max<uint64_t>(16, (100ull << 30) / wbytes));
-        if (const char *v = getenv("POB_EVAL_THREADS")) h->eval_threads = atoi(v);
-        if (const char *v = getenv("POB_SERIALIZE")) h->serialize = atoi(v) != 0;
-        if (const char *v = getenv("POB_EXPAND_SMEM_KB")) h->round_dyn_smem = (uint32_t)atoi(v) * 1024u;
-        if (const char *v = getenv("POB_EXPAND_THREADS")) h->round_threads = (uint32_t)atoi(v);
-        if (const char *v = getenv("POB_CODES_SMEM_KB")) { h->codes_dyn_smem = (uint32_t)atoi(v) * 1024u; if (h->codes_dyn_smem > 48 * 1024) CU(cudaFuncSetAttribute(k_expand_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->codes_dyn_smem)); }
+        if (const char *v = tune_env("POB_EVAL_THREADS")) h->eval_threads = atoi(v);
+        if (const char *v = tune_env("POB_SERIALIZE")) h->serialize = atoi(v) != 0;
+        if (const char *v = tune_env("POB_EXPAND_SMEM_KB")) h->round_dyn_smem = (uint32_t)atoi(v) * 1024u;
+        if (const char *v = tune_env("POB_EXPAND_THREADS")) h->round_threads = (uint32_t)atoi(v);
+        if (const char *v = tune_env("POB_CODES_SMEM_KB")) { h->codes_dyn_smem = (uint32_t)atoi(v) * 1024u; if (h->codes_dyn_smem > 48 * 1024) CU(cudaFuncSetAttribute(k_expand_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->codes_dyn_smem)); }
         if (h->round_dyn_smem > 48 * 1024) {
             CU(cudaFuncSetAttribute(k_expand_round<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
             CU(cudaFuncSetAttribute(k_expand_round<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
             CU(cudaFuncSetAttribute(k_expand_round<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
             CU(cudaFuncSetAttribute(k_expand_round<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
         }
-        if (const char *v = getenv("POB_EXPAND_GROUP")) h->xgroup = (uint32_t)std::max(1, std::min<int>(atoi(v), (int)std::min<uint64_t>(nslots, chunk)));
+        if (const char *v = tune_env("POB_EXPAND_GROUP")) h->xgroup = (uint32_t)std::max(1, std::min<int>(atoi(v), (int)std::min<uint64_t>(nslots, chunk)));
         h->chunk = chunk;
         CU(cudaMalloc(&h->d_stores, (size_t)pob_handle::RING * chunk * h->store_stride * 8));
         CU(cudaMalloc(&h->d_inputs, std::max<size_t>(32, (size_t)pob_handle::RING * chunk * P.n_inputs * 32)));
         for (uint64_t s = 0; s < nslots; s++) { uint64_t *p = nullptr; CU(cudaMalloc(&p, wbytes)); h->slots.push_back(p); }
+        h->slot_owner.assign(nslots, -1); h->slot_rel_pending.assign(nslots, 0);
+        for (uint64_t s = 0; s < nslots; s++) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->slot_rel_ev.push_back(e); }
     } catch (const std::exception &e) {
         std::string m = e.what(); pob_destroy(h);
         return fail(m.find("slot") != std::string::npos ? POB_E_NO_MEMORY : POB_E_CUDA, "pob_create: " + m);
@@ -577,21 +543,9 @@ int pob_describe(const pob_handle *h, pob_desc *out) {
 void *pob_alloc_pinned(uint64_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { g_err = "cudaMallocHost failed"; return nullptr; } return p; }
 void pob_free_pinned(void *p) { if (p) cudaFreeHost(p); }
 
-static void ensure_batch_buffers(pob_handle *h, uint32_t n) {
-    if (n <= h->cap_n) return;
-    const Program &P = h->P;
-    for (void *p : {(void *)h->d_status, (void *)h->d_outputs, (void *)h->d_digests, (void *)h->d_witptr}) if (p) cudaFree(p);
-    for (void *p : {(void *)h->h_status, (void *)h->h_outputs, (void *)h->h_digests, (void *)h->h_witptr}) if (p) cudaFreeHost(p);
-    const size_t no = std::max<uint32_t>(1, P.n_outputs);
-    CU(cudaMalloc(&h->d_status, (size_t)n * 4)); CU(cudaMalloc(&h->d_outputs, (size_t)n * no * 32));
-    CU(cudaMalloc(&h->d_digests, (size_t)n * 8)); CU(cudaMalloc(&h->d_witptr, (size_t)n * sizeof(uint64_t *)));
-    CU(cudaMallocHost(&h->h_status, (size_t)n * 4)); CU(cudaMallocHost(&h->h_outputs, (size_t)n * no * 32));
-    CU(cudaMallocHost(&h->h_digests, (size_t)n * 8)); CU(cudaMallocHost(&h->h_witptr, (size_t)n * sizeof(uint64_t *)));
-    h->cap_n = n;
-}
-
 int pob_stage_inputs(pob_handle *h, const uint64_t *inputs, uint32_t n) {
     if (!h || !inputs || n == 0) return fail(POB_E_BAD_ARG, "pob_stage_inputs: bad argument");
+    if (h->B.active) return fail(POB_E_BUSY, "pob_stage_inputs: a batch is in flight");
     try {
         CU(cudaSetDevice(h->device));
         if (h->d_staged) { cudaFree(h->d_staged); h->d_staged = nullptr; h->n_staged = 0; }
@@ -603,124 +557,110 @@ int pob_stage_inputs(pob_handle *h, const uint64_t *inputs, uint32_t n) {
     return POB_OK;
 }
 
-int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t flags, uint32_t *status, uint64_t *outputs, uint64_t *digests) {
-    if (!h || n == 0 || !status) return fail(POB_E_BAD_ARG, "pob_run_batch: bad argument");
-    const bool staged = (flags & POB_RUN_INPUTS_STAGED) != 0, expand = (flags & (POB_RUN_EXPAND | POB_RUN_DIGEST)) != 0, digest = (flags & POB_RUN_DIGEST) != 0;
-    if (staged ? (h->n_staged < n) : (inputs == nullptr && h->P.n_inputs)) return fail(POB_E_BAD_ARG, "pob_run_batch: no inputs");
-    if (digest && !digests) return fail(POB_E_BAD_ARG, "pob_run_batch: POB_RUN_DIGEST needs a digests array");
+static int run_batch_impl(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t flags, const uint32_t *retain, uint32_t n_retain,
+                          uint32_t *status, uint64_t *outputs, uint64_t *digests, const char *who) {
+    if (!h || n == 0 || !status) return fail(POB_E_BAD_ARG, std::string(who) + ": bad argument");
+    if ((flags & POB_RUN_DIGEST) && !digests) return fail(POB_E_BAD_ARG, std::string(who) + ": POB_RUN_DIGEST needs a digests array");
     try {
-        const Program &P = h->P;
+        int rc = begin_batch(h, inputs, n, flags, retain, n_retain, false, who);
+        if (rc) return rc;
+        return finish_batch(h, status, outputs, digests);
+    } catch (const std::exception &e) { abort_batch(h); return fail(POB_E_CUDA, std::string(who) + ": " + e.what()); }
+}
+int pob_run_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t flags, uint32_t *status, uint64_t *outputs, uint64_t *digests) {
+    return run_batch_impl(h, inputs, n, flags, nullptr, 0, status, outputs, digests, "pob_run_batch");
+}
+int pob_run_batch_retain(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t flags, const uint32_t *retain, uint32_t n_retain,
+                         uint32_t *status, uint64_t *outputs, uint64_t *digests) {
+    static const uint32_t none = 0;
+    if (!retain && n_retain) return fail(POB_E_BAD_ARG, "pob_run_batch_retain: null retain list");
+    return run_batch_impl(h, inputs, n, flags, retain ? retain : &none, n_retain, status, outputs, digests, "pob_run_batch_retain");
+}
+
+// ---- consumer-paced hand-off ------------------------------------------------------------------------------------
+int pob_submit(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t flags) {
+    if (!h || n == 0) return fail(POB_E_BAD_ARG, "pob_submit: bad argument");
+    try { return begin_batch(h, inputs, n, flags | POB_RUN_EXPAND, nullptr, 0, true, "pob_submit"); }
+    catch (const std::exception &e) { abort_batch(h); return fail(POB_E_CUDA, std::string("pob_submit: ") + e.what()); }
+}
+int pob_acquire(pob_handle *h, uint32_t *index, void **dptr, void *consumer_stream) {
+    if (!h || !index || !dptr) return fail(POB_E_BAD_ARG, "pob_acquire: null argument");
+    pob_handle::Batch &B = h->B;
+    if (!B.active || !B.async) return fail(POB_E_BAD_ARG, "pob_acquire: no submitted batch");
+    try {
         CU(cudaSetDevice(h->device));
-        ensure_batch_buffers(h, n);
-        const uint32_t E = h->chunk, R = pob_handle::RING, nchunks = (n + E - 1) / E, nslots = (uint32_t)h->slots.size(), X = h->xgroup;
-        const size_t in_stride = (size_t)P.n_inputs * 4, no = std::max<uint32_t>(1, P.n_outputs);
-        const uint32_t groups_per_chunk = (E + X - 1) / X, ev_per_chunk = 2 + 2 * groups_per_chunk;
-        while (h->ev_pool.size() < (size_t)nchunks * ev_per_chunk) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
-        for (uint32_t i = 0; i < n; i++) h->h_witptr[i] = h->slots[i % nslots];
-        pob_timing T{};
-        CU(cudaEventRecord(h->ev_start, h->s_eval));
-        CU(cudaMemcpyAsync(h->d_witptr, h->h_witptr, (size_t)n * sizeof(uint64_t *), cudaMemcpyHostToDevice, h->s_eval));
-        if (digest) CU(cudaMemsetAsync(h->d_digests, 0, (size_t)n * 8, h->s_eval));
-        CU(cudaEventRecord(h->ev_eval_done[0], h->s_eval));
-        CU(cudaStreamWaitEvent(h->s_h2d, h->ev_eval_done[0], 0));
-        std::vector<uint32_t> group_count;
-        for (uint32_t c = 0; c < nchunks; c++) {
-            const uint32_t r = c % R, first = c * E, cnt = std::min(E, n - first);
-            cudaEvent_t *ev = &h->ev_pool[(size_t)c * ev_per_chunk];
-            const uint64_t *d_in;
-            if (staged) d_in = h->d_staged + (size_t)first * in_stride;
-            else {
-                // inputs travel on their own stream, one chunk ahead of the eval kernel that consumes them
-                uint64_t *dst = h->d_inputs + (size_t)r * E * in_stride;
-                if (c >= R) CU(cudaStreamWaitEvent(h->s_h2d, h->ev_eval_done[r], 0));
-                if (in_stride) { CU(cudaMemcpyAsync(dst, inputs + (size_t)first * in_stride, (size_t)cnt * in_stride * 8, cudaMemcpyHostToDevice, h->s_h2d)); T.h2d_bytes += (uint64_t)cnt * in_stride * 8; }
-                CU(cudaEventRecord(h->ev_h2d[r], h->s_h2d));
-                CU(cudaStreamWaitEvent(h->s_eval, h->ev_h2d[r], 0));
-                d_in = dst;
-            }
-            if (c >= R) CU(cudaStreamWaitEvent(h->s_eval, h->ev_exp_done[r], 0));      // store ring slot r is free again
-            uint64_t *stores = h->d_stores + (size_t)r * E * h->store_stride;
-            EvalArgs ea{h->d_ops, h->d_abs, h->d_pos, h->d_pos_konst, h->d_psums, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.ginv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
-                        h->d_codes + ROUND_SIGNALS + 1, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
-                        h->d_status + first, h->d_outputs + (size_t)first * no * 4, (c == 0) ? h->d_prof : nullptr};
-            CU(cudaEventRecord(ev[0], h->s_eval));
-            switch (h->eval_threads) {
-            case 256: k_eval<256><<<cnt, 256, 0, h->s_eval>>>(ea); break;
-            case 512: k_eval<512><<<cnt, 512, 0, h->s_eval>>>(ea); break;
-            default: k_eval<1024><<<cnt, 1024, 0, h->s_eval>>>(ea); break;
-            }
-            CU(cudaEventRecord(ev[1], h->s_eval));
-            CU(cudaEventRecord(h->ev_eval_done[r], h->s_eval));
-            T.eval_launches++;
-            if (expand) {
-                CU(cudaStreamWaitEvent(h->s_exp, h->ev_eval_done[r], 0));
-                uint32_t g = 0;
-                for (uint32_t off = 0; off < cnt; off += X, g++) {
-                    const uint32_t gc = std::min(X, cnt - off);
-                    ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, reinterpret_cast<const uint2 *>(h->d_round_desc), stores + (size_t)off * h->store_stride, h->store_stride, P.val_base, h->d_witptr + first + off, 0};
-                    CU(cudaEventRecord(ev[2 + 2 * g], h->s_exp));
-                    // launch 1: KeccakfRound tiles, tile-major (each CTA's tables are L1-resident);
-                    // launch 2: code tiles, INSTANCE-major, so that a tile's code stream is fetched from DRAM once and
-                    // served from L2 to the other witnesses of the group
-                    const uint32_t n_round = h->n_round_tiles, n_code = (uint32_t)P.tiles.size() - n_round;
-                    if (n_round) {
-                        xa.tile0 = 0;
-                        if (h->round_threads == 128) k_expand_round<128><<<dim3(n_round, gc), 128, h->round_dyn_smem, h->s_exp>>>(xa);
-                        else if (h->round_threads == 512) k_expand_round<512><<<dim3(n_round, gc), 512, h->round_dyn_smem, h->s_exp>>>(xa);
-                        else if (h->round_threads == 1024) k_expand_round<1024><<<dim3(n_round, gc), 1024, h->round_dyn_smem, h->s_exp>>>(xa);
-                        else k_expand_round<256><<<dim3(n_round, gc), 256, h->round_dyn_smem, h->s_exp>>>(xa);
-                    }
-                    if (n_code) { xa.tile0 = n_round; k_expand_codes<<<dim3(gc, n_code), 256, h->codes_dyn_smem, h->s_exp>>>(xa); T.other_launches++; }
-                    CU(cudaEventRecord(ev[3 + 2 * g], h->s_exp));
-                    T.expand_launches++;
-                    if (digest) for (uint32_t j = 0; j < gc; j++) {
-                        k_digest<<<1184, 256, 0, h->s_exp>>>(h->slots[(first + off + j) % nslots], P.n_signals, h->d_digests + first + off + j);
-                        T.other_launches++;
-                    }
-                }
-                group_count.push_back(g);
-                CU(cudaEventRecord(h->ev_exp_done[r], h->s_exp));
-                if (h->serialize) CU(cudaStreamWaitEvent(h->s_eval, h->ev_exp_done[r], 0));
-            } else {
-                group_count.push_back(0);
-                CU(cudaEventRecord(h->ev_exp_done[r], h->s_eval));
-            }
-        }
-        CU(cudaGetLastError());
-        // results: status + outputs after the last eval; digests after the last expand
-        CU(cudaMemcpyAsync(h->h_status, h->d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, h->s_eval));
-        T.d2h_bytes += (uint64_t)n * 4;
-        if (P.n_outputs) { CU(cudaMemcpyAsync(h->h_outputs, h->d_outputs, (size_t)n * no * 32, cudaMemcpyDeviceToHost, h->s_eval)); T.d2h_bytes += (uint64_t)n * no * 32; }
-        CU(cudaEventRecord(h->ev_eval_done[0], h->s_eval));
-        CU(cudaStreamWaitEvent(h->s_exp, h->ev_eval_done[0], 0));
-        if (digest) { CU(cudaMemcpyAsync(h->h_digests, h->d_digests, (size_t)n * 8, cudaMemcpyDeviceToHost, h->s_exp)); T.d2h_bytes += (uint64_t)n * 8; }
-        CU(cudaEventRecord(h->ev_end, h->s_exp));
-        CU(cudaStreamSynchronize(h->s_exp)); CU(cudaStreamSynchronize(h->s_eval)); CU(cudaStreamSynchronize(h->s_h2d));
-        CU(cudaGetLastError());
-        memcpy(status, h->h_status, (size_t)n * 4);
-        if (outputs && P.n_outputs) memcpy(outputs, h->h_outputs, (size_t)n * no * 32);
-        if (digest) memcpy(digests, h->h_digests, (size_t)n * 8);
-        CU(cudaEventElapsedTime(&T.total_ms, h->ev_start, h->ev_end));
-        for (uint32_t c = 0; c < nchunks; c++) {
-            cudaEvent_t *ev = &h->ev_pool[(size_t)c * ev_per_chunk];
-            float ms = 0; CU(cudaEventElapsedTime(&ms, ev[0], ev[1])); T.eval_ms += ms;
-            for (uint32_t g = 0; g < group_count[c]; g++) { CU(cudaEventElapsedTime(&ms, ev[2 + 2 * g], ev[3 + 2 * g])); T.expand_ms += ms; }
-        }
-        if (h->d_prof) {
-            std::vector<long long> st(P.levels.size() + 2);
-            CU(cudaMemcpy(st.data(), h->d_prof, st.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-            FILE *f = fopen(getenv("POB_EVAL_PROFILE"), "w");
-            if (f) {
-                for (size_t l = 0; l + 1 < st.size(); l++) {
-                    if (l < P.levels.size()) fprintf(f, "level %zu ops %u absorbs %u poseidons %u cycles %lld\n", l, P.levels[l].t_end - P.levels[l].t_begin, P.levels[l].w_end - P.levels[l].w_begin, P.levels[l].p_end - P.levels[l].p_begin, st[l + 1] - st[l]);
-                    else fprintf(f, "inverse-batch ops %u cycles %lld\n", P.inv_end - P.inv_begin, st[l + 1] - st[l]);
-                }
-                fclose(f);
-            }
-        }
-        h->timing = T; h->last_n = n; h->last_expanded = expand;
-    } catch (const std::exception &e) { return fail(POB_E_CUDA, std::string("pob_run_batch: ") + e.what()); }
+        if (B.acq_pos >= B.plan.size()) return POB_DONE;
+        const uint32_t k = B.acq_pos, g = B.group_of[k], i = B.plan[k];
+        advance(h);
+        if (B.next_group <= g) return fail(POB_E_BUSY, "pob_acquire: every witness slot is held by the consumer; pob_release one first");
+        CU(cudaEventSynchronize(B.est[i / h->chunk]));          // accept/reject of this instance (known long before its witness is complete)
+        *index = i;
+        if (h->h_status[i] != 0) { *dptr = nullptr; B.st[k] = 2; B.acq_pos++; advance(h); return fail(POB_E_REJECTED, "pob_acquire: the instance failed a constraint and has no witness"); }
+        if (consumer_stream) CU(cudaStreamWaitEvent((cudaStream_t)consumer_stream, B.groups[g].t1, 0));
+        else CU(cudaEventSynchronize(B.groups[g].t1));
+        *dptr = h->slots[B.slot[k]]; B.st[k] = 1; B.acq_pos++;
+        return POB_OK;
+    } catch (const std::exception &e) { abort_batch(h); return fail(POB_E_CUDA, std::string("pob_acquire: ") + e.what()); }
+}
+int pob_release(pob_handle *h, uint32_t index, void *consumer_stream) {
+    if (!h) return fail(POB_E_BAD_ARG, "pob_release: null argument");
+    pob_handle::Batch &B = h->B;
+    if (!B.active || !B.async) return fail(POB_E_BAD_ARG, "pob_release: no submitted batch");
+    auto it = std::lower_bound(B.plan.begin(), B.plan.end(), index);
+    if (it == B.plan.end() || *it != index) return fail(POB_E_RANGE, "pob_release: no such instance");
+    const uint32_t k = (uint32_t)(it - B.plan.begin());
+    if (B.st[k] != 1) return fail(POB_E_RANGE, "pob_release: the instance is not held by the consumer");
+    try {
+        CU(cudaSetDevice(h->device));
+        const uint32_t s = B.slot[k];
+        if (consumer_stream) { CU(cudaEventRecord(h->slot_rel_ev[s], (cudaStream_t)consumer_stream)); h->slot_rel_pending[s] = 1; }
+        B.st[k] = 2; h->slot_owner[s] = -1;
+        advance(h);
+    } catch (const std::exception &e) { abort_batch(h); return fail(POB_E_CUDA, std::string("pob_release: ") + e.what()); }
     return POB_OK;
+}
+int pob_finish(pob_handle *h, uint32_t *status, uint64_t *outputs, uint64_t *digests) {
+    if (!h) return fail(POB_E_BAD_ARG, "pob_finish: null argument");
+    if (!h->B.active) return fail(POB_E_BAD_ARG, "pob_finish: no batch in flight");
+    try { CU(cudaSetDevice(h->device)); return finish_batch(h, status, outputs, digests); }
+    catch (const std::exception &e) { abort_batch(h); return fail(POB_E_CUDA, std::string("pob_finish: ") + e.what()); }
+}
+
+int pob_export_batch(pob_handle *h, const uint64_t *inputs, uint32_t n, uint32_t flags, const char *const *paths,
+                     uint32_t *status, uint64_t *outputs, pob_export_stats *stats) {
+    if (!h || n == 0 || !status) return fail(POB_E_BAD_ARG, "pob_export_batch: bad argument");
+    const auto t0 = std::chrono::steady_clock::now();
+    bool open_err = false; std::string bad_path;
+    try {
+        CU(cudaSetDevice(h->device));
+        if (!h->exporter) h->exporter = new Exporter(h->device);
+        Exporter &X = *h->exporter; X.io_err = false; const uint64_t bytes0 = X.bytes_moved;
+        int rc = begin_batch(h, inputs, n, (flags & POB_RUN_INPUTS_STAGED) | POB_RUN_EXPAND, nullptr, 0, true, "pob_export_batch");
+        if (rc) return rc;
+        uint64_t nw = 0;
+        for (;;) {
+            uint32_t idx = 0; void *dptr = nullptr;
+            rc = pob_acquire(h, &idx, &dptr, nullptr);
+            if (rc == POB_DONE) break;
+            if (rc == POB_E_REJECTED) continue;
+            if (rc) { if (h->B.active) abort_batch(h); return rc; }
+            int fd = -1;
+            if (paths && paths[idx]) { fd = open(paths[idx], O_WRONLY | O_CREAT | O_TRUNC, 0644); if (fd < 0) { open_err = true; bad_path = paths[idx]; } }
+            if (fd >= 0 || !(paths && paths[idx])) { X.send((const uint64_t *)dptr, h->P.n_signals, fd); nw++; }
+            rc = pob_release(h, idx, X.cs[0]);                 // the slot is reusable once its last D2H copy has run
+            if (rc) return rc;
+        }
+        rc = finish_batch(h, status, outputs, nullptr);
+        X.drain();
+        if (stats) {
+            stats->witnesses = nw; stats->bytes = X.bytes_moved - bytes0 + 76 * nw;
+            stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            stats->d2h_gbs = stats->total_ms > 0 ? (float)(stats->bytes / 1e6 / stats->total_ms) : 0.f;
+        }
+        if (open_err) return fail(POB_E_IO, "pob_export_batch: cannot open " + bad_path);
+        if (X.io_err) return fail(POB_E_IO, "pob_export_batch: short write");
+        return rc;
+    } catch (const std::exception &e) { abort_batch(h); return fail(POB_E_CUDA, std::string("pob_export_batch: ") + e.what()); }
 }
 
 int pob_pow_grind(int device, const uint64_t start_key[4], const uint64_t reveal_amount[4], const uint64_t burn_extra_commitment[4],
@@ -765,11 +705,18 @@ int pob_last_timing(const pob_handle *h, pob_timing *out) {
     *out = h->timing; return POB_OK;
 }
 
+// slot of a resident, ACCEPTED instance of the last finished batch (or of one the consumer currently holds)
 static int resident_slot(pob_handle *h, uint32_t index, uint64_t **slot) {
-    if (!h->last_expanded || index >= h->last_n) return fail(POB_E_RANGE, "witness index not in the last expanded batch");
-    const uint32_t nslots = (uint32_t)h->slots.size();
-    if ((uint64_t)index + nslots < h->last_n) return fail(POB_E_RANGE, "witness slot already overwritten by a later instance");
-    *slot = h->slots[index % nslots]; return POB_OK;
+    const uint32_t *st = nullptr; uint32_t n = 0;
+    if (h->B.active) { st = h->h_status; n = h->B.n; } else { st = h->last_status.data(); n = h->last_n; }
+    if (index >= n) return fail(POB_E_RANGE, "witness index not in the last batch");
+    if (h->B.active) {
+        auto it = std::lower_bound(h->B.plan.begin(), h->B.plan.end(), index);
+        if (it == h->B.plan.end() || *it != index || h->B.st[(size_t)(it - h->B.plan.begin())] != 1) return fail(POB_E_RANGE, "a batch is in flight and the consumer does not hold this witness");
+    }
+    if (st[index] != 0) return fail(POB_E_REJECTED, "the instance failed a circuit constraint: it has no witness");
+    for (size_t s = 0; s < h->slots.size(); s++) if (h->slot_owner[s] == (int64_t)index) { *slot = h->slots[s]; return POB_OK; }
+    return fail(POB_E_RANGE, "witness not resident: not materialised, released, or its slot was reused by a later instance");
 }
 
 int pob_selfcheck_keccak(pob_handle *h, uint32_t index, uint64_t *n_blocks, uint64_t *n_bad) {
@@ -788,15 +735,6 @@ int pob_selfcheck_keccak(pob_handle *h, uint32_t index, uint64_t *n_blocks, uint
     return POB_OK;
 }
 
-int pob_debug_poke_witness(pob_handle *h, uint32_t index, uint64_t signal, const uint64_t value[4]) {
-    if (!h || !value) return fail(POB_E_BAD_ARG, "pob_debug_poke_witness: null argument");
-    uint64_t *s = nullptr; int rc = resident_slot(h, index, &s); if (rc) return rc;
-    if (signal >= h->P.n_signals) return fail(POB_E_RANGE, "pob_debug_poke_witness: signal index out of range");
-    if (cudaSetDevice(h->device) != cudaSuccess || cudaMemcpy(s + 4 * signal, value, 32, cudaMemcpyHostToDevice) != cudaSuccess)
-        return fail(POB_E_CUDA, "pob_debug_poke_witness: cudaMemcpy failed");
-    return POB_OK;
-}
-
 int pob_witness_device_ptr(pob_handle *h, uint32_t index, void **dptr) {
     if (!h || !dptr) return fail(POB_E_BAD_ARG, "pob_witness_device_ptr: null argument");
     uint64_t *s = nullptr; int rc = resident_slot(h, index, &s); if (rc) return rc;
@@ -806,7 +744,8 @@ int pob_witness_device_ptr(pob_handle *h, uint32_t index, void **dptr) {
 int pob_copy_witness(pob_handle *h, uint32_t index, uint64_t first_signal, uint64_t n_signals, uint64_t *dst_host) {
     if (!h || !dst_host) return fail(POB_E_BAD_ARG, "pob_copy_witness: null argument");
     uint64_t *s = nullptr; int rc = resident_slot(h, index, &s); if (rc) return rc;
-    if (first_signal + n_signals > h->P.n_signals) return fail(POB_E_RANGE, "pob_copy_witness: range exceeds the witness");
+    const uint64_t n = h->P.n_signals;
+    if (first_signal > n || n_signals > n - first_signal) return fail(POB_E_RANGE, "pob_copy_witness: range exceeds the witness");
     if (cudaSetDevice(h->device) != cudaSuccess || cudaMemcpy(dst_host, s + 4 * first_signal, (size_t)n_signals * 32, cudaMemcpyDeviceToHost) != cudaSuccess)
         return fail(POB_E_CUDA, "pob_copy_witness: cudaMemcpy failed");
     return POB_OK;
@@ -815,37 +754,17 @@ int pob_copy_witness(pob_handle *h, uint32_t index, uint64_t first_signal, uint6
 int pob_write_wtns(pob_handle *h, uint32_t index, const char *path) {
     if (!h || !path) return fail(POB_E_BAD_ARG, "pob_write_wtns: null argument");
     uint64_t *s = nullptr; int rc = resident_slot(h, index, &s); if (rc) return rc;
-    FILE *f = fopen(path, "wb"); if (!f) return fail(POB_E_IO, std::string("cannot open ") + path);
-    // iden3 binary witness format, version 2 (what the circom runtime's writeBinWitness emits)
-    const uint64_t n = h->P.n_signals; uint32_t u32; uint64_t u64; Fr p = fr_p();
-    bool ok = fwrite("wtns", 1, 4, f) == 4;
-    u32 = 2; ok &= fwrite(&u32, 4, 1, f) == 1; u32 = 2; ok &= fwrite(&u32, 4, 1, f) == 1;
-    u32 = 1; ok &= fwrite(&u32, 4, 1, f) == 1; u64 = 40; ok &= fwrite(&u64, 8, 1, f) == 1;
-    u32 = 32; ok &= fwrite(&u32, 4, 1, f) == 1; ok &= fwrite(p.l, 4, 8, f) == 8; u32 = (uint32_t)n; ok &= fwrite(&u32, 4, 1, f) == 1;
-    u32 = 2; ok &= fwrite(&u32, 4, 1, f) == 1; u64 = 32ull * n; ok &= fwrite(&u64, 8, 1, f) == 1;
-    // double-buffered: the D2H copy of chunk i+1 (pinned, own stream) overlaps the fwrite of chunk i
-    const uint64_t CH = 1ull << 21;     // 2 Mi entries = 64 MiB per hop
-    void *buf[2] = {nullptr, nullptr}; cudaStream_t cs = nullptr; cudaEvent_t ev[2] = {nullptr, nullptr};
-    bool cuda_ok = cudaSetDevice(h->device) == cudaSuccess && cudaMallocHost(&buf[0], CH * 32) == cudaSuccess && cudaMallocHost(&buf[1], CH * 32) == cudaSuccess &&
-                   cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreate(&ev[0]) == cudaSuccess && cudaEventCreate(&ev[1]) == cudaSuccess;
-    const uint64_t nchunk = (n + CH - 1) / CH;
-    auto issue = [&](uint64_t c) {
-        const uint64_t off = c * CH, cnt = std::min(CH, n - off);
-        return cudaMemcpyAsync(buf[c & 1], s + 4 * off, (size_t)cnt * 32, cudaMemcpyDeviceToHost, cs) == cudaSuccess && cudaEventRecord(ev[c & 1], cs) == cudaSuccess;
-    };
-    if (cuda_ok && nchunk) cuda_ok = issue(0);
-    for (uint64_t c = 0; cuda_ok && ok && c < nchunk; c++) {
-        cuda_ok = cudaEventSynchronize(ev[c & 1]) == cudaSuccess;
-        if (cuda_ok && c + 1 < nchunk) cuda_ok = issue(c + 1);
-        const uint64_t cnt = std::min(CH, n - c * CH);
-        if (cuda_ok) ok &= fwrite(buf[c & 1], 32, (size_t)cnt, f) == cnt;
-    }
-    if (cs) cudaStreamSynchronize(cs);
-    for (int i = 0; i < 2; i++) { if (buf[i]) cudaFreeHost(buf[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
-    if (cs) cudaStreamDestroy(cs);
-    if (!cuda_ok) { fclose(f); return fail(POB_E_CUDA, "pob_write_wtns: CUDA copy failed"); }
-    ok &= fclose(f) == 0;
-    return ok ? POB_OK : fail(POB_E_IO, std::string("short write to ") + path);
+    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return fail(POB_E_IO, std::string("cannot open ") + path);
+    try {
+        CU(cudaSetDevice(h->device));
+        if (!h->exporter) h->exporter = new Exporter(h->device);
+        h->exporter->io_err = false;
+        h->exporter->send(s, h->P.n_signals, fd);
+        h->exporter->drain();
+        if (h->exporter->io_err) return fail(POB_E_IO, std::string("short write to ") + path);
+    } catch (const std::exception &e) { return fail(POB_E_CUDA, std::string("pob_write_wtns: ") + e.what()); }
+    return POB_OK;
 }
 
 }  // extern "C"

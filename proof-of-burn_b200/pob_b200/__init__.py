@@ -24,7 +24,8 @@ P = 2188824287183927522224640574525727508854836440041603434369820418657580849561
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpob_b200.so")
 
-RUN_EXPAND, RUN_DIGEST, RUN_INPUTS_STAGED = 1, 2, 4
+RUN_EXPAND, RUN_DIGEST, RUN_INPUTS_STAGED, RUN_DISCARD = 1, 2, 4, 8
+E_RANGE, E_REJECTED, E_BUSY, DONE = -5, -8, -9, 1
 MAIN_PROOF_OF_BURN = "ProofOfBurn(16, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)"   # circuits/main_proof_of_burn.circom:27
 MAIN_SPEND = "Spend(31)"                                                       # circuits/main_spend.circom:6
 TEST_PROOF_OF_BURN = "ProofOfBurn(4, 4, 5, 20, 31, 2, 10 ** 18, 10 ** 19)"     # tests/testcases/proof_of_burn.py:53
@@ -53,6 +54,13 @@ class Timing(ctypes.Structure):
 
     def as_dict(self):
         return {k: (float(getattr(self, k)) if k.endswith("_ms") else int(getattr(self, k))) for k, _ in self._fields_}
+
+
+class ExportStats(ctypes.Structure):
+    _fields_ = [("witnesses", ctypes.c_uint64), ("bytes", ctypes.c_uint64), ("total_ms", ctypes.c_float), ("d2h_gbs", ctypes.c_float)]
+
+    def as_dict(self):
+        return {"witnesses": int(self.witnesses), "bytes": int(self.bytes), "total_ms": float(self.total_ms), "d2h_gbs": float(self.d2h_gbs)}
 
 
 _LIB = None
@@ -93,8 +101,18 @@ def lib():
         L.pob_witness_device_ptr.argtypes = [vp, u32, ctypes.POINTER(vp)]
         L.pob_selfcheck_keccak.restype = ci
         L.pob_selfcheck_keccak.argtypes = [vp, u32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
-        L.pob_debug_poke_witness.restype = ci
-        L.pob_debug_poke_witness.argtypes = [vp, u32, u64, vp]
+        L.pob_run_batch_retain.restype = ci
+        L.pob_run_batch_retain.argtypes = [vp, vp, u32, u32, vp, u32, vp, vp, vp]
+        L.pob_submit.restype = ci
+        L.pob_submit.argtypes = [vp, vp, u32, u32]
+        L.pob_acquire.restype = ci
+        L.pob_acquire.argtypes = [vp, ctypes.POINTER(u32), ctypes.POINTER(vp), vp]
+        L.pob_release.restype = ci
+        L.pob_release.argtypes = [vp, u32, vp]
+        L.pob_finish.restype = ci
+        L.pob_finish.argtypes = [vp, vp, vp, vp]
+        L.pob_export_batch.restype = ci
+        L.pob_export_batch.argtypes = [vp, vp, u32, u32, vp, vp, vp, ctypes.POINTER(ExportStats)]
         L.pob_pow_grind.restype = ci
         L.pob_pow_grind.argtypes = [ci, vp, vp, vp, u32, u64, vp, ctypes.POINTER(u64)]
         L.pob_last_error.restype = ctypes.c_char_p
@@ -109,13 +127,46 @@ def _check(rc):
 
 
 # ---- field / schema helpers --------------------------------------------------------------------------------
+def eval_int_expr(text, env=None):
+    """Template parameters and schema dimensions are tiny integer expressions (`10 ** 19`, `p1*136`, `2*p0`): evaluate
+    them with a whitelisted AST walk -- integers, names from `env`, + - * // ** and unary minus; nothing else."""
+    import ast
+    import operator
+    ops = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, ast.FloorDiv: operator.floordiv, ast.Pow: operator.pow}
+
+    def ev(n):
+        if isinstance(n, ast.Expression):
+            return ev(n.body)
+        if isinstance(n, ast.Constant) and isinstance(n.value, int) and not isinstance(n.value, bool):
+            return n.value
+        if isinstance(n, ast.Name) and env is not None and n.id in env:
+            return int(env[n.id])
+        if isinstance(n, ast.UnaryOp) and isinstance(n.op, ast.USub):
+            return -ev(n.operand)
+        if isinstance(n, ast.BinOp) and type(n.op) in ops:
+            a, b = ev(n.left), ev(n.right)
+            if isinstance(n.op, ast.Pow) and (b < 0 or b > 4096 or abs(a) > 1 << 64):
+                raise ValueError("exponent out of range in %r" % text)
+            return ops[type(n.op)](a, b)
+        raise ValueError("unsupported expression %r" % text)
+    return int(ev(ast.parse(text.strip(), mode="eval")))
+
+
+def parse_int(v):
+    """one input value: JSON int, decimal string, or 0x-prefixed hex string (some circom loaders accept it)"""
+    if isinstance(v, str):
+        t = v.strip()
+        return int(t, 16) if t.lower().startswith(("0x", "-0x")) else int(t)
+    return int(v)
+
+
 def parse_main(expr):
     """'ProofOfBurn(4, 4, 5, 20, 31, 2, 10 ** 18, 10 ** 19)' -> ('ProofOfBurn', [4, 4, 5, 20, 31, 2, 10**18, 10**19])"""
     m = re.match(r"\s*(\w+)\s*(?:\((.*)\))?\s*;?\s*$", expr, re.S)
     if not m:
         raise ValueError("cannot parse main expression %r" % expr)
     args = (m.group(2) or "").strip()
-    return m.group(1), ([int(eval(a, {"__builtins__": {}})) for a in args.split(",")] if args else [])
+    return m.group(1), ([eval_int_expr(a) for a in args.split(",")] if args else [])
 
 
 def to_limbs(vals):
@@ -147,7 +198,7 @@ def input_schema(name, params):
     out = []
     for item in [x for x in s.decode().split(",") if x]:
         m = re.match(r"(\w+)((?:\[[^\]]+\])*)$", item)
-        out.append((m.group(1), [int(eval(d, {"__builtins__": {}}, env)) for d in re.findall(r"\[([^\]]+)\]", m.group(2))]))
+        out.append((m.group(1), [eval_int_expr(d, env) for d in re.findall(r"\[([^\]]+)\]", m.group(2))]))
     return out
 
 
@@ -156,7 +207,7 @@ def _flatten(v, out):
         for e in v:
             _flatten(e, out)
     else:
-        out.append(int(v))
+        out.append(parse_int(v))
 
 
 def flatten_input(schema, inp):
@@ -266,25 +317,82 @@ class Circuit:
         _check(lib().pob_stage_inputs(self._h, packed.ctypes.data, packed.shape[0]))
 
     # ---- run ----
-    def run_packed(self, packed, n=None, expand=True, digest=False, staged=False):
+    def _inputs_ptr(self, packed, n, staged):
         if staged:
             assert n is not None
-            ptr = None
-        else:
-            packed = np.ascontiguousarray(packed, dtype=np.uint64)
-            n = packed.shape[0] if n is None else n
-            ptr = packed.ctypes.data
-        flags = (RUN_EXPAND if expand else 0) | (RUN_DIGEST if digest else 0) | (RUN_INPUTS_STAGED if staged else 0)
+            return None, n, None
+        packed = np.ascontiguousarray(packed, dtype=np.uint64)
+        return packed.ctypes.data, (packed.shape[0] if n is None else n), packed
+
+    def run_packed(self, packed, n=None, expand=True, digest=False, staged=False, discard=False, retain=None):
+        """One synchronous batch (pob_run_batch / pob_run_batch_retain).  With expand and n > n_slots the library wants
+        to know what happens to the witnesses: digest=True (each one is consumed by the on-GPU digest), discard=True
+        (generation-only measurement), retain=[indices] (only those are materialised) -- or use submit()/acquire()."""
+        ptr, n, keep = self._inputs_ptr(packed, n, staged)
+        flags = (RUN_EXPAND if expand else 0) | (RUN_DIGEST if digest else 0) | (RUN_INPUTS_STAGED if staged else 0) | (RUN_DISCARD if discard else 0)
         status = np.zeros(n, dtype=np.uint32)
         outputs = np.zeros((n, max(1, self.n_outputs), 4), dtype=np.uint64)
         digests = np.zeros(n, dtype=np.uint64)
-        _check(lib().pob_run_batch(self._h, ptr, n, flags, status.ctypes.data, outputs.ctypes.data, digests.ctypes.data if digest else None))
+        if retain is None:
+            _check(lib().pob_run_batch(self._h, ptr, n, flags, status.ctypes.data, outputs.ctypes.data, digests.ctypes.data if digest else None))
+        else:
+            r = np.ascontiguousarray(retain, dtype=np.uint32)
+            _check(lib().pob_run_batch_retain(self._h, ptr, n, flags, r.ctypes.data if len(r) else None, len(r), status.ctypes.data, outputs.ctypes.data,
+                                              digests.ctypes.data if digest else None))
+        return BatchResult(status, outputs[:, : self.n_outputs], digests if digest else None, self.last_timing())
+
+    def run(self, inputs, expand=True, digest=False, discard=False, retain=None):
+        return self.run_packed(self.pack(inputs), expand=expand, digest=digest, discard=discard, retain=retain)
+
+    def last_timing(self):
         t = Timing()
         _check(lib().pob_last_timing(self._h, ctypes.byref(t)))
-        return BatchResult(status, outputs[:, : self.n_outputs], digests if digest else None, t.as_dict())
+        return t.as_dict()
 
-    def run(self, inputs, expand=True, digest=False):
-        return self.run_packed(self.pack(inputs), expand=expand, digest=digest)
+    # ---- consumer-paced hand-off (pob_submit / pob_acquire / pob_release / pob_finish) ----
+    def submit(self, packed, n=None, staged=False, digest=False):
+        ptr, n, keep = self._inputs_ptr(packed, n, staged)
+        self._inflight = (keep, n, digest)                   # the input buffer must outlive the batch
+        _check(lib().pob_submit(self._h, ptr, n, (RUN_DIGEST if digest else 0) | (RUN_INPUTS_STAGED if staged else 0)))
+
+    def acquire(self, stream=None):
+        """next witness of the submitted batch: (index, device pointer) ; (index, None) for a rejected instance ;
+        None when the batch is exhausted.  Raises PobError(E_BUSY) when every slot is held."""
+        idx, dptr = ctypes.c_uint32(0), ctypes.c_void_p()
+        rc = lib().pob_acquire(self._h, ctypes.byref(idx), ctypes.byref(dptr), stream)
+        if rc == DONE:
+            return None
+        if rc == E_REJECTED:
+            return int(idx.value), None
+        _check(rc)
+        return int(idx.value), dptr.value
+
+    def release(self, index, stream=None):
+        _check(lib().pob_release(self._h, index, stream))
+
+    def finish(self):
+        keep, n, digest = self._inflight
+        status = np.zeros(n, dtype=np.uint32)
+        outputs = np.zeros((n, max(1, self.n_outputs), 4), dtype=np.uint64)
+        digests = np.zeros(n, dtype=np.uint64)
+        _check(lib().pob_finish(self._h, status.ctypes.data, outputs.ctypes.data, digests.ctypes.data if digest else None))
+        self._inflight = None
+        return BatchResult(status, outputs[:, : self.n_outputs], digests if digest else None, self.last_timing())
+
+    def export_batch(self, packed, paths=None, n=None, staged=False):
+        """== n runs of `./<circuit> input_i.json paths[i]` (reference Makefile:5-6): every accepted instance is exported
+        while later ones are generated; paths=None (or a None entry) moves the .wtns image to host memory only.
+        Returns (BatchResult, export stats)."""
+        ptr, n, keep = self._inputs_ptr(packed, n, staged)
+        arr = None
+        if paths is not None:
+            assert len(paths) == n
+            arr = (ctypes.c_char_p * n)(*[None if q is None else os.fsencode(q) for q in paths])
+        status = np.zeros(n, dtype=np.uint32)
+        outputs = np.zeros((n, max(1, self.n_outputs), 4), dtype=np.uint64)
+        st = ExportStats()
+        _check(lib().pob_export_batch(self._h, ptr, n, RUN_INPUTS_STAGED if staged else 0, arr, status.ctypes.data, outputs.ctypes.data, ctypes.byref(st)))
+        return BatchResult(status, outputs[:, : self.n_outputs], None, self.last_timing()), st.as_dict()
 
     # ---- witness access ----
     def witness(self, index, first=0, count=None):
@@ -294,7 +402,7 @@ class Circuit:
         return out
 
     def write_wtns(self, index, path):
-        _check(lib().pob_write_wtns(self._h, index, path.encode()))
+        _check(lib().pob_write_wtns(self._h, index, os.fsencode(path)))
 
     def selfcheck_keccak(self, index):
         """on-GPU check that every KeccakfRound block of resident witness `index` satisfies out == KeccakRound(in);
@@ -302,11 +410,6 @@ class Circuit:
         nb, bad = ctypes.c_uint64(0), ctypes.c_uint64(0)
         _check(lib().pob_selfcheck_keccak(self._h, index, ctypes.byref(nb), ctypes.byref(bad)))
         return int(nb.value), int(bad.value)
-
-    def poke_witness(self, index, signal, value):
-        """test hook (fault injection for the self-check): overwrite one entry of a resident witness"""
-        v = to_limbs([value])
-        _check(lib().pob_debug_poke_witness(self._h, index, signal, v.ctypes.data))
 
     def witness_device_ptr(self, index):
         p = ctypes.c_void_p()
@@ -357,17 +460,13 @@ def main(argv=None):
         files, outdir = argv[2:k], argv[k + 1]
         os.makedirs(outdir, exist_ok=True)
         c = Circuit(CIRCUIT_ALIASES.get(argv[0], argv[0]))
+        paths = [os.path.join(outdir, os.path.splitext(os.path.basename(f))[0] + ".wtns") for f in files]
+        res, _ = c.export_batch(c.pack([json.load(open(f)) for f in files]), paths)     # consumer-paced: any number of inputs
         rc = 0
-        slots = c.desc["n_slots"]
-        for lo in range(0, len(files), slots):          # at most n_slots witnesses are resident at a time
-            part = files[lo: lo + slots]
-            res = c.run([json.load(open(f)) for f in part])
-            for i, f in enumerate(part):
-                if res.status[i] != 0:
-                    print("%s: constraint failed in the component at witness index %d" % (f, int(res.status[i]) - 1), file=sys.stderr)
-                    rc = 1
-                else:
-                    c.write_wtns(i, os.path.join(outdir, os.path.splitext(os.path.basename(f))[0] + ".wtns"))
+        for i, f in enumerate(files):
+            if res.status[i] != 0:
+                print("%s: constraint failed in the component at witness index %d" % (f, int(res.status[i]) - 1), file=sys.stderr)
+                rc = 1
         return rc
     if len(argv) != 3:
         print("usage: python -m pob_b200 <main_proof_of_burn|main_spend|Template(params)> input.json witness.wtns\n"

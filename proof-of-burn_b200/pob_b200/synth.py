@@ -267,12 +267,23 @@ def pack_instances(insts, shape, out=None):
     return arr
 
 
-def make_batch(n, shape, seed=7503, pool=None):
-    """n distinct valid instances; proof-of-work triples come from the pre-ground pool (pow_pool.json) when present"""
+def _make_one(args):
+    i, shape, seed, triple = args
+    return make_instance(np.random.default_rng(seed + i), shape, triple)
+
+
+def make_batch(n, shape, seed=7503, pool=None, workers=None):
+    """n distinct valid instances (instance i depends on seed + i only); proof-of-work triples come from the pre-ground
+    pool (pow_pool.json) when present.  Large batches are generated by a fork pool of host processes."""
     pool = load_pow_pool() if pool is None else pool
-    out = []
-    for i in range(n):
-        rng = np.random.default_rng(seed + i)
-        triple = pool[i % len(pool)] if pool else None
-        out.append(make_instance(rng, shape, triple))
-    return out
+    jobs = [(i, shape, seed, pool[i % len(pool)] if pool else None) for i in range(n)]
+    if workers is None:
+        try:
+            workers = min(32, len(os.sched_getaffinity(0)))
+        except Exception:
+            workers = 1
+    if n < 128 or workers <= 1:
+        return [_make_one(j) for j in jobs]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(workers) as p:
+        return p.map(_make_one, jobs, chunksize=max(1, n // (4 * workers)))

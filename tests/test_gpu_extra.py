@@ -3,7 +3,7 @@ the full main shape, a second circuit shape, and the proof-of-work grinder.  All
 import numpy as np
 import pytest
 
-from helpers import suite, pob_fixture, repad_pob
+from helpers import suite, pob_fixture, repad_pob, cuda_poke
 
 pytestmark = pytest.mark.gpu
 
@@ -60,7 +60,10 @@ def test_slot_ring_wraps_and_residency_is_enforced():
     c = pob_b200.Circuit("Spend(31)", max_slots=3)
     try:
         assert c.desc["n_slots"] == 3
-        res = c.run(inps)
+        with pytest.raises(pob_b200.PobError) as e:           # 8 witnesses into 3 slots: the library refuses to drop 5 unread
+            c.run(inps)
+        assert e.value.code == pob_b200.E_RANGE
+        res = c.run(inps, discard=True)                       # ... unless told to (generation-only run)
         assert (res.status == 0).all() and len({o[0] for o in res.outputs}) == 8
         for i in (5, 6, 7):                                   # the last three are resident
             w = oracle.run("Spend(31)", inps[i])
@@ -69,13 +72,150 @@ def test_slot_ring_wraps_and_residency_is_enforced():
         for i in (0, 4):                                      # overwritten by later instances
             with pytest.raises(pob_b200.PobError) as e:
                 c.witness(i)
-            assert e.value.code == -5
+            assert e.value.code == pob_b200.E_RANGE
         with pytest.raises(pob_b200.PobError):
             c.witness(8)
         res2 = c.run(inps[:2], expand=False)                  # status/outputs only: nothing resident afterwards
         assert res2.outputs == res.outputs[:2]
         with pytest.raises(pob_b200.PobError):
             c.witness(0)
+    finally:
+        c.close()
+
+
+def test_retain_list_materialises_only_the_named_instances():
+    """SURVEY.md 8(b) "which indices to retain": all instances are evaluated, only the listed ones get a witness"""
+    import pob_b200
+    from oracle import oracle
+    base = suite("test_spend")["cases"][0]["input"]
+    inps = [dict(base, extraCommitment=str(50 + i)) for i in range(40)]          # 40 instances, 3 slots
+    c = pob_b200.Circuit("Spend(31)", max_slots=3)
+    try:
+        res = c.run(inps, retain=[2, 17, 39], digest=True)
+        assert (res.status == 0).all() and len({o[0] for o in res.outputs}) == 40
+        assert res.timing["expand_launches"] >= 1
+        for i in (2, 17, 39):
+            w = oracle.run("Spend(31)", inps[i])
+            assert np.array_equal(c.witness(i), w.limbs) and int(res.digests[i]) == w.digest()
+            w.free()
+        assert int(res.digests[3]) == 0
+        for i in (0, 3, 38):
+            with pytest.raises(pob_b200.PobError) as e:
+                c.witness(i)
+            assert e.value.code == pob_b200.E_RANGE
+        with pytest.raises(pob_b200.PobError):
+            c.run(inps, retain=[1, 2, 3, 4])                 # more than the 3 slots
+        with pytest.raises(pob_b200.PobError):
+            c.run(inps, retain=[5, 5])                       # not strictly ascending
+        res0 = c.run(inps, retain=[])
+        assert res0.outputs == res.outputs and res0.timing["expand_launches"] == 0
+    finally:
+        c.close()
+
+
+def test_rejected_instance_has_no_witness():
+    """a failed instance contributes no witness (the reference calculator aborts, tests/test.py:65-68):
+    every accessor answers POB_E_REJECTED, its digest stays 0, and the neighbours are unaffected."""
+    import pob_b200
+    from oracle import oracle
+    s = suite("test_spend")
+    good, bad = s["cases"][0]["input"], s["cases"][1]["input"]
+    assert s["cases"][1]["expected"] is None
+    c = pob_b200.Circuit("Spend(31)", max_slots=3)
+    try:
+        res = c.run([good, bad, good], digest=True)
+        assert res.status[0] == 0 and res.status[1] != 0 and res.status[2] == 0
+        assert int(res.digests[1]) == 0 and res.digests[0] == res.digests[2] != 0
+        for call in (lambda: c.witness(1), lambda: c.witness_device_ptr(1), lambda: c.write_wtns(1, "/tmp/never.wtns"), lambda: c.selfcheck_keccak(1)):
+            with pytest.raises(pob_b200.PobError) as e:
+                call()
+            assert e.value.code == pob_b200.E_REJECTED
+        import os
+        assert not os.path.exists("/tmp/never.wtns")
+        w = oracle.run("Spend(31)", good)
+        assert np.array_equal(c.witness(2), w.limbs)
+        w.free()
+    finally:
+        c.close()
+
+
+def test_consumer_paced_handoff_drops_nothing():
+    """pob_submit / pob_acquire / pob_release / pob_finish: 11 instances through 3 slots; the consumer (here: a D2H copy)
+    sees EVERY accepted witness, bit-exact, in order; the rejected one is reported and skipped; holding all slots gives
+    POB_E_BUSY instead of an overwrite."""
+    import pob_b200
+    from oracle import oracle
+    s = suite("test_spend")
+    base, bad = s["cases"][0]["input"], s["cases"][1]["input"]
+    inps = [dict(base, extraCommitment=str(300 + i)) for i in range(11)]
+    inps[4] = bad
+    c = pob_b200.Circuit("Spend(31)", max_slots=3)
+    try:
+        packed = c.pack(inps)
+        c.submit(packed, digest=True)
+        seen = []
+        while True:
+            r = c.acquire()
+            if r is None:
+                break
+            idx, dptr = r
+            if dptr is None:
+                assert idx == 4
+                seen.append((idx, None))
+                continue
+            assert dptr == c.witness_device_ptr(idx)         # held witnesses are accessible while the batch is in flight
+            w = oracle.run("Spend(31)", inps[idx])
+            assert np.array_equal(c.witness(idx), w.limbs), "instance %d" % idx
+            w.free()
+            seen.append((idx, dptr))
+            c.release(idx)
+            with pytest.raises(pob_b200.PobError):
+                c.release(idx)                               # double release
+        assert [i for i, _ in seen] == list(range(11))
+        res = c.finish()
+        assert [int(v != 0) for v in res.status] == [0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0] and int(res.digests[4]) == 0
+        # hold everything: generation must stall, not overwrite
+        c.submit(packed)
+        held = []
+        with pytest.raises(pob_b200.PobError) as e:
+            while True:
+                r = c.acquire()
+                if r[1] is not None:
+                    held.append(r[0])
+        assert e.value.code == pob_b200.E_BUSY and len(held) == 3
+        first = {i: c.witness(i, 0, 64).copy() for i in held}
+        c.release(held[0])
+        r = c.acquire()
+        assert r is not None and r[0] == 3
+        for i in held[1:]:
+            assert np.array_equal(c.witness(i, 0, 64), first[i])        # still intact while held
+        res = c.finish()
+        assert res.n_ok == 10
+    finally:
+        c.close()
+
+
+def test_export_batch_writes_every_accepted_witness(tmp_path):
+    """pob_export_batch == n runs of `./main_spend input_i.json witness_i.wtns` (reference Makefile:5-6) with only 2 slots
+    for 7 instances: every accepted instance's file is byte-identical to the oracle's, the rejected one leaves no file."""
+    import os
+    import pob_b200
+    from oracle import oracle
+    s = suite("test_spend")
+    base, bad = s["cases"][0]["input"], s["cases"][1]["input"]
+    inps = [dict(base, extraCommitment=str(900 + i)) for i in range(7)]
+    inps[2] = bad
+    c = pob_b200.Circuit("Spend(31)", max_slots=2)
+    try:
+        paths = [str(tmp_path / ("w%d.wtns" % i)) for i in range(7)]
+        res, st = c.export_batch(c.pack(inps), paths)
+        assert res.status[2] != 0 and res.n_ok == 6 and st["witnesses"] == 6 and st["bytes"] == 6 * 83307596
+        assert not os.path.exists(paths[2])
+        for i in (0, 1, 3, 6):
+            w = oracle.run("Spend(31)", inps[i]); ref = str(tmp_path / "ref.wtns"); w.write_wtns(ref); w.free()
+            assert open(paths[i], "rb").read() == open(ref, "rb").read(), "instance %d" % i
+        res2, st2 = c.export_batch(c.pack(inps))              # host-memory sink only (PCIe measurement mode)
+        assert st2["witnesses"] == 6 and res2.outputs == res.outputs
     finally:
         c.close()
 
@@ -228,7 +368,7 @@ def test_commitments_of_a_batch_match_the_formula_independently_of_the_oracle():
     packed = synth.pack_instances(insts, shape)
     c = pob_b200.Circuit(pob_b200.MAIN_PROOF_OF_BURN)
     try:
-        res = c.run_packed(packed)
+        res = c.run_packed(packed, retain=[47])                # 48 evaluated, one witness materialised
         assert (res.status == 0).all()
         for i, it in enumerate(insts):
             block_root = synth.keccak256(it["blockHeader"])
@@ -255,13 +395,14 @@ def test_on_gpu_keccak_selfcheck_detects_corruption():
         assert res.status[0] == 0
         assert c.selfcheck_keccak(0) == (48, 0)
         w = c.witness(0)
+        dptr = c.witness_device_ptr(0)
         detected = 0
         for idx in range(c.n_signals - 1, 0, -4001):        # ~1280 probes; 3 % of the entries are in/out of a round block
             if w[idx, 1:].any() or w[idx, 0] > 1:
                 continue
-            c.poke_witness(0, idx, int(w[idx, 0]) ^ 1)
+            cuda_poke(dptr, idx, int(w[idx, 0]) ^ 1)
             nb, bad = c.selfcheck_keccak(0)
-            c.poke_witness(0, idx, int(w[idx, 0]))
+            cuda_poke(dptr, idx, int(w[idx, 0]))
             assert nb == 48 and bad in (0, 1)
             detected += bad
         assert detected >= 1, "no injected fault was detected"

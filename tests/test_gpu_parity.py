@@ -112,6 +112,12 @@ def test_main_proof_of_burn_shape():
             assert not wb.ok and int(res.status[1]) == wb.status
         finally:
             wb.free()
+        # a rejected main-shape instance has no witness: all three accessors refuse it, and nothing was expanded for it
+        assert int(res.digests[1]) == 0
+        for call in (lambda: c.witness(1, 0, 8), lambda: c.witness_device_ptr(1), lambda: c.write_wtns(1, "/tmp/rejected_main.wtns")):
+            with pytest.raises(pob_b200.PobError) as e:
+                call()
+            assert e.value.code == pob_b200.E_REJECTED
     finally:
         c.close()
 
@@ -135,3 +141,101 @@ def test_wtns_file_roundtrip(tmp_path):
         assert da[:4] == b"wtns" and int.from_bytes(da[4:8], "little") == 2
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("layers", [4, 12])
+def test_config5_shapes_match_oracle(layers):
+    """BASELINE.json configs[4] shapes ProofOfBurn(L,4,16,...), L = 4 and 12 (8 and 16 are covered elsewhere): synthetic
+    valid instances with numLayers up to L; commitment, 64-bit digest of all S(L) entries and sampled windows against
+    the oracle; a corrupted copy must be rejected with the oracle's status code."""
+    import pob_b200
+    from pob_b200 import synth
+    from oracle import oracle
+    shape = (layers, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)
+    expr = "ProofOfBurn(%d, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)" % layers
+    insts = synth.make_batch(3, shape, seed=1000 + layers)
+    packed = synth.pack_instances(insts, shape)
+    packed[2, 6 + 544 + 3, 0] ^= 1                           # one byte of layer 1 of instance 2: breaks the keccak chain
+    c = pob_b200.Circuit(expr, max_slots=3)
+    try:
+        assert c.n_signals == 51277058 + 10289431 * layers
+        res = c.run_packed(packed, digest=True)
+        assert res.status[0] == 0 and res.status[1] == 0 and res.status[2] != 0
+        for i in (0, 1):
+            w = oracle.run_flat(*oracle.parse_main(expr), packed[i])
+            try:
+                assert w.ok and w.n_signals == c.n_signals and res.outputs[i] == w.outputs() and int(res.digests[i]) == w.digest()
+                if i == 0:
+                    rng = np.random.default_rng(layers)
+                    for first in [0, c.n_signals - 70000] + [int(v) for v in rng.integers(0, c.n_signals - 65536, 6)]:
+                        cnt = min(65536, c.n_signals - first)
+                        assert np.array_equal(c.witness(0, first, cnt), w.limbs[first:first + cnt]), "window at %d" % first
+            finally:
+                w.free()
+        wb = oracle.run_flat(*oracle.parse_main(expr), packed[2])
+        try:
+            assert not wb.ok and int(res.status[2]) == wb.status
+        finally:
+            wb.free()
+        with pytest.raises(pob_b200.PobError) as e:
+            c.witness(2, 0, 16)
+        assert e.value.code == pob_b200.E_REJECTED
+    finally:
+        c.close()
+
+
+def _dir_with_space(tmp_path, need):
+    import shutil
+    for d in (str(tmp_path), "/dev/shm", "/tmp"):
+        try:
+            if shutil.disk_usage(d).free > need:
+                return d
+        except OSError:
+            pass
+    raise RuntimeError("no directory with %.1f GB free for the main-shape .wtns" % (need / 1e9))
+
+
+def test_cli_main_proof_of_burn_wtns_is_the_oracles(tmp_path):
+    """BASELINE.json configs[1] through the reference argv: `python -m pob_b200 main_proof_of_burn input.json witness.wtns`
+    (reference Makefile:5).  The 6,909,054,604-byte file is compared byte for byte with the oracle's witness: the 76-byte
+    iden3 header built here from the format, then all 215,907,954 entries streamed in 64 MiB
+    blocks against the oracle's limbs.  A corrupted input exits non-zero, prints to stderr and writes no file."""
+    import json, os, subprocess, sys
+    import pob_b200
+    from oracle import oracle
+    d = _dir_with_space(tmp_path, 8 << 30)
+    inp_json = repad_pob(pob_fixture(), 16, 4, 16)
+    inp, out = os.path.join(d, "pob_input.json"), os.path.join(d, "pob_witness.wtns")
+    json.dump(inp_json, open(inp, "w"))
+    env = dict(os.environ, PYTHONPATH=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "proof-of-burn_b200"))
+    try:
+        r = subprocess.run([sys.executable, "-m", "pob_b200", "main_proof_of_burn", inp, out], env=env, capture_output=True, text=True)
+        assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+        w = oracle.run(pob_b200.MAIN_PROOF_OF_BURN, inp_json)
+        try:
+            n = w.n_signals
+            assert w.ok and n == 215907954 and os.path.getsize(out) == 76 + 32 * n == 6909054604
+            P = pob_b200.P
+            hdr = (b"wtns" + (2).to_bytes(4, "little") + (2).to_bytes(4, "little") + (1).to_bytes(4, "little") + (40).to_bytes(8, "little")
+                   + (32).to_bytes(4, "little") + P.to_bytes(32, "little") + n.to_bytes(4, "little") + (2).to_bytes(4, "little") + (32 * n).to_bytes(8, "little"))
+            ref = w.limbs.reshape(-1).view(np.uint8)
+            with open(out, "rb") as f:
+                assert f.read(76) == hdr
+                off, step = 0, 64 << 20
+                while off < ref.size:
+                    blk = np.frombuffer(f.read(step), dtype=np.uint8)
+                    assert blk.size == min(step, ref.size - off) and np.array_equal(blk, ref[off:off + blk.size]), "byte offset %d" % (76 + off)
+                    off += blk.size
+                assert f.read(1) == b""
+        finally:
+            w.free()
+        os.remove(out)
+        bad = dict(inp_json); bad["layers"] = [list(l) for l in inp_json["layers"]]
+        bad["layers"][1][0] = str(int(bad["layers"][1][0]) + 1)
+        json.dump(bad, open(inp, "w"))
+        r = subprocess.run([sys.executable, "-m", "pob_b200", "main_proof_of_burn", inp, out], env=env, capture_output=True, text=True)
+        assert r.returncode != 0 and r.stderr.strip() and not os.path.exists(out)
+    finally:
+        for f in (inp, out):
+            if os.path.exists(f):
+                os.remove(f)
