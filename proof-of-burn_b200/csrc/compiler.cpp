@@ -43,9 +43,54 @@ struct FrHash {
     }
 };
 
+// linear combination over witness indices (index 0 = the constant 1), used only by the constraint emitter
+struct LC {
+    std::vector<std::pair<uint64_t, Fr>> t;
+    static Fr I(int64_t v) { return v >= 0 ? fr_from_u64((uint64_t)v) : fr_neg(fr_from_u64((uint64_t)(-v))); }
+    LC &s(uint64_t idx, int64_t c = 1) { t.push_back({idx, I(c)}); return *this; }
+    LC &sf(uint64_t idx, const Fr &c) { t.push_back({idx, c}); return *this; }
+    LC &k(int64_t c) { return s(0, c); }
+    LC &kf(const Fr &c) { return sf(0, c); }
+};
+
+// constraint sink: one for the flat part (absolute witness indices), one for the shared KeccakfRound set (relative)
+struct ConsSink {
+    ConsSet *S = nullptr; std::vector<Fr> *konst = nullptr;
+    std::unordered_map<std::array<uint32_t, 8>, uint32_t, FrHash> *kix = nullptr;
+    uint32_t coef(const Fr &c) const {
+        if (fr_fits64(c) && fr_lo64(c) < (1u << 30)) return (CC_POS << 30) | (uint32_t)fr_lo64(c);
+        Fr n = fr_neg(c);
+        if (fr_fits64(n) && fr_lo64(n) < (1u << 30)) return (CC_NEG << 30) | (uint32_t)fr_lo64(n);
+        std::array<uint32_t, 8> key; memcpy(key.data(), c.l, 32);
+        auto it = kix->find(key);
+        uint32_t ix;
+        if (it != kix->end()) ix = it->second; else { ix = (uint32_t)konst->size(); konst->push_back(c); kix->emplace(key, ix); }
+        return (CC_KONST << 30) | ix;
+    }
+    void eq(uint64_t a, uint64_t b) { S->eq.push_back((uint32_t)a); S->eq.push_back((uint32_t)b); }
+    void kc(uint64_t a, const Fr &v) { S->kc.push_back(ConsTerm{(uint32_t)a, coef(v)}); }
+    void kc_raw(uint64_t a, uint32_t c) { S->kc.push_back(ConsTerm{(uint32_t)a, c}); }
+    void r1(const LC &A, const LC &B, const LC &C, bool hint = false) {
+        if (A.t.size() > 255 || B.t.size() > 255 || C.t.size() > 32767) throw std::runtime_error("pob: internal: constraint with too many terms in one combination");
+        S->r1.push_back(ConsR1{(uint32_t)S->terms.size(), (uint16_t)(C.t.size() | (hint ? 0x8000u : 0u)), (uint8_t)A.t.size(), (uint8_t)B.t.size()});
+        for (const LC *L : {&A, &B, &C}) for (auto &q : L->t) S->terms.push_back(ConsTerm{(uint32_t)q.first, coef(q.second)});
+    }
+};
+
 class Builder {
   public:
     bool hcreate, dry;                 // dry: first pass, only counts lane words
+    // ---- constraint emission (statement by statement from the circom sources; no-ops unless cs.S is set) ----
+    ConsSink cs;
+    bool want_cs() const { return cs.S != nullptr; }
+    void q_eq(uint64_t a, uint64_t b) { if (cs.S) cs.eq(a, b); }                                 // `a <== b`, both signals
+    void q_eqn(uint64_t a, uint64_t b, size_t n, size_t sa = 1, size_t sb = 1) { if (cs.S) for (size_t i = 0; i < n; i++) cs.eq(a + i * sa, b + i * sb); }
+    void q_const(uint64_t a, uint64_t v) { if (cs.S) cs.kc(a, fr_from_u64(v)); }                 // `a <== 5`
+    void q_constf(uint64_t a, const Fr &v) { if (cs.S) cs.kc(a, v); }
+    void q_r1(const LC &A, const LC &Bq, const LC &C) { if (cs.S) cs.r1(A, Bq, C); }             // A * B == C
+    void q_lin(const LC &C) { if (cs.S) cs.r1(LC(), LC(), C); }                                  // C == 0
+    void q_mul(uint64_t a, uint64_t b, uint64_t c) { if (cs.S) cs.r1(LC().s(a), LC().s(b), LC().s(c)); }   // s[a]*s[b] == s[c]
+    void q_hint(const LC &A, const LC &Bq, const LC &C) { if (cs.S) cs.r1(A, Bq, C, true); }     // pins a `<--` value the circuit leaves free
     uint32_t val_base;
     // flat codes (pointer-stable arena)
     Code *flat = nullptr; size_t flat_n = 0, flat_cap = (size_t)1 << 30;
@@ -288,29 +333,55 @@ class Builder {
     }
 };
 
+// ---- constraint-emitter helpers -------------------------------------------------------------------------------
+// What a parent assigns to a sub-component's input signal (`comp.in <== ...`): another signal, a constant, or a
+// linear expression of signals.
+struct Src {
+    int kind; uint64_t idx; Fr kv; LC lc;
+    static Src S(uint64_t i) { return Src{0, i, fr_zero(), LC()}; }
+    static Src K(uint64_t v) { return Src{1, 0, fr_from_u64(v), LC()}; }
+    static Src KF(const Fr &v) { return Src{1, 0, v, LC()}; }
+    static Src L(const LC &l) { return Src{2, 0, fr_zero(), l}; }
+};
+static void wire(Builder &B, uint64_t dst, const Src &s) {          // dst <== s
+    if (!B.want_cs()) return;
+    if (s.kind == 0) B.q_eq(dst, s.idx);
+    else if (s.kind == 1) B.q_constf(dst, s.kv);
+    else { LC l = s.lc; for (auto &q : l.t) q.second = fr_neg(q.second); l.s(dst); B.q_lin(l); }
+}
+static Fr pow2_fr(unsigned n) { Fr r = fr_from_u64(1); for (unsigned i = 0; i < n; i++) r = fr_add(r, r); return r; }
+
 // ============================================================================================================
 // circomlib/circuits/gates.circom
 // ============================================================================================================
 // AND :29-35 (own: out, a, b).  Scalar XOR/OR only occur inside the Keccak lane arrays (handled as lanes).
 static Blk T_AND(Builder &B, Code a, Code b) {
-    Blk o = B.alloc(3); B.at(o.pos + 1) = a; B.at(o.pos + 2) = b; B.at(o.pos) = B.mul(a, b); return o;
+    Blk o = B.alloc(3); B.at(o.pos + 1) = a; B.at(o.pos + 2) = b; B.at(o.pos) = B.mul(a, b);
+    B.q_mul(o.sig + 1, o.sig + 2, o.sig);                                         // out <== a*b            gates.circom:34
+    return o;
 }
 // MultiAND(n) :68-96
 static Blk T_MultiAND(Builder &B, int n, const Code *in) {
     Blk o = B.alloc(1 + (size_t)n); B.copy(o.pos + 1, in, (size_t)n);
-    if (n == 1) B.at(o.pos) = in[0];
-    else if (n == 2) { Blk a = T_AND(B, in[0], in[1]); B.at(o.pos) = B.at(a.pos); }
-    else {
+    if (n == 1) { B.at(o.pos) = in[0]; B.q_eq(o.sig, o.sig + 1); }                // out <== in[0]          :76
+    else if (n == 2) {
+        Blk a = T_AND(B, in[0], in[1]); B.at(o.pos) = B.at(a.pos);
+        B.q_eq(a.sig + 1, o.sig + 1); B.q_eq(a.sig + 2, o.sig + 2); B.q_eq(o.sig, a.sig);   // :79-81
+    } else {
         int n1 = n / 2, n2 = n - n / 2;
+        Blk a2, x0, x1;
         if (B.hcreate) {
-            Blk a2 = B.alloc(3);
-            Blk x0 = T_MultiAND(B, n1, in), x1 = T_MultiAND(B, n2, in + n1);
+            a2 = B.alloc(3);
+            x0 = T_MultiAND(B, n1, in); x1 = T_MultiAND(B, n2, in + n1);
             Code u = B.at(x0.pos), v = B.at(x1.pos);
             B.at(a2.pos + 1) = u; B.at(a2.pos + 2) = v; B.at(a2.pos) = B.mul(u, v); B.at(o.pos) = B.at(a2.pos);
+            B.q_mul(a2.sig + 1, a2.sig + 2, a2.sig);
         } else {
-            Blk x0 = T_MultiAND(B, n1, in), x1 = T_MultiAND(B, n2, in + n1);
-            Blk a2 = T_AND(B, B.at(x0.pos), B.at(x1.pos)); B.at(o.pos) = B.at(a2.pos);
+            x0 = T_MultiAND(B, n1, in); x1 = T_MultiAND(B, n2, in + n1);
+            a2 = T_AND(B, B.at(x0.pos), B.at(x1.pos)); B.at(o.pos) = B.at(a2.pos);
         }
+        B.q_eqn(x0.sig + 1, o.sig + 1, (size_t)n1); B.q_eqn(x1.sig + 1, o.sig + 1 + (size_t)n1, (size_t)n2);   // :90-91
+        B.q_eq(a2.sig + 1, x0.sig); B.q_eq(a2.sig + 2, x1.sig); B.q_eq(o.sig, a2.sig);                           // :92-94
     }
     return o;
 }
@@ -331,13 +402,28 @@ static Blk T_Num2Bits(Builder &B, int n, Code in) {
     for (int i = 0; i < n; i++) B.at(o.pos + (size_t)i) = bit_of(B, in, (unsigned)i);
     B.at(o.pos + (size_t)n) = in;
     B.chk_range(in, (unsigned)n, o.sig);
+    if (B.want_cs()) {
+        LC sum; Fr e2 = fr_from_u64(1);
+        for (int i = 0; i < n; i++) {
+            const uint64_t oi = o.sig + (uint64_t)i;
+            B.q_r1(LC().s(oi), LC().s(oi).k(-1), LC());                          // out[i] * (out[i] - 1) === 0   bitify.circom:33
+            sum.sf(oi, e2); e2 = fr_add(e2, e2);
+        }
+        sum.s(o.sig + (uint64_t)n, -1); B.q_lin(sum);                             // lc1 === in                     :38
+    }
     return o;
 }
 // Bits2Num(n) :55-67  own: out, in[n]
 static Blk T_Bits2Num(Builder &B, int n, const Code *in) {
     Blk o = B.alloc((size_t)n + 1); B.copy(o.pos + 1, in, (size_t)n);
     std::vector<Code> terms; for (int i = 0; i < n; i++) terms.push_back(B.mul(in[i], B.pow2((unsigned)i)));
-    B.at(o.pos) = B.sum_tree(terms); return o;
+    B.at(o.pos) = B.sum_tree(terms);
+    if (B.want_cs()) {
+        LC sum; Fr e2 = fr_from_u64(1);
+        for (int i = 0; i < n; i++) { sum.sf(o.sig + 1 + (uint64_t)i, e2); e2 = fr_add(e2, e2); }
+        sum.s(o.sig, -1); B.q_lin(sum);                                           // lc1 ==> out                    bitify.circom:66
+    }
+    return o;
 }
 // CompConstant(ct) :25-73 with ct = p-1  own: out, in[254], parts[127], sout ; child Num2Bits(135)
 static Blk T_CompConstant(Builder &B, const Fr &ct, const Code *in) {
@@ -347,6 +433,7 @@ static Blk T_CompConstant(Builder &B, const Fr &ct, const Code *in) {
     Fr b; { Fr t = fr_from_u64(1); for (int i = 0; i < 128; i++) t = fr_add(t, t); b = fr_sub(t, one); }
     Fr a = one, e = one;
     std::vector<Code> terms;
+    LC sum;
     for (int i = 0; i < 127; i++) {
         int clsb = fr_bit(ct, (unsigned)(2 * i)), cmsb = fr_bit(ct, (unsigned)(2 * i + 1));
         Code slsb = in[2 * i], smsb = in[2 * i + 1], ml = B.mul(smsb, slsb), p;
@@ -356,12 +443,26 @@ static Blk T_CompConstant(Builder &B, const Fr &ct, const Code *in) {
         else if (cmsb && !clsb)  p = B.fma(smsb, nka, B.fma(ml, kb, ka));
         else                     p = B.fma(ml, nka, ka);
         B.at(parts + (size_t)i) = p; terms.push_back(p);
+        if (B.want_cs()) {                                                        // compconstant.circom:51-58, as (k*smsb) * slsb == linear
+            const uint64_t L = o.sig + 1 + 2 * (uint64_t)i, M = L + 1, Pq = o.sig + 255 + (uint64_t)i;
+            const Fr na = fr_neg(a), nb_ = fr_neg(b);
+            if (!cmsb && !clsb)      B.q_r1(LC().sf(M, b), LC().s(L), LC().sf(M, b).sf(L, b).s(Pq, -1));            // p = -b*m*l + b*m + b*l
+            else if (!cmsb && clsb)  B.q_r1(LC().sf(M, a), LC().s(L), LC().s(Pq).sf(L, a).sf(M, nb_).sf(M, a).kf(na)); // p = a*m*l - a*l + b*m - a*m + a
+            else if (cmsb && !clsb)  B.q_r1(LC().sf(M, b), LC().s(L), LC().s(Pq).sf(M, a).kf(na));                  // p = b*m*l - a*m + a
+            else                     B.q_r1(LC().sf(M, a), LC().s(L), LC().kf(a).s(Pq, -1));                         // p = -a*m*l + a
+            sum.s(Pq);
+        }
         b = fr_sub(b, e); a = fr_add(a, e); e = fr_add(e, e);
     }
-    Code sum = B.sum_tree(terms);
-    B.at(o.pos + 255 + 127) = sum;
-    Blk nb = T_Num2Bits(B, 135, sum);
+    Code sumc = B.sum_tree(terms);
+    B.at(o.pos + 255 + 127) = sumc;
+    Blk nb = T_Num2Bits(B, 135, sumc);
     B.at(o.pos) = B.at(nb.pos + 127);
+    if (B.want_cs()) {
+        sum.s(o.sig + 255 + 127, -1); B.q_lin(sum);                               // sout <== sum                   :65
+        B.q_eq(nb.sig + 135, o.sig + 255 + 127);                                  // num2bits.in <== sout           :69
+        B.q_eq(o.sig, nb.sig + 127);                                              // out <== num2bits.out[127]      :71
+    }
     return o;
 }
 // AliasCheck :24-32  own: in[254]
@@ -370,19 +471,24 @@ static Blk T_AliasCheck(Builder &B, const Code *in) {
     Fr m1; Fr one = fr_from_u64(1); fr_raw_sub(m1, fr_p(), one);
     Blk cc = T_CompConstant(B, m1, in);
     B.chk_eq(B.at(cc.pos), ZERO, o.sig);
+    B.q_eqn(cc.sig + 1, o.sig, 254);                                              // in[i] ==> compConstant.in[i]   aliascheck.circom:29
+    B.q_const(cc.sig, 0);                                                         // compConstant.out === 0         :31
     return o;
 }
 // Num2Bits_strict :41-53  own: out[254], in
 static Blk T_Num2Bits_strict(Builder &B, Code in) {
     Blk o = B.alloc(255); B.at(o.pos + 254) = in;
+    Blk nb, ac;
     if (B.hcreate) {
         std::vector<Code> bits(254); for (int i = 0; i < 254; i++) bits[i] = bit_of(B, in, (unsigned)i);
-        T_AliasCheck(B, bits.data());
-        Blk nb = T_Num2Bits(B, 254, in); B.copy(o.pos, &B.at(nb.pos), 254);
+        ac = T_AliasCheck(B, bits.data());
+        nb = T_Num2Bits(B, 254, in); B.copy(o.pos, &B.at(nb.pos), 254);
     } else {
-        Blk nb = T_Num2Bits(B, 254, in); B.copy(o.pos, &B.at(nb.pos), 254);
-        T_AliasCheck(B, &B.at(nb.pos));
+        nb = T_Num2Bits(B, 254, in); B.copy(o.pos, &B.at(nb.pos), 254);
+        ac = T_AliasCheck(B, &B.at(nb.pos));
     }
+    B.q_eq(nb.sig + 254, o.sig + 254);                                            // in ==> n2b.in                  bitify.circom:48
+    B.q_eqn(o.sig, nb.sig, 254); B.q_eqn(ac.sig, nb.sig, 254);                    // n2b.out[i] ==> out[i], aliasCheck.in[i]   :50-51
     return o;
 }
 
@@ -391,35 +497,58 @@ static Blk T_Num2Bits_strict(Builder &B, Code in) {
 // ============================================================================================================
 // IsZero :24-35  own: out, in, inv
 static Blk T_IsZero(Builder &B, Code in, bool likely_large = false) {
-    Blk o = B.alloc(3); B.at(o.pos + 1) = in; B.at(o.pos + 2) = B.inv(in, likely_large); B.at(o.pos) = B.isz(in); return o;
+    Blk o = B.alloc(3); B.at(o.pos + 1) = in; B.at(o.pos + 2) = B.inv(in, likely_large); B.at(o.pos) = B.isz(in);
+    if (B.want_cs()) {
+        B.q_r1(LC().s(o.sig + 1), LC().s(o.sig + 2), LC().k(1).s(o.sig, -1));     // out <== -in*inv + 1            comparators.circom:32
+        B.q_r1(LC().s(o.sig + 1), LC().s(o.sig), LC());                           // in*out === 0                   :33
+        B.q_hint(LC().s(o.sig + 2), LC().s(o.sig), LC());                         // inv <-- in != 0 ? 1/in : 0     :30 (inv is free when in == 0)
+    }
+    return o;
 }
 // IsEqual :37-46  own: out, in[2] ; isz.in = in[1] - in[0]
 static Blk T_IsEqual(Builder &B, Code in0, Code in1, bool likely_large = false) {
     Blk o = B.alloc(3); B.at(o.pos + 1) = in0; B.at(o.pos + 2) = in1;
-    Blk z = T_IsZero(B, B.sub(in1, in0), likely_large); B.at(o.pos) = B.at(z.pos); return o;
+    Blk z = T_IsZero(B, B.sub(in1, in0), likely_large); B.at(o.pos) = B.at(z.pos);
+    B.q_lin(LC().s(z.sig + 1).s(o.sig + 2, -1).s(o.sig + 1));                     // in[1] - in[0] ==> isz.in       comparators.circom:43
+    B.q_eq(o.sig, z.sig);                                                         // isz.out ==> out                :45
+    return o;
 }
 // LessThan(n) :89-100
 static Blk T_LessThan(Builder &B, int n, Code in0, Code in1) {
     Blk o = B.alloc(3); B.at(o.pos + 1) = in0; B.at(o.pos + 2) = in1;
     Blk nb = T_Num2Bits(B, n + 1, B.sub(B.add(in0, B.pow2((unsigned)n)), in1));
-    B.at(o.pos) = B.not1(B.at(nb.pos + (size_t)n)); return o;
+    B.at(o.pos) = B.not1(B.at(nb.pos + (size_t)n));
+    if (B.want_cs()) {
+        B.q_lin(LC().s(nb.sig + (uint64_t)n + 1).s(o.sig + 1, -1).kf(fr_neg(pow2_fr((unsigned)n))).s(o.sig + 2));   // n2b.in <== in[0] + (1<<n) - in[1]   :96
+        B.q_lin(LC().s(o.sig).k(-1).s(nb.sig + (uint64_t)n));                     // out <== 1 - n2b.out[n]         :98
+    }
+    return o;
 }
 // LessEqThan(n) :105-115
 static Blk T_LessEqThan(Builder &B, int n, Code in0, Code in1) {
     Blk o = B.alloc(3); B.at(o.pos + 1) = in0; B.at(o.pos + 2) = in1;
-    Blk lt = T_LessThan(B, n, in0, B.add(in1, ONE)); B.at(o.pos) = B.at(lt.pos); return o;
+    Blk lt = T_LessThan(B, n, in0, B.add(in1, ONE)); B.at(o.pos) = B.at(lt.pos);
+    B.q_eq(lt.sig + 1, o.sig + 1); B.q_lin(LC().s(lt.sig + 2).s(o.sig + 2, -1).k(-1)); B.q_eq(o.sig, lt.sig);   // comparators.circom:111-113
+    return o;
 }
 // GreaterEqThan(n) :131-141
 static Blk T_GreaterEqThan(Builder &B, int n, Code in0, Code in1) {
     Blk o = B.alloc(3); B.at(o.pos + 1) = in0; B.at(o.pos + 2) = in1;
-    Blk lt = T_LessThan(B, n, in1, B.add(in0, ONE)); B.at(o.pos) = B.at(lt.pos); return o;
+    Blk lt = T_LessThan(B, n, in1, B.add(in0, ONE)); B.at(o.pos) = B.at(lt.pos);
+    B.q_eq(lt.sig + 1, o.sig + 2); B.q_lin(LC().s(lt.sig + 2).s(o.sig + 1, -1).k(-1)); B.q_eq(o.sig, lt.sig);   // comparators.circom:137-139
+    return o;
 }
 // Mux1 :34-48 + MultiMux1(1) :21-32
 static Blk T_Mux1(Builder &B, Code c0, Code c1, Code s) {
     Blk o = B.alloc(4); B.at(o.pos + 1) = c0; B.at(o.pos + 2) = c1; B.at(o.pos + 3) = s;
     Blk m = B.alloc(4); B.at(m.pos + 1) = c0; B.at(m.pos + 2) = c1; B.at(m.pos + 3) = s;
     B.at(m.pos) = B.fma(B.sub(c1, c0), s, c0);
-    B.at(o.pos) = B.at(m.pos); return o;
+    B.at(o.pos) = B.at(m.pos);
+    if (B.want_cs()) {
+        B.q_r1(LC().s(m.sig + 2).s(m.sig + 1, -1), LC().s(m.sig + 3), LC().s(m.sig).s(m.sig + 1, -1));   // out[i] <== (c[i][1] - c[i][0])*s + c[i][0]   mux1.circom:29
+        B.q_eqn(m.sig + 1, o.sig + 1, 2); B.q_eq(m.sig + 3, o.sig + 3); B.q_eq(o.sig, m.sig);             // :43-47
+    }
+    return o;
 }
 
 // ============================================================================================================
@@ -434,33 +563,82 @@ static Blk T_PoseidonEx(Builder &B, int nInputs, const Code *inputs, Code initia
     st[0] = initialState; for (uint32_t j = 1; j < t; j++) st[j] = inputs[j - 1];
     const uint32_t base = B.poseidon(t, st);
     auto V = [&](uint32_t off) { return c_val(base + off); };
-    { Blk a = B.alloc(2 * t); for (uint32_t j = 0; j < t; j++) { B.at(a.pos + j) = V(j); B.at(a.pos + t + j) = st[j]; cur[j] = V(j); } }   // ark[0]
-    auto sigma = [&](Code in, uint32_t off) {            // Sigma :5-16  own: out, in, in2, in4
+    // constraint side: canonical constant tables and the witness index of the signal carrying state element j
+    const bool cs = B.want_cs();
+    const uint64_t (*TC)[4] = t == 3 ? POSEIDON_C_T3 : t == 4 ? POSEIDON_C_T4 : POSEIDON_C_T5;
+    const uint64_t (*TS)[4] = t == 3 ? POSEIDON_S_T3 : t == 4 ? POSEIDON_S_T4 : POSEIDON_S_T5;
+    const uint64_t (*TM)[4] = t == 3 ? POSEIDON_M_T3 : t == 4 ? POSEIDON_M_T4 : POSEIDON_M_T5;
+    const uint64_t (*TP)[4] = t == 3 ? POSEIDON_P_T3 : t == 4 ? POSEIDON_P_T4 : POSEIDON_P_T5;
+    auto F = [](const uint64_t (*tab)[4], uint32_t i) { Fr f; memcpy(f.l, tab[i], 32); return f; };
+    uint64_t cidx[8];
+    {   // ark[0]  (Ark :18-25  own: out[t], in[t])
+        Blk a = B.alloc(2 * t);
+        for (uint32_t j = 0; j < t; j++) {
+            B.at(a.pos + j) = V(j); B.at(a.pos + t + j) = st[j]; cur[j] = V(j);
+            if (cs) {
+                B.q_eq(a.sig + t + j, j ? o.sig + 1 + (j - 1) : o.sig + 1 + (uint64_t)nInputs);      // ark[0].in[j] <== inputs[j-1] | initialState   :84-90
+                B.q_lin(LC().s(a.sig + j).s(a.sig + t + j, -1).kf(fr_neg(F(TC, j))));                // out[i] <== in[i] + C[i + r]                    :23
+            }
+            cidx[j] = a.sig + j;
+        }
+    }
+    auto sigma = [&](Code in, uint32_t off, uint64_t src) -> uint64_t {   // Sigma :5-16  own: out, in, in2, in4
         Blk s = B.alloc(4); B.at(s.pos) = V(off + 2); B.at(s.pos + 1) = in; B.at(s.pos + 2) = V(off); B.at(s.pos + 3) = V(off + 1);
+        if (cs) {
+            B.q_eq(s.sig + 1, src);                                               // sigma.in <== previous layer's out
+            B.q_mul(s.sig + 1, s.sig + 1, s.sig + 2); B.q_mul(s.sig + 2, s.sig + 2, s.sig + 3); B.q_mul(s.sig + 3, s.sig + 1, s.sig);   // :12-15
+        }
+        return s.sig;
     };
-    auto full = [&](uint32_t F) {                        // t x Sigma, Ark :18-25, Mix :27-39
-        for (uint32_t j = 0; j < t; j++) sigma(cur[j], F + 3 * j);
-        Blk a = B.alloc(2 * t); for (uint32_t j = 0; j < t; j++) { B.at(a.pos + j) = V(F + 3 * t + j); B.at(a.pos + t + j) = V(F + 3 * j + 2); }
-        Blk m = B.alloc(2 * t); for (uint32_t j = 0; j < t; j++) { B.at(m.pos + j) = V(F + 4 * t + j); B.at(m.pos + t + j) = V(F + 3 * t + j); cur[j] = V(F + 4 * t + j); }
+    auto full = [&](uint32_t Fo, uint32_t coff, const uint64_t (*MT)[4]) {   // t x Sigma, Ark :18-25, Mix :27-39
+        uint64_t so[8];
+        for (uint32_t j = 0; j < t; j++) so[j] = sigma(cur[j], Fo + 3 * j, cidx[j]);
+        Blk a = B.alloc(2 * t); for (uint32_t j = 0; j < t; j++) { B.at(a.pos + j) = V(Fo + 3 * t + j); B.at(a.pos + t + j) = V(Fo + 3 * j + 2); }
+        Blk m = B.alloc(2 * t); for (uint32_t j = 0; j < t; j++) { B.at(m.pos + j) = V(Fo + 4 * t + j); B.at(m.pos + t + j) = V(Fo + 3 * t + j); cur[j] = V(Fo + 4 * t + j); }
+        if (cs) for (uint32_t j = 0; j < t; j++) {
+            B.q_eq(a.sig + t + j, so[j]);                                         // ark.in[j] <== sigmaF[..][j].out
+            B.q_lin(LC().s(a.sig + j).s(a.sig + t + j, -1).kf(fr_neg(F(TC, coff + j))));
+            B.q_eq(m.sig + t + j, a.sig + j);                                     // mix.in[j] <== ark.out[j]
+            LC l; l.s(m.sig + j, -1); for (uint32_t k = 0; k < t; k++) l.sf(m.sig + t + k, F(MT, k * t + j)); B.q_lin(l);   // out[i] <== sum_j M[j][i]*in[j]   :36
+        }
+        for (uint32_t j = 0; j < t; j++) cidx[j] = m.sig + j;
     };
-    for (uint32_t f = 0; f < 4; f++) full(L.F1 + 5 * t * f);                        // :101-136 (the 4th mixes with P)
+    for (uint32_t f = 0; f < 4; f++) full(L.F1 + 5 * t * f, (f + 1) * t, f == 3 ? TP : TM);              // :101-136 (the 4th mixes with P)
     for (uint32_t r = 0; r < L.rp; r++) {                                            // :138-160
         const uint32_t Bs = L.PB + r * (4 + t);
-        sigma(cur[0], Bs);
+        const uint64_t so = sigma(cur[0], Bs, cidx[0]);
         Blk m = B.alloc(2 * t);                                                      // MixS :52-65  own: out[t], in[t]
         for (uint32_t j = 0; j < t; j++) { B.at(m.pos + j) = V(Bs + 4 + j); B.at(m.pos + t + j) = j == 0 ? V(Bs + 3) : cur[j]; }
         for (uint32_t j = 0; j < t; j++) cur[j] = V(Bs + 4 + j);
+        if (cs) {
+            const uint32_t sb = (2 * t - 1) * r;
+            B.q_lin(LC().s(m.sig + t).s(so, -1).kf(fr_neg(F(TC, 5 * t + r))));    // mixS.in[0] <== sigmaP.out + C[(nRoundsF\2+1)*t + r]   :149
+            for (uint32_t j = 1; j < t; j++) B.q_eq(m.sig + t + j, cidx[j]);      // mixS.in[j] <== previous out[j]                        :151-155
+            LC l; l.s(m.sig, -1); for (uint32_t i = 0; i < t; i++) l.sf(m.sig + t + i, F(TS, sb + i)); B.q_lin(l);        // out[0] <== lc       :60
+            for (uint32_t i = 1; i < t; i++) B.q_lin(LC().s(m.sig + i, -1).s(m.sig + t + i).sf(m.sig + t, F(TS, sb + t + i - 1)));   // :62
+        }
+        for (uint32_t j = 0; j < t; j++) cidx[j] = m.sig + j;
     }
-    for (uint32_t f = 0; f < 3; f++) full(L.SB + 5 * t * f);                        // :162-182
-    for (uint32_t j = 0; j < t; j++) sigma(cur[j], L.LB + 3 * j);                    // :184-187
+    for (uint32_t f = 0; f < 3; f++) full(L.SB + 5 * t * f, 5 * t + L.rp + f * t, TM);                  // :162-182
+    uint64_t so[8];
+    for (uint32_t j = 0; j < t; j++) so[j] = sigma(cur[j], L.LB + 3 * j, cidx[j]);  // :184-187
     Blk ml = B.alloc(1 + t);                                                         // MixLast :41-50  own: out, in[t]
     B.at(ml.pos) = V(L.LB + 3 * t); for (uint32_t j = 0; j < t; j++) B.at(ml.pos + 1 + j) = V(L.LB + 3 * j + 2);
-    B.at(o.pos) = V(L.LB + 3 * t); return o;
+    B.at(o.pos) = V(L.LB + 3 * t);
+    if (cs) {
+        LC l; l.s(ml.sig, -1);
+        for (uint32_t j = 0; j < t; j++) { B.q_eq(ml.sig + 1 + j, so[j]); l.sf(ml.sig + 1 + j, F(TM, j * t)); }
+        B.q_lin(l);                                                               // out <== sum_j M[j][s]*in[j], s = 0   :49
+        B.q_eq(o.sig, ml.sig);                                                    // out[i] <== mixLast[i].out            :194
+    }
+    return o;
 }
 // Poseidon(n) :198-208
 static Blk T_Poseidon(Builder &B, int n, const Code *inputs) {
     Blk o = B.alloc(1 + (size_t)n); B.copy(o.pos + 1, inputs, (size_t)n);
-    Blk e = T_PoseidonEx(B, n, inputs, ZERO); B.at(o.pos) = B.at(e.pos); return o;
+    Blk e = T_PoseidonEx(B, n, inputs, ZERO); B.at(o.pos) = B.at(e.pos);
+    B.q_const(e.sig + 1 + (uint64_t)n, 0); B.q_eqn(e.sig + 1, o.sig + 1, (size_t)n); B.q_eq(o.sig, e.sig);   // poseidon.circom:203-207
+    return o;
 }
 
 // ============================================================================================================
@@ -469,21 +647,26 @@ static Blk T_Poseidon(Builder &B, int n, const Code *inputs) {
 // AssertBits(B) :13-18  own: in, bits[B]
 static Blk T_AssertBits(Builder &B, int nb_, Code in) {
     Blk o = B.alloc(1 + (size_t)nb_); B.at(o.pos) = in;
-    Blk nb = T_Num2Bits(B, nb_, in); B.copy(o.pos + 1, &B.at(nb.pos), (size_t)nb_); return o;
+    Blk nb = T_Num2Bits(B, nb_, in); B.copy(o.pos + 1, &B.at(nb.pos), (size_t)nb_);
+    B.q_eq(nb.sig + (uint64_t)nb_, o.sig); B.q_eqn(o.sig + 1, nb.sig, (size_t)nb_);   // signal bits[B] <== Num2Bits(B)(in)   assert.circom:17
+    return o;
 }
 // AssertByteString(N) :26-31
 static Blk T_AssertByteString(Builder &B, int N, const Code *in) {
     Blk o = B.alloc((size_t)N); B.copy(o.pos, in, (size_t)N);
-    for (int i = 0; i < N; i++) T_AssertBits(B, 8, in[i]);
+    for (int i = 0; i < N; i++) { Blk a = T_AssertBits(B, 8, in[i]); B.q_eq(a.sig, o.sig + (uint64_t)i); }   // AssertBits(8)(in[i])   assert.circom:29
     return o;
 }
 // AssertLessThan :40-47 / AssertLessEqThan :56-63 / AssertGreaterEqThan :72-79  own: a, b, out
 static Blk T_AssertCmp(Builder &B, int kind, int nb, Code a, Code b) {
     Blk o = B.alloc(3); B.at(o.pos) = a; B.at(o.pos + 1) = b;
-    T_AssertBits(B, nb, a); T_AssertBits(B, nb, b);
+    Blk ba = T_AssertBits(B, nb, a), bb = T_AssertBits(B, nb, b);
     Blk r = kind == 0 ? T_LessThan(B, nb, a, b) : kind == 1 ? T_LessEqThan(B, nb, a, b) : T_GreaterEqThan(B, nb, a, b);
     B.at(o.pos + 2) = B.at(r.pos);
     B.chk_eq(B.at(r.pos), ONE, o.sig);
+    B.q_eq(ba.sig, o.sig); B.q_eq(bb.sig, o.sig + 1);                             // AssertBits(B)(a); AssertBits(B)(b)      assert.circom:43-44
+    B.q_eq(r.sig + 1, o.sig); B.q_eq(r.sig + 2, o.sig + 1); B.q_eq(o.sig + 2, r.sig);   // signal out <== LessThan(B)([a, b])   :45
+    B.q_const(o.sig + 2, 1);                                                      // out === 1                                :46
     return o;
 }
 static Blk T_AssertLessThan(Builder &B, int nb, Code a, Code b) { return T_AssertCmp(B, 0, nb, a, b); }
@@ -500,23 +683,34 @@ static Blk T_Filter(Builder &B, int N, Code in) {
         Blk e = T_IsEqual(B, c_const((uint32_t)i), in);
         Code eq = B.at(e.pos); B.at(o.pos + n + 1 + i) = eq;
         B.at(o.pos + i) = B.gtc(in, (uint32_t)i);      // prod_{j<=i} (1 - isEq[j]) == (in > i)
+        if (B.want_cs()) {
+            const uint64_t isEq = o.sig + n + 1 + i;
+            B.q_const(e.sig + 1, i); B.q_eq(e.sig + 2, o.sig + n); B.q_eq(isEq, e.sig);       // isEq[i] <== IsEqual()([i, in])          array.circom:32
+            if (i > 0) B.q_r1(LC().s(o.sig + i - 1), LC().k(1).s(isEq, -1), LC().s(o.sig + i));   // out[i] <== out[i-1] * (1 - isEq[i])   :34
+            else B.q_lin(LC().s(o.sig).k(-1).s(isEq));                                        // out[0] <== 1 - isEq[0]                 :37
+        }
     }
     return o;
 }
 // Fit(M,N) :47-57  own: out[N], in[M]
 static Blk T_Fit(Builder &B, int M, int N, const Code *in) {
     Blk o = B.alloc((size_t)N + (size_t)M); B.copy(o.pos + (size_t)N, in, (size_t)M);
-    for (int i = 0; i < N; i++) B.at(o.pos + (size_t)i) = i < M ? in[i] : ZERO;
+    for (int i = 0; i < N; i++) {
+        B.at(o.pos + (size_t)i) = i < M ? in[i] : ZERO;
+        if (i < M) B.q_eq(o.sig + (uint64_t)i, o.sig + (uint64_t)N + (uint64_t)i); else B.q_const(o.sig + (uint64_t)i, 0);   // array.circom:52-55
+    }
     return o;
 }
 // Flatten(M,N) :64-72 / Reshape(M,N) :79-87: identity on row-major data  own: out[n], in[n]
 static Blk T_CopyArray(Builder &B, size_t n, const Code *in) {
-    Blk o = B.alloc(2 * n); B.copy(o.pos, in, n); B.copy(o.pos + n, in, n); return o;
+    Blk o = B.alloc(2 * n); B.copy(o.pos, in, n); B.copy(o.pos + n, in, n);
+    B.q_eqn(o.sig, o.sig + n, n);                                                 // out[i*N + j] <== in[i][j]   array.circom:69 / :84
+    return o;
 }
 // Reverse(N) :94-99
 static Blk T_Reverse(Builder &B, int N, const Code *in) {
     size_t n = (size_t)N; Blk o = B.alloc(2 * n); B.copy(o.pos + n, in, n);
-    for (size_t i = 0; i < n; i++) B.at(o.pos + i) = in[n - 1 - i];
+    for (size_t i = 0; i < n; i++) { B.at(o.pos + i) = in[n - 1 - i]; B.q_eq(o.sig + i, o.sig + n + (n - 1 - i)); }   // out[i] <== in[N-1-i]   array.circom:97
     return o;
 }
 
@@ -526,15 +720,23 @@ static Blk T_Reverse(Builder &B, int N, const Code *in) {
 // LittleEndianBytes2Num(N) :12-26  own: out, in[N]
 static Blk T_LittleEndianBytes2Num(Builder &B, int N, const Code *in) {
     Blk o = B.alloc(1 + (size_t)N); B.copy(o.pos + 1, in, (size_t)N);
-    T_AssertByteString(B, N, in);
+    Blk abs_ = T_AssertByteString(B, N, in);
     std::vector<Code> terms; for (int i = 0; i < N; i++) terms.push_back(B.mul(in[i], B.pow2((unsigned)(8 * i))));
-    B.at(o.pos) = B.sum_tree(terms); return o;
+    B.at(o.pos) = B.sum_tree(terms);
+    if (B.want_cs()) {
+        B.q_eqn(abs_.sig, o.sig + 1, (size_t)N);                                  // AssertByteString(N)(in)   convert.circom:19
+        LC l; l.s(o.sig, -1); for (int i = 0; i < N; i++) l.sf(o.sig + 1 + (uint64_t)i, pow2_fr((unsigned)(8 * i))); B.q_lin(l);   // out <== lc   :25
+    }
+    return o;
 }
 // BigEndianBytes2Num(N) :33-39  own: out, in[N], inReversed[N]
 static Blk T_BigEndianBytes2Num(Builder &B, int N, const Code *in) {
     size_t n = (size_t)N; Blk o = B.alloc(1 + 2 * n); B.copy(o.pos + 1, in, n);
     Blk r = T_Reverse(B, N, in); B.copy(o.pos + 1 + n, &B.at(r.pos), n);
-    Blk l = T_LittleEndianBytes2Num(B, N, &B.at(r.pos)); B.at(o.pos) = B.at(l.pos); return o;
+    Blk l = T_LittleEndianBytes2Num(B, N, &B.at(r.pos)); B.at(o.pos) = B.at(l.pos);
+    B.q_eqn(r.sig + n, o.sig + 1, n); B.q_eqn(o.sig + 1 + n, r.sig, n);           // signal inReversed[N] <== Reverse(N)(in)             convert.circom:37
+    B.q_eqn(l.sig + 1, o.sig + 1 + n, n); B.q_eq(o.sig, l.sig);                   // out <== LittleEndianBytes2Num(N)(inReversed)        :38
+    return o;
 }
 // Num2BitsSafe(N) :46-56
 static Blk T_Num2BitsSafe(Builder &B, int N, Code in) {
@@ -542,24 +744,37 @@ static Blk T_Num2BitsSafe(Builder &B, int N, Code in) {
     if (N >= 254) {
         Blk o = B.alloc(n + 1 + 254); B.at(o.pos + n) = in;
         Blk st = T_Num2Bits_strict(B, in); B.copy(o.pos + n + 1, &B.at(st.pos), 254);
-        Blk f = T_Fit(B, 254, N, &B.at(st.pos)); B.copy(o.pos, &B.at(f.pos), n); return o;
+        Blk f = T_Fit(B, 254, N, &B.at(st.pos)); B.copy(o.pos, &B.at(f.pos), n);
+        B.q_eq(st.sig + 254, o.sig + n); B.q_eqn(o.sig + n + 1, st.sig, 254);     // signal bitsStrict[254] <== Num2Bits_strict()(in)   convert.circom:51
+        B.q_eqn(f.sig + n, o.sig + n + 1, 254); B.q_eqn(o.sig, f.sig, n);         // out <== Fit(254, N)(bitsStrict)                    :52
+        return o;
     }
     Blk o = B.alloc(n + 1); B.at(o.pos + n) = in;
-    Blk nb = T_Num2Bits(B, N, in); B.copy(o.pos, &B.at(nb.pos), n); return o;
+    Blk nb = T_Num2Bits(B, N, in); B.copy(o.pos, &B.at(nb.pos), n);
+    B.q_eq(nb.sig + n, o.sig + n); B.q_eqn(o.sig, nb.sig, n);                     // out <== Num2Bits(N)(in)                            :54
+    return o;
 }
 // Num2LittleEndianBytes(N) :69-82  own: out[N], in, bits[8N], byteArrays[N][8]
 static Blk T_Num2LittleEndianBytes(Builder &B, int N, Code in) {
     size_t n = (size_t)N; Blk o = B.alloc(n + 1 + 16 * n); B.at(o.pos + n) = in;
     Blk b = T_Num2BitsSafe(B, 8 * N, in); B.copy(o.pos + n + 1, &B.at(b.pos), 8 * n);
     Blk r = T_CopyArray(B, 8 * n, &B.at(b.pos)); B.copy(o.pos + n + 1 + 8 * n, &B.at(r.pos), 8 * n);
-    for (size_t i = 0; i < n; i++) { Blk bn = T_Bits2Num(B, 8, &B.at(r.pos + 8 * i)); B.at(o.pos + i) = B.at(bn.pos); }
+    B.q_eq(b.sig + 8 * n, o.sig + n); B.q_eqn(o.sig + n + 1, b.sig, 8 * n);       // signal bits[N*8] <== Num2BitsSafe(N*8)(in)          convert.circom:77
+    B.q_eqn(r.sig + 8 * n, o.sig + n + 1, 8 * n); B.q_eqn(o.sig + n + 1 + 8 * n, r.sig, 8 * n);   // signal byteArrays[N][8] <== Reshape(N, 8)(bits)   :78
+    for (size_t i = 0; i < n; i++) {
+        Blk bn = T_Bits2Num(B, 8, &B.at(r.pos + 8 * i)); B.at(o.pos + i) = B.at(bn.pos);
+        B.q_eqn(bn.sig + 1, o.sig + n + 1 + 8 * n + 8 * i, 8); B.q_eq(o.sig + i, bn.sig);   // out[i] <== Bits2Num(8)(byteArrays[i])   :80
+    }
     return o;
 }
 // Num2BigEndianBytes(N) :90-96  own: out[N], in, littleEndian[N]
 static Blk T_Num2BigEndianBytes(Builder &B, int N, Code in) {
     size_t n = (size_t)N; Blk o = B.alloc(2 * n + 1); B.at(o.pos + n) = in;
     Blk le = T_Num2LittleEndianBytes(B, N, in); B.copy(o.pos + n + 1, &B.at(le.pos), n);
-    Blk rv = T_Reverse(B, N, &B.at(le.pos)); B.copy(o.pos, &B.at(rv.pos), n); return o;
+    Blk rv = T_Reverse(B, N, &B.at(le.pos)); B.copy(o.pos, &B.at(rv.pos), n);
+    B.q_eq(le.sig + n, o.sig + n); B.q_eqn(o.sig + n + 1, le.sig, n);             // signal littleEndian[N] <== Num2LittleEndianBytes(N)(in)   convert.circom:94
+    B.q_eqn(rv.sig + n, o.sig + n + 1, n); B.q_eqn(o.sig, rv.sig, n);             // out <== Reverse(N)(littleEndian)                          :95
+    return o;
 }
 // Bytes2Nibbles(N) :103-125  own: out[2N], in[N], inDecomposed[N][8]
 static Blk T_Bytes2Nibbles(Builder &B, int N, const Code *in) {
@@ -572,6 +787,13 @@ static Blk T_Bytes2Nibbles(Builder &B, int N, const Code *in) {
             hi = B.fma(B.at(nb.pos + j + 4), B.pow2(j), hi);
         }
         B.at(o.pos + 2 * i) = hi; B.at(o.pos + 2 * i + 1) = lo;
+        if (B.want_cs()) {
+            const uint64_t dec = o.sig + 3 * n + 8 * i;
+            B.q_eq(nb.sig + 8, o.sig + 2 * n + i); B.q_eqn(dec, nb.sig, 8);       // inDecomposed[i] <== Num2Bits(8)(in[i])   convert.circom:110
+            LC h, l; h.s(o.sig + 2 * i, -1); l.s(o.sig + 2 * i + 1, -1);
+            for (unsigned j = 0; j < 4; j++) { l.s(dec + j, 1 << j); h.s(dec + j + 4, 1 << j); }
+            B.q_lin(h); B.q_lin(l);                                               // out[2i] <== higher; out[2i+1] <== lower  :122-123
+        }
     }
     return o;
 }
@@ -579,8 +801,10 @@ static Blk T_Bytes2Nibbles(Builder &B, int N, const Code *in) {
 static Blk T_Nibbles2Bytes(Builder &B, int n_, const Code *nib) {
     size_t n = (size_t)n_; Blk o = B.alloc(3 * n); B.copy(o.pos + n, nib, 2 * n);
     for (size_t i = 0; i < n; i++) {
-        T_AssertBits(B, 4, nib[2 * i]); T_AssertBits(B, 4, nib[2 * i + 1]);
+        Blk a0 = T_AssertBits(B, 4, nib[2 * i]), a1 = T_AssertBits(B, 4, nib[2 * i + 1]);
         B.at(o.pos + i) = B.fma(nib[2 * i], c_const(16), nib[2 * i + 1]);
+        B.q_eq(a0.sig, o.sig + n + 2 * i); B.q_eq(a1.sig, o.sig + n + 2 * i + 1);                      // AssertBits(4)(nibbles[2i]), (nibbles[2i+1])   convert.circom:136-137
+        B.q_lin(LC().s(o.sig + i, -1).s(o.sig + n + 2 * i, 16).s(o.sig + n + 2 * i + 1));             // bytes[i] <== nibbles[2i]*16 + nibbles[2i+1]   :138
     }
     return o;
 }
@@ -595,9 +819,12 @@ static Blk T_Divide(Builder &B, int N, Code a, Code b) {
     if (B.const_val(a, fa) && B.const_val(b, fb) && !fr_is_zero(fb)) { Fr fq, fr_; fr_divmod(fa, fb, fq, fr_); q = B.konst(fq); r = B.konst(fr_); }
     else { q = B.divmod(false, a, b, o.sig); r = B.divmod(true, a, b, o.sig); }
     B.at(o.pos) = q; B.at(o.pos + 1) = r; B.at(o.pos + 2) = a; B.at(o.pos + 3) = b;
-    T_AssertLessThan(B, N, r, b);
-    T_AssertLessEqThan(B, N, q, a);
+    Blk lt = T_AssertLessThan(B, N, r, b);
+    Blk le = T_AssertLessEqThan(B, N, q, a);
     B.chk_eq(B.fma(q, b, r), a, o.sig);
+    B.q_eq(lt.sig, o.sig + 1); B.q_eq(lt.sig + 1, o.sig + 3);                     // AssertLessThan(N)(rem, b)     divide.circom:27
+    B.q_eq(le.sig, o.sig); B.q_eq(le.sig + 1, o.sig + 2);                         // AssertLessEqThan(N)(out, a)   :30
+    B.q_r1(LC().s(o.sig), LC().s(o.sig + 3), LC().s(o.sig + 2).s(o.sig + 1, -1)); // out * b + rem === a           :32
     return o;
 }
 
@@ -609,10 +836,20 @@ static Blk T_Selector(Builder &B, int n_, const Code *vals, Code select) {
     size_t n = (size_t)n_; Blk o = B.alloc(1 + n + 1 + n + n + 1);
     B.copy(o.pos + 1, vals, n); B.at(o.pos + 1 + n) = select;
     size_t isEq = o.pos + 2 + n, sum = isEq + n;
-    B.at(sum) = ZERO;
-    for (size_t i = 0; i < n; i++) { Blk e = T_IsEqual(B, select, c_const((uint32_t)i)); B.at(isEq + i) = B.at(e.pos); }
+    const uint64_t qSel = o.sig + 1 + n, qEq = o.sig + 2 + n, qSum = qEq + n;
+    B.at(sum) = ZERO; B.q_const(qSum, 0);                                         // sum[0] <== 0                            selector.circom:30
+    LC all;
+    for (size_t i = 0; i < n; i++) {
+        Blk e = T_IsEqual(B, select, c_const((uint32_t)i)); B.at(isEq + i) = B.at(e.pos);
+        if (B.want_cs()) {
+            B.q_eq(e.sig + 1, qSel); B.q_const(e.sig + 2, i); B.q_eq(qEq + i, e.sig);                 // isEq[i] <== IsEqual()([select, i])      :33
+            B.q_r1(LC().s(qEq + i), LC().s(o.sig + 1 + i), LC().s(qSum + i + 1).s(qSum + i, -1));    // sum[i+1] <== sum[i] + isEq[i]*vals[i]   :39
+            all.s(qEq + i);
+        }
+    }
     B.selsum(select, vals, n, &B.at(sum + 1));          // sum[i+1] = sum_{j<=i} isEq[j]*vals[j]
     B.chk_eq(B.gtc(select, (uint32_t)(n - 1)), ZERO, o.sig);   // sumIsEq === 1  <=>  select in [0, n)
+    if (B.want_cs()) { all.k(-1); B.q_lin(all); B.q_eq(o.sig, qSum + n); }        // sumIsEq === 1 ; out <== sum[n]           :43-45
     B.at(o.pos) = B.at(sum + n); return o;
 }
 // SelectorArray1D(n,p) :62-77 / SelectorArray2D(n,p,q) :91-110  own: out[cols], arrays[n][cols], select, arraysT[cols][n]
@@ -620,8 +857,12 @@ static Blk T_SelectorArray(Builder &B, int n_, size_t cols, const Code *arrays, 
     size_t n = (size_t)n_; Blk o = B.alloc(cols + n * cols + 1 + cols * n);
     B.copy(o.pos + cols, arrays, n * cols); B.at(o.pos + cols + n * cols) = select;
     size_t T = o.pos + cols + n * cols + 1;
-    for (size_t i = 0; i < n; i++) for (size_t j = 0; j < cols; j++) B.at(T + j * n + i) = arrays[i * cols + j];
-    for (size_t j = 0; j < cols; j++) { Blk s = T_Selector(B, n_, &B.at(T + j * n), select); B.at(o.pos + j) = B.at(s.pos); }
+    const uint64_t qArr = o.sig + cols, qSel = o.sig + cols + n * cols, qT = qSel + 1;
+    for (size_t i = 0; i < n; i++) for (size_t j = 0; j < cols; j++) { B.at(T + j * n + i) = arrays[i * cols + j]; B.q_eq(qT + j * n + i, qArr + i * cols + j); }   // arraysT[j][i] <== arrays[i][j]   :69 / :101
+    for (size_t j = 0; j < cols; j++) {
+        Blk s = T_Selector(B, n_, &B.at(T + j * n), select); B.at(o.pos + j) = B.at(s.pos);
+        B.q_eqn(s.sig + 1, qT + j * n, n); B.q_eq(s.sig + 1 + n, qSel); B.q_eq(o.sig + j, s.sig);   // out[i] <== Selector(n)(arraysT[i], select)   :75 / :107
+    }
     return o;
 }
 
@@ -633,15 +874,24 @@ static Blk T_ShiftLeft(Builder &B, int n_, const Code *in, Code count) {
     size_t n = (size_t)n_; Blk o = B.alloc(2 * n + 1 + 2 * n * n);
     B.copy(o.pos + n, in, n); B.at(o.pos + 2 * n) = count;
     size_t isEq = o.pos + 2 * n + 1, temp = isEq + n * n;
-    T_AssertLessEqThan(B, 16, count, c_const((uint32_t)n));
+    const uint64_t qIn = o.sig + n, qCnt = o.sig + 2 * n, qEq = qCnt + 1, qTmp = qEq + n * n;
+    Blk al = T_AssertLessEqThan(B, 16, count, c_const((uint32_t)n));
+    B.q_eq(al.sig, qCnt); B.q_const(al.sig + 1, n);                               // AssertLessEqThan(16)(count, n)          shift.circom:22
     for (size_t i = 0; i < n; i++) {
         std::vector<Code> terms;
+        LC row;
         for (size_t j = 0; j < n; j++) {
             Blk e = T_IsEqual(B, c_const((uint32_t)i), B.sub(c_const((uint32_t)j), count));
             Code eq = B.at(e.pos); B.at(isEq + i * n + j) = eq;
             Code tv = B.mul(eq, in[j]); B.at(temp + i * n + j) = tv; terms.push_back(tv);
+            if (B.want_cs()) {
+                B.q_const(e.sig + 1, i); B.q_lin(LC().s(e.sig + 2).k(-(int64_t)j).s(qCnt)); B.q_eq(qEq + i * n + j, e.sig);   // isEq[i][j] <== IsEqual()([i, j - count])   :29
+                B.q_mul(qEq + i * n + j, qIn + j, qTmp + i * n + j);                                                             // temp[i][j] <== isEq[i][j] * in[j]          :30
+                row.s(qTmp + i * n + j);
+            }
         }
         B.at(o.pos + i) = B.sum_tree(terms);
+        if (B.want_cs()) { row.s(o.sig + i, -1); B.q_lin(row); }                  // out[i] <== outVars[i]                   :33
     }
     return o;
 }
@@ -650,20 +900,31 @@ static Blk T_ShiftRight(Builder &B, int n_, int ms_, const Code *in, Code count)
     size_t n = (size_t)n_, ms = (size_t)ms_; Blk o = B.alloc(n + ms + n + 1 + ms + 1 + (ms + 1) * n);
     B.copy(o.pos + n + ms, in, n); B.at(o.pos + 2 * n + ms) = count;
     size_t isEq = o.pos + 2 * n + ms + 1, temps = isEq + ms + 1;
-    T_AssertLessEqThan(B, 16, count, c_const((uint32_t)ms));
+    const uint64_t qIn = o.sig + n + ms, qCnt = o.sig + 2 * n + ms, qEq = qCnt + 1, qTmp = qEq + ms + 1;
+    Blk al = T_AssertLessEqThan(B, 16, count, c_const((uint32_t)ms));
+    B.q_eq(al.sig, qCnt); B.q_const(al.sig + 1, ms);                              // AssertLessEqThan(16)(count, maxShift)   shift.circom:56
     std::vector<std::vector<Code>> acc(n + ms);
+    std::vector<LC> rows(B.want_cs() ? n + ms : 0);
     for (size_t i = 0; i <= ms; i++) {
         Blk e = T_IsEqual(B, c_const((uint32_t)i), count); Code eq = B.at(e.pos); B.at(isEq + i) = eq;
-        for (size_t j = 0; j < n; j++) { Code tv = B.mul(eq, in[j]); B.at(temps + i * n + j) = tv; acc[i + j].push_back(tv); }
+        B.q_const(e.sig + 1, i); B.q_eq(e.sig + 2, qCnt); B.q_eq(qEq + i, e.sig);                                // isEq[i] <== IsEqual()([i, count])       :64
+        for (size_t j = 0; j < n; j++) {
+            Code tv = B.mul(eq, in[j]); B.at(temps + i * n + j) = tv; acc[i + j].push_back(tv);
+            if (B.want_cs()) { B.q_mul(qEq + i, qIn + j, qTmp + i * n + j); rows[i + j].s(qTmp + i * n + j); }   // temps[i][j] <== isEq[i] * in[j]         :66
+        }
     }
-    for (size_t k = 0; k < n + ms; k++) B.at(o.pos + k) = B.sum_tree(acc[k]);
+    for (size_t k = 0; k < n + ms; k++) {
+        B.at(o.pos + k) = B.sum_tree(acc[k]);
+        if (B.want_cs()) { rows[k].s(o.sig + k, -1); B.q_lin(rows[k]); }          // out[i] <== outVars[i]                   :72
+    }
     return o;
 }
 // Mask(n) :18-30  own: out[n], in[n], count, filter[n]
 static Blk T_Mask(Builder &B, int n_, const Code *in, Code count) {
     size_t n = (size_t)n_; Blk o = B.alloc(3 * n + 1); B.copy(o.pos + n, in, n); B.at(o.pos + 2 * n) = count;
     Blk f = T_Filter(B, n_, count); B.copy(o.pos + 2 * n + 1, &B.at(f.pos), n);
-    for (size_t i = 0; i < n; i++) B.at(o.pos + i) = B.mul(in[i], B.at(f.pos + i));
+    B.q_eq(f.sig + n, o.sig + 2 * n); B.q_eqn(o.sig + 2 * n + 1, f.sig, n);       // signal filter[n] <== Filter(n)(count)   concat.circom:24
+    for (size_t i = 0; i < n; i++) { B.at(o.pos + i) = B.mul(in[i], B.at(f.pos + i)); B.q_mul(o.sig + n + i, o.sig + 2 * n + 1 + i, o.sig + i); }   // out[i] <== in[i] * filter[i]   :27
     return o;
 }
 // Concat(A,B) :47-84  own: out[A+B], outLen, a[A], aLen, b[B], bLen, maskedA[A], maskedB[B], shiftedB[A+B]
@@ -671,14 +932,26 @@ static Blk T_Concat(Builder &B, int A, int Bn, const Code *a, Code aLen, const C
     size_t NA = (size_t)A, NB = (size_t)Bn, T = NA + NB;
     Blk o = B.alloc(T + 1 + NA + 1 + NB + 1 + NA + NB + T);
     size_t ia = o.pos + T + 1, iaL = ia + NA, ib = iaL + 1, ibL = ib + NB, mA = ibL + 1, mB = mA + NA, sB = mB + NB;
+    const uint64_t d = o.sig - o.pos;                                             // flat position -> witness index inside this block
     B.copy(ia, a, NA); B.at(iaL) = aLen; B.copy(ib, b, NB); B.at(ibL) = bLen;
-    T_AssertLessEqThan(B, 16, aLen, c_const((uint32_t)A));
-    T_AssertLessEqThan(B, 16, bLen, c_const((uint32_t)Bn));
+    Blk la = T_AssertLessEqThan(B, 16, aLen, c_const((uint32_t)A));
+    Blk lb = T_AssertLessEqThan(B, 16, bLen, c_const((uint32_t)Bn));
     Blk ma = T_Mask(B, A, a, aLen); B.copy(mA, &B.at(ma.pos), NA);
     Blk mb = T_Mask(B, Bn, b, bLen); B.copy(mB, &B.at(mb.pos), NB);
     Blk sh = T_ShiftRight(B, Bn, A, &B.at(mb.pos), aLen); B.copy(sB, &B.at(sh.pos), T);
     for (size_t i = 0; i < T; i++) B.at(o.pos + i) = i < NA ? B.add(B.at(ma.pos + i), B.at(sh.pos + i)) : B.at(sh.pos + i);
     B.at(o.pos + T) = B.add(aLen, bLen);
+    if (B.want_cs()) {
+        B.q_eq(la.sig, d + iaL); B.q_const(la.sig + 1, NA); B.q_eq(lb.sig, d + ibL); B.q_const(lb.sig + 1, NB);      // AssertLessEqThan(16)(aLen, maxLenA), (bLen, maxLenB)   concat.circom:67-68
+        B.q_eqn(ma.sig + NA, d + ia, NA); B.q_eq(ma.sig + 2 * NA, d + iaL); B.q_eqn(d + mA, ma.sig, NA);              // maskedA <== Mask(maxLenA)(a, aLen)                     :70
+        B.q_eqn(mb.sig + NB, d + ib, NB); B.q_eq(mb.sig + 2 * NB, d + ibL); B.q_eqn(d + mB, mb.sig, NB);              // maskedB <== Mask(maxLenB)(b, bLen)                     :71
+        B.q_eqn(sh.sig + T, d + mB, NB); B.q_eq(sh.sig + T + NB, d + iaL); B.q_eqn(d + sB, sh.sig, T);                // shiftedB <== ShiftRight(maxLenB, maxLenA)(maskedB, aLen)   :73
+        for (size_t i = 0; i < T; i++) {
+            if (i < NA) B.q_lin(LC().s(o.sig + i, -1).s(d + mA + i).s(d + sB + i));                                   // out[i] <== maskedA[i] + shiftedB[i]                    :77
+            else B.q_eq(o.sig + i, d + sB + i);                                                                       // out[i] <== shiftedB[i]                                 :79
+        }
+        B.q_lin(LC().s(o.sig + T, -1).s(d + iaL).s(d + ibL));                                                         // outLen <== aLen + bLen                                 :83
+    }
     return o;
 }
 
@@ -691,17 +964,29 @@ static Blk T_SubstringCheck(Builder &B, int maxMainLen, int subLen, const Code *
     Blk o = B.alloc(1 + MM + 1 + SL + 1 + (MM + 1) + Kn + Kn + (Kn + 1) + (Kn + 1) + 1);
     size_t iMain = o.pos + 1, iLen = iMain + MM, iSub = iLen + 1, subNum = iSub + SL, Mo = subNum + 1,
            exists = Mo + MM + 1, isLast = exists + Kn, allowed = isLast + Kn, sums = allowed + Kn + 1, dne = sums + Kn + 1;
+    const uint64_t d = o.sig - o.pos;
+    const bool cs = B.want_cs();
     B.copy(iMain, mainInput, MM); B.at(iLen) = mainLen; B.copy(iSub, subInput, SL);
-    T_AssertByteString(B, subLen, subInput);
-    T_AssertByteString(B, maxMainLen, mainInput);
-    T_AssertLessEqThan(B, 16, mainLen, c_const((uint32_t)MM));
-    T_AssertLessEqThan(B, 16, c_const((uint32_t)SL), mainLen);
+    Blk as = T_AssertByteString(B, subLen, subInput);
+    Blk am = T_AssertByteString(B, maxMainLen, mainInput);
+    Blk l1 = T_AssertLessEqThan(B, 16, mainLen, c_const((uint32_t)MM));
+    Blk l2 = T_AssertLessEqThan(B, 16, c_const((uint32_t)SL), mainLen);
     Blk sn = T_LittleEndianBytes2Num(B, subLen, subInput); Code subN = B.at(sn.pos); B.at(subNum) = subN;
+    if (cs) {
+        B.q_eqn(as.sig, d + iSub, SL); B.q_eqn(am.sig, d + iMain, MM);                                    // AssertByteString(subLen)(subInput), (maxMainLen)(mainInput)   substring_check.circom:33-34
+        B.q_eq(l1.sig, d + iLen); B.q_const(l1.sig + 1, MM); B.q_const(l2.sig, SL); B.q_eq(l2.sig + 1, d + iLen);   // :36-37
+        B.q_eqn(sn.sig + 1, d + iSub, SL); B.q_eq(d + subNum, sn.sig);                                    // subInputNum <== LittleEndianBytes2Num(subLen)(subInput)     :40
+        B.q_const(d + Mo, 0); B.q_const(d + allowed, 1); B.q_const(d + sums, 0);                          // M[0] <== 0; allowed[0] <== 1; sums[0] <== 0                 :46, :61, :65
+    }
     B.at(Mo) = ZERO;
     Fr pw = fr_from_u64(1), c256 = fr_from_u64(256);
     {   // M[i+1] = mainInput[i]*256^i + M[i]
         std::vector<Code> terms(MM);
-        for (size_t i = 0; i < MM; i++) { terms[i] = B.mul(mainInput[i], B.konst(pw)); pw = fr_mul(pw, c256); }
+        for (size_t i = 0; i < MM; i++) {
+            terms[i] = B.mul(mainInput[i], B.konst(pw));
+            if (cs) B.q_lin(LC().s(d + Mo + i + 1, -1).sf(d + iMain + i, pw).s(d + Mo + i));              // M[i+1] <== mainInput[i]*(256**i) + M[i]                     :48
+            pw = fr_mul(pw, c256);
+        }
         B.prefix_sum(ZERO, terms.data(), MM, &B.at(Mo + 1));
     }
     B.at(allowed) = ONE; B.at(sums) = ZERO;
@@ -714,11 +999,22 @@ static Blk T_SubstringCheck(Builder &B, int maxMainLen, int subLen, const Code *
         Blk e2 = T_IsEqual(B, B.mul(subN, B.konst(pw)), B.sub(B.at(Mo + i + SL), B.at(Mo + i)), /*likely_large=*/true);
         Code ex = B.at(e2.pos); B.at(exists + i) = ex;
         sterms[i] = B.mul(B.at(allowed + i + 1), ex);
+        if (cs) {
+            B.q_const(e1.sig + 1, i); B.q_lin(LC().s(e1.sig + 2).s(d + iLen, -1).k((int64_t)SL - 1)); B.q_eq(d + isLast + i, e1.sig);   // isLastIndex[i] <== IsEqual()([i, mainLen - subLen + 1])   :72
+            B.q_r1(LC().s(d + allowed + i), LC().k(1).s(d + isLast + i, -1), LC().s(d + allowed + i + 1));                               // allowed[i+1] <== allowed[i] * (1 - isLastIndex[i])         :75
+            B.q_lin(LC().s(e2.sig + 1).sf(d + subNum, fr_neg(pw))); B.q_lin(LC().s(e2.sig + 2).s(d + Mo + i + SL, -1).s(d + Mo + i));
+            B.q_eq(d + exists + i, e2.sig);                                                                                               // exists[i] <== IsEqual()([subInputNum*(256**i), M[i+subLen] - M[i]])   :91
+            B.q_r1(LC().s(d + allowed + i + 1), LC().s(d + exists + i), LC().s(d + sums + i + 1).s(d + sums + i, -1));                   // sums[i+1] <== sums[i] + allowed[i+1]*exists[i]             :95
+        }
         pw = fr_mul(pw, c256);
     }
     B.prefix_sum(ZERO, sterms.data(), Kn, &B.at(sums + 1));   // sums[i+1] = sums[i] + allowed[i+1]*exists[i]
     Blk z = T_IsZero(B, B.at(sums + Kn)); B.at(dne) = B.at(z.pos);
     B.at(o.pos) = B.not1(B.at(z.pos));
+    if (cs) {
+        B.q_eq(z.sig + 1, d + sums + Kn); B.q_eq(d + dne, z.sig);                 // doesNotExist <== IsZero()(sums[maxMainLen - subLen + 1])   :98
+        B.q_lin(LC().s(o.sig).k(-1).s(d + dne));                                  // out <== 1 - doesNotExist                                    :99
+    }
     return o;
 }
 
@@ -806,6 +1102,105 @@ static void emit_round(LaneSink &S) {
     S.gate_array(out[0], ch[0], W(RW_RC));
 }
 
+// The constraint system of one KeccakfRound(r) block (keccak.circom:290-297 and everything below it), over signal indices
+// RELATIVE to the block's first signal.  Same traversal order as emit_round; REL_ONE stands for the constant 1.
+static const uint64_t REL_ONE = 0xffffffffull;
+struct RoundCons {
+    ConsSink &S; uint32_t cur = 0;
+    uint32_t take(uint32_t n) { uint32_t o = cur; cur += n; return o; }
+    void eqn(uint32_t a, uint32_t b, uint32_t n) { for (uint32_t k = 0; k < n; k++) S.eq(a + k, b + k); }
+    void eq64(uint32_t a, uint32_t b) { eqn(a, b, 64); }
+    // XorArray :77-86 / OrArray :104-113 / AndArray :120-129 (64): own out, a, b, then 64 gates [out, a, b]
+    uint32_t gate_array(int kind, uint32_t srcA, uint32_t srcB) {
+        const uint32_t o = take(64), a = take(64), b = take(64);
+        eq64(a, srcA); eq64(b, srcB);
+        for (uint32_t k = 0; k < 64; k++) {
+            const uint32_t g = take(3);
+            S.eq(g + 1, a + k); S.eq(g + 2, b + k);
+            if (kind == 0) S.r1(LC().s(g + 1, 2), LC().s(g + 2), LC().s(g + 1).s(g + 2).s(g, -1));       // XOR: out <== a + b - 2*a*b   gates.circom:26
+            else if (kind == 1) S.r1(LC().s(g + 1), LC().s(g + 2), LC().s(g + 1).s(g + 2).s(g, -1));     // OR : out <== a + b - a*b     gates.circom:42
+            else S.r1(LC().s(g + 1), LC().s(g + 2), LC().s(g));                                           // AND: out <== a*b             gates.circom:34
+            S.eq(o + k, g);
+        }
+        return o;
+    }
+    uint32_t shl(uint32_t src, uint32_t r) {         // ShL(64, r) :40-51  own: out, in
+        const uint32_t o = take(64), in = take(64); eq64(in, src);
+        for (uint32_t i = 0; i < 64; i++) { if (i < r) S.kc(o + i, fr_zero()); else S.eq(o + i, in + i - r); }
+        return o;
+    }
+    uint32_t shr(uint32_t src, uint32_t r) {         // ShR(64, r) :19-30
+        const uint32_t o = take(64), in = take(64); eq64(in, src);
+        for (uint32_t i = 0; i < 64; i++) { if (i + r >= 64) S.kc(o + i, fr_zero()); else S.eq(o + i, in + i + r); }
+        return o;
+    }
+    uint32_t notarr(uint32_t src) {                  // NotArray(64) :92-98  own: out, a ; out[i] <== 1 - a[i]
+        const uint32_t o = take(64), a = take(64); eq64(a, src);
+        for (uint32_t i = 0; i < 64; i++) S.r1(LC(), LC(), LC().s(o + i).s(a + i).s(REL_ONE, -1));
+        return o;
+    }
+    void round() {
+        const uint32_t r_out = take(1600), r_in = take(1600), r_theta = take(1600), r_rhopi = take(1600), r_chi = take(1600);
+        {   // signal theta[25][64] <== Theta()(in)   :293 ; Theta :151-170  own: out, in, c[5], d[5]
+            const uint32_t t_out = take(1600), t_in = take(1600), t_c = take(320), t_d = take(320);
+            eqn(t_in, r_in, 1600);
+            for (uint32_t i = 0; i < 5; i++) {          // c[i] <== Xor5(64)(in[i], in[5+i], in[10+i], in[15+i], in[20+i])   :157 ; Xor5 :58-70
+                const uint32_t x_out = take(64); uint32_t x_in[5]; for (int j = 0; j < 5; j++) x_in[j] = take(64);
+                const uint32_t x_ab = take(64), x_abc = take(64), x_abcd = take(64);
+                for (uint32_t j = 0; j < 5; j++) eq64(x_in[j], t_in + 64 * (5 * j + i));
+                eq64(x_ab, gate_array(0, x_in[0], x_in[1])); eq64(x_abc, gate_array(0, x_ab, x_in[2]));
+                eq64(x_abcd, gate_array(0, x_abc, x_in[3])); eq64(x_out, gate_array(0, x_abcd, x_in[4]));
+                eq64(t_c + 64 * i, x_out);
+            }
+            for (uint32_t i = 0; i < 5; i++) {          // d[i] <== D()(c[(i+1)%5], c[(i+4)%5])   :162 ; D :135-144  own: out, a, b, aux0, aux1, aux2
+                const uint32_t d_out = take(64), d_a = take(64), d_b = take(64), d_0 = take(64), d_1 = take(64), d_2 = take(64);
+                eq64(d_a, t_c + 64 * ((i + 1) % 5)); eq64(d_b, t_c + 64 * ((i + 4) % 5));
+                eq64(d_0, shl(d_a, 1)); eq64(d_1, shr(d_a, 63));
+                eq64(d_2, gate_array(1, d_0, d_1)); eq64(d_out, gate_array(0, d_b, d_2));
+                eq64(t_d + 64 * i, d_out);
+            }
+            for (uint32_t i = 0; i < 5; i++) for (uint32_t j = 0; j < 5; j++)                 // out[i + j*5] <== XorArray(64)(in[i + j*5], d[i])   :167
+                eq64(t_out + 64 * (i + 5 * j), gate_array(0, t_in + 64 * (i + 5 * j), t_d + 64 * i));
+            eqn(r_theta, t_out, 1600);
+        }
+        {   // signal rhopi <== RhoPi()(theta)   :294 ; RhoPi :191-204  own: out, in
+            const uint32_t p_out = take(1600), p_in = take(1600);
+            eqn(p_in, r_theta, 1600);
+            eq64(p_out, p_in);                                                        // out[0] <== in[0]   :197
+            for (int i = 0; i < 24; i++) {              // out[rot[i+1]] <== stepRhoPi(shl, 64 - shl)(in[rot[i]])   :202 ; stepRhoPi :177-184  own: out, a, aux0, aux1
+                const uint32_t sh = (uint32_t)keccak_shl(i);
+                const uint32_t s_out = take(64), s_a = take(64), s_0 = take(64), s_1 = take(64);
+                eq64(s_a, p_in + 64 * (uint32_t)keccak_rot(i));
+                eq64(s_0, shr(s_a, 64 - sh)); eq64(s_1, shl(s_a, sh));
+                eq64(s_out, gate_array(1, s_0, s_1));
+                eq64(p_out + 64 * (uint32_t)keccak_rot(i + 1), s_out);
+            }
+            eqn(r_rhopi, p_out, 1600);
+        }
+        {   // signal chi <== Chi()(rhopi)   :295 ; Chi :228-241  own: out, in
+            const uint32_t c_out = take(1600), c_in = take(1600);
+            eqn(c_in, r_rhopi, 1600);
+            for (int i = 0; i < 25; i++) {              // out[i] <== stepChi()(in[i], in[..], in[..])   :233-239 ; stepChi :212-221  own: out, a, b, c, bXor, bc
+                const uint32_t s_out = take(64), s_a = take(64), s_b = take(64), s_c = take(64), s_bx = take(64), s_bc = take(64);
+                eq64(s_a, c_in + 64 * (uint32_t)i); eq64(s_b, c_in + 64 * (uint32_t)chi_b(i)); eq64(s_c, c_in + 64 * (uint32_t)chi_c(i));
+                eq64(s_bx, notarr(s_b)); eq64(s_bc, gate_array(2, s_bx, s_c)); eq64(s_out, gate_array(0, s_a, s_bc));
+                eq64(c_out + 64 * (uint32_t)i, s_out);
+            }
+            eqn(r_chi, c_out, 1600);
+        }
+        {   // out <== Iota(r)(chi)   :296 ; Iota :273-283  own: out, in, roundConstants ; RoundConstants(r) :248-266  own: out[64]
+            const uint32_t i_out = take(1600), i_in = take(1600), i_rc = take(64);
+            eqn(i_in, r_chi, 1600);
+            const uint32_t rc = take(64);
+            for (uint32_t k = 0; k < 64; k++) S.kc_raw(rc + k, (CC_RCBIT << 30) | k);   // out[i] <== (rc[r] >> i) & 1   :264
+            eq64(i_rc, rc);
+            eq64(i_out, gate_array(0, i_in, i_rc));                                   // out[0] <== XorArray(64)(in[0], roundConstants)   :279
+            eqn(i_out + 64, i_in + 64, 1536);                                         // out[i] <== in[i], i >= 1                          :281
+            eqn(r_out, i_out, 1600);
+        }
+    }
+};
+
 // Absorb :304-323  (s: previous state words or NONE_IDX; blk: 17 block words).  Returns the state-out word base.
 static uint32_t T_Absorb(Builder &B, uint32_t s_idx, uint32_t blk_idx, Blk *own) {
     uint32_t A = B.absorb(s_idx, blk_idx), out_w = A + RW * 24;
@@ -815,16 +1210,35 @@ static uint32_t T_Absorb(Builder &B, uint32_t s_idx, uint32_t blk_idx, Blk *own)
     for (uint32_t l = 0; l < 25; l++) S.lane(Lane{s_idx == NONE_IDX ? NONE_IDX : s_idx + l});
     for (uint32_t l = 0; l < 17; l++) S.lane(Lane{blk_idx + l});
     for (uint32_t l = 0; l < 25; l++) S.lane(Lane{A + l});
+    const uint64_t qS = o.sig + 1600, qBlk = o.sig + 3200, qAux = o.sig + 4288;
     for (uint32_t l = 0; l < 17; l++) {                               // XorArray(64)(s[i], block[i])
         Blk x = B.alloc(384); LaneSink X{&B.at(x.pos), 0};
         X.gate_array(Lane{A + l}, Lane{s_idx == NONE_IDX ? NONE_IDX : s_idx + l}, Lane{blk_idx + l});
+        if (B.want_cs()) {                                            // aux[i] <== XorArray(64)(s[i], block[i])   keccak.circom:316
+            B.q_eqn(x.sig + 64, qS + 64 * l, 64); B.q_eqn(x.sig + 128, qBlk + 64 * l, 64); B.q_eqn(qAux + 64 * l, x.sig, 64);
+            for (uint32_t k = 0; k < 64; k++) {
+                const uint64_t g = x.sig + 192 + 3 * k;
+                B.q_eq(g + 1, x.sig + 64 + k); B.q_eq(g + 2, x.sig + 128 + k);
+                B.q_r1(LC().s(g + 1, 2), LC().s(g + 2), LC().s(g + 1).s(g + 2).s(g, -1));     // XOR   gates.circom:26
+                B.q_eq(x.sig + k, g);
+            }
+        }
     }
+    B.q_eqn(qAux + 64 * 17, qS + 64 * 17, 64 * 8);                    // aux[i] <== s[i], i >= 17                    :318
     // Keccakf :356-367  own: out, in, midRound[25][25][64]
     Blk k = B.alloc(1600 + 1600 + 25 * 1600); LaneSink Kf{&B.at(k.pos), 0};
     for (uint32_t l = 0; l < 25; l++) Kf.lane(Lane{out_w + l});
     for (uint32_t l = 0; l < 25; l++) Kf.lane(Lane{A + l});
     for (uint32_t r = 0; r <= 24; r++) for (uint32_t l = 0; l < 25; l++) Kf.lane(Lane{A + RW * r + l});
-    for (uint32_t r = 0; r < 24; r++) B.round_block(A + RW * r);
+    B.q_eqn(k.sig + 1600, qAux, 1600); B.q_eqn(o.sig, k.sig, 1600);   // out <== Keccakf()(aux)                      :322
+    B.q_eqn(k.sig + 3200, k.sig + 1600, 1600);                        // midRound[0] <== in                          :361
+    for (uint32_t r = 0; r < 24; r++) {
+        const uint64_t rb = B.nsig;
+        B.round_block(A + RW * r);
+        B.q_eqn(rb + 1600, k.sig + 3200 + 1600 * (uint64_t)r, 1600);  // midRound[i+1] <== KeccakfRound(i)(midRound[i])   :363
+        B.q_eqn(k.sig + 3200 + 1600 * (uint64_t)(r + 1), rb, 1600);
+    }
+    B.q_eqn(k.sig, k.sig + 3200 + 1600 * 24, 1600);                   // out <== midRound[24]                        :366
     return out_w;
 }
 // Final(n) :330-349 and Keccak(n) :374-385 ; in_words: n*17 block words ; returns Keccak's own block
@@ -837,16 +1251,27 @@ static Blk T_Keccak(Builder &B, int n_, uint32_t in_words, Code blocks) {
     { LaneSink S{&B.at(fo.pos + 1600), 0}; for (uint32_t w = 0; w < n * 17; w++) S.lane(Lane{in_words + w}); }
     B.at(fo.pos + 1600 + n * 1088) = blocks;
     size_t s = fo.pos + 1600 + n * 1088 + 1;
-    for (size_t i = 0; i < 1600; i++) B.at(s + i) = ZERO;             // s[0] = 0
+    const uint64_t qS = fo.sig + 1600 + n * 1088 + 1, qFin = ko.sig + 256 + n * 1088 + 1;
+    for (size_t i = 0; i < 1600; i++) { B.at(s + i) = ZERO; B.q_const(qS + i, 0); }   // s[0][i][j] <== 0            keccak.circom:339
     uint32_t st = NONE_IDX;
     for (size_t b = 0; b < n; b++) {
-        st = T_Absorb(B, st, in_words + 17 * (uint32_t)b, nullptr);
+        Blk ab;
+        st = T_Absorb(B, st, in_words + 17 * (uint32_t)b, &ab);
         LaneSink S{&B.at(s + 1600 * (b + 1)), 0}; for (uint32_t l = 0; l < 25; l++) S.lane(Lane{st + l});
+        B.q_eqn(ab.sig + 1600, qS + 1600 * b, 1600); B.q_eqn(ab.sig + 3200, fo.sig + 1600 + 1088 * b, 1088);   // s[b+1] <== Absorb()(s[b], in[b])   :344
+        B.q_eqn(qS + 1600 * (b + 1), ab.sig, 1600);
     }
     Blk sel = T_SelectorArray(B, n_ + 1, 1600, &B.at(s), blocks);
     B.copy(fo.pos, &B.at(sel.pos), 1600);
     B.copy(ko.pos + 256 + n * 1088 + 1, &B.at(fo.pos), 1600);
     B.copy(ko.pos, &B.at(fo.pos), 256);
+    if (B.want_cs()) {
+        B.q_eqn(sel.sig + 1600, qS, (n + 1) * 1600); B.q_eq(sel.sig + 1600 + (n + 1) * 1600, fo.sig + 1600 + n * 1088);   // out <== SelectorArray2D(nBlocksIn+1, 25, 64)(s, blocks)   :348
+        B.q_eqn(fo.sig, sel.sig, 1600);
+        B.q_eqn(fo.sig + 1600, ko.sig + 256, n * 1088); B.q_eq(fo.sig + 1600 + n * 1088, ko.sig + 256 + n * 1088);        // finalState <== Final(nBlocksIn)(in, blocks)               :379
+        B.q_eqn(qFin, fo.sig, 1600);
+        B.q_eqn(ko.sig, qFin, 256);                                                                                        // out[i] <== finalState[i \ 64][i % 64]                    :383
+    }
     return ko;
 }
 // Pad(maxBlocks, blockSize) :412-446  own: out[B], numBlocks, in[B], inLen, div, rem, filter[B+1], isEq[B], isLast[B]
@@ -854,19 +1279,34 @@ static Blk T_Pad(Builder &B, int maxBlocks, int blockSize, const Code *in, Code 
     size_t Bn = (size_t)maxBlocks * (size_t)blockSize; Blk o = B.alloc(Bn + 1 + Bn + 1 + 2 + (Bn + 1) + Bn + Bn);
     size_t numBlocks = o.pos + Bn, iIn = numBlocks + 1, iLen = iIn + Bn, div = iLen + 1, rem = div + 1,
            filter = rem + 1, isEq = filter + Bn + 1, isLast = isEq + Bn;
+    const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
     B.copy(iIn, in, Bn); B.at(iLen) = inLen;
-    Blk d = T_Divide(B, 16, inLen, c_const((uint32_t)blockSize)); B.at(div) = B.at(d.pos); B.at(rem) = B.at(d.pos + 1);
+    Blk dv = T_Divide(B, 16, inLen, c_const((uint32_t)blockSize)); B.at(div) = B.at(dv.pos); B.at(rem) = B.at(dv.pos + 1);
     Code nbk = B.add(B.at(div), ONE); B.at(numBlocks) = nbk;
-    T_AssertLessEqThan(B, 16, nbk, c_const((uint32_t)maxBlocks));
+    Blk al = T_AssertLessEqThan(B, 16, nbk, c_const((uint32_t)maxBlocks));
     B.at(filter) = ONE;
+    if (cs) {
+        B.q_eq(dv.sig + 2, d + iLen); B.q_const(dv.sig + 3, (uint64_t)blockSize); B.q_eq(d + div, dv.sig); B.q_eq(d + rem, dv.sig + 1);   // signal (div, rem) <== Divide(16)(inLen, blockSize)   keccak.circom:420
+        B.q_lin(LC().s(d + numBlocks, -1).s(d + div).k(1));                                                                              // numBlocks <== div + 1                                :421
+        B.q_eq(al.sig, d + numBlocks); B.q_const(al.sig + 1, (uint64_t)maxBlocks);                                                       // AssertLessEqThan(16)(numBlocks, maxBlocks)           :423
+        B.q_const(d + filter, 1);                                                                                                        // filter[0] <== 1                                      :428
+    }
     for (size_t i = 0; i < Bn; i++) {
         Blk e = T_IsEqual(B, c_const((uint32_t)i), inLen); Code eq = B.at(e.pos); B.at(isEq + i) = eq;
         B.at(filter + i + 1) = B.gtc(inLen, (uint32_t)i);          // filter[i]*(1 - isEq[i]) == (inLen > i)
+        if (cs) {
+            B.q_const(e.sig + 1, i); B.q_eq(e.sig + 2, d + iLen); B.q_eq(d + isEq + i, e.sig);                         // isEq[i] <== IsEqual()([i, inLen])               :431
+            B.q_r1(LC().s(d + filter + i), LC().k(1).s(d + isEq + i, -1), LC().s(d + filter + i + 1));                // filter[i+1] <== filter[i] * (1 - isEq[i])       :432
+        }
     }
     Code lastPos = B.sub(B.mul(nbk, c_const((uint32_t)blockSize)), ONE);
     for (size_t i = 0; i < Bn; i++) {
         Blk e = T_IsEqual(B, c_const((uint32_t)i), lastPos); Code l = B.at(e.pos); B.at(isLast + i) = l;
         B.at(o.pos + i) = B.fma(l, c_const(0x80), B.fma(in[i], B.at(filter + i + 1), B.at(isEq + i)));
+        if (cs) {
+            B.q_const(e.sig + 1, i); B.q_lin(LC().s(e.sig + 2).s(d + numBlocks, -(int64_t)blockSize).k(1)); B.q_eq(d + isLast + i, e.sig);   // isLast[i] <== IsEqual()([i, numBlocks*blockSize - 1])   :437
+            B.q_r1(LC().s(d + iIn + i), LC().s(d + filter + i + 1), LC().s(o.sig + i).s(d + isEq + i, -1).s(d + isLast + i, -0x80));        // out[i] <== in[i]*filter[i+1] + 0x01*isEq[i] + 0x80*isLast[i]   :444
+        }
     }
     return o;
 }
@@ -876,9 +1316,15 @@ static Blk T_KeccakBytes(Builder &B, int maxBlocks, const Code *in, Code inLen) 
     Blk o = B.alloc(32 + Bn + 1 + Bn + 1 + 24 * Bn + 256 + 256);
     size_t iIn = o.pos + 32, iLen = iIn + Bn, padded = iLen + 1, numBlocks = padded + Bn, inBitsArray = numBlocks + 1,
            inBits = inBitsArray + 8 * Bn, inBlocks = inBits + 8 * Bn, outBits = inBlocks + 8 * Bn, outBytes = outBits + 256;
+    const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
     B.copy(iIn, in, Bn); B.at(iLen) = inLen;
-    T_AssertLessThan(B, 16, inLen, c_const((uint32_t)Bn));
+    Blk al = T_AssertLessThan(B, 16, inLen, c_const((uint32_t)Bn));
     Blk p = T_Pad(B, maxBlocks, 136, in, inLen); B.copy(padded, &B.at(p.pos), Bn); B.at(numBlocks) = B.at(p.pos + Bn);
+    if (cs) {
+        B.q_eq(al.sig, d + iLen); B.q_const(al.sig + 1, Bn);                                                         // AssertLessThan(16)(inLen, maxBlocks*136)          keccak.circom:460
+        B.q_eqn(p.sig + Bn + 1, d + iIn, Bn); B.q_eq(p.sig + 2 * Bn + 1, d + iLen);                                  // (padded, numBlocks) <== Pad(maxBlocks, 136)(in, inLen)   :463-465
+        B.q_eqn(d + padded, p.sig, Bn); B.q_eq(d + numBlocks, p.sig + Bn);
+    }
     uint32_t words = B.pack8_words(&B.at(padded), (uint32_t)(Bn / 8));         // bytes -> 17 lanes per block
     for (size_t i = 0; i < Bn; i++) {                                          // Num2Bits(8)(padded[i])
         Blk nb = B.alloc(9);
@@ -886,12 +1332,27 @@ static Blk T_KeccakBytes(Builder &B, int maxBlocks, const Code *in, Code inLen) 
         B.at(nb.pos + 8) = B.at(padded + i);
         B.chk_range(B.at(padded + i), 8, nb.sig);
         B.copy(inBitsArray + 8 * i, &B.at(nb.pos), 8);
+        if (cs) {
+            LC sum;
+            for (uint32_t k = 0; k < 8; k++) { B.q_r1(LC().s(nb.sig + k), LC().s(nb.sig + k).k(-1), LC()); sum.s(nb.sig + k, 1 << k); }   // Num2Bits(8)   bitify.circom:33, :38
+            sum.s(nb.sig + 8, -1); B.q_lin(sum);
+            B.q_eq(nb.sig + 8, d + padded + i); B.q_eqn(d + inBitsArray + 8 * i, nb.sig, 8);                         // inBitsArray[i] <== Num2Bits(8)(padded[i])         :470
+        }
     }
     Blk fl = T_CopyArray(B, 8 * Bn, &B.at(inBitsArray)); B.copy(inBits, &B.at(fl.pos), 8 * Bn);   // Flatten
     B.copy(inBlocks, &B.at(inBits), 8 * Bn);
     Blk k = T_Keccak(B, maxBlocks, words, B.at(numBlocks)); B.copy(outBits, &B.at(k.pos), 256);
     Blk rs = T_CopyArray(B, 256, &B.at(outBits)); B.copy(outBytes, &B.at(rs.pos), 256);           // Reshape
-    for (size_t i = 0; i < 32; i++) { Blk bn = T_Bits2Num(B, 8, &B.at(outBytes + 8 * i)); B.at(o.pos + i) = B.at(bn.pos); }
+    if (cs) {
+        B.q_eqn(fl.sig + 8 * Bn, d + inBitsArray, 8 * Bn); B.q_eqn(d + inBits, fl.sig, 8 * Bn);                      // inBits <== Flatten(maxBlocks*136, 8)(inBitsArray)   :472
+        B.q_eqn(d + inBlocks, d + inBits, 8 * Bn);                                                                   // inBlocks[i][j][k] <== inBits[i*17*64 + j*64 + k]    :479
+        B.q_eqn(k.sig + 256, d + inBlocks, 8 * Bn); B.q_eq(k.sig + 256 + 8 * Bn, d + numBlocks); B.q_eqn(d + outBits, k.sig, 256);   // outBits <== Keccak(maxBlocks)(inBlocks, numBlocks)   :484
+        B.q_eqn(rs.sig + 256, d + outBits, 256); B.q_eqn(d + outBytes, rs.sig, 256);                                 // outBytes <== Reshape(32, 8)(outBits)                :485
+    }
+    for (size_t i = 0; i < 32; i++) {
+        Blk bn = T_Bits2Num(B, 8, &B.at(outBytes + 8 * i)); B.at(o.pos + i) = B.at(bn.pos);
+        B.q_eqn(bn.sig + 1, d + outBytes + 8 * i, 8); B.q_eq(o.sig + i, bn.sig);                                     // out[i] <== Bits2Num(8)(outBytes[i])                 :487
+    }
     return o;
 }
 
@@ -903,13 +1364,21 @@ static Blk T_PublicCommitment(Builder &B, int N, const Code *in) {
     size_t n32 = (size_t)N * 32; int nb = (N * 32) / 136 + ((N * 32) % 136 != 0); size_t blk = (size_t)nb * 136;
     Blk o = B.alloc(1 + n32 + n32 + blk + 32 + 31);
     size_t iIn = o.pos + 1, flat = iIn + n32, block = flat + n32, hash = block + blk, red = hash + 32;
+    const uint64_t d = o.sig - o.pos;
     B.copy(iIn, in, n32);
-    for (int i = 0; i < N; i++) T_AssertByteString(B, 32, in + 32 * i);
+    for (int i = 0; i < N; i++) { Blk a = T_AssertByteString(B, 32, in + 32 * i); B.q_eqn(a.sig, d + iIn + 32 * (size_t)i, 32); }   // AssertByteString(32)(in[i])   public_commitment.circom:24
     Blk f = T_CopyArray(B, n32, in); B.copy(flat, &B.at(f.pos), n32);
     Blk ft = T_Fit(B, (int)n32, (int)blk, &B.at(flat)); B.copy(block, &B.at(ft.pos), blk);
     Blk k = T_KeccakBytes(B, nb, &B.at(block), c_const((uint32_t)n32)); B.copy(hash, &B.at(k.pos), 32);
     Blk f2 = T_Fit(B, 32, 31, &B.at(hash)); B.copy(red, &B.at(f2.pos), 31);
     Blk be = T_BigEndianBytes2Num(B, 31, &B.at(red)); B.at(o.pos) = B.at(be.pos);
+    if (B.want_cs()) {
+        B.q_eqn(f.sig + n32, d + iIn, n32); B.q_eqn(d + flat, f.sig, n32);                                   // flattenIn <== Flatten(N, 32)(in)                   :33
+        B.q_eqn(ft.sig + blk, d + flat, n32); B.q_eqn(d + block, ft.sig, blk);                               // block <== Fit(N*32, numBlocks*136)(flattenIn)      :34
+        B.q_eqn(k.sig + 32, d + block, blk); B.q_const(k.sig + 32 + blk, n32); B.q_eqn(d + hash, k.sig, 32); // hash <== KeccakBytes(numBlocks)(block, N*32)        :36
+        B.q_eqn(f2.sig + 31, d + hash, 32); B.q_eqn(d + red, f2.sig, 31);                                    // reducedHash <== Fit(32, 31)(hash)                  :39
+        B.q_eqn(be.sig + 1, d + red, 31); B.q_eq(o.sig, be.sig);                                             // out <== BigEndianBytes2Num(31)(reducedHash)        :41
+    }
     return o;
 }
 // constants.circom :3-15
@@ -927,6 +1396,12 @@ static Blk T_BurnAddress(Builder &B, Code burnKey, Code revealAmount, Code bec) 
     Blk p = T_Poseidon(B, 4, ins); B.at(o.pos + 23) = B.at(p.pos);
     Blk b = T_Num2BigEndianBytes(B, 32, B.at(p.pos)); B.copy(o.pos + 24, &B.at(b.pos), 32);
     Blk f = T_Fit(B, 32, 20, &B.at(o.pos + 24)); B.copy(o.pos, &B.at(f.pos), 20);
+    if (B.want_cs()) {
+        Fr pre; B.const_val(ins[0], pre);
+        B.q_constf(p.sig + 1, pre); B.q_eqn(p.sig + 2, o.sig + 20, 3); B.q_eq(o.sig + 23, p.sig);            // hash <== Poseidon(4)([PREFIX, burnKey, revealAmount, burnExtraCommitment])   burn_address.circom:55
+        B.q_eq(b.sig + 32, o.sig + 23); B.q_eqn(o.sig + 24, b.sig, 32);                                      // hashBytes <== Num2BigEndianBytes(32)(hash)                                   :56
+        B.q_eqn(f.sig + 20, o.sig + 24, 32); B.q_eqn(o.sig, f.sig, 20);                                      // addressBytes <== Fit(32, 20)(hashBytes)                                      :57
+    }
     return o;
 }
 // BurnAddressHash :67-83  own: addressHashNibbles[64], 3 inputs, addressBytes[20], addressBytesBlock[136], addressHash[32]
@@ -937,12 +1412,20 @@ static Blk T_BurnAddressHash(Builder &B, Code burnKey, Code revealAmount, Code b
     Blk f = T_Fit(B, 20, 136, &B.at(o.pos + 67)); B.copy(o.pos + 87, &B.at(f.pos), 136);
     Blk k = T_KeccakBytes(B, 1, &B.at(o.pos + 87), c_const(20)); B.copy(o.pos + 223, &B.at(k.pos), 32);
     Blk nb = T_Bytes2Nibbles(B, 32, &B.at(o.pos + 223)); B.copy(o.pos, &B.at(nb.pos), 64);
+    if (B.want_cs()) {
+        B.q_eqn(a.sig + 20, o.sig + 64, 3); B.q_eqn(o.sig + 67, a.sig, 20);                                  // addressBytes <== BurnAddress()(...)                         burn_address.circom:77
+        B.q_eqn(f.sig + 136, o.sig + 67, 20); B.q_eqn(o.sig + 87, f.sig, 136);                               // addressBytesBlock <== Fit(20, 136)(addressBytes)            :78
+        B.q_eqn(k.sig + 32, o.sig + 87, 136); B.q_const(k.sig + 32 + 136, 20); B.q_eqn(o.sig + 223, k.sig, 32);   // addressHash <== KeccakBytes(1)(addressBytesBlock, 20)  :79
+        B.q_eqn(nb.sig + 64, o.sig + 223, 32); B.q_eqn(o.sig, nb.sig, 64);                                   // addressHashNibbles <== Bytes2Nibbles(32)(addressHash)       :82
+    }
     return o;
 }
 // EIP7503 :11-21
 static Blk T_EIP7503(Builder &B) {
     static const uint8_t s[8] = {69, 73, 80, 45, 55, 53, 48, 51};
-    Blk o = B.alloc(8); for (int i = 0; i < 8; i++) B.at(o.pos + (size_t)i) = c_const(s[i]); return o;
+    Blk o = B.alloc(8);
+    for (int i = 0; i < 8; i++) { B.at(o.pos + (size_t)i) = c_const(s[i]); B.q_const(o.sig + (uint64_t)i, s[i]); }   // out[i] <== 'EIP-7503'[i]   proof_of_work.circom:13-20
+    return o;
 }
 // ConcatFixed4(A,B,C,D) :28-48  own: out[A+B+C+D], a, b, c, d
 static Blk T_ConcatFixed4(Builder &B, int A, int Bn, int C, int D, const Code *a, const Code *b, const Code *c, const Code *d) {
@@ -950,22 +1433,35 @@ static Blk T_ConcatFixed4(Builder &B, int A, int Bn, int C, int D, const Code *a
     B.copy(o.pos, a, (size_t)A); B.copy(o.pos + (size_t)A, b, (size_t)Bn); B.copy(o.pos + (size_t)(A + Bn), c, (size_t)C);
     B.copy(o.pos + (size_t)(A + Bn + C), d, (size_t)D);
     B.copy(o.pos + T, &B.at(o.pos), T);
+    B.q_eqn(o.sig, o.sig + T, T);                                                 // out[i] <== a[i]; out[i+A] <== b[i]; ...   proof_of_work.circom:36-47
     return o;
 }
 // ProofOfWorkChecker :54-81
 static Blk T_ProofOfWorkChecker(Builder &B, Code burnKey, Code revealAmount, Code bec, Code minimumZeroBytes) {
     Blk o = B.alloc(4 + 96 + 8 + 104 + 136 + 32 + 32);
     size_t bk = o.pos + 4, ra = bk + 32, be = ra + 32, eip = be + 32, hin = eip + 8, blk = hin + 104, kec = blk + 136, sbz = kec + 32;
+    const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
     B.at(o.pos) = burnKey; B.at(o.pos + 1) = revealAmount; B.at(o.pos + 2) = bec; B.at(o.pos + 3) = minimumZeroBytes;
     Blk x = T_Num2BigEndianBytes(B, 32, burnKey); B.copy(bk, &B.at(x.pos), 32);
+    if (cs) { B.q_eq(x.sig + 32, o.sig); B.q_eqn(d + bk, x.sig, 32); }                                        // burnKeyBytes <== Num2BigEndianBytes(32)(burnKey)   proof_of_work.circom:61
     x = T_Num2BigEndianBytes(B, 32, revealAmount); B.copy(ra, &B.at(x.pos), 32);
+    if (cs) { B.q_eq(x.sig + 32, o.sig + 1); B.q_eqn(d + ra, x.sig, 32); }                                    // :62
     x = T_Num2BigEndianBytes(B, 32, bec); B.copy(be, &B.at(x.pos), 32);
+    if (cs) { B.q_eq(x.sig + 32, o.sig + 2); B.q_eqn(d + be, x.sig, 32); }                                    // :63
     x = T_EIP7503(B); B.copy(eip, &B.at(x.pos), 8);
+    B.q_eqn(d + eip, x.sig, 8);                                                                               // eip7503 <== EIP7503()()                            :64
     x = T_ConcatFixed4(B, 32, 32, 32, 8, &B.at(bk), &B.at(ra), &B.at(be), &B.at(eip)); B.copy(hin, &B.at(x.pos), 104);
+    if (cs) { B.q_eqn(x.sig + 104, d + bk, 104); B.q_eqn(d + hin, x.sig, 104); }                              // hasherInput <== ConcatFixed4(32, 32, 32, 8)(...)   :68 (the four inputs are adjacent own signals)
     x = T_Fit(B, 104, 136, &B.at(hin)); B.copy(blk, &B.at(x.pos), 136);
+    if (cs) { B.q_eqn(x.sig + 136, d + hin, 104); B.q_eqn(d + blk, x.sig, 136); }                             // burnKeyBlock <== Fit(hasherInputLen, 136)(hasherInput)   :73
     x = T_KeccakBytes(B, 1, &B.at(blk), c_const(104)); B.copy(kec, &B.at(x.pos), 32);
+    if (cs) { B.q_eqn(x.sig + 32, d + blk, 136); B.q_const(x.sig + 32 + 136, 104); B.q_eqn(d + kec, x.sig, 32); }   // burnKeyKeccak <== KeccakBytes(1)(burnKeyBlock, hasherInputLen)   :74
     x = T_Filter(B, 32, minimumZeroBytes); B.copy(sbz, &B.at(x.pos), 32);
-    for (size_t i = 0; i < 32; i++) B.chk_eq(B.mul(B.at(kec + i), B.at(sbz + i)), ZERO, o.sig);
+    if (cs) { B.q_eq(x.sig + 32, o.sig + 3); B.q_eqn(d + sbz, x.sig, 32); }                                   // shouldBeZero <== Filter(32)(minimumZeroBytes)      :77
+    for (size_t i = 0; i < 32; i++) {
+        B.chk_eq(B.mul(B.at(kec + i), B.at(sbz + i)), ZERO, o.sig);
+        B.q_r1(LC().s(d + kec + i), LC().s(d + sbz + i), LC());                                               // burnKeyKeccak[i] * shouldBeZero[i] === 0           :79
+    }
     return o;
 }
 
@@ -975,30 +1471,53 @@ static Blk T_ProofOfWorkChecker(Builder &B, Code burnKey, Code revealAmount, Cod
 // CountBytes(N) integer.circom:16-49  own: len, bytes[N], isZero[N], stillZero[N]
 static Blk T_CountBytes(Builder &B, int N, const Code *bytes) {
     size_t n = (size_t)N; Blk o = B.alloc(1 + 3 * n); B.copy(o.pos + 1, bytes, n);
-    for (size_t i = 0; i < n; i++) { Blk z = T_IsZero(B, bytes[i]); B.at(o.pos + 1 + n + i) = B.at(z.pos); }
+    for (size_t i = 0; i < n; i++) {
+        Blk z = T_IsZero(B, bytes[i]); B.at(o.pos + 1 + n + i) = B.at(z.pos);
+        B.q_eq(z.sig + 1, o.sig + 1 + i); B.q_eq(o.sig + 1 + n + i, z.sig);       // isZero[i] <== IsZero()(bytes[i])              integer.circom:24
+    }
     std::vector<Code> terms;
+    LC sum;
     for (size_t i = 0; i < n; i++) {
         Code sz = i == 0 ? B.at(o.pos + 1 + n) : B.mul(B.at(o.pos + 1 + n + i), B.at(o.pos + 1 + 2 * n + i - 1));
         B.at(o.pos + 1 + 2 * n + i) = sz; terms.push_back(sz);
+        if (B.want_cs()) {
+            if (i == 0) B.q_eq(o.sig + 1 + 2 * n, o.sig + 1 + n);                 // stillZero[0] <== isZero[0]                    :32
+            else B.q_mul(o.sig + 1 + n + i, o.sig + 1 + 2 * n + i - 1, o.sig + 1 + 2 * n + i);   // stillZero[i] <== isZero[i] * stillZero[i-1]   :34
+            sum.s(o.sig + 1 + 2 * n + i);
+        }
     }
-    B.at(o.pos) = B.sub(c_const((uint32_t)n), B.sum_tree(terms)); return o;
+    B.at(o.pos) = B.sub(c_const((uint32_t)n), B.sum_tree(terms));
+    if (B.want_cs()) { sum.s(o.sig).k(-(int64_t)n); B.q_lin(sum); }               // len <== N - leadingZeros                      :47
+    return o;
 }
 // RlpInteger(N) integer.circom:67-110
 static Blk T_RlpInteger(Builder &B, int N, Code in) {
     size_t n = (size_t)N; Blk o = B.alloc(n + 1 + 1 + 1 + n + 1 + n + 3);
     size_t outLen = o.pos + n + 1, iIn = outLen + 1, bytes = iIn + 1, length = bytes + n, bigEndian = length + 1,
            isSingle = bigEndian + n, isZero = isSingle + 1, first = isZero + 1;
+    const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
     B.at(iIn) = in;
     Blk x = T_Num2BigEndianBytes(B, N, in); B.copy(bytes, &B.at(x.pos), n);
+    if (cs) { B.q_eq(x.sig + n, d + iIn); B.q_eqn(d + bytes, x.sig, n); }                                     // bytes <== Num2BigEndianBytes(N)(in)               integer.circom:77
     x = T_CountBytes(B, N, &B.at(bytes)); Code len = B.at(x.pos); B.at(length) = len;
+    if (cs) { B.q_eqn(x.sig + 1, d + bytes, n); B.q_eq(d + length, x.sig); }                                  // length <== CountBytes(N)(bytes)                   :80
     x = T_ShiftLeft(B, N, &B.at(bytes), B.sub(c_const((uint32_t)n), len)); B.copy(bigEndian, &B.at(x.pos), n);
+    if (cs) { B.q_eqn(x.sig + n, d + bytes, n); B.q_lin(LC().s(x.sig + 2 * n).k(-(int64_t)n).s(d + length)); B.q_eqn(d + bigEndian, x.sig, n); }   // bigEndian <== ShiftLeft(N)(bytes, N - length)   :83
     x = T_LessThan(B, N * 8, in, c_const(128)); Code single = B.at(x.pos); B.at(isSingle) = single;
+    if (cs) { B.q_eq(x.sig + 1, d + iIn); B.q_const(x.sig + 2, 128); B.q_eq(d + isSingle, x.sig); }           // isSingleByte <== LessThan(N*8)([in, 128])         :86
     x = T_IsZero(B, in); Code iz = B.at(x.pos); B.at(isZero) = iz;
+    if (cs) { B.q_eq(x.sig + 1, d + iIn); B.q_eq(d + isZero, x.sig); }                                        // isZero <== IsZero()(in)                           :89
     x = T_Mux1(B, B.add(c_const(0x80), len), in, single); B.at(first) = B.at(x.pos);
+    if (cs) { B.q_lin(LC().s(x.sig + 1).k(-0x80).s(d + length, -1)); B.q_eq(x.sig + 2, d + iIn); B.q_eq(x.sig + 3, d + isSingle); B.q_eq(d + first, x.sig); }   // firstRlpByte <== Mux1()([0x80 + length, in], isSingleByte)   :95
     B.at(o.pos) = B.fma(iz, c_const(0x80), B.at(first));
     Code ns = B.not1(single);
     for (size_t i = 1; i < n + 1; i++) B.at(o.pos + i) = B.mul(ns, B.at(bigEndian + i - 1));
     B.at(outLen) = B.add(B.add(ns, len), iz);
+    if (cs) {
+        B.q_lin(LC().s(o.sig, -1).s(d + first).s(d + isZero, 0x80));                                          // out[0] <== firstRlpByte + isZero * 0x80           :98
+        for (size_t i = 1; i < n + 1; i++) B.q_r1(LC().k(1).s(d + isSingle, -1), LC().s(d + bigEndian + i - 1), LC().s(o.sig + i));   // out[i] <== (1 - isSingleByte) * bigEndian[i-1]   :103
+        B.q_lin(LC().s(d + outLen, -1).k(1).s(d + isSingle, -1).s(d + length).s(d + isZero));                 // outLen <== (1 - isSingleByte) + length + isZero   :109
+    }
     return o;
 }
 // RlpEmptyAccount(maxBalanceBytes) empty_account.circom:20-134
@@ -1009,6 +1528,7 @@ static Blk T_RlpEmptyAccount(Builder &B, int mbb, Code balance) {
     size_t m = (size_t)mbb, OL = 4 + m + 66; Blk o = B.alloc(OL + 1 + 1 + (4 + m) + 1 + (m + 1) + 1 + 1 + 66);
     size_t outLen = o.pos + OL, iBal = outLen + 1, pre = iBal + 1, preLen = pre + 4 + m, balRlp = preLen + 1,
            balRlpLen = balRlp + m + 1, nabLen = balRlpLen + 1, sc = nabLen + 1;
+    const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
     B.at(iBal) = balance;
     B.at(pre + 2) = c_const(0x80);
     Blk r = T_RlpInteger(B, mbb, balance); B.copy(balRlp, &B.at(r.pos), m + 1); B.at(balRlpLen) = B.at(r.pos + m + 1);
@@ -1020,6 +1540,20 @@ static Blk T_RlpEmptyAccount(Builder &B, int mbb, Code balance) {
     B.at(pre + 1) = B.add(B.at(nabLen), c_const(66));
     Blk cc = T_Concat(B, 4 + mbb, 66, &B.at(pre), B.at(preLen), &B.at(sc), c_const(66));
     B.copy(o.pos, &B.at(cc.pos), OL); B.at(outLen) = B.at(cc.pos + OL);
+    if (cs) {
+        const size_t A = 4 + m;
+        B.q_const(d + pre + 2, 0x80);                                                                         // prefixedNonceAndBalanceRlp[2] <== 0x80            empty_account.circom:32
+        B.q_eq(r.sig + m + 2, d + iBal); B.q_eqn(d + balRlp, r.sig, m + 1); B.q_eq(d + balRlpLen, r.sig + m + 1);   // (balanceRlp, balanceRlpLen) <== RlpInteger(maxBalanceBytes)(balance)   :35
+        B.q_eqn(d + pre + 3, d + balRlp, m + 1);                                                              // prefixedNonceAndBalanceRlp[i+3] <== balanceRlp[i] :37
+        B.q_lin(LC().s(d + nabLen, -1).k(1).s(d + balRlpLen));                                                // nonceAndBalanceRlpLen <== 1 + balanceRlpLen       :41
+        B.q_lin(LC().s(d + preLen, -1).k(2).s(d + nabLen));                                                   // prefixedNonceAndBalanceRlpLen <== 2 + ...         :42
+        for (size_t i = 0; i < 66; i++) B.q_const(d + sc + i, STORAGE_CODE_RLP[i]);                           // storageAndCodeHashRlp[i] <== ...                  :48-115
+        B.q_const(d + pre, 0xf8);                                                                             // prefixedNonceAndBalanceRlp[0] <== 0xf7 + 1        :117
+        B.q_lin(LC().s(d + pre + 1, -1).s(d + nabLen).k(66));                                                 // prefixedNonceAndBalanceRlp[1] <== nonceAndBalanceRlpLen + 66   :118
+        B.q_eqn(cc.sig + OL + 1, d + pre, A); B.q_eq(cc.sig + OL + 1 + A, d + preLen);                        // concat.a, concat.aLen                             :122-123
+        B.q_eqn(cc.sig + OL + 1 + A + 1, d + sc, 66); B.q_const(cc.sig + OL + 1 + A + 1 + 66, 66);            // concat.b, concat.bLen                             :124-125
+        B.q_eqn(o.sig, cc.sig, OL); B.q_eq(d + outLen, cc.sig + OL);                                          // out <== concat.out; outLen <== concat.outLen      :127-128
+    }
     return o;
 }
 // TruncatedAddressHash(addressHashBytes) merkle_patricia_trie_leaf.circom:50-90 (`temp` :76 never assigned => 0)
@@ -1027,19 +1561,36 @@ static Blk T_TruncatedAddressHash(Builder &B, int ahb, const Code *nibbles, Code
     size_t a = (size_t)ahb; Blk o = B.alloc((a + 1) + 1 + 2 * a + 1 + 2 + 2 * a + (2 * a + 2) + (2 * a - 1));
     size_t outLen = o.pos + a + 1, iNib = outLen + 1, iLen = iNib + 2 * a, div = iLen + 1, rem = div + 1, shifted = rem + 1,
            outNib = shifted + 2 * a, temp = outNib + 2 * a + 2;
+    const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
     B.copy(iNib, nibbles, 2 * a); B.at(iLen) = nibLen;
-    for (size_t i = 0; i < 2 * a - 1; i++) B.at(temp + i) = ZERO;
-    T_AssertLessEqThan(B, 7, nibLen, c_const((uint32_t)(2 * a)));
-    Blk d = T_Divide(B, 7, nibLen, c_const(2)); B.at(div) = B.at(d.pos); Code rm = B.at(d.pos + 1); B.at(rem) = rm;
+    for (size_t i = 0; i < 2 * a - 1; i++) { B.at(temp + i) = ZERO; if (cs) B.q_hint(LC(), LC(), LC().s(d + temp + i)); }   // `signal temp[...]` is never assigned (:76): the calculator leaves 0
+    Blk al = T_AssertLessEqThan(B, 7, nibLen, c_const((uint32_t)(2 * a)));
+    Blk dv = T_Divide(B, 7, nibLen, c_const(2)); B.at(div) = B.at(dv.pos); Code rm = B.at(dv.pos + 1); B.at(rem) = rm;
     Blk s = T_ShiftLeft(B, 2 * ahb, nibbles, B.sub(c_const((uint32_t)(2 * a)), nibLen)); B.copy(shifted, &B.at(s.pos), 2 * a);
     B.at(outNib) = B.add(c_const(2), rm);
     B.at(outNib + 1) = B.mul(rm, B.at(shifted));
+    if (cs) {
+        B.q_eq(al.sig, d + iLen); B.q_const(al.sig + 1, 2 * a);                                               // AssertLessEqThan(7)(addressHashNibblesLen, 2*addressHashBytes)   merkle_patricia_trie_leaf.circom:59
+        B.q_eq(dv.sig + 2, d + iLen); B.q_const(dv.sig + 3, 2); B.q_eq(d + div, dv.sig); B.q_eq(d + rem, dv.sig + 1);   // (div, rem) <== Divide(7)(addressHashNibblesLen, 2)    :62
+        B.q_eqn(s.sig + 2 * a, d + iNib, 2 * a); B.q_lin(LC().s(s.sig + 4 * a).k(-(int64_t)(2 * a)).s(d + iLen)); B.q_eqn(d + shifted, s.sig, 2 * a);   // shifted <== ShiftLeft(2a)(nibbles, 2a - len)   :65-66
+        B.q_lin(LC().s(d + outNib, -1).k(2).s(d + rem));                                                      // outNibbles[0] <== 2 + rem                          :73
+        B.q_mul(d + rem, d + shifted, d + outNib + 1);                                                        // outNibbles[1] <== rem * shifted[0]                 :74
+    }
     for (size_t i = 0; i < 2 * a; i++) {
-        if (i < 2 * a - 1) { Blk m = T_Mux1(B, B.at(shifted + i), B.at(shifted + i + 1), rm); B.at(outNib + i + 2) = B.at(m.pos); }
-        else B.at(outNib + i + 2) = B.mul(B.not1(rm), B.at(shifted + i));
+        if (i < 2 * a - 1) {
+            Blk m = T_Mux1(B, B.at(shifted + i), B.at(shifted + i + 1), rm); B.at(outNib + i + 2) = B.at(m.pos);
+            if (cs) { B.q_eq(m.sig + 1, d + shifted + i); B.q_eq(m.sig + 2, d + shifted + i + 1); B.q_eq(m.sig + 3, d + rem); B.q_eq(d + outNib + i + 2, m.sig); }   // outNibbles[i+2] <== Mux1()([shifted[i], shifted[i+1]], rem)   :80
+        } else {
+            B.at(outNib + i + 2) = B.mul(B.not1(rm), B.at(shifted + i));
+            B.q_r1(LC().k(1).s(d + rem, -1), LC().s(d + shifted + i), LC().s(d + outNib + i + 2));            // outNibbles[i+2] <== (1 - rem) * shifted[i]         :82
+        }
     }
     Blk nb = T_Nibbles2Bytes(B, ahb + 1, &B.at(outNib)); B.copy(o.pos, &B.at(nb.pos), a + 1);
     B.at(outLen) = B.add(ONE, B.at(div));
+    if (cs) {
+        B.q_eqn(nb.sig + a + 1, d + outNib, 2 * a + 2); B.q_eqn(o.sig, nb.sig, a + 1);                        // out <== Nibbles2Bytes(addressHashBytes + 1)(outNibbles)   :87
+        B.q_lin(LC().s(d + outLen, -1).k(1).s(d + div));                                                      // outLen <== 1 + div                                 :89
+    }
     return o;
 }
 // RlpMerklePatriciaTrieLeaf(maxAddressHashBytes, maxBalanceBytes) :102-189
@@ -1048,9 +1599,10 @@ static Blk T_RlpMerklePatriciaTrieLeaf(Builder &B, int mahb, int mbb, const Code
     Blk o = B.alloc(MO + 1 + 2 * (size_t)mahb + 1 + 1 + mkl + 1 + mrea + 1 + mpk + 1 + mvr + 1);
     size_t outLen = o.pos + MO, iNib = outLen + 1, iLen = iNib + 2 * (size_t)mahb, iBal = iLen + 1, key = iBal + 1, keyLen = key + mkl,
            rea = keyLen + 1, reaLen = rea + mrea, pk = reaLen + 1, pkLen = pk + mpk, vr = pkLen + 1, vrLen = vr + mvr;
+    const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
     B.copy(iNib, nibbles, 2 * (size_t)mahb); B.at(iLen) = nibLen; B.at(iBal) = balance;
     Blk t = T_TruncatedAddressHash(B, mahb, nibbles, nibLen); B.copy(key, &B.at(t.pos), mkl); Code kl = B.at(t.pos + mkl); B.at(keyLen) = kl;
-    T_AssertGreaterEqThan(B, 16, kl, c_const(2));
+    Blk ag = T_AssertGreaterEqThan(B, 16, kl, c_const(2));
     Blk e = T_RlpEmptyAccount(B, mbb, balance); B.copy(rea, &B.at(e.pos), mrea); Code rl = B.at(e.pos + mrea); B.at(reaLen) = rl;
     B.at(vr) = c_const(0xb8); B.at(vr + 1) = rl;
     for (size_t i = 0; i < mrea; i++) B.at(vr + i + 2) = B.at(rea + i);
@@ -1062,41 +1614,89 @@ static Blk T_RlpMerklePatriciaTrieLeaf(Builder &B, int mahb, int mbb, const Code
     B.at(pkLen) = B.add(c_const(3), kl);
     Blk cc = T_Concat(B, (int)mpk, (int)mvr, &B.at(pk), B.at(pkLen), &B.at(vr), vl);
     B.copy(o.pos, &B.at(cc.pos), MO); B.at(outLen) = B.at(cc.pos + MO);
+    if (cs) {
+        const size_t ah2 = 2 * (size_t)mahb;
+        B.q_eqn(t.sig + mkl + 1, d + iNib, ah2); B.q_eq(t.sig + mkl + 1 + ah2, d + iLen);                     // (key, keyLen) <== TruncatedAddressHash(maxAddressHashBytes)(addressHashNibbles, addressHashNibblesLen)   merkle_patricia_trie_leaf.circom:148
+        B.q_eqn(d + key, t.sig, mkl); B.q_eq(d + keyLen, t.sig + mkl);
+        B.q_eq(ag.sig, d + keyLen); B.q_const(ag.sig + 1, 2);                                                 // AssertGreaterEqThan(16)(keyLen, 2)                 :150
+        B.q_eq(e.sig + mrea + 1, d + iBal); B.q_eqn(d + rea, e.sig, mrea); B.q_eq(d + reaLen, e.sig + mrea);  // (rlpEmptyAccount, len) <== RlpEmptyAccount(maxBalanceBytes)(balance)   :153-155
+        B.q_const(d + vr, 0xb8); B.q_eq(d + vr + 1, d + reaLen); B.q_eqn(d + vr + 2, d + rea, mrea);          // valueRlp[0], [1], [i+2]                            :164-168
+        B.q_lin(LC().s(d + vrLen, -1).k(2).s(d + reaLen));                                                    // valueRlpLen <== 2 + rlpEmptyAccountLen             :170
+        B.q_const(d + pk, 0xf8);                                                                              // prefixedKeyRlp[0] <== 0xf7 + 1                     :173
+        B.q_lin(LC().s(d + pk + 1, -1).s(d + keyLen).k(1).s(d + vrLen));                                      // prefixedKeyRlp[1] <== (keyLen + 1) + valueRlpLen   :174
+        B.q_lin(LC().s(d + pk + 2, -1).k(0x80).s(d + keyLen));                                                // prefixedKeyRlp[2] <== 0x80 + keyLen                :175
+        B.q_eqn(d + pk + 3, d + key, mkl);                                                                    // prefixedKeyRlp[i+3] <== key[i]                     :177
+        B.q_lin(LC().s(d + pkLen, -1).k(3).s(d + keyLen));                                                    // prefixedKeyRlpLen <== 3 + keyLen                   :179
+        B.q_eqn(cc.sig + MO + 1, d + pk, mpk); B.q_eq(cc.sig + MO + 1 + mpk, d + pkLen);                      // (out, outLen) <== Concat(...)(a <== prefixedKeyRlp, aLen <== ..., b <== valueRlp, bLen <== ...)   :182-187
+        B.q_eqn(cc.sig + MO + 1 + mpk + 1, d + vr, mvr); B.q_eq(cc.sig + MO + 1 + mpk + 1 + mvr, d + vrLen);
+        B.q_eqn(o.sig, cc.sig, MO); B.q_eq(d + outLen, cc.sig + MO);
+    }
     return o;
 }
 // IsInRange(B) :196-207  own: out, lower, value, upper, lowerLteValue, valueLteUpper
 static Blk T_IsInRange(Builder &B, int nb, Code lower, Code value, Code upper) {
     Blk o = B.alloc(6); B.at(o.pos + 1) = lower; B.at(o.pos + 2) = value; B.at(o.pos + 3) = upper;
-    T_AssertBits(B, nb, lower); T_AssertBits(B, nb, value); T_AssertBits(B, nb, upper);
+    Blk b1 = T_AssertBits(B, nb, lower), b2 = T_AssertBits(B, nb, value), b3 = T_AssertBits(B, nb, upper);
     Blk a = T_LessEqThan(B, nb, lower, value); B.at(o.pos + 4) = B.at(a.pos);
     Blk b = T_LessEqThan(B, nb, value, upper); B.at(o.pos + 5) = B.at(b.pos);
-    B.at(o.pos) = B.mul(B.at(a.pos), B.at(b.pos)); return o;
+    B.at(o.pos) = B.mul(B.at(a.pos), B.at(b.pos));
+    if (B.want_cs()) {
+        B.q_eq(b1.sig, o.sig + 1); B.q_eq(b2.sig, o.sig + 2); B.q_eq(b3.sig, o.sig + 3);                      // AssertBits(B)(lower), (value), (upper)             merkle_patricia_trie_leaf.circom:201-203
+        B.q_eq(a.sig + 1, o.sig + 1); B.q_eq(a.sig + 2, o.sig + 2); B.q_eq(o.sig + 4, a.sig);                 // lowerLteValue <== LessEqThan(B)([lower, value])    :204
+        B.q_eq(b.sig + 1, o.sig + 2); B.q_eq(b.sig + 2, o.sig + 3); B.q_eq(o.sig + 5, b.sig);                 // valueLteUpper <== LessEqThan(B)([value, upper])    :205
+        B.q_mul(o.sig + 4, o.sig + 5, o.sig);                                                                 // out <== lowerLteValue * valueLteUpper              :206
+    }
+    return o;
 }
 // LeafDetector(N) :247-294
 static Blk T_LeafDetector(Builder &B, int N, const Code *layer, Code layerLen) {
     size_t n = (size_t)N; Blk o = B.alloc(1 + n + 1 + 16);
     B.copy(o.pos + 1, layer, n); B.at(o.pos + 1 + n) = layerLen;
     size_t v = o.pos + 2 + n;
-    T_AssertLessEqThan(B, 16, layerLen, c_const((uint32_t)n));
-    B.at(v + 0) = B.at(T_IsEqual(B, layer[0], c_const(0xf8)).pos);                       // leafPrefixIsF8
-    Code totalLength = layer[1]; B.at(v + 1) = totalLength;
-    B.at(v + 2) = B.at(T_IsEqual(B, B.add(totalLength, c_const(2)), layerLen).pos);      // isConsistentWithLayerLen
-    Code keyPrefix = layer[2]; B.at(v + 3) = keyPrefix;
-    B.at(v + 4) = B.at(T_LessEqThan(B, 16, keyPrefix, c_const(0xb7)).pos);               // keyPrefixIsValid
-    Code multi = B.at(T_IsInRange(B, 16, c_const(0x81), keyPrefix, c_const(0xb7)).pos); B.at(v + 5) = multi;
+    const uint64_t qL = o.sig + 1, qLen = o.sig + 1 + n, qv = o.sig + 2 + n; const bool cs = B.want_cs();
+    Blk al = T_AssertLessEqThan(B, 16, layerLen, c_const((uint32_t)n));
+    if (cs) { B.q_eq(al.sig, qLen); B.q_const(al.sig + 1, n); }                                               // AssertLessEqThan(16)(layerLen, N)                  merkle_patricia_trie_leaf.circom:253
+    Blk x = T_IsEqual(B, layer[0], c_const(0xf8)); B.at(v + 0) = B.at(x.pos);                              // leafPrefixIsF8
+    if (cs) { B.q_eq(x.sig + 1, qL); B.q_const(x.sig + 2, 0xf8); B.q_eq(qv + 0, x.sig); }                     // :256
+    Code totalLength = layer[1]; B.at(v + 1) = totalLength; B.q_eq(qv + 1, qL + 1);                          // totalLength <== layer[1]   :258
+    x = T_IsEqual(B, B.add(totalLength, c_const(2)), layerLen); B.at(v + 2) = B.at(x.pos);                 // isConsistentWithLayerLen
+    if (cs) { B.q_lin(LC().s(x.sig + 1).s(qv + 1, -1).k(-2)); B.q_eq(x.sig + 2, qLen); B.q_eq(qv + 2, x.sig); }   // :259
+    Code keyPrefix = layer[2]; B.at(v + 3) = keyPrefix; B.q_eq(qv + 3, qL + 2);                              // keyPrefix <== layer[2]     :261
+    x = T_LessEqThan(B, 16, keyPrefix, c_const(0xb7)); B.at(v + 4) = B.at(x.pos);                          // keyPrefixIsValid
+    if (cs) { B.q_eq(x.sig + 1, qv + 3); B.q_const(x.sig + 2, 0xb7); B.q_eq(qv + 4, x.sig); }                 // :262
+    x = T_IsInRange(B, 16, c_const(0x81), keyPrefix, c_const(0xb7)); Code multi = B.at(x.pos); B.at(v + 5) = multi;
+    if (cs) { B.q_const(x.sig + 1, 0x81); B.q_eq(x.sig + 2, qv + 3); B.q_const(x.sig + 3, 0xb7); B.q_eq(qv + 5, x.sig); }   // keyIsMultiByte <== IsInRange(16)(0x81, keyPrefix, 0xb7)   :267
     Code extra = B.mul(multi, B.sub(keyPrefix, c_const(0x80))); B.at(v + 6) = extra;
+    B.q_r1(LC().s(qv + 5), LC().s(qv + 3).k(-0x80), LC().s(qv + 6));                                          // keyExtraLen <== keyIsMultiByte * (keyPrefix - 0x80)   :268
     Code keyLen = B.add(ONE, extra); B.at(v + 7) = keyLen;
+    B.q_lin(LC().s(qv + 7, -1).k(1).s(qv + 6));                                                               // keyLen <== 1 + keyExtraLen                        :269
     Code base = B.add(c_const(2), keyLen);
-    Code vwp = B.at(T_Selector(B, N, layer, base).pos); B.at(v + 8) = vwp;
-    B.at(v + 9) = B.at(T_IsEqual(B, vwp, c_const(0xb8)).pos);
-    Code vwl = B.at(T_Selector(B, N, layer, B.add(base, ONE)).pos); B.at(v + 10) = vwl;
-    Code vp = B.at(T_Selector(B, N, layer, B.add(base, c_const(2))).pos); B.at(v + 11) = vp;
-    B.at(v + 12) = B.at(T_IsEqual(B, vp, c_const(0xf8)).pos);
-    Code vlen = B.at(T_Selector(B, N, layer, B.add(base, c_const(3))).pos); B.at(v + 13) = vlen;
-    B.at(v + 14) = B.at(T_IsEqual(B, vwl, B.add(vlen, c_const(2))).pos);
-    B.at(v + 15) = B.at(T_IsEqual(B, B.add(B.add(keyLen, vlen), c_const(6)), layerLen).pos);
+    auto sel = [&](int off, size_t dst) {                   // Selector(N)(layer, 2 + keyLen + off)          :272, :275, :278, :281
+        Blk sx = T_Selector(B, N, layer, off ? B.add(base, c_const((uint32_t)off)) : base);
+        B.at(v + dst) = B.at(sx.pos);
+        if (cs) { B.q_eqn(sx.sig + 1, qL, n); B.q_lin(LC().s(sx.sig + 1 + n).k(-(2 + off)).s(qv + 7, -1)); B.q_eq(qv + dst, sx.sig); }
+        return B.at(sx.pos);
+    };
+    Code vwp = sel(0, 8);
+    x = T_IsEqual(B, vwp, c_const(0xb8)); B.at(v + 9) = B.at(x.pos);
+    if (cs) { B.q_eq(x.sig + 1, qv + 8); B.q_const(x.sig + 2, 0xb8); B.q_eq(qv + 9, x.sig); }                 // valueWrapperPrefixIsB8     :273
+    Code vwl = sel(1, 10);
+    Code vp = sel(2, 11);
+    x = T_IsEqual(B, vp, c_const(0xf8)); B.at(v + 12) = B.at(x.pos);
+    if (cs) { B.q_eq(x.sig + 1, qv + 11); B.q_const(x.sig + 2, 0xf8); B.q_eq(qv + 12, x.sig); }               // valuePrefixIsF8            :279
+    Code vlen = sel(3, 13);
+    x = T_IsEqual(B, vwl, B.add(vlen, c_const(2))); B.at(v + 14) = B.at(x.pos);
+    if (cs) { B.q_eq(x.sig + 1, qv + 10); B.q_lin(LC().s(x.sig + 2).s(qv + 13, -1).k(-2)); B.q_eq(qv + 14, x.sig); }   // isValueWrapperLenConsistent   :284
+    x = T_IsEqual(B, B.add(B.add(keyLen, vlen), c_const(6)), layerLen); B.at(v + 15) = B.at(x.pos);
+    if (cs) { B.q_lin(LC().s(x.sig + 1).s(qv + 7, -1).s(qv + 13, -1).k(-6)); B.q_eq(x.sig + 2, qLen); B.q_eq(qv + 15, x.sig); }   // isKeyValueLenEqualWithLayerLen   :287
     Code ands[7] = {B.at(v + 0), B.at(v + 2), B.at(v + 4), B.at(v + 9), B.at(v + 14), B.at(v + 12), B.at(v + 15)};
-    B.at(o.pos) = B.at(T_MultiAND(B, 7, ands).pos);
+    x = T_MultiAND(B, 7, ands);
+    B.at(o.pos) = B.at(x.pos);
+    if (cs) {
+        static const int order[7] = {0, 2, 4, 9, 14, 12, 15};
+        for (int k = 0; k < 7; k++) B.q_eq(x.sig + 1 + (uint64_t)k, qv + (uint64_t)order[k]);
+        B.q_eq(o.sig, x.sig);                                                                                 // isLeaf <== MultiAND(7)([...])                     :289-293
+    }
     return o;
 }
 
@@ -1108,16 +1708,24 @@ static Blk T_Spend(Builder &B, int mab, Code burnKey, Code balance, Code withdra
     Blk o = B.alloc(1 + 4 + 2 + 128);
     B.at(o.pos + 1) = burnKey; B.at(o.pos + 2) = balance; B.at(o.pos + 3) = withdrawn; B.at(o.pos + 4) = extra;
     size_t coin = o.pos + 5, rem = o.pos + 6, by = o.pos + 7;
-    T_AssertGreaterEqThan(B, mab * 8, balance, withdrawn);
+    const bool cs = B.want_cs();
+    Blk ag = T_AssertGreaterEqThan(B, mab * 8, balance, withdrawn);
+    if (cs) { B.q_eq(ag.sig, o.sig + 2); B.q_eq(ag.sig + 1, o.sig + 3); }                                     // AssertGreaterEqThan(maxAmountBytes*8)(balance, withdrawnBalance)   spend.circom:41
     Code i1[3] = {POSEIDON_PREFIX(B, 2), burnKey, balance};
-    B.at(coin) = B.at(T_Poseidon(B, 3, i1).pos);
+    Fr pre; B.const_val(i1[0], pre);
+    Blk p = T_Poseidon(B, 3, i1); B.at(coin) = B.at(p.pos);
+    if (cs) { B.q_constf(p.sig + 1, pre); B.q_eq(p.sig + 2, o.sig + 1); B.q_eq(p.sig + 3, o.sig + 2); B.q_eq(o.sig + 5, p.sig); }   // coin <== Poseidon(3)([PREFIX, burnKey, balance])   :43
     Code i2[3] = {POSEIDON_PREFIX(B, 2), burnKey, B.sub(balance, withdrawn)};
-    B.at(rem) = B.at(T_Poseidon(B, 3, i2).pos);
-    Blk x = T_Num2BigEndianBytes(B, 32, B.at(coin)); B.copy(by, &B.at(x.pos), 32);
-    x = T_Num2BigEndianBytes(B, 32, withdrawn); B.copy(by + 32, &B.at(x.pos), 32);
-    x = T_Num2BigEndianBytes(B, 32, B.at(rem)); B.copy(by + 64, &B.at(x.pos), 32);
-    x = T_Num2BigEndianBytes(B, 32, extra); B.copy(by + 96, &B.at(x.pos), 32);
-    x = T_PublicCommitment(B, 4, &B.at(by)); B.at(o.pos) = B.at(x.pos);
+    p = T_Poseidon(B, 3, i2); B.at(rem) = B.at(p.pos);
+    if (cs) { B.q_constf(p.sig + 1, pre); B.q_eq(p.sig + 2, o.sig + 1); B.q_lin(LC().s(p.sig + 3).s(o.sig + 2, -1).s(o.sig + 3)); B.q_eq(o.sig + 6, p.sig); }   // remainingCoin <== Poseidon(3)([PREFIX, burnKey, balance - withdrawnBalance])   :44
+    const uint64_t src[4] = {o.sig + 5, o.sig + 3, o.sig + 6, o.sig + 4};
+    const Code srcc[4] = {B.at(coin), withdrawn, B.at(rem), extra};
+    for (int k = 0; k < 4; k++) {                                                                             // coinBytes / withdrawnBalanceBytes / remainingCoinBytes / extraCommmitmentBytes   :46-49
+        Blk x = T_Num2BigEndianBytes(B, 32, srcc[k]); B.copy(by + 32 * (size_t)k, &B.at(x.pos), 32);
+        if (cs) { B.q_eq(x.sig + 32, src[k]); B.q_eqn(o.sig + 7 + 32 * (uint64_t)k, x.sig, 32); }
+    }
+    Blk x = T_PublicCommitment(B, 4, &B.at(by)); B.at(o.pos) = B.at(x.pos);
+    if (cs) { B.q_eqn(x.sig + 1, o.sig + 7, 128); B.q_eq(o.sig, x.sig); }                                     // commitment <== PublicCommitment(4)([...])         :51
     return o;
 }
 struct PobParams { int maxNumLayers, maxNodeBlocks, maxHeaderBlocks, minLeafAddressNibbles, amountBytes, powMinimumZeroBytes; Fr maxIntendedBalance, maxActualBalance; };

@@ -101,6 +101,32 @@ struct Tile { uint64_t dst; uint32_t n, code_off, ubase, pad; };  // BIT codes a
 static const uint32_t TILE_SIGNALS = 8192;
 static const uint32_t MAX_TILE_SIGNALS = 32768;  // upper bound for the POB_TILE_SIGNALS tuning knob
 
+// ---- constraint system of the circuit (on-GPU self-check; rank 2: reduced witness map) -------
+// Written from the circom sources statement by statement (every `<==` / `===` of the include closure), over WITNESS
+// INDICES -- independent of the codes/ops that produce the witness values.  Three record kinds:
+//   eq   : s[a] == s[b]                                       (`x <== y` between two signals -- the vast majority)
+//   kc   : s[a] == constant                                   (`x <== 5`, RoundConstants bits)
+//   r1   : (sum A_i s_i) * (sum B_i s_i) == (sum C_i s_i)     (everything else; no A/B terms: a linear constraint)
+// Index 0 is witness[0] = 1 (constant terms), as in an .r1cs.  `hint` records are not constraints of the circuit: they
+// pin signals the circuit itself leaves free (`inv <-- in != 0 ? 1/in : 0`, comparators.circom:30; the unassigned
+// `temp[]` of merkle_patricia_trie_leaf.circom:76) to the values the reference calculator writes.
+// Coefficients: top two bits 0 = +small (30 bits), 1 = -small, 2 = index into Program::cons_konst, 3 = bit k of the
+// Keccak round constant of the block's round (only in the shared KeccakfRound set).
+struct ConsTerm { uint32_t idx, coef; };
+enum : uint32_t { CC_POS = 0, CC_NEG = 1, CC_KONST = 2, CC_RCBIT = 3 };
+POB_HD uint32_t cc_kind(uint32_t c) { return c >> 30; }
+POB_HD uint32_t cc_payload(uint32_t c) { return c & 0x3fffffffu; }
+struct ConsR1 { uint32_t off; uint16_t nc_hint; uint8_t na, nb; };   // terms[off .. off+na) = A, then B, then C (nc = low 15 bits; bit 15 = hint)
+POB_HD uint32_t r1_nc(const ConsR1 &r) { return r.nc_hint & 0x7fffu; }
+POB_HD bool r1_hint(const ConsR1 &r) { return (r.nc_hint >> 15) != 0; }
+struct ConsSet {
+    std::vector<uint32_t> eq;          // 2 per record
+    std::vector<ConsTerm> kc;          // s[idx] == coef
+    std::vector<ConsR1> r1;
+    std::vector<ConsTerm> terms;
+    uint64_t n_records() const { return eq.size() / 2 + kc.size() + r1.size(); }
+};
+
 struct Program {
     // identity
     std::string main_name;
@@ -134,6 +160,13 @@ struct Program {
     //   mode 0: a lane -- signal t is bit t of w0;  mode 1+f: 64-signal phase f of a 192-signal gate block
     //   [out_i, a_i, b_i]_i -- signal s = 64 f + t is bit s/3 of w_{s%3}
     std::vector<uint64_t> round_desc;
+    // constraint system (only when compiled with want_constraints): flat part over absolute witness indices, the shared
+    // KeccakfRound set over indices relative to a round block's first signal; round_block_sig[i] = first signal of block i
+    // (blocks are emitted 24 per Keccakf, in round order: round = i % 24)
+    bool has_constraints = false;
+    ConsSet cons_flat, cons_round;
+    std::vector<Fr> cons_konst;
+    std::vector<uint64_t> round_block_sig;
     // statistics
     uint64_t n_round_blocks = 0, n_flat_signals = 0;
 };
