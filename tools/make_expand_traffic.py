@@ -13,7 +13,8 @@ def grab(fn):
     g = lambda k: float(vals[col[k]]) * UNIT[units[col[k]]]
     return {"kernel": vals[col["Kernel Name"]], "dram_read_bytes": g("dram__bytes_read.sum"), "dram_write_bytes": g("dram__bytes_write.sum"),
             "duration_s": g("gpu__time_duration.sum"), "registers": int(float(vals[col["launch__registers_per_thread"]])),
-            "dram_pct_of_peak": float(vals[col["FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed"]])}
+            "dram_write_pct_of_peak": float(vals[col["dram__bytes_write.sum.pct_of_peak_sustained_elapsed"]]),
+            "dram_read_pct_of_peak": float(vals[col["dram__bytes_read.sum.pct_of_peak_sustained_elapsed"]])}
 
 
 def main(argv):
