@@ -137,7 +137,9 @@ class Builder {
         segs.back().n += n; flat_n += n; nsig += n;
         return b;
     }
+    std::vector<uint64_t> round_sigs;  // first signal of every KeccakfRound block, in emission order
     void round_block(uint32_t ubase) {
+        round_sigs.push_back(nsig);
         segs.push_back({nsig, 0, ROUND_SIGNALS, true, ubase});
         nsig += ROUND_SIGNALS; n_round_blocks++;
     }
@@ -334,21 +336,6 @@ class Builder {
 };
 
 // ---- constraint-emitter helpers -------------------------------------------------------------------------------
-// What a parent assigns to a sub-component's input signal (`comp.in <== ...`): another signal, a constant, or a
-// linear expression of signals.
-struct Src {
-    int kind; uint64_t idx; Fr kv; LC lc;
-    static Src S(uint64_t i) { return Src{0, i, fr_zero(), LC()}; }
-    static Src K(uint64_t v) { return Src{1, 0, fr_from_u64(v), LC()}; }
-    static Src KF(const Fr &v) { return Src{1, 0, v, LC()}; }
-    static Src L(const LC &l) { return Src{2, 0, fr_zero(), l}; }
-};
-static void wire(Builder &B, uint64_t dst, const Src &s) {          // dst <== s
-    if (!B.want_cs()) return;
-    if (s.kind == 0) B.q_eq(dst, s.idx);
-    else if (s.kind == 1) B.q_constf(dst, s.kv);
-    else { LC l = s.lc; for (auto &q : l.t) q.second = fr_neg(q.second); l.s(dst); B.q_lin(l); }
-}
 static Fr pow2_fr(unsigned n) { Fr r = fr_from_u64(1); for (unsigned i = 0; i < n; i++) r = fr_add(r, r); return r; }
 
 // ============================================================================================================
@@ -1746,64 +1733,111 @@ static Blk T_ProofOfBurn(Builder &B, const PobParams &P, const Code *in) {
            nullB = stateRoot + 32, remB = nullB + 32, revB = remB + 32, becB = revB + 32, ecB = becB + 32, lastLayer = ecB + 32,
            lastLayerLen = lastLayer + NB, layerExists = lastLayerLen + 1, subChk = layerExists + L, layerKec = subChk + (L - 1),
            redKec = layerKec + L * 32, isLeaf = redKec + L * 31, isLastLeaf = isLeaf + L, leaf = isLastLeaf + 1, leafLen = leaf + 139;
+    // constraint side: witness indices of the inputs (circuits/proof_of_burn.circom:43-72) and of the intermediates above
+    const bool cs = B.want_cs();
+    const uint64_t d = o.sig - o.pos, qI = o.sig + 1, qBurnKey = qI, qActual = qI + 1, qIntended = qI + 2, qReveal = qI + 3, qBec = qI + 4, qNumNib = qI + 5,
+                   qLayers = qI + 6, qLens = qLayers + L * NB, qNumLayers = qLens + L, qHeader = qNumLayers + 1, qHeaderLen = qHeader + HB, qRelax = qHeaderLen + 1, qExtra = qRelax + 1;
     int ab8 = P.amountBytes * 8;
-    T_AssertLessEqThan(B, ab8, intendedBalance, B.konst(P.maxIntendedBalance));
-    T_AssertLessEqThan(B, ab8, actualBalance, B.konst(P.maxActualBalance));
-    T_AssertLessEqThan(B, ab8, intendedBalance, actualBalance);
+    Blk x = T_AssertLessEqThan(B, ab8, intendedBalance, B.konst(P.maxIntendedBalance));
+    if (cs) { B.q_eq(x.sig, qIntended); B.q_constf(x.sig + 1, P.maxIntendedBalance); }                        // AssertLessEqThan(amountBytes*8)(intendedBalance, maxIntendedBalance)   proof_of_burn.circom:84
+    x = T_AssertLessEqThan(B, ab8, actualBalance, B.konst(P.maxActualBalance));
+    if (cs) { B.q_eq(x.sig, qActual); B.q_constf(x.sig + 1, P.maxActualBalance); }                            // (actualBalance, maxActualBalance)                  :85
+    x = T_AssertLessEqThan(B, ab8, intendedBalance, actualBalance);
+    if (cs) { B.q_eq(x.sig, qIntended); B.q_eq(x.sig + 1, qActual); }                                         // (intendedBalance, actualBalance)                   :86
     Code relax2 = B.mul(relax, c_const(2)), minNib = c_const((uint32_t)P.minLeafAddressNibbles);
-    T_AssertLessEqThan(B, 16, relax2, minNib);
-    T_AssertGreaterEqThan(B, 16, numLeafNib, B.sub(minNib, relax2));
-    T_AssertBits(B, ab8, revealAmount);
-    T_AssertLessEqThan(B, ab8, revealAmount, intendedBalance);
+    x = T_AssertLessEqThan(B, 16, relax2, minNib);
+    if (cs) { B.q_lin(LC().s(x.sig).s(qRelax, -2)); B.q_const(x.sig + 1, (uint64_t)P.minLeafAddressNibbles); }   // AssertLessEqThan(16)(byteSecurityRelax*2, minLeafAddressNibbles)   :89
+    x = T_AssertGreaterEqThan(B, 16, numLeafNib, B.sub(minNib, relax2));
+    if (cs) { B.q_eq(x.sig, qNumNib); B.q_lin(LC().s(x.sig + 1).k(-(int64_t)P.minLeafAddressNibbles).s(qRelax, 2)); }   // AssertGreaterEqThan(16)(numLeafAddressNibbles, min - relax*2)   :90
+    x = T_AssertBits(B, ab8, revealAmount);
+    B.q_eq(x.sig, qReveal);                                                                                   // AssertBits(amountBytes*8)(revealAmount)            :93
+    x = T_AssertLessEqThan(B, ab8, revealAmount, intendedBalance);
+    if (cs) { B.q_eq(x.sig, qReveal); B.q_eq(x.sig + 1, qIntended); }                                         // AssertLessEqThan(..)(revealAmount, intendedBalance)   :97
     for (size_t i = 0; i < L; i++) {
-        T_AssertLessThan(B, 16, layerLens[i], c_const((uint32_t)(NB * 8)));
-        T_AssertByteString(B, (int)NB, layers + i * NB);
+        x = T_AssertLessThan(B, 16, layerLens[i], c_const((uint32_t)(NB * 8)));
+        if (cs) { B.q_eq(x.sig, qLens + i); B.q_const(x.sig + 1, NB * 8); }                                   // AssertLessThan(16)(layerLens[i], maxNodeBlocks*136*8)   :101
+        x = T_AssertByteString(B, (int)NB, layers + i * NB);
+        B.q_eqn(x.sig, qLayers + i * NB, NB);                                                                 // AssertByteString(maxNodeBlocks*136)(layers[i])     :102
     }
-    T_AssertLessThan(B, 16, blockHeaderLen, c_const((uint32_t)(HB * 8)));
-    T_AssertByteString(B, (int)HB, blockHeader);
+    x = T_AssertLessThan(B, 16, blockHeaderLen, c_const((uint32_t)(HB * 8)));
+    if (cs) { B.q_eq(x.sig, qHeaderLen); B.q_const(x.sig + 1, HB * 8); }                                      // :105
+    x = T_AssertByteString(B, (int)HB, blockHeader);
+    B.q_eqn(x.sig, qHeader, HB);                                                                              // :106
     Code p3[3] = {POSEIDON_PREFIX(B, 2), burnKey, B.sub(intendedBalance, revealAmount)};
-    B.at(remainingCoin) = B.at(T_Poseidon(B, 3, p3).pos);
+    x = T_Poseidon(B, 3, p3); B.at(remainingCoin) = B.at(x.pos);
+    if (cs) { Fr pre; B.const_val(p3[0], pre); B.q_constf(x.sig + 1, pre); B.q_eq(x.sig + 2, qBurnKey); B.q_lin(LC().s(x.sig + 3).s(qIntended, -1).s(qReveal)); B.q_eq(d + remainingCoin, x.sig); }   // remainingCoin <== Poseidon(3)([COIN_PREFIX, burnKey, intendedBalance - revealAmount])   :113
     Code p2[2] = {POSEIDON_PREFIX(B, 1), burnKey};
-    B.at(nullifier) = B.at(T_Poseidon(B, 2, p2).pos);
-    Blk x = T_BurnAddressHash(B, burnKey, revealAmount, bec); B.copy(addrNib, &B.at(x.pos), 64);
+    x = T_Poseidon(B, 2, p2); B.at(nullifier) = B.at(x.pos);
+    if (cs) { Fr pre; B.const_val(p2[0], pre); B.q_constf(x.sig + 1, pre); B.q_eq(x.sig + 2, qBurnKey); B.q_eq(d + nullifier, x.sig); }   // nullifier <== Poseidon(2)([NULLIFIER_PREFIX, burnKey])   :116
+    x = T_BurnAddressHash(B, burnKey, revealAmount, bec); B.copy(addrNib, &B.at(x.pos), 64);
+    if (cs) { B.q_eq(x.sig + 64, qBurnKey); B.q_eq(x.sig + 65, qReveal); B.q_eq(x.sig + 66, qBec); B.q_eqn(d + addrNib, x.sig, 64); }     // addressHashNibbles <== BurnAddressHash()(...)   :119
     x = T_KeccakBytes(B, P.maxHeaderBlocks, blockHeader, blockHeaderLen); B.copy(blockRoot, &B.at(x.pos), 32);
+    if (cs) { B.q_eqn(x.sig + 32, qHeader, HB); B.q_eq(x.sig + 32 + HB, qHeaderLen); B.q_eqn(d + blockRoot, x.sig, 32); }                 // blockRoot <== KeccakBytes(maxHeaderBlocks)(blockHeader, blockHeaderLen)   :122
     for (size_t i = 0; i < 32; i++) B.at(stateRoot + i) = blockHeader[91 + i];
-    x = T_Num2BigEndianBytes(B, 32, B.at(nullifier)); B.copy(nullB, &B.at(x.pos), 32);
-    x = T_Num2BigEndianBytes(B, 32, B.at(remainingCoin)); B.copy(remB, &B.at(x.pos), 32);
-    x = T_Num2BigEndianBytes(B, 32, revealAmount); B.copy(revB, &B.at(x.pos), 32);
-    x = T_Num2BigEndianBytes(B, 32, bec); B.copy(becB, &B.at(x.pos), 32);
-    x = T_Num2BigEndianBytes(B, 32, proofExtra); B.copy(ecB, &B.at(x.pos), 32);
+    B.q_eqn(d + stateRoot, qHeader + 91, 32);                                                                 // stateRoot[i] <== blockHeader[91 + i]               :128
+    {
+        const size_t dst[5] = {nullB, remB, revB, becB, ecB};
+        const uint64_t src[5] = {d + nullifier, d + remainingCoin, qReveal, qBec, qExtra};
+        const Code srcc[5] = {B.at(nullifier), B.at(remainingCoin), revealAmount, bec, proofExtra};
+        for (int k = 0; k < 5; k++) {                                                                         // nullifierBytes ... extraCommitmentBytes <== Num2BigEndianBytes(32)(..)   :131-135
+            x = T_Num2BigEndianBytes(B, 32, srcc[k]); B.copy(dst[k], &B.at(x.pos), 32);
+            if (cs) { B.q_eq(x.sig + 32, src[k]); B.q_eqn(d + dst[k], x.sig, 32); }
+        }
+    }
     {
         std::vector<Code> six(192);
         memcpy(&six[0], &B.at(blockRoot), 128); memcpy(&six[32], &B.at(nullB), 128); memcpy(&six[64], &B.at(remB), 128);
         memcpy(&six[96], &B.at(revB), 128); memcpy(&six[128], &B.at(becB), 128); memcpy(&six[160], &B.at(ecB), 128);
         x = T_PublicCommitment(B, 6, six.data()); B.at(o.pos) = B.at(x.pos);
+        if (cs) { B.q_eqn(x.sig + 1, d + blockRoot, 32); B.q_eqn(x.sig + 33, d + nullB, 160); B.q_eq(o.sig, x.sig); }   // commitment <== PublicCommitment(6)([...])   :136-138
     }
     Code selLast = B.sub(numLayers, ONE);
     x = T_SelectorArray(B, P.maxNumLayers, NB, layers, selLast); B.copy(lastLayer, &B.at(x.pos), NB);
-    B.at(lastLayerLen) = B.at(T_Selector(B, P.maxNumLayers, layerLens, selLast).pos);
+    if (cs) { B.q_eqn(x.sig + NB, qLayers, L * NB); B.q_lin(LC().s(x.sig + NB + L * NB).s(qNumLayers, -1).k(1)); B.q_eqn(d + lastLayer, x.sig, NB); }   // lastLayer <== SelectorArray1D(maxNumLayers, NB)(layers, numLayers - 1)   :141-142
+    x = T_Selector(B, P.maxNumLayers, layerLens, selLast); B.at(lastLayerLen) = B.at(x.pos);
+    if (cs) { B.q_eqn(x.sig + 1, qLens, L); B.q_lin(LC().s(x.sig + 1 + L).s(qNumLayers, -1).k(1)); B.q_eq(d + lastLayerLen, x.sig); }                  // lastLayerLen <== Selector(maxNumLayers)(layerLens, numLayers - 1)   :143
     x = T_Filter(B, P.maxNumLayers, numLayers); B.copy(layerExists, &B.at(x.pos), L);
+    if (cs) { B.q_eq(x.sig + L, qNumLayers); B.q_eqn(d + layerExists, x.sig, L); }                            // layerExists <== Filter(maxNumLayers)(numLayers)    :146
     Code numLeaves = ZERO;
+    LC leaves;
     for (size_t i = 0; i < L; i++) {
-        Code lf = B.at(T_LeafDetector(B, (int)NB, layers + i * NB, layerLens[i]).pos); B.at(isLeaf + i) = lf;
+        x = T_LeafDetector(B, (int)NB, layers + i * NB, layerLens[i]); Code lf = B.at(x.pos); B.at(isLeaf + i) = lf;
+        if (cs) { B.q_eqn(x.sig + 1, qLayers + i * NB, NB); B.q_eq(x.sig + 1 + NB, qLens + i); B.q_eq(d + isLeaf + i, x.sig); leaves.s(d + isLeaf + i); }   // isLeaf[i] <== LeafDetector(NB)(layers[i], layerLens[i])   :159
         numLeaves = B.add(numLeaves, lf);
         x = T_KeccakBytes(B, P.maxNodeBlocks, layers + i * NB, layerLens[i]); B.copy(layerKec + 32 * i, &B.at(x.pos), 32);
+        if (cs) { B.q_eqn(x.sig + 32, qLayers + i * NB, NB); B.q_eq(x.sig + 32 + NB, qLens + i); B.q_eqn(d + layerKec + 32 * i, x.sig, 32); }              // layerKeccaks[i] <== KeccakBytes(maxNodeBlocks)(layers[i], layerLens[i])   :163
         x = T_Fit(B, 32, 31, &B.at(layerKec + 32 * i)); B.copy(redKec + 31 * i, &B.at(x.pos), 31);
+        if (cs) { B.q_eqn(x.sig + 31, d + layerKec + 32 * i, 32); B.q_eqn(d + redKec + 31 * i, x.sig, 31); }                                              // reducedLayerKeccaks[i] <== Fit(32, 31)(layerKeccaks[i])   :164
         if (i > 0) {
-            Code sc = B.at(T_SubstringCheck(B, (int)NB, 31, layers + (i - 1) * NB, layerLens[i - 1], &B.at(redKec + 31 * i)).pos);
+            x = T_SubstringCheck(B, (int)NB, 31, layers + (i - 1) * NB, layerLens[i - 1], &B.at(redKec + 31 * i));
+            Code sc = B.at(x.pos);
             B.at(subChk + i - 1) = sc;
             B.chk_eq(B.mul(B.not1(sc), B.at(layerExists + i)), ZERO, o.sig);
+            if (cs) {
+                B.q_eqn(x.sig + 1, qLayers + (i - 1) * NB, NB); B.q_eq(x.sig + 1 + NB, qLens + i - 1); B.q_eqn(x.sig + 2 + NB, d + redKec + 31 * i, 31);   // substringCheckers[i-1] <== SubstringCheck(NB, 31)(subInput, mainLen, mainInput)   :171-175
+                B.q_eq(d + subChk + i - 1, x.sig);
+                B.q_r1(LC().k(1).s(d + subChk + i - 1, -1), LC().s(d + layerExists + i), LC());               // (1 - substringCheckers[i-1]) * layerExists[i] === 0   :180
+            }
         }
     }
     B.chk_eq(numLeaves, ONE, o.sig);
-    B.at(isLastLeaf) = B.at(T_LeafDetector(B, (int)NB, &B.at(lastLayer), B.at(lastLayerLen)).pos);
+    if (cs) { leaves.k(-1); B.q_lin(leaves); }                                                                // numDetectedLeaves === 1                            :186
+    x = T_LeafDetector(B, (int)NB, &B.at(lastLayer), B.at(lastLayerLen)); B.at(isLastLeaf) = B.at(x.pos);
+    if (cs) { B.q_eqn(x.sig + 1, d + lastLayer, NB); B.q_eq(x.sig + 1 + NB, d + lastLayerLen); B.q_eq(d + isLastLeaf, x.sig); B.q_const(d + isLastLeaf, 1); }   // isLastLayerLeaf <== LeafDetector(..)(lastLayer, lastLayerLen); === 1   :187-188
     B.chk_eq(B.at(isLastLeaf), ONE, o.sig);
     for (size_t i = 0; i < 32; i++) B.chk_eq(B.at(layerKec + i), B.at(stateRoot + i), o.sig);
+    B.q_eqn(d + layerKec, d + stateRoot, 32);                                                                 // layerKeccaks[0][i] === stateRoot[i]                :192
     x = T_RlpMerklePatriciaTrieLeaf(B, 32, P.amountBytes, &B.at(addrNib), numLeafNib, actualBalance);
     B.copy(leaf, &B.at(x.pos), 139); B.at(leafLen) = B.at(x.pos + 139);
+    if (cs) {
+        B.q_eqn(x.sig + 140, d + addrNib, 64); B.q_eq(x.sig + 204, qNumNib); B.q_eq(x.sig + 205, qActual);    // (leaf, leafLen) <== RlpMerklePatriciaTrieLeaf(32, amountBytes)(addressHashNibbles, numLeafAddressNibbles, actualBalance)   :198-200
+        B.q_eqn(d + leaf, x.sig, 139); B.q_eq(d + leafLen, x.sig + 139);
+        B.q_eqn(d + leaf, d + lastLayer, 139); B.q_eq(d + leafLen, d + lastLayerLen);                         // leaf[i] === lastLayer[i]; leafLen === lastLayerLen   :204, :206
+    }
     for (size_t i = 0; i < 139; i++) B.chk_eq(B.at(leaf + i), B.at(lastLayer + i), o.sig);
     B.chk_eq(B.at(leafLen), B.at(lastLayerLen), o.sig);
-    T_ProofOfWorkChecker(B, burnKey, revealAmount, bec, B.add(c_const((uint32_t)P.powMinimumZeroBytes), relax));
+    x = T_ProofOfWorkChecker(B, burnKey, revealAmount, bec, B.add(c_const((uint32_t)P.powMinimumZeroBytes), relax));
+    if (cs) { B.q_eq(x.sig, qBurnKey); B.q_eq(x.sig + 1, qReveal); B.q_eq(x.sig + 2, qBec); B.q_lin(LC().s(x.sig + 3).k(-(int64_t)P.powMinimumZeroBytes).s(qRelax, -1)); }   // ProofOfWorkChecker()(burnKey, revealAmount, burnExtraCommitment, powMinimumZeroBytes + byteSecurityRelax)   :211
     return o;
 }
 
@@ -1937,7 +1971,7 @@ const char *main_input_schema(const std::string &main_name, int *nparams) {
     return nullptr;
 }
 
-Program compile_circuit(const std::string &main_name, const std::vector<Fr> &params, bool hcreate) {
+Program compile_circuit(const std::string &main_name, const std::vector<Fr> &params, bool hcreate, bool want_constraints) {
     int np = 0; const char *schema = main_input_schema(main_name, &np);
     if (!schema) throw std::runtime_error("pob: unknown main template '" + main_name + "'");
     if ((int)params.size() < np) throw std::runtime_error("pob: too few template parameters for " + main_name);
@@ -1947,9 +1981,21 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     { Builder dry(hcreate, true, 0); build(dry, main_name, params, n_in, &n_out); n_words = dry.n_words; }
     uint32_t val_base = (n_words + 3u) & ~3u;
     Builder B(hcreate, false, val_base);
-    build(B, main_name, params, n_in, &n_out);
-
     Program P;
+    std::unordered_map<std::array<uint32_t, 8>, uint32_t, FrHash> cons_kix;
+    if (want_constraints) {
+        B.cs.S = &P.cons_flat; B.cs.konst = &P.cons_konst; B.cs.kix = &cons_kix;
+        B.q_const(0, 1);                                                          // witness[0] is the constant 1
+    }
+    build(B, main_name, params, n_in, &n_out);
+    if (want_constraints) {
+        ConsSink rs; rs.S = &P.cons_round; rs.konst = &P.cons_konst; rs.kix = &cons_kix;
+        RoundCons rc{rs}; rc.round();
+        if (rc.cur != ROUND_SIGNALS) throw std::runtime_error("pob: internal: KeccakfRound constraint walk covers " + std::to_string(rc.cur) + " signals");
+        P.round_block_sig = B.round_sigs; P.has_constraints = true;
+        if (P.cons_konst.empty()) P.cons_konst.push_back(fr_zero());
+    }
+
     P.main_name = main_name; P.params = params; P.hcreate = hcreate;
     P.n_signals = B.nsig; P.n_outputs = n_out; P.n_inputs = (uint32_t)n_in; P.input_schema = schema;
     P.n_words = B.n_words; P.val_base = val_base; P.n_vals = B.n_vals;

@@ -10,7 +10,7 @@ _LIB = None
 def build():
     so = os.path.join(_HERE, "libpob_emu.so")
     srcs = [os.path.join(_HERE, "pob_emu.cpp"), os.path.join(_HERE, "host_ref.h")] + [os.path.join(_CSRC, f) for f in
-            ("compiler.cpp", "compiler.h", "program.h", "vm_exec.h", "fr_hd.h", "poseidon_constants_data.h")]
+            ("compiler.cpp", "compiler.h", "program.h", "vm_exec.h", "fr_hd.h", "poseidon_constants_data.h", "cons_check.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I", _CSRC,
                                "-I", _HERE, "-o", so, srcs[0], srcs[2]])
@@ -29,8 +29,26 @@ def lib():
         L.pob_emu_schema.argtypes = [ctypes.c_void_p]
         L.pob_emu_run.restype = ctypes.c_uint64
         L.pob_emu_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.pob_emu_check_constraints.restype = ctypes.c_int
+        L.pob_emu_check_constraints.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64,
+                                                ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
         _LIB = L
     return _LIB
+
+
+CHECK_NAMES = ["n_constraints", "n_hints", "n_failed", "n_hint_failed", "first_failed", "flat_eq", "flat_kc", "flat_r1",
+               "round_eq", "round_kc", "round_r1", "round_blocks", "signals_referenced"]
+
+
+def check_constraints(name, params_limbs, nparams, witness_limbs, hcreate=False):
+    """compile `name(params)` WITH its constraint system and evaluate every record against `witness_limbs` (n x 4 uint64)"""
+    out = np.zeros(13, dtype=np.uint64)
+    err = ctypes.create_string_buffer(512)
+    w = np.ascontiguousarray(witness_limbs, dtype=np.uint64)
+    rc = lib().pob_emu_check_constraints(name.encode(), params_limbs.ctypes.data, nparams, int(hcreate), w.ctypes.data, w.shape[0], out.ctypes.data, err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return dict(zip(CHECK_NAMES, (int(v) for v in out)))
 
 
 STAT_NAMES = ["n_signals", "n_outputs", "n_inputs", "n_words", "n_vals", "n_ops", "n_absorbs", "n_levels", "n_tiles",

@@ -13,6 +13,7 @@
 #include "compiler.h"
 #include "vm_exec.h"
 #include "host_ref.h"
+#include "cons_check.h"
 
 using namespace pob;
 
@@ -135,4 +136,39 @@ extern "C" uint32_t pob_emu_mul_selftest(uint32_t n) {
     }
     (void)sizeof(u128);
     return bad;
+}
+
+// ---- constraint system (csrc/cons_check.h, host instantiation): compile with constraints and evaluate every record against
+// a witness supplied by the caller (the oracle's).  out[0] = circuit constraints evaluated, out[1] = hint records evaluated,
+// out[2] = failing circuit constraints, out[3] = failing hints, out[4] = id of the first failing record (~0 if none),
+// out[5..7] = flat eq / kc / r1 counts, out[8..10] = per-round-block eq / kc / r1 counts, out[11] = round blocks,
+// out[12] = distinct witness entries referenced by at least one record.
+extern "C" int pob_emu_check_constraints(const char *main_name, const uint64_t *params, int nparams, int hcreate,
+                                         const uint64_t *witness, uint64_t n_signals, uint64_t *out, char *err, int errlen) {
+    try {
+        std::vector<Fr> ps((size_t)nparams);
+        for (int i = 0; i < nparams; i++) memcpy(ps[(size_t)i].l, params + 4 * i, 32);
+        Program P = compile_circuit(main_name, ps, hcreate != 0, true);
+        if (P.n_signals != n_signals) throw std::runtime_error("witness size mismatch");
+        uint64_t n_cons = 0, n_hint = 0, bad = 0, hbad = 0, first = ~0ull, id = 0;
+        std::vector<uint8_t> seen(n_signals, 0);
+        auto run = [&](const ConsSet &S, uint64_t base, uint64_t rc) {
+            auto mark = [&](uint32_t idx) { if (idx != CONS_ONE) seen[base + idx] = 1; };
+            for (size_t i = 0; i + 1 < S.eq.size(); i += 2, id++) { n_cons++; mark(S.eq[i]); mark(S.eq[i + 1]); if (!cons_eq_ok(witness, base, S.eq[i], S.eq[i + 1])) { bad++; if (first == ~0ull) first = id; } }
+            for (const ConsTerm &t : S.kc) { n_cons++; mark(t.idx); if (!cons_kc_ok(witness, base, t, P.cons_konst.data(), rc)) { bad++; if (first == ~0ull) first = id; } id++; }
+            for (const ConsR1 &r : S.r1) {
+                for (uint32_t k = 0; k < (uint32_t)r.na + r.nb + r1_nc(r); k++) mark(S.terms[r.off + k].idx);
+                const bool ok = cons_r1_ok(witness, base, r, S.terms.data(), P.cons_konst.data());
+                if (r1_hint(r)) { n_hint++; if (!ok) { hbad++; if (first == ~0ull) first = id; } } else { n_cons++; if (!ok) { bad++; if (first == ~0ull) first = id; } }
+                id++;
+            }
+        };
+        run(P.cons_flat, 0, 0);
+        for (size_t b = 0; b < P.round_block_sig.size(); b++) run(P.cons_round, P.round_block_sig[b], keccak_rc((int)(b % 24)));
+        out[0] = n_cons; out[1] = n_hint; out[2] = bad; out[3] = hbad; out[4] = first;
+        out[5] = P.cons_flat.eq.size() / 2; out[6] = P.cons_flat.kc.size(); out[7] = P.cons_flat.r1.size();
+        out[8] = P.cons_round.eq.size() / 2; out[9] = P.cons_round.kc.size(); out[10] = P.cons_round.r1.size(); out[11] = P.round_block_sig.size();
+        uint64_t ns = 0; for (uint8_t v : seen) ns += v; out[12] = ns;
+        return 0;
+    } catch (const std::exception &ex) { if (err) snprintf(err, (size_t)errlen, "%s", ex.what()); return -1; }
 }
