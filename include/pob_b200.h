@@ -165,6 +165,29 @@ int pob_witness_device_ptr(pob_handle *h, uint32_t index, void **dptr);
  * are 0 or 1.  *n_blocks = blocks examined, *n_bad = blocks that fail. */
 int pob_selfcheck_keccak(pob_handle *h, uint32_t index, uint64_t *n_blocks, uint64_t *n_bad);
 
+/* ---- full constraint self-check ------------------------------------------------------------------
+ * Evaluates EVERY constraint of the circuit against resident witness `index`, on the GPU.  The constraint system is written
+ * from the circom sources statement by statement -- every `<==` and `===` of the include closure: the gate equations of
+ * circuits/utils/keccak.circom:58-297 (out = a + b - 2ab, ...), circomlib/circuits/poseidon.circom:5-65 (Sigma, Ark, Mix,
+ * MixS, MixLast), bitify.circom:33,38 (Num2Bits bits and sum), comparators.circom:32-33 (IsZero), selector.circom:33-45,
+ * substring_check.circom:46-99, ... -- over witness INDICES, independently of the program that produced the values.  It
+ * reads 100 % of the witness entries.  `hint` records additionally pin the signals the circuit itself leaves free
+ * (`inv <-- in != 0 ? 1/in : 0`; the never-assigned temp[] of merkle_patricia_trie_leaf.circom:76) to the values the
+ * reference calculator writes.  The first call compiles and uploads the constraint system (seconds for the main shape). */
+typedef struct {
+    uint64_t n_constraints;     /* circuit constraints evaluated (the shared KeccakfRound set counted once per round block) */
+    uint64_t n_nonlinear;       /* of those, A*B = C records with a non-empty A (an .r1cs would call them non-linear) */
+    uint64_t n_hints;           /* hint records evaluated */
+    uint64_t n_failed;          /* failing circuit constraints */
+    uint64_t n_hint_failed;     /* failing hint records */
+    uint64_t first_failed;      /* smallest failing record id, UINT64_MAX when everything holds */
+    uint64_t signals_read;      /* distinct witness entries referenced by at least one record (== n_signals) */
+    float ms;                   /* device time of the check */
+} pob_check_report;
+int pob_selfcheck(pob_handle *h, uint32_t index, pob_check_report *out);
+/* host-only: compile the constraint system of a circuit shape and report its size (no GPU needed) */
+int pob_constraint_info(const char *main_name, const uint64_t *params, int nparams, int hcreate, pob_check_report *out);
+
 /* ---- the step just before the path ------------------------------------------------------
  * replaces: find_burn_key() of the reference input generator (tests/main.py:47-56): starting at start_key, find the
  * first burnKey >= start_key whose keccak256(burnKey[32 BE] | revealAmount[32 BE] | burnExtraCommitment[32 BE] |

@@ -16,7 +16,7 @@ struct ConsView {                                    // one ConsSet in device (o
     const ConsTerm *kc; uint64_t n_kc;
     const ConsR1 *r1; uint64_t n_r1;
     const ConsTerm *terms;
-    uint64_t n_records() const { return n_eq + n_kc + n_r1; }
+    POB_HD uint64_t n_records() const { return n_eq + n_kc + n_r1; }
 };
 
 POB_HD Fr cons_load(const uint64_t *wit, uint64_t base, uint32_t idx) {

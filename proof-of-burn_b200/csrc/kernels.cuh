@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "vm_exec.h"
+#include "cons_check.h"
 
 using namespace pob;
 
@@ -375,6 +376,42 @@ __global__ void __launch_bounds__(256) k_check_rounds(const uint64_t *wit, const
 #pragma unroll
         for (int i = 0; i < 25; i++) bad |= (s[i] != o[i]);
         if (bad) atomicAdd(n_bad, 1ull);
+    }
+}
+
+
+// ---- full constraint self-check: every `<==` / `===` of the circuit against a resident witness ----
+// One thread per record; the shared KeccakfRound set is replayed for every round block (grid = records x blocks).
+// rep[0] = failing circuit constraints, rep[1] = failing hint records, rep[2] = smallest failing record id.
+struct CheckArgs {
+    ConsView V; const Fr *konst; const uint64_t *wit;
+    const uint64_t *bases; uint32_t n_blocks;       // null / 0: the flat set (absolute indices)
+    uint64_t id0;                                   // record id of (block 0, first eq record) of this set
+    unsigned long long *rep;
+};
+__device__ __forceinline__ void check_fail(const CheckArgs &a, uint64_t id, bool hint) {
+    atomicAdd(a.rep + (hint ? 1 : 0), 1ull); atomicMin(a.rep + 2, (unsigned long long)id);
+}
+__global__ void __launch_bounds__(256) k_check_eq(const CheckArgs a) {
+    const uint64_t per = a.V.n_eq, total = per * (a.bases ? a.n_blocks : 1u);
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t blk = t / per, r = t - blk * per, base = a.bases ? a.bases[blk] : 0;
+        if (!cons_eq_ok(a.wit, base, a.V.eq[2 * r], a.V.eq[2 * r + 1])) check_fail(a, a.id0 + blk * a.V.n_records() + r, false);
+    }
+}
+__global__ void __launch_bounds__(256) k_check_kc(const CheckArgs a) {
+    const uint64_t per = a.V.n_kc, total = per * (a.bases ? a.n_blocks : 1u);
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t blk = t / per, r = t - blk * per, base = a.bases ? a.bases[blk] : 0;
+        if (!cons_kc_ok(a.wit, base, a.V.kc[r], a.konst, keccak_rc((int)(blk % 24)))) check_fail(a, a.id0 + blk * a.V.n_records() + a.V.n_eq + r, false);
+    }
+}
+__global__ void __launch_bounds__(256) k_check_r1(const CheckArgs a) {
+    const uint64_t per = a.V.n_r1, total = per * (a.bases ? a.n_blocks : 1u);
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t blk = t / per, r = t - blk * per, base = a.bases ? a.bases[blk] : 0;
+        const ConsR1 rec = a.V.r1[r];
+        if (!cons_r1_ok(a.wit, base, rec, a.V.terms, a.konst)) check_fail(a, a.id0 + blk * a.V.n_records() + a.V.n_eq + a.V.n_kc + r, r1_hint(rec));
     }
 }
 

@@ -174,7 +174,41 @@ struct pob_handle {
     } B;
     Exporter *exporter = nullptr;
     pob_timing timing{};
+    // constraint system for pob_selfcheck, built on first use
+    struct DevCons {
+        bool ready = false; ConsView flat{}, round{}; Fr *konst = nullptr; uint64_t *bases = nullptr; uint32_t n_blocks = 0;
+        unsigned long long *rep = nullptr; std::vector<void *> allocs; pob_check_report info{};
+    } cons;
 };
+
+static void cons_info(const Program &P, pob_check_report *r) {
+    memset(r, 0, sizeof *r);
+    const uint64_t nb = P.round_block_sig.size();
+    auto count = [&](const ConsSet &S, uint64_t mult) {
+        r->n_constraints += mult * (S.eq.size() / 2 + S.kc.size());
+        for (const ConsR1 &q : S.r1) { if (r1_hint(q)) r->n_hints += mult; else { r->n_constraints += mult; if (q.na) r->n_nonlinear += mult; } }
+    };
+    count(P.cons_flat, 1); count(P.cons_round, nb);
+    std::vector<uint8_t> seen(P.n_signals, 0);
+    auto mark = [&](const ConsSet &S, uint64_t base) {
+        for (uint32_t i : S.eq) seen[base + i] = 1;
+        for (const ConsTerm &t : S.kc) seen[base + t.idx] = 1;
+        for (const ConsTerm &t : S.terms) if (t.idx != CONS_ONE) seen[base + t.idx] = 1;
+    };
+    mark(P.cons_flat, 0);
+    for (uint64_t b : P.round_block_sig) mark(P.cons_round, b);
+    for (uint8_t v : seen) r->signals_read += v;
+    r->first_failed = ~0ull;
+}
+static ConsView upload_cons(pob_handle *h, const ConsSet &S) {
+    ConsView v{};
+    auto up = [&](const void *src, size_t bytes) { void *d = nullptr; CU(cudaMalloc(&d, std::max<size_t>(16, bytes))); if (bytes) CU(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice)); h->cons.allocs.push_back(d); return d; };
+    v.eq = (const uint32_t *)up(S.eq.data(), S.eq.size() * 4); v.n_eq = S.eq.size() / 2;
+    v.kc = (const ConsTerm *)up(S.kc.data(), S.kc.size() * sizeof(ConsTerm)); v.n_kc = S.kc.size();
+    v.r1 = (const ConsR1 *)up(S.r1.data(), S.r1.size() * sizeof(ConsR1)); v.n_r1 = S.r1.size();
+    v.terms = (const ConsTerm *)up(S.terms.data(), S.terms.size() * sizeof(ConsTerm));
+    return v;
+}
 
 static void fill_desc(const Program &P, pob_desc *d) {
     memset(d, 0, sizeof *d);
@@ -433,6 +467,7 @@ void pob_destroy(pob_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     delete h->exporter; h->exporter = nullptr;
+    for (void *p : h->cons.allocs) cudaFree(p);
     if (h->s_eval) cudaStreamSynchronize(h->s_eval);
     if (h->s_exp) cudaStreamSynchronize(h->s_exp);
     if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
@@ -732,6 +767,56 @@ int pob_selfcheck_keccak(pob_handle *h, uint32_t index, uint64_t *n_blocks, uint
         cudaFree(d_bad);
     } catch (const std::exception &e) { if (d_bad) cudaFree(d_bad); return fail(POB_E_CUDA, std::string("pob_selfcheck_keccak: ") + e.what()); }
     *n_blocks = h->n_blocks; *n_bad = bad;
+    return POB_OK;
+}
+
+int pob_constraint_info(const char *main_name, const uint64_t *params, int nparams, int hcreate, pob_check_report *out) {
+    if (!main_name || !out || (nparams > 0 && !params)) return fail(POB_E_BAD_ARG, "pob_constraint_info: null argument");
+    try { Program P = compile_circuit(main_name, params_vec(params, nparams), hcreate != 0, true); cons_info(P, out); }
+    catch (const std::exception &e) { return fail(POB_E_COMPILE, e.what()); }
+    return POB_OK;
+}
+
+int pob_selfcheck(pob_handle *h, uint32_t index, pob_check_report *out) {
+    if (!h || !out) return fail(POB_E_BAD_ARG, "pob_selfcheck: null argument");
+    uint64_t *s = nullptr; int rc = resident_slot(h, index, &s); if (rc) return rc;
+    try {
+        CU(cudaSetDevice(h->device));
+        pob_handle::DevCons &C = h->cons;
+        if (!C.ready) {
+            Program Q = compile_circuit(h->P.main_name, h->P.params, h->P.hcreate, true);
+            if (Q.n_signals != h->P.n_signals) throw std::runtime_error("internal: constraint compile disagrees on the witness size");
+            cons_info(Q, &C.info);
+            C.flat = upload_cons(h, Q.cons_flat); C.round = upload_cons(h, Q.cons_round);
+            C.konst = upload(Q.cons_konst); C.allocs.push_back(C.konst);
+            C.bases = upload(Q.round_block_sig); C.allocs.push_back(C.bases); C.n_blocks = (uint32_t)Q.round_block_sig.size();
+            CU(cudaMalloc(&C.rep, 24)); C.allocs.push_back(C.rep);
+            C.ready = true;
+        }
+        const unsigned long long init[3] = {0, 0, ~0ull};
+        CU(cudaMemcpy(C.rep, init, 24, cudaMemcpyHostToDevice));
+        cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, 0));
+        auto grid = [](uint64_t n) { return (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 64); };
+        CheckArgs fa{C.flat, C.konst, s, nullptr, 0, 0, C.rep};
+        if (C.flat.n_eq) k_check_eq<<<grid(C.flat.n_eq), 256>>>(fa);
+        if (C.flat.n_kc) k_check_kc<<<grid(C.flat.n_kc), 256>>>(fa);
+        if (C.flat.n_r1) k_check_r1<<<grid(C.flat.n_r1), 256>>>(fa);
+        if (C.n_blocks) {
+            CheckArgs ra{C.round, C.konst, s, C.bases, C.n_blocks, C.flat.n_records(), C.rep};
+            k_check_eq<<<grid(C.round.n_eq * C.n_blocks), 256>>>(ra);
+            k_check_kc<<<grid(C.round.n_kc * C.n_blocks), 256>>>(ra);
+            k_check_r1<<<grid(C.round.n_r1 * C.n_blocks), 256>>>(ra);
+        }
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaGetLastError());
+        unsigned long long rep[3];
+        CU(cudaMemcpy(rep, C.rep, 24, cudaMemcpyDeviceToHost));
+        *out = C.info;
+        CU(cudaEventElapsedTime(&out->ms, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        out->n_failed = rep[0]; out->n_hint_failed = rep[1]; out->first_failed = rep[2];
+    } catch (const std::exception &e) { return fail(POB_E_CUDA, std::string("pob_selfcheck: ") + e.what()); }
     return POB_OK;
 }
 

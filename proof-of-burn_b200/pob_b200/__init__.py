@@ -63,6 +63,14 @@ class ExportStats(ctypes.Structure):
         return {"witnesses": int(self.witnesses), "bytes": int(self.bytes), "total_ms": float(self.total_ms), "d2h_gbs": float(self.d2h_gbs)}
 
 
+class CheckReport(ctypes.Structure):
+    _fields_ = [("n_constraints", ctypes.c_uint64), ("n_nonlinear", ctypes.c_uint64), ("n_hints", ctypes.c_uint64), ("n_failed", ctypes.c_uint64),
+                ("n_hint_failed", ctypes.c_uint64), ("first_failed", ctypes.c_uint64), ("signals_read", ctypes.c_uint64), ("ms", ctypes.c_float)]
+
+    def as_dict(self):
+        return {k: (float(getattr(self, k)) if k == "ms" else int(getattr(self, k))) for k, _ in self._fields_}
+
+
 _LIB = None
 
 
@@ -101,6 +109,10 @@ def lib():
         L.pob_witness_device_ptr.argtypes = [vp, u32, ctypes.POINTER(vp)]
         L.pob_selfcheck_keccak.restype = ci
         L.pob_selfcheck_keccak.argtypes = [vp, u32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+        L.pob_selfcheck.restype = ci
+        L.pob_selfcheck.argtypes = [vp, u32, ctypes.POINTER(CheckReport)]
+        L.pob_constraint_info.restype = ci
+        L.pob_constraint_info.argtypes = [ctypes.c_char_p, vp, ci, ci, ctypes.POINTER(CheckReport)]
         L.pob_run_batch_retain.restype = ci
         L.pob_run_batch_retain.argtypes = [vp, vp, u32, u32, vp, u32, vp, vp, vp]
         L.pob_submit.restype = ci
@@ -233,6 +245,15 @@ def layout_info(main_expr, hcreate=False):
     d = Desc()
     _check(lib().pob_layout_info(name.encode(), pl.ctypes.data, len(params), int(hcreate), ctypes.byref(d)))
     return d.as_dict()
+
+
+def constraint_info(main_expr, hcreate=False):
+    """size of a circuit shape's constraint system (host only): constraints, non-linear ones, hint records, signals covered"""
+    name, params = parse_main(main_expr)
+    pl = to_limbs(params) if params else np.zeros((1, 4), dtype=np.uint64)
+    r = CheckReport()
+    _check(lib().pob_constraint_info(name.encode(), pl.ctypes.data, len(params), int(hcreate), ctypes.byref(r)))
+    return r.as_dict()
 
 
 class PinnedArray:
@@ -410,6 +431,13 @@ class Circuit:
         nb, bad = ctypes.c_uint64(0), ctypes.c_uint64(0)
         _check(lib().pob_selfcheck_keccak(self._h, index, ctypes.byref(nb), ctypes.byref(bad)))
         return int(nb.value), int(bad.value)
+
+    def selfcheck(self, index):
+        """on-GPU evaluation of EVERY constraint of the circuit (all `<==` / `===` of the circom sources) against resident
+        witness `index`; returns the report dict (n_constraints, n_failed, n_hint_failed, first_failed, signals_read, ms)"""
+        r = CheckReport()
+        _check(lib().pob_selfcheck(self._h, index, ctypes.byref(r)))
+        return r.as_dict()
 
     def witness_device_ptr(self, index):
         p = ctypes.c_void_p()

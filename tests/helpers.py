@@ -36,14 +36,24 @@ def repad_pob(inp, max_layers, node_blocks, header_blocks):
     return out
 
 
+_RT = None
+
+
+def _cudart():
+    global _RT
+    if _RT is None:
+        import ctypes, glob
+        _RT = ctypes.CDLL(sorted(glob.glob("/usr/local/cuda/lib64/libcudart.so.*"))[-1])
+    return _RT
+
+
 def cuda_poke(dptr, signal, value):
     """Fault injection for the self-check tests: overwrite ONE 32-byte witness entry at device pointer `dptr`
     (pob_witness_device_ptr) through the CUDA runtime -- the product API has no write access to a witness."""
-    import ctypes, glob
+    import ctypes
     import numpy as np
-    rt = ctypes.CDLL(sorted(glob.glob("/usr/local/cuda/lib64/libcudart.so.*"))[-1])
+    rt = _cudart()
     v = int(value)
     limbs = np.array([(v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)], dtype=np.uint64)
     rc = rt.cudaMemcpy(ctypes.c_void_p(dptr + 32 * int(signal)), ctypes.c_void_p(limbs.ctypes.data), ctypes.c_size_t(32), ctypes.c_int(1))
     assert rc == 0, "cudaMemcpy H2D failed: %d" % rc
-    rt.cudaDeviceSynchronize()
