@@ -65,7 +65,18 @@ typedef struct {
     uint32_t n_slots;          /* witness slots resident in HBM (0 when no device handle) */
     uint32_t chunk;            /* instances evaluated per eval launch */
     uint32_t expand_group;     /* instances materialised per expand launch (<= n_slots) */
+    uint32_t opt_level;        /* 0 = circom --O0 witness (every signal), 1 = reduced witness (POB_CREATE_O1) */
+    uint64_t n_signals_o0;     /* witness entries of the --O0 layout (== n_signals when opt_level == 0) */
 } pob_desc;
+
+/* `hcreate` argument of pob_create / pob_layout_info / pob_constraint_info: bit 0 = creation-order sub-component numbering
+ * (SURVEY.md App. C R3), POB_CREATE_O1 = produce the REDUCED witness the circom simplifier's `--O1` level implies (the reference
+ * deploys through circom's default simplifier: .github/workflows/circuitscan.yml:29,36; its Makefile builds --O0): every signal
+ * tied to an earlier signal or to a constant by a `signal = signal` / `signal = constant` constraint is dropped, main inputs and
+ * outputs always stay, the rest keeps its --O0 order.  main_proof_of_burn: 215,907,954 -> see pob_desc.n_signals.  Which member
+ * of an equality class circom itself keeps is not pinned by the reference: the reduced ORDER is "parity unpinned" like the
+ * --O0 order; every retained value equals the --O0 witness through pob_witness_map (tested). */
+enum { POB_CREATE_HCREATE = 1, POB_CREATE_O1 = 0x100 };
 
 /* replaces: `circom -c <main>.circom --O0 && make` (reference Makefile:2-3, tests/test.py:32,55).
  * main_name/params = the `component main = Name(p0, p1, ...)` expression; params are nparams x 4 limbs.
@@ -81,6 +92,8 @@ int pob_layout_info(const char *main_name, const uint64_t *params, int nparams, 
 const char *pob_input_schema(const char *main_name, int *nparams);
 
 int pob_describe(const pob_handle *h, pob_desc *out);
+/* reduced witness only: map[k] = --O0 signal index of reduced witness entry k (n_signals entries) */
+int pob_witness_map(const pob_handle *h, uint32_t *map);
 
 /* pinned host memory for the caller's input / output arrays (so H2D/D2H inside pob_run_batch are async DMA) */
 void *pob_alloc_pinned(uint64_t bytes);

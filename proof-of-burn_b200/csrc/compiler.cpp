@@ -1971,7 +1971,22 @@ const char *main_input_schema(const std::string &main_name, int *nparams) {
     return nullptr;
 }
 
-Program compile_circuit(const std::string &main_name, const std::vector<Fr> &params, bool hcreate, bool want_constraints) {
+// ---- `--O1`-style reduction --------------------------------------------------------------------
+// circom's default simplifier (the reference deploys through it: .github/workflows/circuitscan.yml:29,36) removes signals
+// tied by `signal = signal` and `signal = constant` constraints.  Here: union-find over the eq records of the constraint
+// system (the shared KeccakfRound set is resolved once and stamped into every round block), a class is "constant" when one
+// of its members has a kc record; a signal stays iff it is a main input / output, or the lowest-numbered member of a
+// non-constant class.  Which member circom keeps, and whether it also folds constraints that BECOME linear after the
+// substitution, is not pinned by anything in the reference (no circom here): parity of the reduced ORDER is unpinned; every
+// retained value equals the --O0 witness through witness_map (tested).
+struct Reduction { std::vector<uint32_t> round_keep; std::vector<uint8_t> keep_flat; uint64_t n_kept = 0; };
+static uint32_t uf_find(std::vector<uint32_t> &p, uint32_t x) { while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; } return x; }
+static void uf_union(std::vector<uint32_t> &p, uint32_t a, uint32_t b) { a = uf_find(p, a); b = uf_find(p, b); if (a == b) return; if (a < b) p[b] = a; else p[a] = b; }
+
+Program compile_circuit(const std::string &main_name, const std::vector<Fr> &params, bool hcreate, bool want_constraints, int opt_level) {
+    if (opt_level < 0 || opt_level > 1) throw std::runtime_error("pob: opt_level must be 0 (--O0) or 1 (signal=signal / signal=constant elimination)");
+    const bool user_wants_constraints = want_constraints;
+    if (opt_level) want_constraints = true;
     int np = 0; const char *schema = main_input_schema(main_name, &np);
     if (!schema) throw std::runtime_error("pob: unknown main template '" + main_name + "'");
     if ((int)params.size() < np) throw std::runtime_error("pob: too few template parameters for " + main_name);
@@ -2066,6 +2081,46 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
         std::stable_sort(P.ops.begin() + tstart[l], P.ops.begin() + tstart[l] + tcount[l], [&](const Op &x, const Op &y) { return op_key(x) < op_key(y); });
         P.levels.push_back(Level{tstart[l], tstart[l] + tcount[l], wstart[l], wstart[l] + wcount[l], pstart[l], pstart[l] + pcount[l], sstart[l], sstart[l] + scount[l]});
     }
+    // ---- reduced witness: which signals stay ----
+    std::vector<uint32_t> round_keep;            // retained relative indices inside a KeccakfRound block (same for every block)
+    std::vector<uint32_t> parent;                // union-find over all --O0 signals
+    std::vector<uint8_t> is_const_root;
+    if (opt_level) {
+        const uint64_t N = B.nsig;
+        // the shared round set, resolved once: relative representative (lowest index) and constness per relative signal
+        std::vector<uint32_t> rp(ROUND_SIGNALS); for (uint32_t i = 0; i < ROUND_SIGNALS; i++) rp[i] = i;
+        for (size_t i = 0; i + 1 < P.cons_round.eq.size(); i += 2) uf_union(rp, P.cons_round.eq[i], P.cons_round.eq[i + 1]);
+        std::vector<uint8_t> rconst(ROUND_SIGNALS, 0);
+        for (const ConsTerm &t : P.cons_round.kc) rconst[uf_find(rp, t.idx)] = 1;
+        parent.resize(N); is_const_root.assign(N, 0);
+        for (uint64_t i = 0; i < N; i++) parent[i] = (uint32_t)i;
+        for (uint64_t base : B.round_sigs) for (uint32_t i = 0; i < ROUND_SIGNALS; i++) { const uint32_t r = uf_find(rp, i); parent[base + i] = (uint32_t)(base + r); if (r == i && rconst[i]) is_const_root[base + i] = 1; }
+        for (size_t i = 0; i + 1 < P.cons_flat.eq.size(); i += 2) {
+            uint32_t a = uf_find(parent, P.cons_flat.eq[i]), b2 = uf_find(parent, P.cons_flat.eq[i + 1]);
+            if (a == b2) continue;
+            const uint8_t c = is_const_root[a] | is_const_root[b2];
+            if (a < b2) { parent[b2] = a; is_const_root[a] = c; } else { parent[a] = b2; is_const_root[b2] = c; }
+        }
+        for (const ConsTerm &t : P.cons_flat.kc) is_const_root[uf_find(parent, t.idx)] = 1;
+        const uint64_t n_io = 1ull + n_out + n_in;
+        is_const_root[uf_find(parent, 0)] = 1;                                    // witness[0] itself is kept as main I/O
+        auto kept = [&](uint64_t s) { if (s < n_io) return true; const uint32_t r = uf_find(parent, (uint32_t)s); return r == s && !is_const_root[r]; };
+        // inside a round block the retained set must be the same for all blocks (it is: in/out tie to the enclosing Keccakf's
+        // lower-numbered midRound signals, everything else is block-internal); verified below while the map is built
+        if (!B.round_sigs.empty()) { const uint64_t b0 = B.round_sigs[0]; for (uint32_t i = 0; i < ROUND_SIGNALS; i++) if (kept(b0 + i)) round_keep.push_back(i); }
+        P.witness_map.reserve(N / 8);
+        for (auto &sg : B.segs) {
+            if (sg.round) {
+                size_t k = 0;
+                for (uint32_t i = 0; i < ROUND_SIGNALS; i++) {
+                    const bool kp = kept(sg.dst + i);
+                    const bool want = k < round_keep.size() && round_keep[k] == i;
+                    if (kp != want) throw std::runtime_error("pob: internal: KeccakfRound blocks do not reduce uniformly");
+                    if (kp) { P.witness_map.push_back((uint32_t)(sg.dst + i)); k++; }
+                }
+            } else for (uint64_t i = 0; i < sg.n; i++) if (kept(sg.dst + i)) P.witness_map.push_back((uint32_t)(sg.dst + i));
+        }
+    }
     // ---- codes + tiles ----
     P.codes.resize(ROUND_SIGNALS);
     { LaneSink S{P.codes.data(), 0}; emit_round(S);
@@ -2099,8 +2154,34 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
             throw std::runtime_error("pob: internal: round table group does not fit a descriptor");
         P.round_desc[g] = d;
     }
+    P.n_round_blocks = B.n_round_blocks; P.n_flat_signals = B.flat_n; P.n_signals_o0 = B.nsig; P.opt_level = opt_level;
+    if (opt_level) {
+        // reduced program: codes = [retained entries of the shared round table | retained flat codes]; every tile goes
+        // through the generic code path (k_expand_codes), round blocks as tiles over the shared table with their own ubase
+        std::vector<Code> rt(round_keep.size()); for (size_t k = 0; k < round_keep.size(); k++) rt[k] = P.codes[round_keep[k]];
+        P.codes = rt; P.round_desc.assign(1, 0);
+        const uint32_t RT = (uint32_t)round_keep.size();
+        P.out_code_off = RT + 1;
+        uint64_t dst = 0; size_t mp = 0;
+        const uint32_t ts = TILE_SIGNALS;
+        for (auto &sg : B.segs) {
+            if (sg.round) {
+                for (uint32_t done = 0; done < RT; done += ts) { Tile t; t.dst = dst + done; t.n = std::min(ts, RT - done); t.code_off = done; t.ubase = sg.ubase; t.pad = 0; P.tiles.push_back(t); }
+                dst += RT; mp += RT;
+            } else {
+                const size_t first = P.codes.size();
+                while (mp < P.witness_map.size() && P.witness_map[mp] < sg.dst + sg.n) { P.codes.push_back(B.flat[sg.pos + (P.witness_map[mp] - sg.dst)]); mp++; }
+                const uint64_t n = P.codes.size() - first;
+                for (uint64_t done = 0; done < n; done += ts) { Tile t; t.dst = dst + done; t.n = (uint32_t)std::min<uint64_t>(ts, n - done); t.code_off = (uint32_t)(first + done); t.ubase = 0; t.pad = 0; P.tiles.push_back(t); }
+                dst += n;
+            }
+        }
+        if (dst != P.witness_map.size() || mp != P.witness_map.size()) throw std::runtime_error("pob: internal: reduced layout does not add up");
+        P.n_signals = dst;
+        if (!user_wants_constraints) { P.cons_flat = ConsSet(); P.cons_round = ConsSet(); P.has_constraints = false; }
+        return P;
+    }
     P.codes.insert(P.codes.end(), B.flat, B.flat + B.flat_n);
-    P.n_round_blocks = B.n_round_blocks; P.n_flat_signals = B.flat_n;
     uint32_t tile_signals = TILE_SIGNALS;
 #ifdef POB_TUNING
     if (const char *v = getenv("POB_TILE_SIGNALS")) { uint32_t t = (uint32_t)atoi(v); if (t >= 64 && t <= MAX_TILE_SIGNALS && t % 64 == 0) tile_signals = t; }

@@ -16,7 +16,8 @@ namespace pob {
 // accepted too.  hcreate selects creation-order numbering at the two sites where it differs from
 // completion order (Num2Bits_strict, MultiAND n>=3).  Throws std::runtime_error on unknown template/shape.
 // want_constraints additionally emits the circuit's constraint system (Program::cons_*; see program.h).
-Program compile_circuit(const std::string &main_name, const std::vector<Fr> &params, bool hcreate, bool want_constraints = false);
+// opt_level 1 produces the reduced (`--O1`-style) witness program (program.h: Program::witness_map).
+Program compile_circuit(const std::string &main_name, const std::vector<Fr> &params, bool hcreate, bool want_constraints = false, int opt_level = 0);
 
 // Input schema of a main template ("name[d0][d1],name2,...", dims are expressions over p0..p7) or nullptr.
 const char *main_input_schema(const std::string &main_name, int *nparams);

@@ -216,7 +216,10 @@ static void fill_desc(const Program &P, pob_desc *d) {
     d->witness_bytes = 32ull * P.n_signals; d->wtns_file_bytes = 76ull + 32ull * P.n_signals;
     d->store_bytes = 8ull * P.store_u64(); d->n_ops = P.ops.size(); d->n_absorbs = (uint32_t)P.absorbs.size();
     d->n_levels = (uint32_t)P.levels.size(); d->n_tiles = (uint32_t)P.tiles.size();
+    d->opt_level = (uint32_t)P.opt_level; d->n_signals_o0 = P.n_signals_o0;
 }
+static bool flag_hcreate(int f) { return (f & POB_CREATE_HCREATE) != 0; }
+static int flag_opt(int f) { return (f & POB_CREATE_O1) ? 1 : 0; }
 static std::vector<Fr> params_vec(const uint64_t *params, int nparams) {
     std::vector<Fr> ps((size_t)(nparams > 0 ? nparams : 0));
     for (int i = 0; i < nparams; i++) memcpy(ps[(size_t)i].l, params + 4 * i, 32);
@@ -267,7 +270,7 @@ static void enqueue_eval(pob_handle *h, uint32_t c) {
     if (c >= R) CU(cudaStreamWaitEvent(h->s_eval, h->ev_exp_done[r], 0));      // store ring half r is free again
     uint64_t *stores = h->d_stores + (size_t)r * E * h->store_stride;
     EvalArgs ea{h->d_ops, h->d_abs, h->d_pos, h->d_pos_konst, h->d_psums, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.ginv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
-                h->d_codes + ROUND_SIGNALS + 1, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
+                h->d_codes + P.out_code_off, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
                 h->d_status + first, h->d_outputs + (size_t)first * no * 4, (c == 0) ? h->d_prof : nullptr};
     CU(cudaEventRecord(B.e0[c], h->s_eval));
     switch (h->eval_threads) {
@@ -458,7 +461,7 @@ const char *pob_input_schema(const char *main_name, int *nparams) {
 
 int pob_layout_info(const char *main_name, const uint64_t *params, int nparams, int hcreate, pob_desc *out) {
     if (!main_name || !out || (nparams > 0 && !params)) return fail(POB_E_BAD_ARG, "pob_layout_info: null argument");
-    try { Program P = compile_circuit(main_name, params_vec(params, nparams), hcreate != 0); fill_desc(P, out); }
+    try { Program P = compile_circuit(main_name, params_vec(params, nparams), flag_hcreate(hcreate), false, flag_opt(hcreate)); fill_desc(P, out); }
     catch (const std::exception &e) { return fail(POB_E_COMPILE, e.what()); }
     return POB_OK;
 }
@@ -496,7 +499,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(POB_E_NO_DEVICE, "pob_create: no CUDA device (this library has no CPU path)");
     if (device < 0 || device >= ndev) return fail(POB_E_NO_DEVICE, "pob_create: device index out of range");
     pob_handle *h = new pob_handle(); h->device = device;
-    try { h->P = compile_circuit(main_name, params_vec(params, nparams), hcreate != 0); }
+    try { h->P = compile_circuit(main_name, params_vec(params, nparams), flag_hcreate(hcreate), false, flag_opt(hcreate)); }
     catch (const std::exception &e) { delete h; return fail(POB_E_COMPILE, e.what()); }
     try {
         const Program &P = h->P;
@@ -568,6 +571,13 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         return fail(m.find("slot") != std::string::npos ? POB_E_NO_MEMORY : POB_E_CUDA, "pob_create: " + m);
     }
     *out = h; return POB_OK;
+}
+
+int pob_witness_map(const pob_handle *h, uint32_t *map) {
+    if (!h || !map) return fail(POB_E_BAD_ARG, "pob_witness_map: null argument");
+    if (!h->P.opt_level) return fail(POB_E_BAD_ARG, "pob_witness_map: the handle produces the full --O0 witness (identity map)");
+    memcpy(map, h->P.witness_map.data(), h->P.witness_map.size() * 4);
+    return POB_OK;
 }
 
 int pob_describe(const pob_handle *h, pob_desc *out) {
@@ -756,6 +766,7 @@ static int resident_slot(pob_handle *h, uint32_t index, uint64_t **slot) {
 
 int pob_selfcheck_keccak(pob_handle *h, uint32_t index, uint64_t *n_blocks, uint64_t *n_bad) {
     if (!h || !n_blocks || !n_bad) return fail(POB_E_BAD_ARG, "pob_selfcheck_keccak: null argument");
+    if (h->P.opt_level) return fail(POB_E_BAD_ARG, "pob_selfcheck_keccak: needs the --O0 witness layout");
     uint64_t *s = nullptr; int rc = resident_slot(h, index, &s); if (rc) return rc;
     unsigned long long *d_bad = nullptr, bad = 0;
     try {
@@ -772,13 +783,14 @@ int pob_selfcheck_keccak(pob_handle *h, uint32_t index, uint64_t *n_blocks, uint
 
 int pob_constraint_info(const char *main_name, const uint64_t *params, int nparams, int hcreate, pob_check_report *out) {
     if (!main_name || !out || (nparams > 0 && !params)) return fail(POB_E_BAD_ARG, "pob_constraint_info: null argument");
-    try { Program P = compile_circuit(main_name, params_vec(params, nparams), hcreate != 0, true); cons_info(P, out); }
+    try { Program P = compile_circuit(main_name, params_vec(params, nparams), flag_hcreate(hcreate), true); cons_info(P, out); }
     catch (const std::exception &e) { return fail(POB_E_COMPILE, e.what()); }
     return POB_OK;
 }
 
 int pob_selfcheck(pob_handle *h, uint32_t index, pob_check_report *out) {
     if (!h || !out) return fail(POB_E_BAD_ARG, "pob_selfcheck: null argument");
+    if (h->P.opt_level) return fail(POB_E_BAD_ARG, "pob_selfcheck: the constraint system is stated over the --O0 witness; create the handle without POB_CREATE_O1");
     uint64_t *s = nullptr; int rc = resident_slot(h, index, &s); if (rc) return rc;
     try {
         CU(cudaSetDevice(h->device));

@@ -167,6 +167,14 @@ struct Program {
     ConsSet cons_flat, cons_round;
     std::vector<Fr> cons_konst;
     std::vector<uint64_t> round_block_sig;
+    // reduced (`--O1`-style) witness: opt_level 1 drops every signal that a `signal = signal` or `signal = constant`
+    // constraint of the circuit ties to an earlier signal / a constant (main inputs and outputs always stay); the
+    // retained signals keep their --O0 order.  n_signals / codes / tiles then describe the REDUCED vector;
+    // n_signals_o0 is the full count and witness_map[k] the --O0 index of reduced entry k.
+    int opt_level = 0;
+    uint64_t n_signals_o0 = 0;
+    std::vector<uint32_t> witness_map;
+    uint32_t out_code_off = ROUND_SIGNALS + 1;   // position in `codes` of the code of witness[1] (the first output)
     // statistics
     uint64_t n_round_blocks = 0, n_flat_signals = 0;
 };

@@ -25,6 +25,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpob_b200.so")
 
 RUN_EXPAND, RUN_DIGEST, RUN_INPUTS_STAGED, RUN_DISCARD = 1, 2, 4, 8
+CREATE_HCREATE, CREATE_O1 = 1, 0x100
 E_RANGE, E_REJECTED, E_BUSY, DONE = -5, -8, -9, 1
 MAIN_PROOF_OF_BURN = "ProofOfBurn(16, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)"   # circuits/main_proof_of_burn.circom:27
 MAIN_SPEND = "Spend(31)"                                                       # circuits/main_spend.circom:6
@@ -41,7 +42,8 @@ class Desc(ctypes.Structure):
     _fields_ = [("n_signals", ctypes.c_uint64), ("n_outputs", ctypes.c_uint32), ("n_inputs", ctypes.c_uint32),
                 ("witness_bytes", ctypes.c_uint64), ("wtns_file_bytes", ctypes.c_uint64), ("store_bytes", ctypes.c_uint64),
                 ("n_ops", ctypes.c_uint64), ("n_absorbs", ctypes.c_uint32), ("n_levels", ctypes.c_uint32),
-                ("n_tiles", ctypes.c_uint32), ("n_slots", ctypes.c_uint32), ("chunk", ctypes.c_uint32), ("expand_group", ctypes.c_uint32)]
+                ("n_tiles", ctypes.c_uint32), ("n_slots", ctypes.c_uint32), ("chunk", ctypes.c_uint32), ("expand_group", ctypes.c_uint32),
+                ("opt_level", ctypes.c_uint32), ("n_signals_o0", ctypes.c_uint64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -113,6 +115,8 @@ def lib():
         L.pob_selfcheck.argtypes = [vp, u32, ctypes.POINTER(CheckReport)]
         L.pob_constraint_info.restype = ci
         L.pob_constraint_info.argtypes = [ctypes.c_char_p, vp, ci, ci, ctypes.POINTER(CheckReport)]
+        L.pob_witness_map.restype = ci
+        L.pob_witness_map.argtypes = [vp, vp]
         L.pob_run_batch_retain.restype = ci
         L.pob_run_batch_retain.argtypes = [vp, vp, u32, u32, vp, u32, vp, vp, vp]
         L.pob_submit.restype = ci
@@ -238,12 +242,12 @@ def flatten_input(schema, inp):
     return flat
 
 
-def layout_info(main_expr, hcreate=False):
+def layout_info(main_expr, hcreate=False, opt=0):
     """Shape of a circuit's witness program; runs the host-side layout compiler only (no GPU needed)."""
     name, params = parse_main(main_expr)
     pl = to_limbs(params) if params else np.zeros((1, 4), dtype=np.uint64)
     d = Desc()
-    _check(lib().pob_layout_info(name.encode(), pl.ctypes.data, len(params), int(hcreate), ctypes.byref(d)))
+    _check(lib().pob_layout_info(name.encode(), pl.ctypes.data, len(params), (CREATE_HCREATE if hcreate else 0) | (CREATE_O1 if opt else 0), ctypes.byref(d)))
     return d.as_dict()
 
 
@@ -296,13 +300,15 @@ class BatchResult:
 class Circuit:
     """One compiled circuit shape bound to one GPU (== the executable `circom -c ... && make` produces)."""
 
-    def __init__(self, main_expr, device=0, hcreate=False, max_slots=0):
+    def __init__(self, main_expr, device=0, hcreate=False, max_slots=0, opt=0):
+        """opt=1: the reduced (`--O1`-style) witness (pob_b200.h: POB_CREATE_O1); witness_map() gives the --O0 index of each entry"""
         self.main_expr = main_expr
         self.name, self.params = parse_main(main_expr)
         self.schema = input_schema(self.name, self.params)
         pl = to_limbs(self.params) if self.params else np.zeros((1, 4), dtype=np.uint64)
         h = ctypes.c_void_p()
-        _check(lib().pob_create(self.name.encode(), pl.ctypes.data, len(self.params), int(hcreate), int(device), int(max_slots), ctypes.byref(h)))
+        _check(lib().pob_create(self.name.encode(), pl.ctypes.data, len(self.params), (CREATE_HCREATE if hcreate else 0) | (CREATE_O1 if opt else 0),
+                                int(device), int(max_slots), ctypes.byref(h)))
         self._h = h
         d = Desc()
         _check(lib().pob_describe(self._h, ctypes.byref(d)))
@@ -438,6 +444,11 @@ class Circuit:
         r = CheckReport()
         _check(lib().pob_selfcheck(self._h, index, ctypes.byref(r)))
         return r.as_dict()
+
+    def witness_map(self):
+        m = np.zeros(self.n_signals, dtype=np.uint32)
+        _check(lib().pob_witness_map(self._h, m.ctypes.data))
+        return m
 
     def witness_device_ptr(self, index):
         p = ctypes.c_void_p()

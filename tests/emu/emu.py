@@ -56,15 +56,22 @@ STAT_NAMES = ["n_signals", "n_outputs", "n_inputs", "n_words", "n_vals", "n_ops"
 
 
 class EmuProgram:
-    def __init__(self, name, params_limbs, nparams, hcreate=False):
+    def __init__(self, name, params_limbs, nparams, hcreate=False, opt=0):
         err = ctypes.create_string_buffer(512)
-        self.h = lib().pob_emu_compile(name.encode(), params_limbs.ctypes.data, nparams, int(hcreate), err, 512)
+        self.h = lib().pob_emu_compile(name.encode(), params_limbs.ctypes.data, nparams, (1 if hcreate else 0) | (0x100 if opt else 0), err, 512)
         if not self.h:
             raise RuntimeError(err.value.decode())
         st = np.zeros(12, dtype=np.uint64)
         lib().pob_emu_stats(self.h, st.ctypes.data)
         self.stats = dict(zip(STAT_NAMES, (int(v) for v in st)))
         self.schema = lib().pob_emu_schema(self.h).decode()
+
+    def witness_map(self):
+        lib().pob_emu_witness_map.restype = ctypes.c_uint64
+        lib().pob_emu_witness_map.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        m = np.zeros(self.stats["n_signals"], dtype=np.uint32)
+        n0 = lib().pob_emu_witness_map(self.h, m.ctypes.data)
+        return m, int(n0)
 
     def run(self, input_limbs, want_witness=True):
         n = self.stats["n_signals"]

@@ -26,7 +26,7 @@ void *pob_emu_compile(const char *main_name, const uint64_t *params, int nparams
         std::vector<Fr> ps((size_t)nparams);
         for (int i = 0; i < nparams; i++) memcpy(ps[(size_t)i].l, params + 4 * i, 32);
         EmuProgram *e = new EmuProgram();
-        e->P = compile_circuit(main_name, ps, hcreate != 0);
+        e->P = compile_circuit(main_name, ps, (hcreate & 1) != 0, false, (hcreate & 0x100) ? 1 : 0);
         e->invtab = build_inverse_table();
         return e;
     } catch (const std::exception &ex) { if (err) snprintf(err, (size_t)errlen, "%s", ex.what()); return nullptr; }
@@ -39,6 +39,12 @@ void pob_emu_stats(void *h, uint64_t *out) {
     out[0] = P.n_signals; out[1] = P.n_outputs; out[2] = P.n_inputs; out[3] = P.n_words; out[4] = P.n_vals;
     out[5] = P.ops.size(); out[6] = P.absorbs.size(); out[7] = P.levels.size(); out[8] = P.tiles.size();
     out[9] = P.codes.size(); out[10] = P.konst.size(); out[11] = P.n_round_blocks;
+}
+// reduced program: map[k] = --O0 index of reduced entry k; returns the --O0 signal count
+uint64_t pob_emu_witness_map(void *h, uint32_t *map) {
+    const Program &P = ((EmuProgram *)h)->P;
+    if (map) memcpy(map, P.witness_map.data(), P.witness_map.size() * 4);
+    return P.n_signals_o0;
 }
 const char *pob_emu_schema(void *h) { return ((EmuProgram *)h)->P.input_schema.c_str(); }
 
@@ -75,7 +81,7 @@ uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_
             }
     if (outputs)
         for (uint32_t i = 0; i < P.n_outputs; i++)
-            vm_expand(P.codes[ROUND_SIGNALS + 1 + i], U.data(), 0, P.val_base, P.konst.data(), outputs + 4 * i);
+            vm_expand(P.codes[P.out_code_off + i], U.data(), 0, P.val_base, P.konst.data(), outputs + 4 * i);
     return status == STATUS_OK ? 0 : status;
 }
 }
