@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the timed oracle leg (the in-run digest parity check still runs: --parity)")
     ap.add_argument("--parity", type=int, default=2, help="instances whose whole-witness digest is compared with the oracle when the cpu baseline is skipped (0 = none)")
     ap.add_argument("--consume-batch", type=int, default=256, help="instances of the 'every witness consumed on the GPU' figure (0 = skip)")
+    ap.add_argument("--reduced-batch", type=int, default=256, help="instances of the reduced (--O1-style) witness figure (0 = skip)")
     ap.add_argument("--export-sample", type=int, default=24, help="instances of the 'every witness exported to the host' figure (0 = skip)")
     ap.add_argument("--seed", type=int, default=7503)
     a = ap.parse_args()
@@ -322,6 +323,22 @@ def main():
         rx, st = circuit.export_batch(None, n=ne, staged=True)
         handoff["exported_to_host"] = {"value": st["witnesses"] / (st["total_ms"] / 1e3), "unit": "witnesses/s", "instances": int(st["witnesses"]), "d2h_gbs": st["d2h_gbs"],
                                        "sink": "pinned host staging ring over 2 copy streams (pob_export_batch, paths=NULL); PCIe-bound"}
+    reduced = None
+    if a.reduced_batch > 0 and rank == 0:
+        # the reduced (`--O1`-style) witness of the same instances (POB_CREATE_O1), informational
+        nb = min(a.batch, a.reduced_batch)
+        circuit.close()
+        cr = pob_b200.Circuit(expr, device=local_rank, opt=1)
+        cr.stage(pinned.array[:nb])
+        cr.run_packed(None, n=nb, staged=True, discard=True)
+        rr = cr.run_packed(None, n=nb, staged=True, discard=True)
+        reduced = {"value": nb / (rr.timing["total_ms"] / 1e3), "unit": "witnesses/s", "instances": nb, "n_signals": cr.n_signals, "witness_bytes": 32 * cr.n_signals,
+                   "fraction_of_o0": cr.n_signals / desc["n_signals"], "expand_gbs": 32.0 * cr.n_signals * nb / (rr.timing["expand_ms"] / 1e3) / 1e9,
+                   "eval_ms_total": rr.timing["eval_ms"], "expand_ms_total": rr.timing["expand_ms"], "ok": int(rr.n_ok),
+                   "what": "signals tied by signal=signal / signal=constant constraints dropped (pob_b200.h POB_CREATE_O1); order parity unpinned"}
+        cr.close()
+        circuit = pob_b200.Circuit(expr, device=local_rank)
+        circuit.stage(pinned.array)
     if rank == 0:
         one = pinned.array[:1]
         circuit.run_packed(one)
@@ -363,7 +380,7 @@ def main():
                 "details": {"resident_slots": desc["n_slots"], "wall_ms_per_step": wall_ms_max / a.steps, "eval_chunk": desc["chunk"], "expand_group": desc["expand_group"],
                             "eval_kernel": {"ms_per_launch": eval_ms / max(1, eval_launches), "instances_per_launch": min(desc["chunk"], a.batch),
                                             "note": "runs concurrently with the expand kernels on a higher-priority stream"}},
-                "handoff": handoff, "latency": latency,
+                "handoff": handoff, "latency": latency, "reduced_witness": reduced,
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "witnesses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": "host pinned inputs -> pob_run_batch(POB_RUN_DISCARD) -> status + output signals on host; generation-only: see `handoff` for the runs in which every witness is consumed / exported"},

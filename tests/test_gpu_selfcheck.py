@@ -80,3 +80,48 @@ def test_selfcheck_main_shape():
         assert c.selfcheck_keccak(0) == (2016, 0)
     finally:
         c.close()
+
+
+def test_reduced_witness_on_gpu_equals_o0_through_the_map(tmp_path):
+    """POB_CREATE_O1: the reduced witness of Spend(31) and of main_proof_of_burn, entry by entry, equals
+    the oracle's --O0 witness through pob_witness_map; outputs and rejection are unchanged; the .wtns header carries the
+    reduced count."""
+    import pob_b200
+    from pob_b200 import synth
+    from oracle import oracle
+    s = suite("test_spend")
+    c = pob_b200.Circuit("Spend(31)", max_slots=2, opt=1)
+    try:
+        assert (c.n_signals, c.desc["n_signals_o0"], c.desc["opt_level"]) == (259945, 2603360, 1)
+        m = c.witness_map()
+        res = c.run([s["cases"][0]["input"], s["cases"][1]["input"]])
+        assert res.status[0] == 0 and res.status[1] != 0
+        w = oracle.run("Spend(31)", s["cases"][0]["input"])
+        assert res.outputs[0] == w.outputs() and np.array_equal(c.witness(0), w.limbs[m])
+        w.free()
+        f = str(tmp_path / "reduced.wtns")
+        c.write_wtns(0, f)
+        raw = open(f, "rb").read()
+        assert len(raw) == 76 + 32 * 259945 and int.from_bytes(raw[60:64], "little") == 259945
+        with pytest.raises(pob_b200.PobError):
+            c.selfcheck(0)                                   # the constraint system is stated over the --O0 layout
+    finally:
+        c.close()
+    shape = (16, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)
+    insts = synth.make_batch(40, shape, seed=808)
+    packed = synth.pack_instances(insts, shape)
+    c = pob_b200.Circuit(pob_b200.MAIN_PROOF_OF_BURN, opt=1, max_slots=40)
+    try:
+        assert (c.n_signals, c.desc["n_signals_o0"]) == (21454051, 215907954) and c.desc["n_slots"] == 40
+        m = c.witness_map()
+        res = c.run_packed(packed)
+        assert (res.status == 0).all()
+        for i in (0, 39):
+            w = oracle.run_flat(*oracle.parse_main(pob_b200.MAIN_PROOF_OF_BURN), packed[i])
+            try:
+                assert w.ok and res.outputs[i] == w.outputs()
+                assert np.array_equal(c.witness(i), w.limbs[m]), "instance %d" % i
+            finally:
+                w.free()
+    finally:
+        c.close()
