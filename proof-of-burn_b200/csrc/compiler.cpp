@@ -1971,6 +1971,41 @@ const char *main_input_schema(const std::string &main_name, int *nparams) {
     return nullptr;
 }
 
+// 64-signal group descriptors of a table of BIT codes relative to a round's word base (program.h: Program::round_desc);
+// throws when a group is neither a lane nor a phase of a gate array (the derivation doubles as a check of the table)
+static std::vector<uint64_t> derive_round_desc(const Code *codes, uint32_t n) {
+    if (n % 64) throw std::runtime_error("pob: internal: round table size is not a multiple of 64");
+    std::vector<uint64_t> desc(n / 64);
+    for (uint32_t g = 0; g < n / 64; g++) {
+        const Code *c = codes + 64 * g;
+        auto W = [&](int j) { return (code_payload(c[j]) >> 6); };
+        auto Bt = [&](int j) { return (code_payload(c[j]) & 63u); };
+        bool ok = true, lane = true;
+        for (int j = 0; j < 64; j++) { if (code_kind(c[j]) != K_BIT) ok = false; if (W(j) != W(0) || Bt(j) != (uint32_t)j) lane = false; }
+        uint64_t d = 0;
+        if (ok && lane) d = (uint64_t)W(0);
+        else if (ok) {
+            bool found = false;
+            for (uint32_t f = 0; f < 3 && !found; f++) {
+                uint32_t w[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}; bool m = true;
+                for (uint32_t j = 0; j < 64 && m; j++) {
+                    uint32_t sidx = 64 * f + j, gi = sidx / 3, mem = sidx % 3;
+                    if (Bt((int)j) != gi) m = false;
+                    else if (w[mem] == 0xffffffffu) w[mem] = W((int)j);
+                    else if (w[mem] != W((int)j)) m = false;
+                }
+                if (m) { d = (uint64_t)w[0] | ((uint64_t)w[1] << 16) | ((uint64_t)w[2] << 32) | ((uint64_t)(1 + f) << 48); found = true; }
+            }
+            ok = found;
+        }
+        // k_expand_round indexes its shared-memory word table with all three descriptor words
+        if (!ok || (d & 0xffff) >= ROUND_WORDS_SPAN || ((d >> 48) && (((d >> 16) & 0xffff) >= ROUND_WORDS_SPAN || ((d >> 32) & 0xffff) >= ROUND_WORDS_SPAN)))
+            throw std::runtime_error("pob: internal: round table group does not fit a descriptor");
+        desc[g] = d;
+    }
+    return desc;
+}
+
 // ---- `--O1`-style reduction --------------------------------------------------------------------
 // circom's default simplifier (the reference deploys through it: .github/workflows/circuitscan.yml:29,36) removes signals
 // tied by `signal = signal` and `signal = constant` constraints.  Here: union-find over the eq records of the constraint
@@ -2125,48 +2160,25 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     P.codes.resize(ROUND_SIGNALS);
     { LaneSink S{P.codes.data(), 0}; emit_round(S);
       if ((size_t)(S.p - P.codes.data()) != ROUND_SIGNALS) throw std::runtime_error("pob: internal: round table size mismatch"); }
-    // derive (and thereby verify) the 64-signal group descriptors of the round table
-    P.round_desc.resize(ROUND_SIGNALS / 64);
-    for (uint32_t g = 0; g < ROUND_SIGNALS / 64; g++) {
-        const Code *c = &P.codes[64 * g];
-        auto W = [&](int j) { return (code_payload(c[j]) >> 6); };
-        auto Bt = [&](int j) { return (code_payload(c[j]) & 63u); };
-        bool ok = true, lane = true;
-        for (int j = 0; j < 64; j++) { if (code_kind(c[j]) != K_BIT) ok = false; if (W(j) != W(0) || Bt(j) != (uint32_t)j) lane = false; }
-        uint64_t d = 0;
-        if (ok && lane) d = (uint64_t)W(0);
-        else if (ok) {
-            bool found = false;
-            for (uint32_t f = 0; f < 3 && !found; f++) {
-                uint32_t w[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}; bool m = true;
-                for (uint32_t j = 0; j < 64 && m; j++) {
-                    uint32_t sidx = 64 * f + j, gi = sidx / 3, mem = sidx % 3;
-                    if (Bt((int)j) != gi) m = false;
-                    else if (w[mem] == 0xffffffffu) w[mem] = W((int)j);
-                    else if (w[mem] != W((int)j)) m = false;
-                }
-                if (m) { d = (uint64_t)w[0] | ((uint64_t)w[1] << 16) | ((uint64_t)w[2] << 32) | ((uint64_t)(1 + f) << 48); found = true; }
-            }
-            ok = found;
-        }
-        // k_expand_round indexes its shared-memory word table with all three descriptor words
-        if (!ok || (d & 0xffff) >= ROUND_WORDS_SPAN || ((d >> 48) && (((d >> 16) & 0xffff) >= ROUND_WORDS_SPAN || ((d >> 32) & 0xffff) >= ROUND_WORDS_SPAN)))
-            throw std::runtime_error("pob: internal: round table group does not fit a descriptor");
-        P.round_desc[g] = d;
-    }
+    P.round_desc = derive_round_desc(P.codes.data(), ROUND_SIGNALS);
     P.n_round_blocks = B.n_round_blocks; P.n_flat_signals = B.flat_n; P.n_signals_o0 = B.nsig; P.opt_level = opt_level;
     if (opt_level) {
         // reduced program: codes = [retained entries of the shared round table | retained flat codes]; every tile goes
         // through the generic code path (k_expand_codes), round blocks as tiles over the shared table with their own ubase
         std::vector<Code> rt(round_keep.size()); for (size_t k = 0; k < round_keep.size(); k++) rt[k] = P.codes[round_keep[k]];
-        P.codes = rt; P.round_desc.assign(1, 0);
+        P.codes = rt;
         const uint32_t RT = (uint32_t)round_keep.size();
+        // what stays of a round block are whole 64-signal lanes (the `out` of every gate of a gate array, the NotArray outputs):
+        // the descriptor-driven k_expand_round applies to the reduced blocks too
+        bool fast_round = true;
+        try { P.round_desc = derive_round_desc(rt.data(), RT); } catch (const std::exception &) { fast_round = false; P.round_desc.assign(1, 0); }
+        if (P.round_desc.empty()) P.round_desc.assign(1, 0);
         P.out_code_off = RT + 1;
         uint64_t dst = 0; size_t mp = 0;
         const uint32_t ts = TILE_SIGNALS;
         for (auto &sg : B.segs) {
             if (sg.round) {
-                for (uint32_t done = 0; done < RT; done += ts) { Tile t; t.dst = dst + done; t.n = std::min(ts, RT - done); t.code_off = done; t.ubase = sg.ubase; t.pad = 0; P.tiles.push_back(t); }
+                for (uint32_t done = 0; done < RT; done += ts) { Tile t; t.dst = dst + done; t.n = std::min(ts, RT - done); t.code_off = done; t.ubase = sg.ubase; t.pad = fast_round ? 1 : 0; P.tiles.push_back(t); }
                 dst += RT; mp += RT;
             } else {
                 const size_t first = P.codes.size();
@@ -2179,6 +2191,7 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
         if (dst != P.witness_map.size() || mp != P.witness_map.size()) throw std::runtime_error("pob: internal: reduced layout does not add up");
         P.n_signals = dst;
         if (!user_wants_constraints) { P.cons_flat = ConsSet(); P.cons_round = ConsSet(); P.has_constraints = false; }
+        std::stable_sort(P.tiles.begin(), P.tiles.end(), [](const Tile &a, const Tile &b) { return a.pad > b.pad; });
         return P;
     }
     P.codes.insert(P.codes.end(), B.flat, B.flat + B.flat_n);

@@ -159,44 +159,93 @@ struct EvalArgs {
     const uint64_t *inputs;                       // chunk base: instance j at inputs + j * n_inputs * 4
     uint32_t *status; uint64_t *outputs;          // chunk base
     long long *prof;                              // tuning only: per-level clock64 stamps of instance 0 (or null)
+    uint32_t pos_konst_bytes, levels_bytes;       // sizes of the two TMA-staged tables (multiples of 16 bytes)
 };
 
+// ---- TMA (bulk async copy engine) and cluster primitives ---------------------------------------------------------------
+// cp.async.bulk global -> shared with mbarrier completion (SASS: UBLKCP.S.G + SYNCS.ARRIVE.TRANS64); the copies are issued by
+// one thread and land while the CTA does other work.  Addresses and sizes must be multiples of 16 bytes.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// all threads of all CTAs of the cluster; release/acquire at cluster scope orders the global-memory store traffic of a level
+// before the loads of the next one
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// k_eval: one thread-block CLUSTER per proof instance (cluster size C = 1, 2, 4 or 8 CTAs of THREADS threads; C = 1 is a plain
+// CTA).  The levelised program is spread over all C*THREADS threads / all warps of the cluster, levels are separated by a
+// cluster barrier; the instance store lives in global memory (L2-resident).  Poseidon round / MDS constants (C, S, M, P of
+// circomlib/circuits/poseidon_constants.circom, Montgomery form) and the level table are staged in shared memory by TMA.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
-    const uint32_t inst = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    extern __shared__ __align__(128) uint8_t dyn_smem[];
+    const uint32_t C = cluster_nctarank(), rank = cluster_ctarank();
+    const uint32_t inst = blockIdx.x / C, tid = threadIdx.x;
+    const uint32_t gt = rank * THREADS + tid, GT = C * THREADS;
     uint64_t *U = a.stores + (uint64_t)inst * a.store_stride;
     __shared__ uint32_t s_status;
-    if (tid == 0) s_status = STATUS_OK;
+    __shared__ __align__(8) uint64_t s_bar;
+    Fr *s_pk = reinterpret_cast<Fr *>(dyn_smem);
+    Level *s_levels = reinterpret_cast<Level *>(dyn_smem + a.pos_konst_bytes);
+    if (tid == 0) { s_status = STATUS_OK; mbar_init(&s_bar, 1); if (rank == 0) a.status[inst] = STATUS_OK; }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar, a.pos_konst_bytes + a.levels_bytes);
+        tma_load_1d(s_pk, a.pos_konst, a.pos_konst_bytes, &s_bar);
+        tma_load_1d(s_levels, a.levels, a.levels_bytes, &s_bar);
+    }
     const uint64_t *in = a.inputs + (uint64_t)inst * a.n_inputs * 4;
     // inputs -> first value slots, reduced mod p like the circom loader does (a caller may hand over limbs >= p)
-    for (uint32_t i = tid; i < a.n_inputs; i += nthr) {
+    for (uint32_t i = gt; i < a.n_inputs; i += GT) {
         Fr v = vm_load_val(in + 4ull * i);
         while (fr_geq_p(v)) { Fr t; fr_raw_sub(t, v, fr_p()); v = t; }
         vm_store_val(U + a.val_base + 4ull * i, v);
     }
-    __syncthreads();
+    mbar_wait(&s_bar, 0);
+    cluster_sync_all();
     VmCtx x{U, a.val_base, a.konst, a.aux, a.invtab, &s_status};
-    const uint32_t warp = tid >> 5, nwarp = nthr >> 5;
+    const uint32_t gwarp = gt >> 5, nwarp = GT >> 5;
     for (uint32_t lv = 0; lv < a.n_levels; lv++) {
-        if (a.prof && inst == 0 && tid == 0) a.prof[lv] = clock64();
-        const Level L = a.levels[lv];
-        for (uint32_t i = L.t_begin + tid; i < L.t_end; i += nthr) vm_exec_op(x, a.ops[i]);
+        if (a.prof && inst == 0 && gt == 0) a.prof[lv] = clock64();
+        const Level L = s_levels[lv];
+        for (uint32_t i = L.t_begin + gt; i < L.t_end; i += GT) vm_exec_op(x, a.ops[i]);
         // warp ops: Poseidons take the first warps (long), Keccak absorbs the next ones
-        for (uint32_t q = L.p_begin + warp; q < L.p_end; q += nwarp) poseidon_warp(x, a.poseidons[q], a.pos_konst);
-        { const uint32_t np = (L.p_end - L.p_begin) % nwarp, wv = (warp + nwarp - np) % nwarp;
+        for (uint32_t q = L.p_begin + gwarp; q < L.p_end; q += nwarp) poseidon_warp(x, a.poseidons[q], s_pk);
+        { const uint32_t np = (L.p_end - L.p_begin) % nwarp, wv = (gwarp + nwarp - np) % nwarp;
           for (uint32_t w = L.w_begin + wv; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]);
-          const uint32_t nw2 = (np + (L.w_end - L.w_begin)) % nwarp, sv = (warp + nwarp - nw2) % nwarp;
+          const uint32_t nw2 = (np + (L.w_end - L.w_begin)) % nwarp, sv = (gwarp + nwarp - nw2) % nwarp;
           for (uint32_t q = L.s_begin + sv; q < L.s_end; q += nwarp) psum_warp(x, a.psums[q]); }
-        __syncthreads();
+        cluster_sync_all();
     }
-    if (a.prof && inst == 0 && tid == 0) a.prof[a.n_levels] = clock64();
+    if (a.prof && inst == 0 && gt == 0) a.prof[a.n_levels] = clock64();
     // IsZero inverse hints: no consumers, done last.  Table-sized inputs are spread over all threads; the ones expected
-    // to need a real inversion go to 256 threads so that only 8 warps pay for a Fermat ladder (one per thread).
-    vm_inv_batch(x, a.ops, a.inv_begin, a.ginv_begin, tid, nthr);
-    if (tid < 256) vm_inv_batch(x, a.ops, a.ginv_begin, a.inv_end, tid, 256);
-    if (a.prof && inst == 0) { __syncthreads(); if (tid == 0) a.prof[a.n_levels + 1] = clock64(); }
-    if (tid == 0) a.status[inst] = (s_status == STATUS_OK) ? 0u : s_status;
-    for (uint32_t i = tid; i < a.n_outputs; i += nthr) {
+    // to need a real inversion go to 256 threads per CTA so that only 8 warps per SM pay for an inversion (one per thread).
+    vm_inv_batch(x, a.ops, a.inv_begin, a.ginv_begin, gt, GT);
+    if (tid < 256) vm_inv_batch(x, a.ops, a.ginv_begin, a.inv_end, rank * 256 + tid, C * 256);
+    if (a.prof && inst == 0) { cluster_sync_all(); if (gt == 0) a.prof[a.n_levels + 1] = clock64(); }
+    __syncthreads();
+    if (tid == 0 && s_status != STATUS_OK) atomicMin(a.status + inst, s_status);
+    cluster_sync_all();
+    if (gt == 0 && a.status[inst] == STATUS_OK) a.status[inst] = 0u;
+    for (uint32_t i = gt; i < a.n_outputs; i += GT) {
         uint64_t v[4]; vm_expand(a.out_codes[i], U, 0, a.val_base, a.konst, v);
         uint64_t *o = a.outputs + ((uint64_t)inst * a.n_outputs + i) * 4;
         o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3];
@@ -230,11 +279,22 @@ __global__ void __launch_bounds__(T) k_expand_round(const ExpandArgs a) {
     const Tile t = a.tiles[blockIdx.x];
     const uint64_t *Ub = a.stores + (uint64_t)(gi - a.chunk_first) * a.store_stride + t.ubase;
     uint64_t *W = a.wit[blockIdx.y] + t.dst * 4;
-    __shared__ uint2 sD[MAX_TILE_SIGNALS / 64]; __shared__ uint64_t sW[ROUND_WORDS_SPAN + 1];
-    const uint2 *D = a.round_desc + (t.code_off >> 6);
-    for (uint32_t i = threadIdx.x; i < ((t.n + 63) >> 6); i += T) sD[i] = __ldg(D + i);
-    for (uint32_t i = threadIdx.x; i < ROUND_WORDS_SPAN; i += T) sW[i] = Ub[i];
+    __shared__ __align__(16) uint2 sD[MAX_TILE_SIGNALS / 64];
+    __shared__ __align__(16) uint64_t sWraw[ROUND_WORDS_SPAN + 3];
+    __shared__ __align__(8) uint64_t s_bar;
+    // the tile's descriptors and the round's lane words arrive by TMA: two bulk copies issued by one thread, completion on an
+    // mbarrier.  The word window starts at the 16-byte boundary at or below the round base (the base is only 8-byte aligned).
+    const uint32_t odd = (uint32_t)((reinterpret_cast<uintptr_t>(Ub) >> 3) & 1u);
+    const uint32_t nd = (t.n + 63) >> 6, d_bytes = ((nd + 1) & ~1u) * 8u, w_bytes = (ROUND_WORDS_SPAN + 3) / 2 * 16u;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&s_bar, d_bytes + w_bytes);
+        tma_load_1d(sD, a.round_desc + (t.code_off >> 6), d_bytes, &s_bar);
+        tma_load_1d(sWraw, Ub - odd, w_bytes, &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+    const uint64_t *sW = sWraw + odd;
 #pragma unroll 8
     for (uint32_t k = threadIdx.x; k < t.n; k += T) {
         const uint2 d = sD[k >> 6];

@@ -155,7 +155,9 @@ struct pob_handle {
     // per SM: fewer concurrent write streams give the DRAM controllers longer same-row bursts -- measured 7.35 TB/s with
     // 2 CTAs/SM vs 7.26 / 7.19 / 7.09 / 6.97 TB/s with 3 / 4 / 5 / 8, and 5.96 TB/s with 1 (profiles/r01_expand_sweep.md)
     uint32_t round_dyn_smem = 85 * 1024;
-    uint32_t round_threads = 256, codes_dyn_smem = 0; int eval_threads = 1024; bool serialize = false;   // changed by POB_TUNING knobs only
+    uint32_t round_threads = 256, codes_dyn_smem = 0; bool serialize = false;   // changed by POB_TUNING knobs only
+    int eval_threads = 1024; uint32_t eval_cluster = 1;   // k_eval: threads per CTA, CTAs per instance (thread-block cluster)
+    uint32_t pos_konst_bytes = 0, levels_bytes = 0, eval_smem = 0;
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
     cudaEvent_t ev_eval_done[RING] = {nullptr, nullptr}, ev_exp_done[RING] = {nullptr, nullptr}, ev_h2d[RING] = {nullptr, nullptr},
                 ev_start = nullptr, ev_end = nullptr, ev_tmp = nullptr;
@@ -271,12 +273,18 @@ static void enqueue_eval(pob_handle *h, uint32_t c) {
     uint64_t *stores = h->d_stores + (size_t)r * E * h->store_stride;
     EvalArgs ea{h->d_ops, h->d_abs, h->d_pos, h->d_pos_konst, h->d_psums, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.ginv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
                 h->d_codes + P.out_code_off, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
-                h->d_status + first, h->d_outputs + (size_t)first * no * 4, (c == 0) ? h->d_prof : nullptr};
+                h->d_status + first, h->d_outputs + (size_t)first * no * 4, (c == 0) ? h->d_prof : nullptr, h->pos_konst_bytes, h->levels_bytes};
     CU(cudaEventRecord(B.e0[c], h->s_eval));
-    switch (h->eval_threads) {
-    case 256: k_eval<256><<<cnt, 256, 0, h->s_eval>>>(ea); break;
-    case 512: k_eval<512><<<cnt, 512, 0, h->s_eval>>>(ea); break;
-    default: k_eval<1024><<<cnt, 1024, 0, h->s_eval>>>(ea); break;
+    {   // one cluster of eval_cluster CTAs per instance
+        cudaLaunchConfig_t cfg{}; cudaLaunchAttribute at[1];
+        cfg.gridDim = dim3(cnt * h->eval_cluster); cfg.blockDim = dim3((unsigned)h->eval_threads); cfg.dynamicSmemBytes = h->eval_smem; cfg.stream = h->s_eval;
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = h->eval_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        switch (h->eval_threads) {
+        case 256: CU(cudaLaunchKernelEx(&cfg, k_eval<256>, ea)); break;
+        case 512: CU(cudaLaunchKernelEx(&cfg, k_eval<512>, ea)); break;
+        default: CU(cudaLaunchKernelEx(&cfg, k_eval<1024>, ea)); break;
+        }
     }
     CU(cudaEventRecord(B.e1[c], h->s_eval));
     CU(cudaEventRecord(h->ev_eval_done[r], h->s_eval));
@@ -505,6 +513,8 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         const Program &P = h->P;
         CU(cudaSetDevice(device));
         h->d_ops = upload(P.ops); h->d_psums = upload(P.psums); h->d_pos = upload(P.poseidons); h->d_pos_konst = upload(P.pos_konst); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
+        h->pos_konst_bytes = (uint32_t)(P.pos_konst.size() * sizeof(Fr)); h->levels_bytes = (uint32_t)(std::max<size_t>(1, P.levels.size()) * sizeof(Level));   // both multiples of 32
+        h->eval_smem = h->pos_konst_bytes + h->levels_bytes;
         h->d_konst = upload(P.konst); h->d_codes = upload(P.codes);
         if (const char *v = tune_env("POB_TILE_FILTER")) {      // TUNING build only: 1 = KeccakfRound tiles only, 2 = the others only (witness incomplete!)
             std::vector<Tile> sub; for (const Tile &t : P.tiles) if ((atoi(v) == 1) == (t.pad != 0)) sub.push_back(t);
@@ -515,7 +525,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         { std::vector<uint64_t> bases; for (const Tile &t : P.tiles) if (t.pad && t.code_off == 0) bases.push_back(t.dst);
           std::sort(bases.begin(), bases.end()); h->n_blocks = (uint32_t)bases.size(); h->d_block_base = upload(bases); }
         h->d_invtab = upload(build_inverse_table());
-        h->d_round_desc = upload(P.round_desc);
+        { std::vector<uint64_t> rd = P.round_desc; rd.resize(rd.size() + 2, 0); h->d_round_desc = upload(rd); }   // + 16 bytes: TMA copies whole 16-byte units
         // the small eval grid must get SMs while the expand grid (hundreds of thousands of CTAs) is draining:
         // eval runs on the highest-priority stream, expand on the lowest
         int pr_least = 0, pr_greatest = 0; CU(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
@@ -538,6 +548,9 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         // eval chunk: enough instances per launch to keep the SMs busy on small circuits, bounded by a ~0.5 GB store ring
         // half (main_proof_of_burn: 32; Spend: 1024)
         uint32_t chunk = (uint32_t)std::min<uint64_t>(1024, std::max<uint64_t>(32, (512ull << 20) / (h->store_stride * 8)));
+        // the reduced witness is ~10x smaller, so the eval kernel must cover all SMs to keep up with the expand kernels:
+        // one wave of one-CTA-per-SM instances (store ring 2 x 128 x 22.7 MB for the main shape)
+        if (P.opt_level) chunk = std::max<uint32_t>(chunk, 128);
         chunk -= chunk % 32;
         if (const char *v = tune_env("POB_EVAL_CHUNK")) chunk = (uint32_t)std::max(1, atoi(v));
         const uint64_t ring_bytes_per_inst = pob_handle::RING * (h->store_stride * 8 + (uint64_t)P.n_inputs * 32);
@@ -549,6 +562,12 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         // expand group: ~100 GB of witness per launch pair (main_proof_of_burn: 16 witnesses; Spend: up to the whole chunk)
         h->xgroup = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(nslots, chunk), std::max<uint64_t>(16, (100ull << 30) / wbytes));
         if (const char *v = tune_env("POB_EVAL_THREADS")) h->eval_threads = atoi(v);
+        if (const char *v = tune_env("POB_EVAL_CLUSTER")) h->eval_cluster = (uint32_t)std::max(1, std::min(8, atoi(v)));
+        if (h->eval_threads != 256 && h->eval_threads != 512) h->eval_threads = 1024;
+        if (h->eval_smem > 200 * 1024) throw std::runtime_error("the Poseidon constant and level tables do not fit in shared memory");
+        CU(cudaFuncSetAttribute(k_eval<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->eval_smem));
+        CU(cudaFuncSetAttribute(k_eval<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->eval_smem));
+        CU(cudaFuncSetAttribute(k_eval<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->eval_smem));
         if (const char *v = tune_env("POB_SERIALIZE")) h->serialize = atoi(v) != 0;
         if (const char *v = tune_env("POB_EXPAND_SMEM_KB")) h->round_dyn_smem = (uint32_t)atoi(v) * 1024u;
         if (const char *v = tune_env("POB_EXPAND_THREADS")) h->round_threads = (uint32_t)atoi(v);
