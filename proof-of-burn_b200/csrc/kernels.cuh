@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     __syncthreads();
     if (tid == 0 && s_status != STATUS_OK) atomicMin(a.status + inst, s_status);
     cluster_sync_all();
-    if (gt == 0 && a.status[inst] == STATUS_OK) a.status[inst] = 0u;
+    if (gt == 0 && atomicAdd(a.status + inst, 0u) == STATUS_OK) a.status[inst] = 0u;
     for (uint32_t i = gt; i < a.n_outputs; i += GT) {
         uint64_t v[4]; vm_expand(a.out_codes[i], U, 0, a.val_base, a.konst, v);
         uint64_t *o = a.outputs + ((uint64_t)inst * a.n_outputs + i) * 4;
