@@ -91,6 +91,11 @@ int pob_layout_info(const char *main_name, const uint64_t *params, int nparams, 
 /* input schema "name[d0][d1],name2,..." with dims as expressions over p0..p7; NULL if unknown template */
 const char *pob_input_schema(const char *main_name, int *nparams);
 
+/* host-only, order-pinning kit (the reference pins no witness ORDER: it holds no .sym / .wtns).  Writes
+ * one line `first_signal,n_own_signals,template` per component instance of the --O0 layout, in numbering order, for
+ * tools/diff_sym.py to compare with the `.sym` of a real `circom --O0 --sym` build.  *n_components receives the line count. */
+int pob_write_components(const char *main_name, const uint64_t *params, int nparams, int hcreate, const char *path, uint64_t *n_components);
+
 int pob_describe(const pob_handle *h, pob_desc *out);
 /* reduced witness only: map[k] = --O0 signal index of reduced witness entry k (n_signals entries) */
 int pob_witness_map(const pob_handle *h, uint32_t *map);

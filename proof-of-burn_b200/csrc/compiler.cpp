@@ -130,7 +130,11 @@ class Builder {
     ~Builder() { if (flat && flat != MAP_FAILED) munmap(flat, flat_cap * sizeof(Code)); }
 
     // ---- signals ----
-    Blk alloc(size_t n) {
+    // component list for the order-pinning kit (tools/diff_sym.py): every sub-component's own signals are one alloc()
+    struct Comp { uint64_t sig; uint64_t n; const char *tmpl; };
+    std::vector<Comp> *comps = nullptr;
+    Blk alloc(size_t n, const char *tmpl = nullptr) {
+        if (comps && tmpl) comps->push_back(Comp{nsig, n, tmpl});
         if (segs.empty() || segs.back().round) segs.push_back({nsig, flat_n, 0, false, 0});
         if (flat_n + n > flat_cap) throw std::runtime_error("pob: code arena exhausted");
         Blk b{nsig, flat_n};
@@ -139,6 +143,7 @@ class Builder {
     }
     std::vector<uint64_t> round_sigs;  // first signal of every KeccakfRound block, in emission order
     void round_block(uint32_t ubase) {
+        if (comps) comps->push_back(Comp{nsig, ROUND_SIGNALS, "KeccakfRound*"});       // expanded from the shared walk by the writer
         round_sigs.push_back(nsig);
         segs.push_back({nsig, 0, ROUND_SIGNALS, true, ubase});
         nsig += ROUND_SIGNALS; n_round_blocks++;
@@ -343,13 +348,13 @@ static Fr pow2_fr(unsigned n) { Fr r = fr_from_u64(1); for (unsigned i = 0; i < 
 // ============================================================================================================
 // AND :29-35 (own: out, a, b).  Scalar XOR/OR only occur inside the Keccak lane arrays (handled as lanes).
 static Blk T_AND(Builder &B, Code a, Code b) {
-    Blk o = B.alloc(3); B.at(o.pos + 1) = a; B.at(o.pos + 2) = b; B.at(o.pos) = B.mul(a, b);
+    Blk o = B.alloc(3, "AND"); B.at(o.pos + 1) = a; B.at(o.pos + 2) = b; B.at(o.pos) = B.mul(a, b);
     B.q_mul(o.sig + 1, o.sig + 2, o.sig);                                         // out <== a*b            gates.circom:34
     return o;
 }
 // MultiAND(n) :68-96
 static Blk T_MultiAND(Builder &B, int n, const Code *in) {
-    Blk o = B.alloc(1 + (size_t)n); B.copy(o.pos + 1, in, (size_t)n);
+    Blk o = B.alloc(1 + (size_t)n, "MultiAND"); B.copy(o.pos + 1, in, (size_t)n);
     if (n == 1) { B.at(o.pos) = in[0]; B.q_eq(o.sig, o.sig + 1); }                // out <== in[0]          :76
     else if (n == 2) {
         Blk a = T_AND(B, in[0], in[1]); B.at(o.pos) = B.at(a.pos);
@@ -358,7 +363,7 @@ static Blk T_MultiAND(Builder &B, int n, const Code *in) {
         int n1 = n / 2, n2 = n - n / 2;
         Blk a2, x0, x1;
         if (B.hcreate) {
-            a2 = B.alloc(3);
+            a2 = B.alloc(3, "AND");
             x0 = T_MultiAND(B, n1, in); x1 = T_MultiAND(B, n2, in + n1);
             Code u = B.at(x0.pos), v = B.at(x1.pos);
             B.at(a2.pos + 1) = u; B.at(a2.pos + 2) = v; B.at(a2.pos) = B.mul(u, v); B.at(o.pos) = B.at(a2.pos);
@@ -385,7 +390,7 @@ static Code bit_of(Builder &B, Code in, unsigned i) {
 }
 // Num2Bits(n) :25-39  own: out[n], in
 static Blk T_Num2Bits(Builder &B, int n, Code in) {
-    Blk o = B.alloc((size_t)n + 1);
+    Blk o = B.alloc((size_t)n + 1, "Num2Bits");
     for (int i = 0; i < n; i++) B.at(o.pos + (size_t)i) = bit_of(B, in, (unsigned)i);
     B.at(o.pos + (size_t)n) = in;
     B.chk_range(in, (unsigned)n, o.sig);
@@ -402,7 +407,7 @@ static Blk T_Num2Bits(Builder &B, int n, Code in) {
 }
 // Bits2Num(n) :55-67  own: out, in[n]
 static Blk T_Bits2Num(Builder &B, int n, const Code *in) {
-    Blk o = B.alloc((size_t)n + 1); B.copy(o.pos + 1, in, (size_t)n);
+    Blk o = B.alloc((size_t)n + 1, "Bits2Num"); B.copy(o.pos + 1, in, (size_t)n);
     std::vector<Code> terms; for (int i = 0; i < n; i++) terms.push_back(B.mul(in[i], B.pow2((unsigned)i)));
     B.at(o.pos) = B.sum_tree(terms);
     if (B.want_cs()) {
@@ -414,7 +419,7 @@ static Blk T_Bits2Num(Builder &B, int n, const Code *in) {
 }
 // CompConstant(ct) :25-73 with ct = p-1  own: out, in[254], parts[127], sout ; child Num2Bits(135)
 static Blk T_CompConstant(Builder &B, const Fr &ct, const Code *in) {
-    Blk o = B.alloc(1 + 254 + 127 + 1); B.copy(o.pos + 1, in, 254);
+    Blk o = B.alloc(1 + 254 + 127 + 1, "CompConstant"); B.copy(o.pos + 1, in, 254);
     size_t parts = o.pos + 255;
     Fr one = fr_from_u64(1);
     Fr b; { Fr t = fr_from_u64(1); for (int i = 0; i < 128; i++) t = fr_add(t, t); b = fr_sub(t, one); }
@@ -454,7 +459,7 @@ static Blk T_CompConstant(Builder &B, const Fr &ct, const Code *in) {
 }
 // AliasCheck :24-32  own: in[254]
 static Blk T_AliasCheck(Builder &B, const Code *in) {
-    Blk o = B.alloc(254); B.copy(o.pos, in, 254);
+    Blk o = B.alloc(254, "AliasCheck"); B.copy(o.pos, in, 254);
     Fr m1; Fr one = fr_from_u64(1); fr_raw_sub(m1, fr_p(), one);
     Blk cc = T_CompConstant(B, m1, in);
     B.chk_eq(B.at(cc.pos), ZERO, o.sig);
@@ -464,7 +469,7 @@ static Blk T_AliasCheck(Builder &B, const Code *in) {
 }
 // Num2Bits_strict :41-53  own: out[254], in
 static Blk T_Num2Bits_strict(Builder &B, Code in) {
-    Blk o = B.alloc(255); B.at(o.pos + 254) = in;
+    Blk o = B.alloc(255, "Num2Bits_strict"); B.at(o.pos + 254) = in;
     Blk nb, ac;
     if (B.hcreate) {
         std::vector<Code> bits(254); for (int i = 0; i < 254; i++) bits[i] = bit_of(B, in, (unsigned)i);
@@ -484,7 +489,7 @@ static Blk T_Num2Bits_strict(Builder &B, Code in) {
 // ============================================================================================================
 // IsZero :24-35  own: out, in, inv
 static Blk T_IsZero(Builder &B, Code in, bool likely_large = false) {
-    Blk o = B.alloc(3); B.at(o.pos + 1) = in; B.at(o.pos + 2) = B.inv(in, likely_large); B.at(o.pos) = B.isz(in);
+    Blk o = B.alloc(3, "IsZero"); B.at(o.pos + 1) = in; B.at(o.pos + 2) = B.inv(in, likely_large); B.at(o.pos) = B.isz(in);
     if (B.want_cs()) {
         B.q_r1(LC().s(o.sig + 1), LC().s(o.sig + 2), LC().k(1).s(o.sig, -1));     // out <== -in*inv + 1            comparators.circom:32
         B.q_r1(LC().s(o.sig + 1), LC().s(o.sig), LC());                           // in*out === 0                   :33
@@ -494,7 +499,7 @@ static Blk T_IsZero(Builder &B, Code in, bool likely_large = false) {
 }
 // IsEqual :37-46  own: out, in[2] ; isz.in = in[1] - in[0]
 static Blk T_IsEqual(Builder &B, Code in0, Code in1, bool likely_large = false) {
-    Blk o = B.alloc(3); B.at(o.pos + 1) = in0; B.at(o.pos + 2) = in1;
+    Blk o = B.alloc(3, "IsEqual"); B.at(o.pos + 1) = in0; B.at(o.pos + 2) = in1;
     Blk z = T_IsZero(B, B.sub(in1, in0), likely_large); B.at(o.pos) = B.at(z.pos);
     B.q_lin(LC().s(z.sig + 1).s(o.sig + 2, -1).s(o.sig + 1));                     // in[1] - in[0] ==> isz.in       comparators.circom:43
     B.q_eq(o.sig, z.sig);                                                         // isz.out ==> out                :45
@@ -502,7 +507,7 @@ static Blk T_IsEqual(Builder &B, Code in0, Code in1, bool likely_large = false) 
 }
 // LessThan(n) :89-100
 static Blk T_LessThan(Builder &B, int n, Code in0, Code in1) {
-    Blk o = B.alloc(3); B.at(o.pos + 1) = in0; B.at(o.pos + 2) = in1;
+    Blk o = B.alloc(3, "LessThan"); B.at(o.pos + 1) = in0; B.at(o.pos + 2) = in1;
     Blk nb = T_Num2Bits(B, n + 1, B.sub(B.add(in0, B.pow2((unsigned)n)), in1));
     B.at(o.pos) = B.not1(B.at(nb.pos + (size_t)n));
     if (B.want_cs()) {
@@ -513,22 +518,22 @@ static Blk T_LessThan(Builder &B, int n, Code in0, Code in1) {
 }
 // LessEqThan(n) :105-115
 static Blk T_LessEqThan(Builder &B, int n, Code in0, Code in1) {
-    Blk o = B.alloc(3); B.at(o.pos + 1) = in0; B.at(o.pos + 2) = in1;
+    Blk o = B.alloc(3, "LessEqThan"); B.at(o.pos + 1) = in0; B.at(o.pos + 2) = in1;
     Blk lt = T_LessThan(B, n, in0, B.add(in1, ONE)); B.at(o.pos) = B.at(lt.pos);
     B.q_eq(lt.sig + 1, o.sig + 1); B.q_lin(LC().s(lt.sig + 2).s(o.sig + 2, -1).k(-1)); B.q_eq(o.sig, lt.sig);   // comparators.circom:111-113
     return o;
 }
 // GreaterEqThan(n) :131-141
 static Blk T_GreaterEqThan(Builder &B, int n, Code in0, Code in1) {
-    Blk o = B.alloc(3); B.at(o.pos + 1) = in0; B.at(o.pos + 2) = in1;
+    Blk o = B.alloc(3, "GreaterEqThan"); B.at(o.pos + 1) = in0; B.at(o.pos + 2) = in1;
     Blk lt = T_LessThan(B, n, in1, B.add(in0, ONE)); B.at(o.pos) = B.at(lt.pos);
     B.q_eq(lt.sig + 1, o.sig + 2); B.q_lin(LC().s(lt.sig + 2).s(o.sig + 1, -1).k(-1)); B.q_eq(o.sig, lt.sig);   // comparators.circom:137-139
     return o;
 }
 // Mux1 :34-48 + MultiMux1(1) :21-32
 static Blk T_Mux1(Builder &B, Code c0, Code c1, Code s) {
-    Blk o = B.alloc(4); B.at(o.pos + 1) = c0; B.at(o.pos + 2) = c1; B.at(o.pos + 3) = s;
-    Blk m = B.alloc(4); B.at(m.pos + 1) = c0; B.at(m.pos + 2) = c1; B.at(m.pos + 3) = s;
+    Blk o = B.alloc(4, "Mux1"); B.at(o.pos + 1) = c0; B.at(o.pos + 2) = c1; B.at(o.pos + 3) = s;
+    Blk m = B.alloc(4, "MultiMux1"); B.at(m.pos + 1) = c0; B.at(m.pos + 2) = c1; B.at(m.pos + 3) = s;
     B.at(m.pos) = B.fma(B.sub(c1, c0), s, c0);
     B.at(o.pos) = B.at(m.pos);
     if (B.want_cs()) {
@@ -545,7 +550,7 @@ static Blk T_Mux1(Builder &B, Code c0, Code c1, Code s) {
 // here only the circom numbering of its ~1100 signals is laid out over the op's value block.
 static Blk T_PoseidonEx(Builder &B, int nInputs, const Code *inputs, Code initialState) {
     const uint32_t t = (uint32_t)nInputs + 1; const PosLayout L = pos_layout(t);
-    Blk o = B.alloc(2 + (size_t)nInputs); B.copy(o.pos + 1, inputs, (size_t)nInputs); B.at(o.pos + 1 + (size_t)nInputs) = initialState;
+    Blk o = B.alloc(2 + (size_t)nInputs, "PoseidonEx"); B.copy(o.pos + 1, inputs, (size_t)nInputs); B.at(o.pos + 1 + (size_t)nInputs) = initialState;
     Code st[8], cur[8];
     st[0] = initialState; for (uint32_t j = 1; j < t; j++) st[j] = inputs[j - 1];
     const uint32_t base = B.poseidon(t, st);
@@ -559,7 +564,7 @@ static Blk T_PoseidonEx(Builder &B, int nInputs, const Code *inputs, Code initia
     auto F = [](const uint64_t (*tab)[4], uint32_t i) { Fr f; memcpy(f.l, tab[i], 32); return f; };
     uint64_t cidx[8];
     {   // ark[0]  (Ark :18-25  own: out[t], in[t])
-        Blk a = B.alloc(2 * t);
+        Blk a = B.alloc(2 * t, "Ark");
         for (uint32_t j = 0; j < t; j++) {
             B.at(a.pos + j) = V(j); B.at(a.pos + t + j) = st[j]; cur[j] = V(j);
             if (cs) {
@@ -570,7 +575,7 @@ static Blk T_PoseidonEx(Builder &B, int nInputs, const Code *inputs, Code initia
         }
     }
     auto sigma = [&](Code in, uint32_t off, uint64_t src) -> uint64_t {   // Sigma :5-16  own: out, in, in2, in4
-        Blk s = B.alloc(4); B.at(s.pos) = V(off + 2); B.at(s.pos + 1) = in; B.at(s.pos + 2) = V(off); B.at(s.pos + 3) = V(off + 1);
+        Blk s = B.alloc(4, "Sigma"); B.at(s.pos) = V(off + 2); B.at(s.pos + 1) = in; B.at(s.pos + 2) = V(off); B.at(s.pos + 3) = V(off + 1);
         if (cs) {
             B.q_eq(s.sig + 1, src);                                               // sigma.in <== previous layer's out
             B.q_mul(s.sig + 1, s.sig + 1, s.sig + 2); B.q_mul(s.sig + 2, s.sig + 2, s.sig + 3); B.q_mul(s.sig + 3, s.sig + 1, s.sig);   // :12-15
@@ -580,8 +585,8 @@ static Blk T_PoseidonEx(Builder &B, int nInputs, const Code *inputs, Code initia
     auto full = [&](uint32_t Fo, uint32_t coff, const uint64_t (*MT)[4]) {   // t x Sigma, Ark :18-25, Mix :27-39
         uint64_t so[8];
         for (uint32_t j = 0; j < t; j++) so[j] = sigma(cur[j], Fo + 3 * j, cidx[j]);
-        Blk a = B.alloc(2 * t); for (uint32_t j = 0; j < t; j++) { B.at(a.pos + j) = V(Fo + 3 * t + j); B.at(a.pos + t + j) = V(Fo + 3 * j + 2); }
-        Blk m = B.alloc(2 * t); for (uint32_t j = 0; j < t; j++) { B.at(m.pos + j) = V(Fo + 4 * t + j); B.at(m.pos + t + j) = V(Fo + 3 * t + j); cur[j] = V(Fo + 4 * t + j); }
+        Blk a = B.alloc(2 * t, "Ark"); for (uint32_t j = 0; j < t; j++) { B.at(a.pos + j) = V(Fo + 3 * t + j); B.at(a.pos + t + j) = V(Fo + 3 * j + 2); }
+        Blk m = B.alloc(2 * t, "Mix"); for (uint32_t j = 0; j < t; j++) { B.at(m.pos + j) = V(Fo + 4 * t + j); B.at(m.pos + t + j) = V(Fo + 3 * t + j); cur[j] = V(Fo + 4 * t + j); }
         if (cs) for (uint32_t j = 0; j < t; j++) {
             B.q_eq(a.sig + t + j, so[j]);                                         // ark.in[j] <== sigmaF[..][j].out
             B.q_lin(LC().s(a.sig + j).s(a.sig + t + j, -1).kf(fr_neg(F(TC, coff + j))));
@@ -594,7 +599,7 @@ static Blk T_PoseidonEx(Builder &B, int nInputs, const Code *inputs, Code initia
     for (uint32_t r = 0; r < L.rp; r++) {                                            // :138-160
         const uint32_t Bs = L.PB + r * (4 + t);
         const uint64_t so = sigma(cur[0], Bs, cidx[0]);
-        Blk m = B.alloc(2 * t);                                                      // MixS :52-65  own: out[t], in[t]
+        Blk m = B.alloc(2 * t, "MixS");                                              // MixS :52-65  own: out[t], in[t]
         for (uint32_t j = 0; j < t; j++) { B.at(m.pos + j) = V(Bs + 4 + j); B.at(m.pos + t + j) = j == 0 ? V(Bs + 3) : cur[j]; }
         for (uint32_t j = 0; j < t; j++) cur[j] = V(Bs + 4 + j);
         if (cs) {
@@ -609,7 +614,7 @@ static Blk T_PoseidonEx(Builder &B, int nInputs, const Code *inputs, Code initia
     for (uint32_t f = 0; f < 3; f++) full(L.SB + 5 * t * f, 5 * t + L.rp + f * t, TM);                  // :162-182
     uint64_t so[8];
     for (uint32_t j = 0; j < t; j++) so[j] = sigma(cur[j], L.LB + 3 * j, cidx[j]);  // :184-187
-    Blk ml = B.alloc(1 + t);                                                         // MixLast :41-50  own: out, in[t]
+    Blk ml = B.alloc(1 + t, "MixLast");                                                         // MixLast :41-50  own: out, in[t]
     B.at(ml.pos) = V(L.LB + 3 * t); for (uint32_t j = 0; j < t; j++) B.at(ml.pos + 1 + j) = V(L.LB + 3 * j + 2);
     B.at(o.pos) = V(L.LB + 3 * t);
     if (cs) {
@@ -622,7 +627,7 @@ static Blk T_PoseidonEx(Builder &B, int nInputs, const Code *inputs, Code initia
 }
 // Poseidon(n) :198-208
 static Blk T_Poseidon(Builder &B, int n, const Code *inputs) {
-    Blk o = B.alloc(1 + (size_t)n); B.copy(o.pos + 1, inputs, (size_t)n);
+    Blk o = B.alloc(1 + (size_t)n, "Poseidon"); B.copy(o.pos + 1, inputs, (size_t)n);
     Blk e = T_PoseidonEx(B, n, inputs, ZERO); B.at(o.pos) = B.at(e.pos);
     B.q_const(e.sig + 1 + (uint64_t)n, 0); B.q_eqn(e.sig + 1, o.sig + 1, (size_t)n); B.q_eq(o.sig, e.sig);   // poseidon.circom:203-207
     return o;
@@ -633,20 +638,20 @@ static Blk T_Poseidon(Builder &B, int n, const Code *inputs) {
 // ============================================================================================================
 // AssertBits(B) :13-18  own: in, bits[B]
 static Blk T_AssertBits(Builder &B, int nb_, Code in) {
-    Blk o = B.alloc(1 + (size_t)nb_); B.at(o.pos) = in;
+    Blk o = B.alloc(1 + (size_t)nb_, "AssertBits"); B.at(o.pos) = in;
     Blk nb = T_Num2Bits(B, nb_, in); B.copy(o.pos + 1, &B.at(nb.pos), (size_t)nb_);
     B.q_eq(nb.sig + (uint64_t)nb_, o.sig); B.q_eqn(o.sig + 1, nb.sig, (size_t)nb_);   // signal bits[B] <== Num2Bits(B)(in)   assert.circom:17
     return o;
 }
 // AssertByteString(N) :26-31
 static Blk T_AssertByteString(Builder &B, int N, const Code *in) {
-    Blk o = B.alloc((size_t)N); B.copy(o.pos, in, (size_t)N);
+    Blk o = B.alloc((size_t)N, "AssertByteString"); B.copy(o.pos, in, (size_t)N);
     for (int i = 0; i < N; i++) { Blk a = T_AssertBits(B, 8, in[i]); B.q_eq(a.sig, o.sig + (uint64_t)i); }   // AssertBits(8)(in[i])   assert.circom:29
     return o;
 }
 // AssertLessThan :40-47 / AssertLessEqThan :56-63 / AssertGreaterEqThan :72-79  own: a, b, out
 static Blk T_AssertCmp(Builder &B, int kind, int nb, Code a, Code b) {
-    Blk o = B.alloc(3); B.at(o.pos) = a; B.at(o.pos + 1) = b;
+    Blk o = B.alloc(3, kind == 0 ? "AssertLessThan" : kind == 1 ? "AssertLessEqThan" : "AssertGreaterEqThan"); B.at(o.pos) = a; B.at(o.pos + 1) = b;
     Blk ba = T_AssertBits(B, nb, a), bb = T_AssertBits(B, nb, b);
     Blk r = kind == 0 ? T_LessThan(B, nb, a, b) : kind == 1 ? T_LessEqThan(B, nb, a, b) : T_GreaterEqThan(B, nb, a, b);
     B.at(o.pos + 2) = B.at(r.pos);
@@ -665,7 +670,7 @@ static Blk T_AssertGreaterEqThan(Builder &B, int nb, Code a, Code b) { return T_
 // ============================================================================================================
 // Filter(N) :26-40  own: out[N], in, isEq[N]
 static Blk T_Filter(Builder &B, int N, Code in) {
-    size_t n = (size_t)N; Blk o = B.alloc(2 * n + 1); B.at(o.pos + n) = in;
+    size_t n = (size_t)N; Blk o = B.alloc(2 * n + 1, "Filter"); B.at(o.pos + n) = in;
     for (size_t i = 0; i < n; i++) {
         Blk e = T_IsEqual(B, c_const((uint32_t)i), in);
         Code eq = B.at(e.pos); B.at(o.pos + n + 1 + i) = eq;
@@ -681,7 +686,7 @@ static Blk T_Filter(Builder &B, int N, Code in) {
 }
 // Fit(M,N) :47-57  own: out[N], in[M]
 static Blk T_Fit(Builder &B, int M, int N, const Code *in) {
-    Blk o = B.alloc((size_t)N + (size_t)M); B.copy(o.pos + (size_t)N, in, (size_t)M);
+    Blk o = B.alloc((size_t)N + (size_t)M, "Fit"); B.copy(o.pos + (size_t)N, in, (size_t)M);
     for (int i = 0; i < N; i++) {
         B.at(o.pos + (size_t)i) = i < M ? in[i] : ZERO;
         if (i < M) B.q_eq(o.sig + (uint64_t)i, o.sig + (uint64_t)N + (uint64_t)i); else B.q_const(o.sig + (uint64_t)i, 0);   // array.circom:52-55
@@ -690,13 +695,13 @@ static Blk T_Fit(Builder &B, int M, int N, const Code *in) {
 }
 // Flatten(M,N) :64-72 / Reshape(M,N) :79-87: identity on row-major data  own: out[n], in[n]
 static Blk T_CopyArray(Builder &B, size_t n, const Code *in) {
-    Blk o = B.alloc(2 * n); B.copy(o.pos, in, n); B.copy(o.pos + n, in, n);
+    Blk o = B.alloc(2 * n, "Flatten/Reshape"); B.copy(o.pos, in, n); B.copy(o.pos + n, in, n);
     B.q_eqn(o.sig, o.sig + n, n);                                                 // out[i*N + j] <== in[i][j]   array.circom:69 / :84
     return o;
 }
 // Reverse(N) :94-99
 static Blk T_Reverse(Builder &B, int N, const Code *in) {
-    size_t n = (size_t)N; Blk o = B.alloc(2 * n); B.copy(o.pos + n, in, n);
+    size_t n = (size_t)N; Blk o = B.alloc(2 * n, "Reverse"); B.copy(o.pos + n, in, n);
     for (size_t i = 0; i < n; i++) { B.at(o.pos + i) = in[n - 1 - i]; B.q_eq(o.sig + i, o.sig + n + (n - 1 - i)); }   // out[i] <== in[N-1-i]   array.circom:97
     return o;
 }
@@ -706,7 +711,7 @@ static Blk T_Reverse(Builder &B, int N, const Code *in) {
 // ============================================================================================================
 // LittleEndianBytes2Num(N) :12-26  own: out, in[N]
 static Blk T_LittleEndianBytes2Num(Builder &B, int N, const Code *in) {
-    Blk o = B.alloc(1 + (size_t)N); B.copy(o.pos + 1, in, (size_t)N);
+    Blk o = B.alloc(1 + (size_t)N, "LittleEndianBytes2Num"); B.copy(o.pos + 1, in, (size_t)N);
     Blk abs_ = T_AssertByteString(B, N, in);
     std::vector<Code> terms; for (int i = 0; i < N; i++) terms.push_back(B.mul(in[i], B.pow2((unsigned)(8 * i))));
     B.at(o.pos) = B.sum_tree(terms);
@@ -718,7 +723,7 @@ static Blk T_LittleEndianBytes2Num(Builder &B, int N, const Code *in) {
 }
 // BigEndianBytes2Num(N) :33-39  own: out, in[N], inReversed[N]
 static Blk T_BigEndianBytes2Num(Builder &B, int N, const Code *in) {
-    size_t n = (size_t)N; Blk o = B.alloc(1 + 2 * n); B.copy(o.pos + 1, in, n);
+    size_t n = (size_t)N; Blk o = B.alloc(1 + 2 * n, "BigEndianBytes2Num"); B.copy(o.pos + 1, in, n);
     Blk r = T_Reverse(B, N, in); B.copy(o.pos + 1 + n, &B.at(r.pos), n);
     Blk l = T_LittleEndianBytes2Num(B, N, &B.at(r.pos)); B.at(o.pos) = B.at(l.pos);
     B.q_eqn(r.sig + n, o.sig + 1, n); B.q_eqn(o.sig + 1 + n, r.sig, n);           // signal inReversed[N] <== Reverse(N)(in)             convert.circom:37
@@ -729,21 +734,21 @@ static Blk T_BigEndianBytes2Num(Builder &B, int N, const Code *in) {
 static Blk T_Num2BitsSafe(Builder &B, int N, Code in) {
     size_t n = (size_t)N;
     if (N >= 254) {
-        Blk o = B.alloc(n + 1 + 254); B.at(o.pos + n) = in;
+        Blk o = B.alloc(n + 1 + 254, "Num2BitsSafe"); B.at(o.pos + n) = in;
         Blk st = T_Num2Bits_strict(B, in); B.copy(o.pos + n + 1, &B.at(st.pos), 254);
         Blk f = T_Fit(B, 254, N, &B.at(st.pos)); B.copy(o.pos, &B.at(f.pos), n);
         B.q_eq(st.sig + 254, o.sig + n); B.q_eqn(o.sig + n + 1, st.sig, 254);     // signal bitsStrict[254] <== Num2Bits_strict()(in)   convert.circom:51
         B.q_eqn(f.sig + n, o.sig + n + 1, 254); B.q_eqn(o.sig, f.sig, n);         // out <== Fit(254, N)(bitsStrict)                    :52
         return o;
     }
-    Blk o = B.alloc(n + 1); B.at(o.pos + n) = in;
+    Blk o = B.alloc(n + 1, "Num2BitsSafe"); B.at(o.pos + n) = in;
     Blk nb = T_Num2Bits(B, N, in); B.copy(o.pos, &B.at(nb.pos), n);
     B.q_eq(nb.sig + n, o.sig + n); B.q_eqn(o.sig, nb.sig, n);                     // out <== Num2Bits(N)(in)                            :54
     return o;
 }
 // Num2LittleEndianBytes(N) :69-82  own: out[N], in, bits[8N], byteArrays[N][8]
 static Blk T_Num2LittleEndianBytes(Builder &B, int N, Code in) {
-    size_t n = (size_t)N; Blk o = B.alloc(n + 1 + 16 * n); B.at(o.pos + n) = in;
+    size_t n = (size_t)N; Blk o = B.alloc(n + 1 + 16 * n, "Num2LittleEndianBytes"); B.at(o.pos + n) = in;
     Blk b = T_Num2BitsSafe(B, 8 * N, in); B.copy(o.pos + n + 1, &B.at(b.pos), 8 * n);
     Blk r = T_CopyArray(B, 8 * n, &B.at(b.pos)); B.copy(o.pos + n + 1 + 8 * n, &B.at(r.pos), 8 * n);
     B.q_eq(b.sig + 8 * n, o.sig + n); B.q_eqn(o.sig + n + 1, b.sig, 8 * n);       // signal bits[N*8] <== Num2BitsSafe(N*8)(in)          convert.circom:77
@@ -756,7 +761,7 @@ static Blk T_Num2LittleEndianBytes(Builder &B, int N, Code in) {
 }
 // Num2BigEndianBytes(N) :90-96  own: out[N], in, littleEndian[N]
 static Blk T_Num2BigEndianBytes(Builder &B, int N, Code in) {
-    size_t n = (size_t)N; Blk o = B.alloc(2 * n + 1); B.at(o.pos + n) = in;
+    size_t n = (size_t)N; Blk o = B.alloc(2 * n + 1, "Num2BigEndianBytes"); B.at(o.pos + n) = in;
     Blk le = T_Num2LittleEndianBytes(B, N, in); B.copy(o.pos + n + 1, &B.at(le.pos), n);
     Blk rv = T_Reverse(B, N, &B.at(le.pos)); B.copy(o.pos, &B.at(rv.pos), n);
     B.q_eq(le.sig + n, o.sig + n); B.q_eqn(o.sig + n + 1, le.sig, n);             // signal littleEndian[N] <== Num2LittleEndianBytes(N)(in)   convert.circom:94
@@ -765,7 +770,7 @@ static Blk T_Num2BigEndianBytes(Builder &B, int N, Code in) {
 }
 // Bytes2Nibbles(N) :103-125  own: out[2N], in[N], inDecomposed[N][8]
 static Blk T_Bytes2Nibbles(Builder &B, int N, const Code *in) {
-    size_t n = (size_t)N; Blk o = B.alloc(11 * n); B.copy(o.pos + 2 * n, in, n);
+    size_t n = (size_t)N; Blk o = B.alloc(11 * n, "Bytes2Nibbles"); B.copy(o.pos + 2 * n, in, n);
     for (size_t i = 0; i < n; i++) {
         Blk nb = T_Num2Bits(B, 8, in[i]); B.copy(o.pos + 3 * n + 8 * i, &B.at(nb.pos), 8);
         Code lo = ZERO, hi = ZERO;
@@ -786,7 +791,7 @@ static Blk T_Bytes2Nibbles(Builder &B, int N, const Code *in) {
 }
 // Nibbles2Bytes(n) :132-141  own: bytes[n], nibbles[2n]
 static Blk T_Nibbles2Bytes(Builder &B, int n_, const Code *nib) {
-    size_t n = (size_t)n_; Blk o = B.alloc(3 * n); B.copy(o.pos + n, nib, 2 * n);
+    size_t n = (size_t)n_; Blk o = B.alloc(3 * n, "Nibbles2Bytes"); B.copy(o.pos + n, nib, 2 * n);
     for (size_t i = 0; i < n; i++) {
         Blk a0 = T_AssertBits(B, 4, nib[2 * i]), a1 = T_AssertBits(B, 4, nib[2 * i + 1]);
         B.at(o.pos + i) = B.fma(nib[2 * i], c_const(16), nib[2 * i + 1]);
@@ -801,7 +806,7 @@ static Blk T_Nibbles2Bytes(Builder &B, int n_, const Code *nib) {
 // ============================================================================================================
 // Divide(N) :17-33  own: out, rem, a, b
 static Blk T_Divide(Builder &B, int N, Code a, Code b) {
-    Blk o = B.alloc(4);
+    Blk o = B.alloc(4, "Divide");
     Code q, r; Fr fa, fb;
     if (B.const_val(a, fa) && B.const_val(b, fb) && !fr_is_zero(fb)) { Fr fq, fr_; fr_divmod(fa, fb, fq, fr_); q = B.konst(fq); r = B.konst(fr_); }
     else { q = B.divmod(false, a, b, o.sig); r = B.divmod(true, a, b, o.sig); }
@@ -820,7 +825,7 @@ static Blk T_Divide(Builder &B, int N, Code a, Code b) {
 // ============================================================================================================
 // Selector(n) :21-46  own: out, vals[n], select, isEq[n], sum[n+1]
 static Blk T_Selector(Builder &B, int n_, const Code *vals, Code select) {
-    size_t n = (size_t)n_; Blk o = B.alloc(1 + n + 1 + n + n + 1);
+    size_t n = (size_t)n_; Blk o = B.alloc(1 + n + 1 + n + n + 1, "Selector");
     B.copy(o.pos + 1, vals, n); B.at(o.pos + 1 + n) = select;
     size_t isEq = o.pos + 2 + n, sum = isEq + n;
     const uint64_t qSel = o.sig + 1 + n, qEq = o.sig + 2 + n, qSum = qEq + n;
@@ -841,7 +846,7 @@ static Blk T_Selector(Builder &B, int n_, const Code *vals, Code select) {
 }
 // SelectorArray1D(n,p) :62-77 / SelectorArray2D(n,p,q) :91-110  own: out[cols], arrays[n][cols], select, arraysT[cols][n]
 static Blk T_SelectorArray(Builder &B, int n_, size_t cols, const Code *arrays, Code select) {
-    size_t n = (size_t)n_; Blk o = B.alloc(cols + n * cols + 1 + cols * n);
+    size_t n = (size_t)n_; Blk o = B.alloc(cols + n * cols + 1 + cols * n, "SelectorArray1D/2D");
     B.copy(o.pos + cols, arrays, n * cols); B.at(o.pos + cols + n * cols) = select;
     size_t T = o.pos + cols + n * cols + 1;
     const uint64_t qArr = o.sig + cols, qSel = o.sig + cols + n * cols, qT = qSel + 1;
@@ -858,7 +863,7 @@ static Blk T_SelectorArray(Builder &B, int n_, size_t cols, const Code *arrays, 
 // ============================================================================================================
 // ShiftLeft(n) :17-36  own: out[n], in[n], count, isEq[n][n], temp[n][n]
 static Blk T_ShiftLeft(Builder &B, int n_, const Code *in, Code count) {
-    size_t n = (size_t)n_; Blk o = B.alloc(2 * n + 1 + 2 * n * n);
+    size_t n = (size_t)n_; Blk o = B.alloc(2 * n + 1 + 2 * n * n, "ShiftLeft");
     B.copy(o.pos + n, in, n); B.at(o.pos + 2 * n) = count;
     size_t isEq = o.pos + 2 * n + 1, temp = isEq + n * n;
     const uint64_t qIn = o.sig + n, qCnt = o.sig + 2 * n, qEq = qCnt + 1, qTmp = qEq + n * n;
@@ -884,7 +889,7 @@ static Blk T_ShiftLeft(Builder &B, int n_, const Code *in, Code count) {
 }
 // ShiftRight(n,maxShift) :51-75  own: out[n+ms], in[n], count, isEq[ms+1], temps[ms+1][n]
 static Blk T_ShiftRight(Builder &B, int n_, int ms_, const Code *in, Code count) {
-    size_t n = (size_t)n_, ms = (size_t)ms_; Blk o = B.alloc(n + ms + n + 1 + ms + 1 + (ms + 1) * n);
+    size_t n = (size_t)n_, ms = (size_t)ms_; Blk o = B.alloc(n + ms + n + 1 + ms + 1 + (ms + 1) * n, "ShiftRight");
     B.copy(o.pos + n + ms, in, n); B.at(o.pos + 2 * n + ms) = count;
     size_t isEq = o.pos + 2 * n + ms + 1, temps = isEq + ms + 1;
     const uint64_t qIn = o.sig + n + ms, qCnt = o.sig + 2 * n + ms, qEq = qCnt + 1, qTmp = qEq + ms + 1;
@@ -908,7 +913,7 @@ static Blk T_ShiftRight(Builder &B, int n_, int ms_, const Code *in, Code count)
 }
 // Mask(n) :18-30  own: out[n], in[n], count, filter[n]
 static Blk T_Mask(Builder &B, int n_, const Code *in, Code count) {
-    size_t n = (size_t)n_; Blk o = B.alloc(3 * n + 1); B.copy(o.pos + n, in, n); B.at(o.pos + 2 * n) = count;
+    size_t n = (size_t)n_; Blk o = B.alloc(3 * n + 1, "Mask"); B.copy(o.pos + n, in, n); B.at(o.pos + 2 * n) = count;
     Blk f = T_Filter(B, n_, count); B.copy(o.pos + 2 * n + 1, &B.at(f.pos), n);
     B.q_eq(f.sig + n, o.sig + 2 * n); B.q_eqn(o.sig + 2 * n + 1, f.sig, n);       // signal filter[n] <== Filter(n)(count)   concat.circom:24
     for (size_t i = 0; i < n; i++) { B.at(o.pos + i) = B.mul(in[i], B.at(f.pos + i)); B.q_mul(o.sig + n + i, o.sig + 2 * n + 1 + i, o.sig + i); }   // out[i] <== in[i] * filter[i]   :27
@@ -917,7 +922,7 @@ static Blk T_Mask(Builder &B, int n_, const Code *in, Code count) {
 // Concat(A,B) :47-84  own: out[A+B], outLen, a[A], aLen, b[B], bLen, maskedA[A], maskedB[B], shiftedB[A+B]
 static Blk T_Concat(Builder &B, int A, int Bn, const Code *a, Code aLen, const Code *b, Code bLen) {
     size_t NA = (size_t)A, NB = (size_t)Bn, T = NA + NB;
-    Blk o = B.alloc(T + 1 + NA + 1 + NB + 1 + NA + NB + T);
+    Blk o = B.alloc(T + 1 + NA + 1 + NB + 1 + NA + NB + T, "Concat");
     size_t ia = o.pos + T + 1, iaL = ia + NA, ib = iaL + 1, ibL = ib + NB, mA = ibL + 1, mB = mA + NA, sB = mB + NB;
     const uint64_t d = o.sig - o.pos;                                             // flat position -> witness index inside this block
     B.copy(ia, a, NA); B.at(iaL) = aLen; B.copy(ib, b, NB); B.at(ibL) = bLen;
@@ -948,7 +953,7 @@ static Blk T_Concat(Builder &B, int A, int Bn, const Code *a, Code aLen, const C
 // SubstringCheck(maxMainLen, subLen) :24-100
 static Blk T_SubstringCheck(Builder &B, int maxMainLen, int subLen, const Code *mainInput, Code mainLen, const Code *subInput) {
     size_t MM = (size_t)maxMainLen, SL = (size_t)subLen, Kn = MM - SL + 1;
-    Blk o = B.alloc(1 + MM + 1 + SL + 1 + (MM + 1) + Kn + Kn + (Kn + 1) + (Kn + 1) + 1);
+    Blk o = B.alloc(1 + MM + 1 + SL + 1 + (MM + 1) + Kn + Kn + (Kn + 1) + (Kn + 1) + 1, "SubstringCheck");
     size_t iMain = o.pos + 1, iLen = iMain + MM, iSub = iLen + 1, subNum = iSub + SL, Mo = subNum + 1,
            exists = Mo + MM + 1, isLast = exists + Kn, allowed = isLast + Kn, sums = allowed + Kn + 1, dne = sums + Kn + 1;
     const uint64_t d = o.sig - o.pos;
@@ -1092,17 +1097,22 @@ static void emit_round(LaneSink &S) {
 // The constraint system of one KeccakfRound(r) block (keccak.circom:290-297 and everything below it), over signal indices
 // RELATIVE to the block's first signal.  Same traversal order as emit_round; REL_ONE stands for the constant 1.
 static const uint64_t REL_ONE = 0xffffffffull;
+struct RelComp { uint32_t off, n; const char *tmpl; };
 struct RoundCons {
     ConsSink &S; uint32_t cur = 0;
+    std::vector<RelComp> *comps = nullptr;
+    void comp(uint32_t off, uint32_t n, const char *t) { if (comps) comps->push_back(RelComp{off, n, t}); }
     uint32_t take(uint32_t n) { uint32_t o = cur; cur += n; return o; }
     void eqn(uint32_t a, uint32_t b, uint32_t n) { for (uint32_t k = 0; k < n; k++) S.eq(a + k, b + k); }
     void eq64(uint32_t a, uint32_t b) { eqn(a, b, 64); }
     // XorArray :77-86 / OrArray :104-113 / AndArray :120-129 (64): own out, a, b, then 64 gates [out, a, b]
     uint32_t gate_array(int kind, uint32_t srcA, uint32_t srcB) {
         const uint32_t o = take(64), a = take(64), b = take(64);
+        comp(o, 192, kind == 0 ? "XorArray" : kind == 1 ? "OrArray" : "AndArray");
         eq64(a, srcA); eq64(b, srcB);
         for (uint32_t k = 0; k < 64; k++) {
             const uint32_t g = take(3);
+            comp(g, 3, kind == 0 ? "XOR" : kind == 1 ? "OR" : "AND");
             S.eq(g + 1, a + k); S.eq(g + 2, b + k);
             if (kind == 0) S.r1(LC().s(g + 1, 2), LC().s(g + 2), LC().s(g + 1).s(g + 2).s(g, -1));       // XOR: out <== a + b - 2*a*b   gates.circom:26
             else if (kind == 1) S.r1(LC().s(g + 1), LC().s(g + 2), LC().s(g + 1).s(g + 2).s(g, -1));     // OR : out <== a + b - a*b     gates.circom:42
@@ -1112,28 +1122,31 @@ struct RoundCons {
         return o;
     }
     uint32_t shl(uint32_t src, uint32_t r) {         // ShL(64, r) :40-51  own: out, in
-        const uint32_t o = take(64), in = take(64); eq64(in, src);
+        const uint32_t o = take(64), in = take(64); eq64(in, src); comp(o, 128, "ShL");
         for (uint32_t i = 0; i < 64; i++) { if (i < r) S.kc(o + i, fr_zero()); else S.eq(o + i, in + i - r); }
         return o;
     }
     uint32_t shr(uint32_t src, uint32_t r) {         // ShR(64, r) :19-30
-        const uint32_t o = take(64), in = take(64); eq64(in, src);
+        const uint32_t o = take(64), in = take(64); eq64(in, src); comp(o, 128, "ShR");
         for (uint32_t i = 0; i < 64; i++) { if (i + r >= 64) S.kc(o + i, fr_zero()); else S.eq(o + i, in + i + r); }
         return o;
     }
     uint32_t notarr(uint32_t src) {                  // NotArray(64) :92-98  own: out, a ; out[i] <== 1 - a[i]
-        const uint32_t o = take(64), a = take(64); eq64(a, src);
+        const uint32_t o = take(64), a = take(64); eq64(a, src); comp(o, 128, "NotArray");
         for (uint32_t i = 0; i < 64; i++) S.r1(LC(), LC(), LC().s(o + i).s(a + i).s(REL_ONE, -1));
         return o;
     }
     void round() {
         const uint32_t r_out = take(1600), r_in = take(1600), r_theta = take(1600), r_rhopi = take(1600), r_chi = take(1600);
+        comp(r_out, 8000, "KeccakfRound");
         {   // signal theta[25][64] <== Theta()(in)   :293 ; Theta :151-170  own: out, in, c[5], d[5]
             const uint32_t t_out = take(1600), t_in = take(1600), t_c = take(320), t_d = take(320);
+            comp(t_out, 3840, "Theta");
             eqn(t_in, r_in, 1600);
             for (uint32_t i = 0; i < 5; i++) {          // c[i] <== Xor5(64)(in[i], in[5+i], in[10+i], in[15+i], in[20+i])   :157 ; Xor5 :58-70
                 const uint32_t x_out = take(64); uint32_t x_in[5]; for (int j = 0; j < 5; j++) x_in[j] = take(64);
                 const uint32_t x_ab = take(64), x_abc = take(64), x_abcd = take(64);
+                comp(x_out, 576, "Xor5");
                 for (uint32_t j = 0; j < 5; j++) eq64(x_in[j], t_in + 64 * (5 * j + i));
                 eq64(x_ab, gate_array(0, x_in[0], x_in[1])); eq64(x_abc, gate_array(0, x_ab, x_in[2]));
                 eq64(x_abcd, gate_array(0, x_abc, x_in[3])); eq64(x_out, gate_array(0, x_abcd, x_in[4]));
@@ -1141,6 +1154,7 @@ struct RoundCons {
             }
             for (uint32_t i = 0; i < 5; i++) {          // d[i] <== D()(c[(i+1)%5], c[(i+4)%5])   :162 ; D :135-144  own: out, a, b, aux0, aux1, aux2
                 const uint32_t d_out = take(64), d_a = take(64), d_b = take(64), d_0 = take(64), d_1 = take(64), d_2 = take(64);
+                comp(d_out, 384, "D");
                 eq64(d_a, t_c + 64 * ((i + 1) % 5)); eq64(d_b, t_c + 64 * ((i + 4) % 5));
                 eq64(d_0, shl(d_a, 1)); eq64(d_1, shr(d_a, 63));
                 eq64(d_2, gate_array(1, d_0, d_1)); eq64(d_out, gate_array(0, d_b, d_2));
@@ -1152,11 +1166,13 @@ struct RoundCons {
         }
         {   // signal rhopi <== RhoPi()(theta)   :294 ; RhoPi :191-204  own: out, in
             const uint32_t p_out = take(1600), p_in = take(1600);
+            comp(p_out, 3200, "RhoPi");
             eqn(p_in, r_theta, 1600);
             eq64(p_out, p_in);                                                        // out[0] <== in[0]   :197
             for (int i = 0; i < 24; i++) {              // out[rot[i+1]] <== stepRhoPi(shl, 64 - shl)(in[rot[i]])   :202 ; stepRhoPi :177-184  own: out, a, aux0, aux1
                 const uint32_t sh = (uint32_t)keccak_shl(i);
                 const uint32_t s_out = take(64), s_a = take(64), s_0 = take(64), s_1 = take(64);
+                comp(s_out, 256, "stepRhoPi");
                 eq64(s_a, p_in + 64 * (uint32_t)keccak_rot(i));
                 eq64(s_0, shr(s_a, 64 - sh)); eq64(s_1, shl(s_a, sh));
                 eq64(s_out, gate_array(1, s_0, s_1));
@@ -1166,9 +1182,11 @@ struct RoundCons {
         }
         {   // signal chi <== Chi()(rhopi)   :295 ; Chi :228-241  own: out, in
             const uint32_t c_out = take(1600), c_in = take(1600);
+            comp(c_out, 3200, "Chi");
             eqn(c_in, r_rhopi, 1600);
             for (int i = 0; i < 25; i++) {              // out[i] <== stepChi()(in[i], in[..], in[..])   :233-239 ; stepChi :212-221  own: out, a, b, c, bXor, bc
                 const uint32_t s_out = take(64), s_a = take(64), s_b = take(64), s_c = take(64), s_bx = take(64), s_bc = take(64);
+                comp(s_out, 384, "stepChi");
                 eq64(s_a, c_in + 64 * (uint32_t)i); eq64(s_b, c_in + 64 * (uint32_t)chi_b(i)); eq64(s_c, c_in + 64 * (uint32_t)chi_c(i));
                 eq64(s_bx, notarr(s_b)); eq64(s_bc, gate_array(2, s_bx, s_c)); eq64(s_out, gate_array(0, s_a, s_bc));
                 eq64(c_out + 64 * (uint32_t)i, s_out);
@@ -1177,8 +1195,10 @@ struct RoundCons {
         }
         {   // out <== Iota(r)(chi)   :296 ; Iota :273-283  own: out, in, roundConstants ; RoundConstants(r) :248-266  own: out[64]
             const uint32_t i_out = take(1600), i_in = take(1600), i_rc = take(64);
+            comp(i_out, 3264, "Iota");
             eqn(i_in, r_chi, 1600);
             const uint32_t rc = take(64);
+            comp(rc, 64, "RoundConstants");
             for (uint32_t k = 0; k < 64; k++) S.kc_raw(rc + k, (CC_RCBIT << 30) | k);   // out[i] <== (rc[r] >> i) & 1   :264
             eq64(i_rc, rc);
             eq64(i_out, gate_array(0, i_in, i_rc));                                   // out[0] <== XorArray(64)(in[0], roundConstants)   :279
@@ -1191,7 +1211,7 @@ struct RoundCons {
 // Absorb :304-323  (s: previous state words or NONE_IDX; blk: 17 block words).  Returns the state-out word base.
 static uint32_t T_Absorb(Builder &B, uint32_t s_idx, uint32_t blk_idx, Blk *own) {
     uint32_t A = B.absorb(s_idx, blk_idx), out_w = A + RW * 24;
-    Blk o = B.alloc(1600 + 1600 + 1088 + 1600); if (own) *own = o;
+    Blk o = B.alloc(1600 + 1600 + 1088 + 1600, "Absorb"); if (own) *own = o;
     LaneSink S{&B.at(o.pos), 0};
     for (uint32_t l = 0; l < 25; l++) S.lane(Lane{out_w + l});
     for (uint32_t l = 0; l < 25; l++) S.lane(Lane{s_idx == NONE_IDX ? NONE_IDX : s_idx + l});
@@ -1199,6 +1219,7 @@ static uint32_t T_Absorb(Builder &B, uint32_t s_idx, uint32_t blk_idx, Blk *own)
     for (uint32_t l = 0; l < 25; l++) S.lane(Lane{A + l});
     const uint64_t qS = o.sig + 1600, qBlk = o.sig + 3200, qAux = o.sig + 4288;
     for (uint32_t l = 0; l < 17; l++) {                               // XorArray(64)(s[i], block[i])
+        if (B.comps) { B.comps->push_back(Builder::Comp{B.nsig, 192, "XorArray"}); for (uint32_t k = 0; k < 64; k++) B.comps->push_back(Builder::Comp{B.nsig + 192 + 3 * k, 3, "XOR"}); }
         Blk x = B.alloc(384); LaneSink X{&B.at(x.pos), 0};
         X.gate_array(Lane{A + l}, Lane{s_idx == NONE_IDX ? NONE_IDX : s_idx + l}, Lane{blk_idx + l});
         if (B.want_cs()) {                                            // aux[i] <== XorArray(64)(s[i], block[i])   keccak.circom:316
@@ -1213,7 +1234,7 @@ static uint32_t T_Absorb(Builder &B, uint32_t s_idx, uint32_t blk_idx, Blk *own)
     }
     B.q_eqn(qAux + 64 * 17, qS + 64 * 17, 64 * 8);                    // aux[i] <== s[i], i >= 17                    :318
     // Keccakf :356-367  own: out, in, midRound[25][25][64]
-    Blk k = B.alloc(1600 + 1600 + 25 * 1600); LaneSink Kf{&B.at(k.pos), 0};
+    Blk k = B.alloc(1600 + 1600 + 25 * 1600, "Keccakf"); LaneSink Kf{&B.at(k.pos), 0};
     for (uint32_t l = 0; l < 25; l++) Kf.lane(Lane{out_w + l});
     for (uint32_t l = 0; l < 25; l++) Kf.lane(Lane{A + l});
     for (uint32_t r = 0; r <= 24; r++) for (uint32_t l = 0; l < 25; l++) Kf.lane(Lane{A + RW * r + l});
@@ -1231,10 +1252,10 @@ static uint32_t T_Absorb(Builder &B, uint32_t s_idx, uint32_t blk_idx, Blk *own)
 // Final(n) :330-349 and Keccak(n) :374-385 ; in_words: n*17 block words ; returns Keccak's own block
 static Blk T_Keccak(Builder &B, int n_, uint32_t in_words, Code blocks) {
     size_t n = (size_t)n_;
-    Blk ko = B.alloc(256 + n * 1088 + 1 + 1600);                      // Keccak own: out[256], in, blocks, finalState
+    Blk ko = B.alloc(256 + n * 1088 + 1 + 1600, "Keccak");                      // Keccak own: out[256], in, blocks, finalState
     { LaneSink S{&B.at(ko.pos + 256), 0}; for (uint32_t w = 0; w < n * 17; w++) S.lane(Lane{in_words + w}); }
     B.at(ko.pos + 256 + n * 1088) = blocks;
-    Blk fo = B.alloc(1600 + n * 1088 + 1 + (n + 1) * 1600);           // Final own: out, in, blocks, s[n+1]
+    Blk fo = B.alloc(1600 + n * 1088 + 1 + (n + 1) * 1600, "Final");           // Final own: out, in, blocks, s[n+1]
     { LaneSink S{&B.at(fo.pos + 1600), 0}; for (uint32_t w = 0; w < n * 17; w++) S.lane(Lane{in_words + w}); }
     B.at(fo.pos + 1600 + n * 1088) = blocks;
     size_t s = fo.pos + 1600 + n * 1088 + 1;
@@ -1263,7 +1284,7 @@ static Blk T_Keccak(Builder &B, int n_, uint32_t in_words, Code blocks) {
 }
 // Pad(maxBlocks, blockSize) :412-446  own: out[B], numBlocks, in[B], inLen, div, rem, filter[B+1], isEq[B], isLast[B]
 static Blk T_Pad(Builder &B, int maxBlocks, int blockSize, const Code *in, Code inLen) {
-    size_t Bn = (size_t)maxBlocks * (size_t)blockSize; Blk o = B.alloc(Bn + 1 + Bn + 1 + 2 + (Bn + 1) + Bn + Bn);
+    size_t Bn = (size_t)maxBlocks * (size_t)blockSize; Blk o = B.alloc(Bn + 1 + Bn + 1 + 2 + (Bn + 1) + Bn + Bn, "Pad");
     size_t numBlocks = o.pos + Bn, iIn = numBlocks + 1, iLen = iIn + Bn, div = iLen + 1, rem = div + 1,
            filter = rem + 1, isEq = filter + Bn + 1, isLast = isEq + Bn;
     const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
@@ -1300,7 +1321,7 @@ static Blk T_Pad(Builder &B, int maxBlocks, int blockSize, const Code *in, Code 
 // KeccakBytes(maxBlocks) :454-489
 static Blk T_KeccakBytes(Builder &B, int maxBlocks, const Code *in, Code inLen) {
     size_t Bn = (size_t)maxBlocks * 136;
-    Blk o = B.alloc(32 + Bn + 1 + Bn + 1 + 24 * Bn + 256 + 256);
+    Blk o = B.alloc(32 + Bn + 1 + Bn + 1 + 24 * Bn + 256 + 256, "KeccakBytes");
     size_t iIn = o.pos + 32, iLen = iIn + Bn, padded = iLen + 1, numBlocks = padded + Bn, inBitsArray = numBlocks + 1,
            inBits = inBitsArray + 8 * Bn, inBlocks = inBits + 8 * Bn, outBits = inBlocks + 8 * Bn, outBytes = outBits + 256;
     const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
@@ -1314,7 +1335,7 @@ static Blk T_KeccakBytes(Builder &B, int maxBlocks, const Code *in, Code inLen) 
     }
     uint32_t words = B.pack8_words(&B.at(padded), (uint32_t)(Bn / 8));         // bytes -> 17 lanes per block
     for (size_t i = 0; i < Bn; i++) {                                          // Num2Bits(8)(padded[i])
-        Blk nb = B.alloc(9);
+        Blk nb = B.alloc(9, "Num2Bits");
         for (uint32_t k = 0; k < 8; k++) B.at(nb.pos + k) = c_bit(words + (uint32_t)(i / 8), 8 * (uint32_t)(i % 8) + k);
         B.at(nb.pos + 8) = B.at(padded + i);
         B.chk_range(B.at(padded + i), 8, nb.sig);
@@ -1349,7 +1370,7 @@ static Blk T_KeccakBytes(Builder &B, int maxBlocks, const Code *in, Code inLen) 
 // PublicCommitment(N) :18-42  own: out, in[N][32], flattenIn, block, hash[32], reducedHash[31]
 static Blk T_PublicCommitment(Builder &B, int N, const Code *in) {
     size_t n32 = (size_t)N * 32; int nb = (N * 32) / 136 + ((N * 32) % 136 != 0); size_t blk = (size_t)nb * 136;
-    Blk o = B.alloc(1 + n32 + n32 + blk + 32 + 31);
+    Blk o = B.alloc(1 + n32 + n32 + blk + 32 + 31, "PublicCommitment");
     size_t iIn = o.pos + 1, flat = iIn + n32, block = flat + n32, hash = block + blk, red = hash + 32;
     const uint64_t d = o.sig - o.pos;
     B.copy(iIn, in, n32);
@@ -1377,7 +1398,7 @@ static Code POSEIDON_PREFIX(Builder &B, int add) {
 }
 // BurnAddress :47-58  own: addressBytes[20], burnKey, revealAmount, burnExtraCommitment, hash, hashBytes[32]
 static Blk T_BurnAddress(Builder &B, Code burnKey, Code revealAmount, Code bec) {
-    Blk o = B.alloc(20 + 3 + 1 + 32);
+    Blk o = B.alloc(20 + 3 + 1 + 32, "BurnAddress");
     B.at(o.pos + 20) = burnKey; B.at(o.pos + 21) = revealAmount; B.at(o.pos + 22) = bec;
     Code ins[4] = {POSEIDON_PREFIX(B, 0), burnKey, revealAmount, bec};
     Blk p = T_Poseidon(B, 4, ins); B.at(o.pos + 23) = B.at(p.pos);
@@ -1393,7 +1414,7 @@ static Blk T_BurnAddress(Builder &B, Code burnKey, Code revealAmount, Code bec) 
 }
 // BurnAddressHash :67-83  own: addressHashNibbles[64], 3 inputs, addressBytes[20], addressBytesBlock[136], addressHash[32]
 static Blk T_BurnAddressHash(Builder &B, Code burnKey, Code revealAmount, Code bec) {
-    Blk o = B.alloc(64 + 3 + 20 + 136 + 32);
+    Blk o = B.alloc(64 + 3 + 20 + 136 + 32, "BurnAddressHash");
     B.at(o.pos + 64) = burnKey; B.at(o.pos + 65) = revealAmount; B.at(o.pos + 66) = bec;
     Blk a = T_BurnAddress(B, burnKey, revealAmount, bec); B.copy(o.pos + 67, &B.at(a.pos), 20);
     Blk f = T_Fit(B, 20, 136, &B.at(o.pos + 67)); B.copy(o.pos + 87, &B.at(f.pos), 136);
@@ -1410,13 +1431,13 @@ static Blk T_BurnAddressHash(Builder &B, Code burnKey, Code revealAmount, Code b
 // EIP7503 :11-21
 static Blk T_EIP7503(Builder &B) {
     static const uint8_t s[8] = {69, 73, 80, 45, 55, 53, 48, 51};
-    Blk o = B.alloc(8);
+    Blk o = B.alloc(8, "EIP7503");
     for (int i = 0; i < 8; i++) { B.at(o.pos + (size_t)i) = c_const(s[i]); B.q_const(o.sig + (uint64_t)i, s[i]); }   // out[i] <== 'EIP-7503'[i]   proof_of_work.circom:13-20
     return o;
 }
 // ConcatFixed4(A,B,C,D) :28-48  own: out[A+B+C+D], a, b, c, d
 static Blk T_ConcatFixed4(Builder &B, int A, int Bn, int C, int D, const Code *a, const Code *b, const Code *c, const Code *d) {
-    size_t T = (size_t)(A + Bn + C + D); Blk o = B.alloc(2 * T);
+    size_t T = (size_t)(A + Bn + C + D); Blk o = B.alloc(2 * T, "ConcatFixed4");
     B.copy(o.pos, a, (size_t)A); B.copy(o.pos + (size_t)A, b, (size_t)Bn); B.copy(o.pos + (size_t)(A + Bn), c, (size_t)C);
     B.copy(o.pos + (size_t)(A + Bn + C), d, (size_t)D);
     B.copy(o.pos + T, &B.at(o.pos), T);
@@ -1425,7 +1446,7 @@ static Blk T_ConcatFixed4(Builder &B, int A, int Bn, int C, int D, const Code *a
 }
 // ProofOfWorkChecker :54-81
 static Blk T_ProofOfWorkChecker(Builder &B, Code burnKey, Code revealAmount, Code bec, Code minimumZeroBytes) {
-    Blk o = B.alloc(4 + 96 + 8 + 104 + 136 + 32 + 32);
+    Blk o = B.alloc(4 + 96 + 8 + 104 + 136 + 32 + 32, "ProofOfWorkChecker");
     size_t bk = o.pos + 4, ra = bk + 32, be = ra + 32, eip = be + 32, hin = eip + 8, blk = hin + 104, kec = blk + 136, sbz = kec + 32;
     const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
     B.at(o.pos) = burnKey; B.at(o.pos + 1) = revealAmount; B.at(o.pos + 2) = bec; B.at(o.pos + 3) = minimumZeroBytes;
@@ -1457,7 +1478,7 @@ static Blk T_ProofOfWorkChecker(Builder &B, Code burnKey, Code revealAmount, Cod
 // ============================================================================================================
 // CountBytes(N) integer.circom:16-49  own: len, bytes[N], isZero[N], stillZero[N]
 static Blk T_CountBytes(Builder &B, int N, const Code *bytes) {
-    size_t n = (size_t)N; Blk o = B.alloc(1 + 3 * n); B.copy(o.pos + 1, bytes, n);
+    size_t n = (size_t)N; Blk o = B.alloc(1 + 3 * n, "CountBytes"); B.copy(o.pos + 1, bytes, n);
     for (size_t i = 0; i < n; i++) {
         Blk z = T_IsZero(B, bytes[i]); B.at(o.pos + 1 + n + i) = B.at(z.pos);
         B.q_eq(z.sig + 1, o.sig + 1 + i); B.q_eq(o.sig + 1 + n + i, z.sig);       // isZero[i] <== IsZero()(bytes[i])              integer.circom:24
@@ -1479,7 +1500,7 @@ static Blk T_CountBytes(Builder &B, int N, const Code *bytes) {
 }
 // RlpInteger(N) integer.circom:67-110
 static Blk T_RlpInteger(Builder &B, int N, Code in) {
-    size_t n = (size_t)N; Blk o = B.alloc(n + 1 + 1 + 1 + n + 1 + n + 3);
+    size_t n = (size_t)N; Blk o = B.alloc(n + 1 + 1 + 1 + n + 1 + n + 3, "RlpInteger");
     size_t outLen = o.pos + n + 1, iIn = outLen + 1, bytes = iIn + 1, length = bytes + n, bigEndian = length + 1,
            isSingle = bigEndian + n, isZero = isSingle + 1, first = isZero + 1;
     const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
@@ -1512,7 +1533,7 @@ static const uint8_t STORAGE_CODE_RLP[66] = {
     160, 86, 232, 31, 23, 27, 204, 85, 166, 255, 131, 69, 230, 146, 192, 248, 110, 91, 72, 224, 27, 153, 108, 173, 192, 1, 98, 47, 181, 227, 99, 180, 33,
     160, 197, 210, 70, 1, 134, 247, 35, 60, 146, 126, 125, 178, 220, 199, 3, 192, 229, 0, 182, 83, 202, 130, 39, 59, 123, 250, 216, 4, 93, 133, 164, 112};
 static Blk T_RlpEmptyAccount(Builder &B, int mbb, Code balance) {
-    size_t m = (size_t)mbb, OL = 4 + m + 66; Blk o = B.alloc(OL + 1 + 1 + (4 + m) + 1 + (m + 1) + 1 + 1 + 66);
+    size_t m = (size_t)mbb, OL = 4 + m + 66; Blk o = B.alloc(OL + 1 + 1 + (4 + m) + 1 + (m + 1) + 1 + 1 + 66, "RlpEmptyAccount");
     size_t outLen = o.pos + OL, iBal = outLen + 1, pre = iBal + 1, preLen = pre + 4 + m, balRlp = preLen + 1,
            balRlpLen = balRlp + m + 1, nabLen = balRlpLen + 1, sc = nabLen + 1;
     const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
@@ -1545,7 +1566,7 @@ static Blk T_RlpEmptyAccount(Builder &B, int mbb, Code balance) {
 }
 // TruncatedAddressHash(addressHashBytes) merkle_patricia_trie_leaf.circom:50-90 (`temp` :76 never assigned => 0)
 static Blk T_TruncatedAddressHash(Builder &B, int ahb, const Code *nibbles, Code nibLen) {
-    size_t a = (size_t)ahb; Blk o = B.alloc((a + 1) + 1 + 2 * a + 1 + 2 + 2 * a + (2 * a + 2) + (2 * a - 1));
+    size_t a = (size_t)ahb; Blk o = B.alloc((a + 1) + 1 + 2 * a + 1 + 2 + 2 * a + (2 * a + 2) + (2 * a - 1), "TruncatedAddressHash");
     size_t outLen = o.pos + a + 1, iNib = outLen + 1, iLen = iNib + 2 * a, div = iLen + 1, rem = div + 1, shifted = rem + 1,
            outNib = shifted + 2 * a, temp = outNib + 2 * a + 2;
     const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
@@ -1583,7 +1604,7 @@ static Blk T_TruncatedAddressHash(Builder &B, int ahb, const Code *nibbles, Code
 // RlpMerklePatriciaTrieLeaf(maxAddressHashBytes, maxBalanceBytes) :102-189
 static Blk T_RlpMerklePatriciaTrieLeaf(Builder &B, int mahb, int mbb, const Code *nibbles, Code nibLen, Code balance) {
     size_t mrea = 4 + (size_t)mbb + 66, mvr = 2 + mrea, mkl = 1 + (size_t)mahb, mkr = 1 + mkl, mpk = 2 + mkr, MO = mpk + mvr;
-    Blk o = B.alloc(MO + 1 + 2 * (size_t)mahb + 1 + 1 + mkl + 1 + mrea + 1 + mpk + 1 + mvr + 1);
+    Blk o = B.alloc(MO + 1 + 2 * (size_t)mahb + 1 + 1 + mkl + 1 + mrea + 1 + mpk + 1 + mvr + 1, "RlpMerklePatriciaTrieLeaf");
     size_t outLen = o.pos + MO, iNib = outLen + 1, iLen = iNib + 2 * (size_t)mahb, iBal = iLen + 1, key = iBal + 1, keyLen = key + mkl,
            rea = keyLen + 1, reaLen = rea + mrea, pk = reaLen + 1, pkLen = pk + mpk, vr = pkLen + 1, vrLen = vr + mvr;
     const uint64_t d = o.sig - o.pos; const bool cs = B.want_cs();
@@ -1622,7 +1643,7 @@ static Blk T_RlpMerklePatriciaTrieLeaf(Builder &B, int mahb, int mbb, const Code
 }
 // IsInRange(B) :196-207  own: out, lower, value, upper, lowerLteValue, valueLteUpper
 static Blk T_IsInRange(Builder &B, int nb, Code lower, Code value, Code upper) {
-    Blk o = B.alloc(6); B.at(o.pos + 1) = lower; B.at(o.pos + 2) = value; B.at(o.pos + 3) = upper;
+    Blk o = B.alloc(6, "IsInRange"); B.at(o.pos + 1) = lower; B.at(o.pos + 2) = value; B.at(o.pos + 3) = upper;
     Blk b1 = T_AssertBits(B, nb, lower), b2 = T_AssertBits(B, nb, value), b3 = T_AssertBits(B, nb, upper);
     Blk a = T_LessEqThan(B, nb, lower, value); B.at(o.pos + 4) = B.at(a.pos);
     Blk b = T_LessEqThan(B, nb, value, upper); B.at(o.pos + 5) = B.at(b.pos);
@@ -1637,7 +1658,7 @@ static Blk T_IsInRange(Builder &B, int nb, Code lower, Code value, Code upper) {
 }
 // LeafDetector(N) :247-294
 static Blk T_LeafDetector(Builder &B, int N, const Code *layer, Code layerLen) {
-    size_t n = (size_t)N; Blk o = B.alloc(1 + n + 1 + 16);
+    size_t n = (size_t)N; Blk o = B.alloc(1 + n + 1 + 16, "LeafDetector");
     B.copy(o.pos + 1, layer, n); B.at(o.pos + 1 + n) = layerLen;
     size_t v = o.pos + 2 + n;
     const uint64_t qL = o.sig + 1, qLen = o.sig + 1 + n, qv = o.sig + 2 + n; const bool cs = B.want_cs();
@@ -1692,7 +1713,7 @@ static Blk T_LeafDetector(Builder &B, int N, const Code *layer, Code layerLen) {
 // ============================================================================================================
 // Spend(maxAmountBytes) :32-53
 static Blk T_Spend(Builder &B, int mab, Code burnKey, Code balance, Code withdrawn, Code extra) {
-    Blk o = B.alloc(1 + 4 + 2 + 128);
+    Blk o = B.alloc(1 + 4 + 2 + 128, "Spend");
     B.at(o.pos + 1) = burnKey; B.at(o.pos + 2) = balance; B.at(o.pos + 3) = withdrawn; B.at(o.pos + 4) = extra;
     size_t coin = o.pos + 5, rem = o.pos + 6, by = o.pos + 7;
     const bool cs = B.want_cs();
@@ -1721,7 +1742,7 @@ static Blk T_ProofOfBurn(Builder &B, const PobParams &P, const Code *in) {
     size_t L = (size_t)P.maxNumLayers, NB = (size_t)P.maxNodeBlocks * 136, HB = (size_t)P.maxHeaderBlocks * 136;
     size_t nIn = 6 + L * NB + L + 1 + HB + 3;
     size_t nMid = 2 + 64 + 32 + 32 + 5 * 32 + NB + 1 + L + (L - 1) + L * 32 + L * 31 + L + 1 + 139 + 1;
-    Blk o = B.alloc(1 + nIn + nMid);
+    Blk o = B.alloc(1 + nIn + nMid, "ProofOfBurn");
     B.copy(o.pos + 1, in, nIn);
     const Code *I = &B.at(o.pos + 1);
     Code burnKey = I[0], actualBalance = I[1], intendedBalance = I[2], revealAmount = I[3], bec = I[4], numLeafNib = I[5];
@@ -2214,6 +2235,34 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     // stream costs DRAM efficiency (profiles/r01_expand_sweep.md), so all round tiles go first, the rest last.
     std::stable_sort(P.tiles.begin(), P.tiles.end(), [](const Tile &a, const Tile &b) { return a.pad > b.pad; });
     return P;
+}
+
+// Component list of a circuit shape in numbering order: one line `first_signal,n_own_signals,template` per component instance
+// (KeccakfRound blocks expanded from the shared walk).  tools/diff_sym.py compares it with the component structure of a real
+// circom `.sym` (the only way to pin the ORDER the reference leaves unpinned).
+uint64_t write_components(const std::string &main_name, const std::vector<Fr> &params, bool hcreate, const std::string &path) {
+    int np = 0; const char *schema = main_input_schema(main_name, &np);
+    if (!schema) throw std::runtime_error("pob: unknown main template '" + main_name + "'");
+    if ((int)params.size() < np) throw std::runtime_error("pob: too few template parameters for " + main_name);
+    size_t n_in = count_inputs(schema, params);
+    uint32_t n_out = 0, n_words;
+    { Builder dry(hcreate, true, 0); build(dry, main_name, params, n_in, &n_out); n_words = dry.n_words; }
+    Builder B(hcreate, false, (n_words + 3u) & ~3u);
+    std::vector<Builder::Comp> comps; B.comps = &comps;
+    build(B, main_name, params, n_in, &n_out);
+    ConsSet dummy; std::vector<Fr> dk; std::unordered_map<std::array<uint32_t, 8>, uint32_t, FrHash> dix;
+    ConsSink rs; rs.S = &dummy; rs.konst = &dk; rs.kix = &dix;
+    std::vector<RelComp> rel; RoundCons rc{rs}; rc.comps = &rel; rc.round();
+    FILE *f = fopen(path.c_str(), "w");
+    if (!f) throw std::runtime_error("pob: cannot open " + path);
+    fprintf(f, "# pob_b200 component list: %s hcreate=%d n_signals=%llu\n# first_signal,n_own_signals,template\n", main_name.c_str(), hcreate ? 1 : 0, (unsigned long long)B.nsig);
+    uint64_t n = 0;
+    for (const Builder::Comp &c : comps) {
+        if (c.n == ROUND_SIGNALS && strcmp(c.tmpl, "KeccakfRound*") == 0) { for (const RelComp &r : rel) { fprintf(f, "%llu,%u,%s\n", (unsigned long long)(c.sig + r.off), r.n, r.tmpl); n++; } }
+        else { fprintf(f, "%llu,%llu,%s\n", (unsigned long long)c.sig, (unsigned long long)c.n, c.tmpl); n++; }
+    }
+    if (fclose(f) != 0) throw std::runtime_error("pob: short write to " + path);
+    return n;
 }
 
 std::vector<Fr> build_inverse_table() {

@@ -19,6 +19,9 @@ namespace pob {
 // opt_level 1 produces the reduced (`--O1`-style) witness program (program.h: Program::witness_map).
 Program compile_circuit(const std::string &main_name, const std::vector<Fr> &params, bool hcreate, bool want_constraints = false, int opt_level = 0);
 
+// order-pinning kit: writes `first_signal,n_own_signals,template` for every component instance in numbering order; returns the count
+uint64_t write_components(const std::string &main_name, const std::vector<Fr> &params, bool hcreate, const std::string &path);
+
 // Input schema of a main template ("name[d0][d1],name2,...", dims are expressions over p0..p7) or nullptr.
 const char *main_input_schema(const std::string &main_name, int *nparams);
 

@@ -474,6 +474,13 @@ int pob_layout_info(const char *main_name, const uint64_t *params, int nparams, 
     return POB_OK;
 }
 
+int pob_write_components(const char *main_name, const uint64_t *params, int nparams, int hcreate, const char *path, uint64_t *n_components) {
+    if (!main_name || !path || (nparams > 0 && !params)) return fail(POB_E_BAD_ARG, "pob_write_components: null argument");
+    try { uint64_t n = write_components(main_name, params_vec(params, nparams), flag_hcreate(hcreate), path); if (n_components) *n_components = n; }
+    catch (const std::exception &e) { return fail(POB_E_COMPILE, e.what()); }
+    return POB_OK;
+}
+
 void pob_destroy(pob_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);

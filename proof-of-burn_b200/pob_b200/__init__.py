@@ -115,6 +115,8 @@ def lib():
         L.pob_selfcheck.argtypes = [vp, u32, ctypes.POINTER(CheckReport)]
         L.pob_constraint_info.restype = ci
         L.pob_constraint_info.argtypes = [ctypes.c_char_p, vp, ci, ci, ctypes.POINTER(CheckReport)]
+        L.pob_write_components.restype = ci
+        L.pob_write_components.argtypes = [ctypes.c_char_p, vp, ci, ci, ctypes.c_char_p, ctypes.POINTER(u64)]
         L.pob_witness_map.restype = ci
         L.pob_witness_map.argtypes = [vp, vp]
         L.pob_run_batch_retain.restype = ci
@@ -258,6 +260,15 @@ def constraint_info(main_expr, hcreate=False):
     r = CheckReport()
     _check(lib().pob_constraint_info(name.encode(), pl.ctypes.data, len(params), int(hcreate), ctypes.byref(r)))
     return r.as_dict()
+
+
+def write_components(main_expr, path, hcreate=False):
+    """order-pinning kit: component list (`first_signal,n_own_signals,template` per line) of the --O0 layout; see tools/diff_sym.py"""
+    name, params = parse_main(main_expr)
+    pl = to_limbs(params) if params else np.zeros((1, 4), dtype=np.uint64)
+    n = ctypes.c_uint64(0)
+    _check(lib().pob_write_components(name.encode(), pl.ctypes.data, len(params), CREATE_HCREATE if hcreate else 0, os.fsencode(path), ctypes.byref(n)))
+    return int(n.value)
 
 
 class PinnedArray:
