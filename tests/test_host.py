@@ -97,6 +97,55 @@ def test_build_pob_input_packages_a_proof_like_the_reference_generator():
         inputs.build_pob_input(inst["layers"] * 3, inst["blockHeader"], 1, 1, 1, 1, shape=shape[:3])
 
 
+def test_header_rlp_assembly_reproduces_the_reference_fixture_header():
+    """pob_b200.inputs.header_rlp_from_block == the header assembly of the reference generator (tests/main.py:84-122).  Test
+    vector: the 612-byte header of tests/test_pob_input.json (keccak e36499b5...368d, tests/testcases/proof_of_burn.py:22): its 21
+    RLP fields are taken apart here, handed back as an eth_getBlockByNumber-style record (integers for the numeric fields, hex /
+    bytes for the hashes) and must re-assemble to the identical bytes -- zero difficulty and zero blob-gas fields as EMPTY strings,
+    the zero miner / nonce / bloom with their full width."""
+    from helpers import pob_fixture
+    from pob_b200 import inputs, synth
+    f = pob_fixture()
+    hdr = bytes(int(v) for v in f["blockHeader"][: int(f["blockHeaderLen"])])
+    assert len(hdr) == 612 and synth.keccak256(hdr).hex() == "e36499b50da290131c3fa32d4f60717c8c529ae1bc3a216f32d05c05fe80368d"
+    is_list, pos, n = inputs._rlp_item(hdr, 0)
+    assert is_list and pos + n == len(hdr)
+    items = []
+    while pos < len(hdr):
+        _, st, ln = inputs._rlp_item(hdr, pos)
+        items.append(hdr[st: st + ln]); pos = st + ln
+    names = inputs.HEADER_FIELDS + inputs.OPTIONAL_HEADER_FIELDS
+    assert len(items) == len(names) == 21
+    numeric = {"difficulty", "number", "gasLimit", "gasUsed", "timestamp", "baseFeePerGas", "blobGasUsed", "excessBlobGas"}
+    block = {}
+    for k, v in zip(names, items):
+        if k in numeric:
+            block[k] = int.from_bytes(v, "big")                         # what a JSON-RPC client hands back
+        elif k in ("stateRoot", "miner"):
+            block[k] = "0x" + v.hex()                                   # hex text is accepted too
+        else:
+            block[k] = v
+    assert block["difficulty"] == 0 and block["number"] == 3 and block["blobGasUsed"] == 0
+    assert inputs.header_rlp_from_block(block) == hdr
+    class Obj:                                                           # attribute access like web3's AttributeDict
+        pass
+    o = Obj(); o.__dict__.update(block)
+    assert inputs.header_rlp_from_block(o) == hdr
+    pre_london = {k: block[k] for k in inputs.HEADER_FIELDS}
+    short = inputs.header_rlp_from_block(pre_london)
+    assert len(short) < len(hdr) and inputs._rlp_item(short, 0)[0]
+    with pytest.raises(KeyError):
+        inputs.header_rlp_from_block({k: block[k] for k in inputs.HEADER_FIELDS[:-1]})
+    # and through the packager: block= instead of header_rlp=
+    shape = (4, 4, 5)
+    layers = [bytes(int(v) for v in f["layers"][i][: int(f["layerLens"][i])]) for i in range(int(f["numLayers"]))]
+    j = inputs.build_pob_input(layers, None, int(f["actualBalance"]), int(f["burnKey"]), int(f["revealAmount"]), int(f["burnExtraCommitment"]),
+                               shape=shape, block=block)
+    assert [int(v) for v in j["blockHeader"]] == [int(v) for v in f["blockHeader"]] and int(j["blockHeaderLen"]) == 612
+    assert [[int(v) for v in l] for l in j["layers"]] == [[int(v) for v in l] for l in f["layers"]]
+    assert int(j["numLeafAddressNibbles"]) == int(f["numLeafAddressNibbles"])
+
+
 def test_bench_helpers():
     """bench.py host logic: shape expression round-trips through the layout compiler; the CPU-baseline process count is
     bounded by available memory (a witness is 6.9 GB per oracle process)."""
