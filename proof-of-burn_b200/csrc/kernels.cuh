@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(T) k_expand_round(const ExpandArgs a) {
 // k_expand_codes: grid = (instances in the group, code tiles) -- INSTANCE-major, so that a tile's code stream is fetched
 // from DRAM once and served from L2 to the other witnesses of the group.  One 32-bit code per entry, loads issued 4
 // entries ahead of the stores.
-__global__ void __launch_bounds__(256, 5) k_expand_codes(const ExpandArgs a) {
+template <int UG>
+__global__ void __launch_bounds__(256, UG == 4 ? 5 : 4) k_expand_codes(const ExpandArgs a) {
     const uint32_t gi = a.inst[blockIdx.x];
     if (a.status[gi] != 0) return;
     const Tile t = a.tiles[a.tile0 + blockIdx.y];
@@ -319,7 +320,6 @@ __global__ void __launch_bounds__(256, 5) k_expand_codes(const ExpandArgs a) {
     uint64_t *W = a.wit[blockIdx.x] + t.dst * 4;
     const uint64_t *Ub = U + t.ubase;
     const Code *c = a.codes + t.code_off;
-    constexpr int UG = 4;
     for (uint32_t base = threadIdx.x; base < t.n; base += 256 * UG) {
         Code cd[UG];
 #pragma unroll

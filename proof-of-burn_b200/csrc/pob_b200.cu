@@ -155,7 +155,7 @@ struct pob_handle {
     // per SM: fewer concurrent write streams give the DRAM controllers longer same-row bursts -- measured 7.35 TB/s with
     // 2 CTAs/SM vs 7.26 / 7.19 / 7.09 / 6.97 TB/s with 3 / 4 / 5 / 8, and 5.96 TB/s with 1 (profiles/r01_expand_sweep.md)
     uint32_t round_dyn_smem = 85 * 1024;
-    uint32_t round_threads = 256, codes_dyn_smem = 0; bool serialize = false;   // changed by POB_TUNING knobs only
+    uint32_t round_threads = 256, codes_dyn_smem = 0, codes_ug = 4; bool serialize = false;   // changed by POB_TUNING knobs only
     int eval_threads = 1024; uint32_t eval_cluster = 1;   // k_eval: threads per CTA, CTAs per instance (thread-block cluster)
     uint32_t pos_konst_bytes = 0, levels_bytes = 0, eval_smem = 0;
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
@@ -322,7 +322,12 @@ static void enqueue_group(pob_handle *h, uint32_t g) {
         else if (h->round_threads == 1024) k_expand_round<1024><<<dim3(n_round, gc), 1024, h->round_dyn_smem, h->s_exp>>>(xa);
         else k_expand_round<256><<<dim3(n_round, gc), 256, h->round_dyn_smem, h->s_exp>>>(xa);
     }
-    if (n_code) { xa.tile0 = n_round; k_expand_codes<<<dim3(gc, n_code), 256, h->codes_dyn_smem, h->s_exp>>>(xa); B.T.other_launches++; }
+    if (n_code) {
+        xa.tile0 = n_round;
+        if (h->codes_ug == 8) k_expand_codes<8><<<dim3(gc, n_code), 256, h->codes_dyn_smem, h->s_exp>>>(xa);
+        else k_expand_codes<4><<<dim3(gc, n_code), 256, h->codes_dyn_smem, h->s_exp>>>(xa);
+        B.T.other_launches++;
+    }
     CU(cudaEventRecord(G.t1, h->s_exp));
     B.T.expand_launches++;
     if (B.digest) for (uint32_t k = G.begin; k < G.end; k++) {     // built-in on-GPU consumer: reads every entry of the witness once
@@ -578,7 +583,8 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (const char *v = tune_env("POB_SERIALIZE")) h->serialize = atoi(v) != 0;
         if (const char *v = tune_env("POB_EXPAND_SMEM_KB")) h->round_dyn_smem = (uint32_t)atoi(v) * 1024u;
         if (const char *v = tune_env("POB_EXPAND_THREADS")) h->round_threads = (uint32_t)atoi(v);
-        if (const char *v = tune_env("POB_CODES_SMEM_KB")) { h->codes_dyn_smem = (uint32_t)atoi(v) * 1024u; if (h->codes_dyn_smem > 48 * 1024) CU(cudaFuncSetAttribute(k_expand_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->codes_dyn_smem)); }
+        if (const char *v = tune_env("POB_CODES_UG")) h->codes_ug = (uint32_t)atoi(v);
+        if (const char *v = tune_env("POB_CODES_SMEM_KB")) { h->codes_dyn_smem = (uint32_t)atoi(v) * 1024u; if (h->codes_dyn_smem > 48 * 1024) { CU(cudaFuncSetAttribute(k_expand_codes<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->codes_dyn_smem)); CU(cudaFuncSetAttribute(k_expand_codes<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->codes_dyn_smem)); } }
         if (h->round_dyn_smem > 48 * 1024) {
             CU(cudaFuncSetAttribute(k_expand_round<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
             CU(cudaFuncSetAttribute(k_expand_round<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
