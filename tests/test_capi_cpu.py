@@ -98,3 +98,34 @@ def test_input_schema_and_flatten():
     assert pob_b200.parse_main("component main = 0;".replace("component main = 0", "Spend(31)")) == ("Spend", [31])
     lim = pob_b200.to_limbs([-1, pob_b200.P + 5, 2 ** 200])
     assert pob_b200.from_limbs(lim[0]) == pob_b200.P - 1 and pob_b200.from_limbs(lim[1]) == 5 and pob_b200.from_limbs(lim[2]) == 2 ** 200
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """The boundary is a C ABI: include/pob_b200.h must compile as C99 (no C++, no CUDA, no torch types) and a plain C host
+    must link against the shared library and reach its host-only entry points (no GPU needed for these)."""
+    import subprocess
+    import pob_b200
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "pob_b200.h"
+int main(void) {
+    uint64_t p[1][4] = {{31, 0, 0, 0}};
+    pob_desc d; pob_check_report r; int np = -1;
+    if (pob_layout_info("Spend", &p[0][0], 1, 0, &d) != POB_OK) { printf("layout: %s\n", pob_last_error()); return 1; }
+    if (pob_layout_info("Spend", &p[0][0], 1, POB_CREATE_O1, &d) != POB_OK || d.opt_level != 1 || d.n_signals_o0 != 2603360) return 2;
+    if (pob_constraint_info("Spend", &p[0][0], 1, 0, &r) != POB_OK || r.signals_read != 2603360) return 3;
+    if (!pob_input_schema("Spend", &np) || np != 1) return 4;
+    if (pob_layout_info("NoSuch", 0, 0, 0, &d) != POB_E_COMPILE || strlen(pob_last_error()) == 0) return 5;
+    printf("%llu %llu %s\n", (unsigned long long)d.n_signals, (unsigned long long)r.n_constraints, pob_version());
+    return 0;
+}
+''')
+    exe = str(tmp_path / "host")
+    libdir = os.path.dirname(pob_b200.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe,
+                           "-L", libdir, "-l:libpob_b200.so", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.split()[:2] == ["259945", "2605282"]
