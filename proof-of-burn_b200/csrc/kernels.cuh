@@ -190,6 +190,20 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ Op ldg_op(const Op *p) { const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p)); return Op{v.x, v.y, v.z, v.w}; }
+__device__ __forceinline__ void prefetch_code(const VmCtx &x, Code c) {
+    const uint32_t k = code_kind(c), p = code_payload(c);
+    const void *q = (k == K_VAL) ? (const void *)(x.U + x.val_base + 4ull * p) : (k == K_BIT) ? (const void *)(x.U + (p >> 6)) : nullptr;
+    if (q) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+}
+__device__ __forceinline__ void prefetch_operands(const VmCtx &x, const Op &o) {
+    const uint32_t opc = op_opc(o);
+    if (opc == OP_PACK8 || opc == OP_SELSUM) { if (opc == OP_SELSUM) prefetch_code(x, o.a); return; }   // their operand lists live in aux[]
+    prefetch_code(x, o.a);
+    if (opc == OP_FMA || opc == OP_CHK_EQ || opc == OP_DIV || opc == OP_MOD) prefetch_code(x, o.b);
+    if (opc == OP_FMA) prefetch_code(x, o.c);
+}
+
 // k_eval: one thread-block CLUSTER per proof instance (cluster size C = 1, 2, 4 or 8 CTAs of THREADS threads; C = 1 is a plain
 // CTA).  The levelised program is spread over all C*THREADS threads / all warps of the cluster, levels are separated by a
 // cluster barrier; the instance store lives in global memory (L2-resident).  Poseidon round / MDS constants (C, S, M, P of
@@ -226,7 +240,18 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     for (uint32_t lv = 0; lv < a.n_levels; lv++) {
         if (a.prof && inst == 0 && gt == 0) a.prof[lv] = clock64();
         const Level L = s_levels[lv];
-        for (uint32_t i = L.t_begin + gt; i < L.t_end; i += GT) vm_exec_op(x, a.ops[i]);
+        // thread ops of one level are mutually independent: the next op record is fetched, and the cache lines of its operands
+        // are requested (prefetch.global.L1), while the current op executes -- two of the three dependent memory latencies
+        // of an op (record -> operand -> result) overlap with the previous op
+        {
+            uint32_t i = L.t_begin + gt;
+            Op nxt = i < L.t_end ? ldg_op(a.ops + i) : Op{0, 0, 0, 0};
+            for (; i < L.t_end; i += GT) {
+                const Op cur = nxt;
+                if (i + GT < L.t_end) { nxt = ldg_op(a.ops + i + GT); prefetch_operands(x, nxt); }
+                vm_exec_op(x, cur);
+            }
+        }
         // warp ops: Poseidons take the first warps (long), Keccak absorbs the next ones
         for (uint32_t q = L.p_begin + gwarp; q < L.p_end; q += nwarp) poseidon_warp(x, a.poseidons[q], s_pk);
         { const uint32_t np = (L.p_end - L.p_begin) % nwarp, wv = (gwarp + nwarp - np) % nwarp;

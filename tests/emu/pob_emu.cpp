@@ -178,3 +178,28 @@ extern "C" int pob_emu_check_constraints(const char *main_name, const uint64_t *
         return 0;
     } catch (const std::exception &ex) { if (err) snprintf(err, (size_t)errlen, "%s", ex.what()); return -1; }
 }
+
+// tuning aid: how many IsZero inverses of the "table" group miss the small-value table on this input (they pay a real inversion)
+extern "C" void pob_emu_inv_miss_count(void *h, const uint64_t *inputs, uint64_t *out) {
+    EmuProgram *e = (EmuProgram *)h; const Program &P = e->P;
+    std::vector<uint64_t> U(P.store_u64() + 4, 0);
+    for (uint32_t i = 0; i < P.n_inputs; i++) vm_store_val(U.data() + P.val_base + 4ull * i, vm_load_val(inputs + 4ull * i));
+    uint32_t status = STATUS_OK;
+    VmCtx x{U.data(), P.val_base, P.konst.data(), P.aux.data(), e->invtab.data(), &status};
+    for (const Level &lv : P.levels) {
+        for (uint32_t i = lv.t_begin; i < lv.t_end; i++) vm_exec_op(x, P.ops[i]);
+        for (uint32_t i = lv.w_begin; i < lv.w_end; i++) vm_absorb_scalar(U.data(), P.absorbs[i]);
+        for (uint32_t i = lv.p_begin; i < lv.p_end; i++) vm_poseidon_scalar(x, P.poseidons[i], P.pos_konst.data());
+        for (uint32_t i = lv.s_begin; i < lv.s_end; i++) vm_psum_scalar(x, P.psums[i]);
+    }
+    out[0] = P.ginv_begin - P.inv_begin; out[1] = P.inv_end - P.ginv_begin; out[2] = out[3] = 0;
+    std::vector<uint8_t> thr(1024, 0);
+    for (uint32_t i = P.inv_begin; i < P.inv_end; i++) {
+        Fr a = vm_load(x, P.ops[i].a), d;
+        const bool miss = vm_inv_class(x, a, d) != 0;
+        if (i < P.ginv_begin) { if (miss) { out[2]++; thr[(i - P.inv_begin) % 1024] = 1; } } else if (!miss) out[3]++;
+    }
+    out[4] = 0; for (uint8_t v : thr) out[4] += v;
+    uint64_t warps = 0; for (int w = 0; w < 32; w++) { bool any = false; for (int l = 0; l < 32; l++) any |= thr[w * 32 + l]; warps += any; }
+    out[5] = warps;
+}
