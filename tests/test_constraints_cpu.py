@@ -88,3 +88,20 @@ def test_constraint_counts_of_the_main_shape():
     import pob_b200
     r = pob_b200.constraint_info(pob_b200.MAIN_PROOF_OF_BURN)
     assert r["signals_read"] == 215907954 and r["n_constraints"] == 215962293 and r["n_nonlinear"] == 17910859 and r["n_hints"] == 256010
+
+
+def test_constraints_follow_the_numbering_policy():
+    """the constraint records are stated over witness indices, so they hold on a witness of the SAME numbering policy only: the
+    creation-order (hcreate) system accepts the oracle's hcreate witness, the default system rejects it"""
+    import emu
+    from oracle import oracle
+    s = suite("test_num_2_bits_safe_256")
+    name, params = oracle.parse_main(s["main"])
+    w = oracle.run(s["main"], s["cases"][0]["input"], hcreate=True)
+    try:
+        same = emu.check_constraints(name, _limbs(params), len(params), w.limbs, hcreate=True)
+        other = emu.check_constraints(name, _limbs(params), len(params), w.limbs, hcreate=False)
+        assert same["n_failed"] == 0 and same["n_hint_failed"] == 0 and same["signals_referenced"] == w.n_signals
+        assert other["n_failed"] > 0
+    finally:
+        w.free()
