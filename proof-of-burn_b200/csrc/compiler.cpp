@@ -2199,7 +2199,8 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
         const uint32_t ts = TILE_SIGNALS;
         for (auto &sg : B.segs) {
             if (sg.round) {
-                for (uint32_t done = 0; done < RT; done += ts) { Tile t; t.dst = dst + done; t.n = std::min(ts, RT - done); t.code_off = done; t.ubase = sg.ubase; t.pad = fast_round ? 1 : 0; P.tiles.push_back(t); }
+                const uint32_t rts = (fast_round && RT <= MAX_TILE_SIGNALS) ? RT : ts;      // one CTA streams what is left of a round block (266 KB)
+                for (uint32_t done = 0; done < RT; done += rts) { Tile t; t.dst = dst + done; t.n = std::min(rts, RT - done); t.code_off = done; t.ubase = sg.ubase; t.pad = fast_round ? 1 : 0; P.tiles.push_back(t); }
                 dst += RT; mp += RT;
             } else {
                 const size_t first = P.codes.size();

@@ -160,6 +160,7 @@ struct EvalArgs {
     uint32_t *status; uint64_t *outputs;          // chunk base
     long long *prof;                              // tuning only: per-level clock64 stamps of instance 0 (or null)
     uint32_t pos_konst_bytes, levels_bytes;       // sizes of the two TMA-staged tables (multiples of 16 bytes)
+    uint32_t prefetch;                            // 1: fetch the next op record / prefetch its operand lines while the current op runs
 };
 
 // ---- TMA (bulk async copy engine) and cluster primitives ---------------------------------------------------------------
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
             Op nxt = i < L.t_end ? ldg_op(a.ops + i) : Op{0, 0, 0, 0};
             for (; i < L.t_end; i += GT) {
                 const Op cur = nxt;
-                if (i + GT < L.t_end) { nxt = ldg_op(a.ops + i + GT); prefetch_operands(x, nxt); }
+                if (i + GT < L.t_end) { nxt = ldg_op(a.ops + i + GT); if (a.prefetch) prefetch_operands(x, nxt); }
                 vm_exec_op(x, cur);
             }
         }

@@ -156,7 +156,7 @@ struct pob_handle {
     // 2 CTAs/SM vs 7.26 / 7.19 / 7.09 / 6.97 TB/s with 3 / 4 / 5 / 8, and 5.96 TB/s with 1 (profiles/r01_expand_sweep.md)
     uint32_t round_dyn_smem = 85 * 1024;
     uint32_t round_threads = 256, codes_dyn_smem = 0, codes_ug = 4; bool serialize = false;   // changed by POB_TUNING knobs only
-    int eval_threads = 1024; uint32_t eval_cluster = 1;   // k_eval: threads per CTA, CTAs per instance (thread-block cluster)
+    int eval_threads = 512; uint32_t eval_cluster = 0, eval_prefetch = 1;   // k_eval: threads per CTA; CTAs per instance (0 = chosen per launch)
     uint32_t pos_konst_bytes = 0, levels_bytes = 0, eval_smem = 0;
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
     cudaEvent_t ev_eval_done[RING] = {nullptr, nullptr}, ev_exp_done[RING] = {nullptr, nullptr}, ev_h2d[RING] = {nullptr, nullptr},
@@ -273,12 +273,16 @@ static void enqueue_eval(pob_handle *h, uint32_t c) {
     uint64_t *stores = h->d_stores + (size_t)r * E * h->store_stride;
     EvalArgs ea{h->d_ops, h->d_abs, h->d_pos, h->d_pos_konst, h->d_psums, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.ginv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
                 h->d_codes + P.out_code_off, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
-                h->d_status + first, h->d_outputs + (size_t)first * no * 4, (c == 0) ? h->d_prof : nullptr, h->pos_konst_bytes, h->levels_bytes};
+                h->d_status + first, h->d_outputs + (size_t)first * no * 4, (c == 0) ? h->d_prof : nullptr, h->pos_konst_bytes, h->levels_bytes, h->eval_prefetch};
     CU(cudaEventRecord(B.e0[c], h->s_eval));
-    {   // one cluster of eval_cluster CTAs per instance
+    {   // one thread-block cluster per instance.  Cluster size: the largest power of two (<= 8) that still lets every instance of
+        // the launch have its own SMs -- 8 CTAs for a single witness (latency), 4 for the 32-instance chunks of the main shape,
+        // 1 when a chunk fills the GPU anyway (reduced witness, Spend); profiles/r02b_eval_sweep.log
+        uint32_t C = h->eval_cluster;
+        if (C == 0) { C = 8; while (C > 1 && cnt * C > 148) C >>= 1; }
         cudaLaunchConfig_t cfg{}; cudaLaunchAttribute at[1];
-        cfg.gridDim = dim3(cnt * h->eval_cluster); cfg.blockDim = dim3((unsigned)h->eval_threads); cfg.dynamicSmemBytes = h->eval_smem; cfg.stream = h->s_eval;
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = h->eval_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(cnt * C); cfg.blockDim = dim3((unsigned)h->eval_threads); cfg.dynamicSmemBytes = h->eval_smem; cfg.stream = h->s_eval;
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         switch (h->eval_threads) {
         case 256: CU(cudaLaunchKernelEx(&cfg, k_eval<256>, ea)); break;
@@ -574,7 +578,8 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         // expand group: ~100 GB of witness per launch pair (main_proof_of_burn: 16 witnesses; Spend: up to the whole chunk)
         h->xgroup = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(nslots, chunk), std::max<uint64_t>(16, (100ull << 30) / wbytes));
         if (const char *v = tune_env("POB_EVAL_THREADS")) h->eval_threads = atoi(v);
-        if (const char *v = tune_env("POB_EVAL_CLUSTER")) h->eval_cluster = (uint32_t)std::max(1, std::min(8, atoi(v)));
+        if (const char *v = tune_env("POB_EVAL_CLUSTER")) h->eval_cluster = (uint32_t)std::max(0, std::min(8, atoi(v)));
+        if (const char *v = tune_env("POB_EVAL_PREFETCH")) h->eval_prefetch = (uint32_t)(atoi(v) != 0);
         if (h->eval_threads != 256 && h->eval_threads != 512) h->eval_threads = 1024;
         if (h->eval_smem > 200 * 1024) throw std::runtime_error("the Poseidon constant and level tables do not fit in shared memory");
         CU(cudaFuncSetAttribute(k_eval<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->eval_smem));

@@ -15,8 +15,9 @@ shape = (16, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)
 opt = int(os.environ.get("SWEEP_OPT", "0"))
 packed = synth.pack_instances(synth.make_batch(256, shape, seed=5), shape)
 ref = None
-for threads, cluster in [(1024, 1), (512, 1), (512, 2), (1024, 2), (512, 4), (256, 4), (1024, 4), (512, 8), (256, 8)]:
-    os.environ["POB_EVAL_THREADS"], os.environ["POB_EVAL_CLUSTER"] = str(threads), str(cluster)
+SHAPES = [(512, 0, 1), (512, 0, 0), (1024, 1, 1), (1024, 1, 0), (512, 4, 1), (512, 4, 0), (512, 2, 1), (256, 8, 1), (1024, 0, 1)]   # cluster 0 = chosen per launch
+for threads, cluster, pf in SHAPES:
+    os.environ["POB_EVAL_THREADS"], os.environ["POB_EVAL_CLUSTER"], os.environ["POB_EVAL_PREFETCH"] = str(threads), str(cluster), str(pf)
     try:
         c = pob_b200.Circuit(pob_b200.MAIN_PROOF_OF_BURN, opt=opt)
         one = packed[:1]
@@ -33,7 +34,7 @@ for threads, cluster in [(1024, 1), (512, 1), (512, 2), (1024, 2), (512, 4), (25
         if ref is None:
             ref = dg.digests.copy()
         same = bool(np.array_equal(dg.digests, ref))
-        print(json.dumps({"threads": threads, "cluster": cluster, "latency_ms": round(lat, 3), "lat_eval_ms": round(t1["eval_ms"], 3), "lat_expand_ms": round(t1["expand_ms"], 3),
+        print(json.dumps({"threads": threads, "cluster": cluster, "prefetch": pf, "latency_ms": round(lat, 3), "lat_eval_ms": round(t1["eval_ms"], 3), "lat_expand_ms": round(t1["expand_ms"], 3),
                           "eval128_ms": round(ev["total_ms"], 3), "eval128_kernel_ms": round(ev["eval_ms"], 3), "batch256_wit_s": round(256 / (th["total_ms"] / 1e3), 1),
                           "batch256_eval_ms": round(th["eval_ms"], 2), "ok": ok, "digests_equal_default": same}), flush=True)
         c.close()
