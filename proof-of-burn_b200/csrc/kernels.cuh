@@ -335,8 +335,10 @@ __global__ void __launch_bounds__(T) k_expand_round(const ExpandArgs a) {
 }
 
 // k_expand_codes: grid = (instances in the group, code tiles) -- INSTANCE-major, so that a tile's code stream is fetched
-// from DRAM once and served from L2 to the other witnesses of the group.  One 32-bit code per entry, loads issued 4
-// entries ahead of the stores.
+// from DRAM once and served from L2 to the other witnesses of the group.  One 32-bit code per entry.  The tile's code stream
+// (<= 32 KiB, contiguous) is brought into shared memory by ONE TMA bulk copy, so the first of the two dependent memory hops of
+// an entry (code -> store word / value -> witness) costs a shared-memory read; the gathers of UG entries per thread are then in
+// flight together, ahead of the stores.
 template <int UG>
 __global__ void __launch_bounds__(256, UG == 4 ? 5 : 4) k_expand_codes(const ExpandArgs a) {
     const uint32_t gi = a.inst[blockIdx.x];
@@ -345,15 +347,21 @@ __global__ void __launch_bounds__(256, UG == 4 ? 5 : 4) k_expand_codes(const Exp
     const uint64_t *U = a.stores + (uint64_t)(gi - a.chunk_first) * a.store_stride;
     uint64_t *W = a.wit[blockIdx.x] + t.dst * 4;
     const uint64_t *Ub = U + t.ubase;
-    const Code *c = a.codes + t.code_off;
+    __shared__ __align__(16) Code sC[TILE_SIGNALS + 4];
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t off4 = t.code_off & 3u, bytes = (((t.n + off4) * 4u) + 15u) & ~15u;     // TMA wants 16-byte aligned source and size
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, bytes); tma_load_1d(sC, a.codes + (t.code_off - off4), bytes, &s_bar); }
+    mbar_wait(&s_bar, 0);
+    const Code *c = sC + off4;
     for (uint32_t base = threadIdx.x; base < t.n; base += 256 * UG) {
-        Code cd[UG];
-#pragma unroll
-        for (int u = 0; u < UG; u++) { const uint32_t k = base + 256 * u; cd[u] = k < t.n ? __ldg(c + k) : 0u; }
         uint64_t v[UG][4];
 #pragma unroll
         for (int u = 0; u < UG; u++) {
-            const uint32_t kind = code_kind(cd[u]), p = code_payload(cd[u]);
+            const uint32_t k = base + 256 * u;
+            const Code cd = k < t.n ? c[k] : 0u;
+            const uint32_t kind = code_kind(cd), p = code_payload(cd);
             v[u][1] = v[u][2] = v[u][3] = 0;
             if (kind == K_BIT) v[u][0] = (Ub[p >> 6] >> (p & 63)) & 1ull;
             else if (kind == K_CONST) v[u][0] = p;
