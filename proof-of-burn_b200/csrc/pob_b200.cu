@@ -156,7 +156,7 @@ struct pob_handle {
     // 2 CTAs/SM vs 7.26 / 7.19 / 7.09 / 6.97 TB/s with 3 / 4 / 5 / 8, and 5.96 TB/s with 1 (profiles/r01_expand_sweep.md)
     uint32_t round_dyn_smem = 85 * 1024;
     uint32_t round_threads = 256, codes_dyn_smem = 0, codes_ug = 4; bool serialize = false;   // changed by POB_TUNING knobs only
-    int eval_threads = 512; uint32_t eval_cluster = 0, eval_prefetch = 1;   // k_eval: threads per CTA; CTAs per instance (0 = chosen per launch)
+    int eval_threads = 512; uint32_t eval_cluster = 0, eval_prefetch = 0;   // operand prefetch measured no gain (profiles/r02c_eval_sweep.log)   // k_eval: threads per CTA; CTAs per instance (0 = chosen per launch)
     uint32_t pos_konst_bytes = 0, levels_bytes = 0, eval_smem = 0;
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
     cudaEvent_t ev_eval_done[RING] = {nullptr, nullptr}, ev_exp_done[RING] = {nullptr, nullptr}, ev_h2d[RING] = {nullptr, nullptr},
