@@ -284,6 +284,11 @@ __device__ __forceinline__ void st256(uint64_t *p, uint64_t a, uint64_t b, uint6
     asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d));
 }
 
+// streaming flavour: evict-first in L2, so that the 7 TB/s write stream does not flush the eval kernel's working set out of L2
+__device__ __forceinline__ void st256cs(uint64_t *p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
+    asm volatile("st.global.cs.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d));
+}
+
 struct ExpandArgs {
     const Tile *tiles; const Code *codes; const Fr *konst; const uint2 *round_desc;
     const uint64_t *stores; uint64_t store_stride; uint32_t val_base;   // store of chunk-local instance 0
@@ -292,6 +297,7 @@ struct ExpandArgs {
     const uint32_t *status;                       // per instance of the batch; a rejected instance contributes no witness
     uint32_t chunk_first;                         // batch index of the chunk's first instance (store = inst - chunk_first)
     uint32_t tile0;                               // first tile of this launch (k_expand_codes)
+    uint32_t cs;                                  // 1: streaming (evict-first) witness stores
 };
 
 // k_expand_round: grid = (KeccakfRound tiles, instances in the group) -- 95.8 % of the witness.  One CTA streams one
@@ -330,7 +336,7 @@ __global__ void __launch_bounds__(T) k_expand_round(const ExpandArgs a) {
             const uint32_t sidx = (mode - 1) * 64 + tt, g = sidx / 3, m = sidx - 3 * g;
             b = g; w = (m == 0) ? (d.x & 0xffffu) : (m == 1) ? (d.x >> 16) : (d.y & 0xffffu);
         }
-        st256(W + 4ull * k, (sW[w] >> b) & 1ull, 0, 0, 0);
+        if (a.cs) st256cs(W + 4ull * k, (sW[w] >> b) & 1ull, 0, 0, 0); else st256(W + 4ull * k, (sW[w] >> b) & 1ull, 0, 0, 0);
     }
 }
 
@@ -371,7 +377,7 @@ __global__ void __launch_bounds__(256, UG == 4 ? 5 : 4) k_expand_codes(const Exp
             }
         }
 #pragma unroll
-        for (int u = 0; u < UG; u++) { const uint32_t k = base + 256 * u; if (k < t.n) st256(W + 4ull * k, v[u][0], v[u][1], v[u][2], v[u][3]); }
+        for (int u = 0; u < UG; u++) { const uint32_t k = base + 256 * u; if (k < t.n) { if (a.cs) st256cs(W + 4ull * k, v[u][0], v[u][1], v[u][2], v[u][3]); else st256(W + 4ull * k, v[u][0], v[u][1], v[u][2], v[u][3]); } }
     }
 }
 

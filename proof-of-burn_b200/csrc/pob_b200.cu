@@ -158,6 +158,7 @@ struct pob_handle {
     uint32_t round_threads = 256, codes_dyn_smem = 0, codes_ug = 4; bool serialize = false;   // changed by POB_TUNING knobs only
     int eval_threads = 512; uint32_t eval_cluster = 0, eval_prefetch = 0;   // operand prefetch measured no gain (profiles/r02c_eval_sweep.log)   // k_eval: threads per CTA; CTAs per instance (0 = chosen per launch)
     uint32_t pos_konst_bytes = 0, levels_bytes = 0, eval_smem = 0;
+    uint32_t expand_cs = 0, eval_l2_mb = 0;     // tuning: streaming witness stores; persisting-L2 window (MB) for the eval stream's store accesses
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
     cudaEvent_t ev_eval_done[RING] = {nullptr, nullptr}, ev_exp_done[RING] = {nullptr, nullptr}, ev_h2d[RING] = {nullptr, nullptr},
                 ev_start = nullptr, ev_end = nullptr, ev_tmp = nullptr;
@@ -313,7 +314,7 @@ static void enqueue_group(pob_handle *h, uint32_t g) {
         h->slot_owner[s] = (int64_t)B.plan[k];
     }
     ExpandArgs xa{h->d_tiles, h->d_codes, h->d_konst, reinterpret_cast<const uint2 *>(h->d_round_desc), h->d_stores + (size_t)r * E * h->store_stride, h->store_stride, P.val_base,
-                  h->d_witptr + G.begin, h->d_planinst + G.begin, h->d_status, G.chunk * E, 0};
+                  h->d_witptr + G.begin, h->d_planinst + G.begin, h->d_status, G.chunk * E, 0, h->expand_cs};
     CU(cudaEventRecord(G.t0, h->s_exp));
     // launch 1: KeccakfRound tiles, tile-major (each CTA's tables are staged in shared memory);
     // launch 2: code tiles, INSTANCE-major, so that a tile's code stream is fetched from DRAM once and
@@ -581,6 +582,8 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (const char *v = tune_env("POB_EVAL_THREADS")) h->eval_threads = atoi(v);
         if (const char *v = tune_env("POB_EVAL_CLUSTER")) h->eval_cluster = (uint32_t)std::max(0, std::min(8, atoi(v)));
         if (const char *v = tune_env("POB_EVAL_PREFETCH")) h->eval_prefetch = (uint32_t)(atoi(v) != 0);
+        if (const char *v = tune_env("POB_EXPAND_CS")) h->expand_cs = (uint32_t)(atoi(v) != 0);
+        if (const char *v = tune_env("POB_EVAL_L2_MB")) h->eval_l2_mb = (uint32_t)std::max(0, atoi(v));
         if (h->eval_threads != 256 && h->eval_threads != 512) h->eval_threads = 1024;
         if (h->eval_smem > 200 * 1024) throw std::runtime_error("the Poseidon constant and level tables do not fit in shared memory");
         CU(cudaFuncSetAttribute(k_eval<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->eval_smem));
@@ -602,6 +605,17 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         CU(cudaMalloc(&h->d_stores, (size_t)pob_handle::RING * chunk * h->store_stride * 8));
         CU(cudaMalloc(&h->d_inputs, std::max<size_t>(32, (size_t)pob_handle::RING * chunk * P.n_inputs * 32)));
         for (uint64_t s = 0; s < nslots; s++) { uint64_t *p = nullptr; CU(cudaMalloc(&p, wbytes)); h->slots.push_back(p); }
+        if (h->eval_l2_mb) {       // tuning: keep (part of) the store ring persisting in L2 for the kernels of the eval stream
+            const size_t ring = (size_t)pob_handle::RING * chunk * h->store_stride * 8, carve = (size_t)h->eval_l2_mb << 20;
+            CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+            cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = h->d_stores;
+            av.accessPolicyWindow.num_bytes = std::min<size_t>(ring, (size_t)prop.accessPolicyMaxWindowSize);
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)av.accessPolicyWindow.num_bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            CU(cudaStreamSetAttribute(h->s_eval, cudaStreamAttributeAccessPolicyWindow, &av));
+        }
         h->slot_owner.assign(nslots, -1); h->slot_rel_pending.assign(nslots, 0);
         for (uint64_t s = 0; s < nslots; s++) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->slot_rel_ev.push_back(e); }
     } catch (const std::exception &e) {
