@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the timed oracle leg (the in-run digest parity check still runs: --parity)")
     ap.add_argument("--parity", type=int, default=2, help="instances whose whole-witness digest is compared with the oracle when the cpu baseline is skipped (0 = none)")
     ap.add_argument("--consume-batch", type=int, default=256, help="instances of the 'every witness consumed on the GPU' figure (0 = skip)")
+    ap.add_argument("--no-selfcheck", dest="selfcheck", action="store_false", help="skip the on-GPU constraint check of one witness")
     ap.add_argument("--reduced-batch", type=int, default=256, help="instances of the reduced (--O1-style) witness figure (0 = skip)")
     ap.add_argument("--export-sample", type=int, default=24, help="instances of the 'every witness exported to the host' figure (0 = skip)")
     ap.add_argument("--seed", type=int, default=7503)
@@ -339,6 +340,15 @@ def main():
         cr.close()
         circuit = pob_b200.Circuit(expr, device=local_rank)
         circuit.stage(pinned.array)
+    selfcheck = None
+    if a.selfcheck and rank == 0:
+        # every constraint of the circuit evaluated on the GPU against one freshly generated witness
+        circuit.run_packed(pinned.array[:1])
+        circuit.selfcheck(0)                                    # first call compiles + uploads the constraint system
+        sc = circuit.selfcheck(0)
+        selfcheck = {"ms": sc["ms"], "n_constraints": sc["n_constraints"], "n_nonlinear": sc["n_nonlinear"], "n_hints": sc["n_hints"], "n_failed": sc["n_failed"] + sc["n_hint_failed"],
+                     "signals_read": sc["signals_read"], "what": "pob_selfcheck: every <== / === of the circom sources over witness indices, 100 % of the entries read"}
+        assert selfcheck["n_failed"] == 0, "the generated witness violates a circuit constraint"
     if rank == 0:
         one = pinned.array[:1]
         circuit.run_packed(one)
@@ -380,7 +390,7 @@ def main():
                 "details": {"resident_slots": desc["n_slots"], "wall_ms_per_step": wall_ms_max / a.steps, "eval_chunk": desc["chunk"], "expand_group": desc["expand_group"],
                             "eval_kernel": {"ms_per_launch": eval_ms / max(1, eval_launches), "instances_per_launch": min(desc["chunk"], a.batch),
                                             "note": "runs concurrently with the expand kernels on a higher-priority stream"}},
-                "handoff": handoff, "latency": latency, "reduced_witness": reduced,
+                "handoff": handoff, "latency": latency, "reduced_witness": reduced, "selfcheck": selfcheck,
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "witnesses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": "host pinned inputs -> pob_run_batch(POB_RUN_DISCARD) -> status + output signals on host; generation-only: see `handoff` for the runs in which every witness is consumed / exported"},

@@ -5,7 +5,7 @@
 #   N GPUs      : L in {4, 8, 12, 16} x batch 1024 per GPU (torchrun, one rank per GPU)
 NG=${1:-1}; MODE=${2:-full}; TAG=${3:-r02}; OUT=gpurun_out; mkdir -p $OUT
 LOG=$OUT/config5_${NG}gpu_$TAG.log; : > $LOG
-COMMON="--steps 2 --warmup 3 --no-cpu-baseline --parity 2 --consume-batch 0 --export-sample 0 --reduced-batch 0"
+COMMON="--steps 2 --warmup 3 --no-cpu-baseline --parity 2 --consume-batch 0 --export-sample 0 --reduced-batch 0 --no-selfcheck"
 fmt() { python -c "
 import sys, json
 for l in sys.stdin:

@@ -2,7 +2,7 @@
 # round 2, GPU session C: evidence for the final build -- bench, reference arm, ncu launch list, ncu --set full of both expand kernels
 # (1 witness per launch) and of k_eval, config-5 sweep on one GPU with in-run parity
 TAG=${1:-r02c}; OUT=gpurun_out; mkdir -p $OUT
-NOEX="--no-cpu-baseline --parity 0 --consume-batch 0 --export-sample 0 --reduced-batch 0"
+NOEX="--no-cpu-baseline --parity 0 --consume-batch 0 --export-sample 0 --reduced-batch 0 --no-selfcheck"
 echo "== pytest -m gpu"; timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee $OUT/pytest_gpu_$TAG.log
 echo "== k_eval sweep (O0)"; timeout 900 python tools/eval_sweep.py 2>&1 | tee $OUT/eval_sweep_$TAG.log
 echo "== k_eval sweep (reduced witness)"; SWEEP_OPT=1 timeout 900 python tools/eval_sweep.py 2>&1 | tee $OUT/eval_sweep_o1_$TAG.log

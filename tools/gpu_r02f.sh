@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, GPU session F: reduced-witness shape sweep; ncu of the TMA-staged k_expand_codes (1 witness, and inside a 16-witness group)
 TAG=${1:-r02f}; OUT=gpurun_out; mkdir -p $OUT
-NOEX="--no-cpu-baseline --parity 0 --consume-batch 0 --export-sample 0 --reduced-batch 0"
+NOEX="--no-cpu-baseline --parity 0 --consume-batch 0 --export-sample 0 --reduced-batch 0 --no-selfcheck"
 echo "== O1 sweep"; timeout 1500 python tools/o1_sweep.py 2>&1 | tee $OUT/o1_sweep_$TAG.log
 echo "== ncu full k_expand_codes (1 witness per launch)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_expand_codes -s 1 -c 1 -o $OUT/prof_k_expand_codes_$TAG -f \
