@@ -1,19 +1,22 @@
 // kernels.cuh -- device code (sm_100a) of the batched witness generator; included by pob_b200.cu only.
 //
-//   k_eval    one CTA per proof instance: runs the levelised witness program over the instance store.
-//             Thread ops: BN254-Fr FMA / IsZero / inverse / div-mod / byte packing / constraint checks
-//             (vm_exec.h).  Warp ops: one Keccak absorb per warp, state lane l held by thread l, Theta
-//             column parities / D, RhoPi lane walk and Chi neighbours exchanged with warp shuffles; every
-//             intermediate lane word the bit-level circuit exposes (utils/keccak.circom:58-297) is written
-//             to the store (238 words per round).  One Poseidon permutation per warp (state element j in
-//             Montgomery form on lane j, Mix/MixS via shuffles).  Prefix sums by warp scan.  IsZero inverse
-//             hints batch-inverted at the end (table for small inputs, one binary-EEA inversion per thread).
-//   k_pow_grind  proof-of-work burn-key search (the step before the path): one candidate key per thread.
+//   k_eval    one thread-block cluster (1, 2, 4 or 8 CTAs) per proof instance: runs the levelised witness program over the
+//             instance store, levels separated by a cluster barrier.  Thread ops: BN254-Fr FMA / IsZero / inverse / div-mod /
+//             byte packing / constraint checks (vm_exec.h).  Warp ops: one Keccak absorb per warp, state lane l held by
+//             thread l, Theta column parities / D, RhoPi lane walk and Chi neighbours exchanged with warp shuffles; every
+//             intermediate lane word the bit-level circuit exposes (utils/keccak.circom:58-297) is written to the store
+//             (238 words per round).  One Poseidon permutation per warp (state element j in Montgomery form on lane j,
+//             Mix/MixS via shuffles; round constants and MDS matrices staged in shared memory by TMA).  Prefix sums by warp
+//             scan.  IsZero inverse hints batch-inverted at the end (table for small inputs, one inversion per thread).
 //   k_expand_round / k_expand_codes  the HBM-bound kernels: materialise every witness entry as a 32-byte little-endian
 //             field element with one 256-bit store (STG.E.ENL2.256).  Algorithmic bytes = 32 * n_signals per instance
 //             (6.909 GB for main_proof_of_burn).  KeccakfRound blocks (95.8 %) are driven by 8-byte group descriptors
-//             and the round's lane words staged in shared memory; everything else by one 32-bit code per entry.
+//             and the round's lane words, everything else by one 32-bit code per entry; both kernels stage their
+//             tables in shared memory with TMA bulk copies (cp.async.bulk + mbarrier).
+//   k_check_eq / k_check_kc / k_check_r1  every constraint of the circuit evaluated against a resident witness (cons_check.h).
+//   k_check_rounds  layout-independent check of every KeccakfRound block (textbook round on its in/out signals).
 //   k_digest  64-bit digest of a materialised witness (parity tests at full size; the built-in on-GPU consumer).
+//   k_pow_grind  proof-of-work burn-key search (the step before the path): one candidate key per thread.
 #pragma once
 #include <cuda_runtime.h>
 #include "vm_exec.h"
@@ -302,8 +305,8 @@ struct ExpandArgs {
 
 // k_expand_round: grid = (KeccakfRound tiles, instances in the group) -- 95.8 % of the witness.  One CTA streams one
 // tile (<= 8192 entries = 256 KiB) with one 256-bit store per entry.  The source of every entry follows from an 8-byte
-// descriptor per 64 entries and a lane word of the round; the tile's <= 128 descriptors and the round's 263 words are
-// staged in shared memory in one burst, so the streaming loop touches no global memory but the witness itself.
+// descriptor per 64 entries and a lane word of the round; the tile's <= 130 descriptors and the round's 263 words are
+// staged in shared memory by two TMA bulk copies, so the streaming loop touches no global memory but the witness itself.
 template <int T>
 __global__ void __launch_bounds__(T) k_expand_round(const ExpandArgs a) {
     const uint32_t gi = a.inst[blockIdx.y];
