@@ -61,25 +61,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """summary of the samples taken inside [t0, t1] (the timed region); nvidia-smi needs a second or two to come up on an
+        8-GPU box, so the sampler is started before the warm-up and the window is cut out afterwards"""
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.2)]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        hi = sm[len(sm) // 4:]          # drop idle samples at the edges
-        return {"sm_mhz": hi[len(hi) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ---- CPU baseline: the oracle on host cores ------------------------------------------------------------------------
@@ -284,11 +286,11 @@ def main():
     def step_e2e():
         return circuit.run_packed(pinned.array, expand=True, discard=True)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(a.warmup):
         r = step_resident()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     t_wall = time.time()
     dev_ms, exp_ms, exp_launches, launches, ok, eval_ms, eval_launches = 0.0, 0.0, 0, 0, 0, 0.0, 0
     for _ in range(a.steps):
@@ -299,7 +301,7 @@ def main():
         ok += r.n_ok
     barrier()
     wall_ms = 1e3 * (time.time() - t_wall)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall, time.time())
     # end-to-end arm (host buffers)
     for _ in range(min(a.warmup, 1)):
         step_e2e()
