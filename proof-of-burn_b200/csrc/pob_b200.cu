@@ -158,6 +158,7 @@ struct pob_handle {
     uint32_t round_threads = 256, codes_dyn_smem = 0, codes_ug = 4; bool serialize = false;   // changed by POB_TUNING knobs only
     int eval_threads = 512; uint32_t eval_cluster = 0, eval_prefetch = 0;   // operand prefetch measured no gain (profiles/r02c_eval_sweep.log)   // k_eval: threads per CTA; CTAs per instance (0 = chosen per launch)
     uint32_t pos_konst_bytes = 0, levels_bytes = 0, eval_smem = 0;
+    bool skip_eval = false;                     // tuning: evaluate only the first two chunks, then re-expand their stores (isolates the cost of concurrency)
     uint32_t expand_cs = 0, eval_l2_mb = 0;     // tuning: streaming witness stores; persisting-L2 window (MB) for the eval stream's store accesses
     cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
     cudaEvent_t ev_eval_done[RING] = {nullptr, nullptr}, ev_exp_done[RING] = {nullptr, nullptr}, ev_h2d[RING] = {nullptr, nullptr},
@@ -285,7 +286,8 @@ static void enqueue_eval(pob_handle *h, uint32_t c) {
         cfg.gridDim = dim3(cnt * C); cfg.blockDim = dim3((unsigned)h->eval_threads); cfg.dynamicSmemBytes = h->eval_smem; cfg.stream = h->s_eval;
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        switch (h->eval_threads) {
+        if (h->skip_eval && c >= R) CU(cudaMemsetAsync(h->d_status + first, 0, (size_t)cnt * 4, h->s_eval));   // TUNING: expand-only timing (stale stores)
+        else switch (h->eval_threads) {
         case 256: CU(cudaLaunchKernelEx(&cfg, k_eval<256>, ea)); break;
         case 512: CU(cudaLaunchKernelEx(&cfg, k_eval<512>, ea)); break;
         default: CU(cudaLaunchKernelEx(&cfg, k_eval<1024>, ea)); break;
@@ -582,6 +584,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (const char *v = tune_env("POB_EVAL_THREADS")) h->eval_threads = atoi(v);
         if (const char *v = tune_env("POB_EVAL_CLUSTER")) h->eval_cluster = (uint32_t)std::max(0, std::min(8, atoi(v)));
         if (const char *v = tune_env("POB_EVAL_PREFETCH")) h->eval_prefetch = (uint32_t)(atoi(v) != 0);
+        if (const char *v = tune_env("POB_SKIP_EVAL")) h->skip_eval = atoi(v) != 0;
         if (const char *v = tune_env("POB_EXPAND_CS")) h->expand_cs = (uint32_t)(atoi(v) != 0);
         if (const char *v = tune_env("POB_EVAL_L2_MB")) h->eval_l2_mb = (uint32_t)std::max(0, atoi(v));
         if (h->eval_threads != 256 && h->eval_threads != 512) h->eval_threads = 1024;
