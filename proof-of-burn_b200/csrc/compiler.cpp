@@ -2137,6 +2137,46 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
         std::stable_sort(P.ops.begin() + tstart[l], P.ops.begin() + tstart[l] + tcount[l], [&](const Op &x, const Op &y) { return op_key(x) < op_key(y); });
         P.levels.push_back(Level{tstart[l], tstart[l] + tcount[l], wstart[l], wstart[l] + wcount[l], pstart[l], pstart[l] + pcount[l], sstart[l], sstart[l] + scount[l]});
     }
+    // ---- renumber the value slots in execution order ----
+    // Slot numbers are labels; after levelising and sorting they are scattered.  Renumbered in (level, op order) the 32 lanes of a
+    // warp store 32 consecutive slots (one 1 KB run instead of 32 scattered sectors) and next-level operand loads fall into the
+    // same lines.  Inputs keep slots [0, n_in); Poseidon / prefix-sum blocks move as blocks; the deferred inverses come last.
+    {
+        const uint32_t NV = B.n_vals;
+        std::vector<uint32_t> remap(NV, 0xffffffffu);
+        uint32_t next = 0;
+        for (uint32_t i = 0; i < (uint32_t)n_in; i++) remap[i] = next++;
+        auto has_dst = [](uint32_t opc) { return opc == OP_FMA || opc == OP_ISZ || opc == OP_INV || opc == OP_DIV || opc == OP_MOD || opc == OP_GTC || opc == OP_SELSUM; };
+        auto take = [&](uint32_t old, uint32_t n) { for (uint32_t k = 0; k < n; k++) { if (remap[old + k] != 0xffffffffu) throw std::runtime_error("pob: internal: value slot defined twice"); remap[old + k] = next++; } };
+        for (const Level &L : P.levels) {
+            for (uint32_t i = L.t_begin; i < L.t_end; i++) if (has_dst(op_opc(P.ops[i]))) take(op_dst(P.ops[i]), 1);
+            for (uint32_t q = L.p_begin; q < L.p_end; q++) take(P.poseidons[q].base, pos_layout(P.poseidons[q].t).total);
+            for (uint32_t q = L.s_begin; q < L.s_end; q++) take(P.psums[q].dst, P.psums[q].n);
+        }
+        for (uint32_t i = P.inv_begin; i < P.inv_end; i++) take(op_dst(P.ops[i]), 1);
+        if (next != NV) throw std::runtime_error("pob: internal: slot renumbering covers " + std::to_string(next) + " of " + std::to_string(NV) + " slots");
+        auto rc = [&](Code c) -> Code {
+            const uint32_t k = code_kind(c), pl = code_payload(c);
+            if (k == K_VAL) return c_val(remap[pl]);
+            if (k == K_BIT) {
+                const uint32_t idx = pl >> 6;
+                if (idx >= val_base) { const uint32_t slot = (idx - val_base) / 4, limb = (idx - val_base) % 4; return c_bit(val_base + 4 * remap[slot] + limb, pl & 63u); }
+            }
+            return c;
+        };
+        for (Op &o : P.ops) {
+            const uint32_t opc = op_opc(o);
+            if (has_dst(opc)) o.opc_dst = (opc << 26) | remap[op_dst(o)];
+            if (opc == OP_PACK8) continue;                       // a = raw aux offset
+            o.a = rc(o.a);
+            if (opc == OP_FMA || opc == OP_CHK_EQ || opc == OP_DIV || opc == OP_MOD) o.b = rc(o.b);
+            if (opc == OP_FMA) o.c = rc(o.c);
+        }
+        for (Code &c : P.aux) c = rc(c);
+        for (PsumOp &q : P.psums) { q.dst = remap[q.dst]; q.x0 = rc(q.x0); }
+        for (PoseidonOp &q : P.poseidons) q.base = remap[q.base];
+        for (size_t i = 0; i < B.flat_n; i++) B.flat[i] = rc(B.flat[i]);
+    }
     // ---- reduced witness: which signals stay ----
     std::vector<uint32_t> round_keep;            // retained relative indices inside a KeccakfRound block (same for every block)
     std::vector<uint32_t> parent;                // union-find over all --O0 signals
