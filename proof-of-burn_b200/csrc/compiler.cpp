@@ -325,8 +325,9 @@ class Builder {
         uint32_t lv = 0; for (uint32_t j = 0; j < t; j++) lv = std::max(lv, level_of(in[j]));
         uint32_t a0 = (uint32_t)aux.size(); aux.insert(aux.end(), in, in + t);
         uint32_t base = n_vals;
-        for (uint32_t i = 0; i < L.total; i++) new_val(lv + 1);
-        poseidons.push_back({PoseidonOp{t, a0, base, pos_koff[t]}, lv + 1});
+        const uint32_t Q = pos_steps(L), Kseg = POS_SEGMENTS;
+        for (uint32_t i = 0; i < L.total; i++) new_val(lv + Kseg);              // consumers see the block after the last segment
+        for (uint32_t k = 0; k < Kseg; k++) poseidons.push_back({PoseidonOp{t, a0, base, pos_koff[t], k * Q / Kseg, (k + 1) * Q / Kseg}, lv + 1 + k});
         return base;
     }
     // one Absorb: returns base word of its ABSORB_WORDS block
@@ -2150,7 +2151,7 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
         auto take = [&](uint32_t old, uint32_t n) { for (uint32_t k = 0; k < n; k++) { if (remap[old + k] != 0xffffffffu) throw std::runtime_error("pob: internal: value slot defined twice"); remap[old + k] = next++; } };
         for (const Level &L : P.levels) {
             for (uint32_t i = L.t_begin; i < L.t_end; i++) if (has_dst(op_opc(P.ops[i]))) take(op_dst(P.ops[i]), 1);
-            for (uint32_t q = L.p_begin; q < L.p_end; q++) take(P.poseidons[q].base, pos_layout(P.poseidons[q].t).total);
+            for (uint32_t q = L.p_begin; q < L.p_end; q++) if (P.poseidons[q].q0 == 0) take(P.poseidons[q].base, pos_layout(P.poseidons[q].t).total);
             for (uint32_t q = L.s_begin; q < L.s_end; q++) take(P.psums[q].dst, P.psums[q].n);
         }
         for (uint32_t i = P.inv_begin; i < P.inv_end; i++) take(op_dst(P.ops[i]), 1);

@@ -90,11 +90,14 @@ __device__ void poseidon_warp(const VmCtx &x, const PoseidonOp op, const Fr *pk)
     const bool act = (uint32_t)lane < t; const uint32_t j = act ? (uint32_t)lane : 0u;
     const Fr *K = pk + op.koff;
     uint64_t *V = x.U + x.val_base + 4ull * op.base;
-    // values are parked in their slots in MONTGOMERY form (nothing but this warp reads them before the sweep below):
-    // no conversion sits on the dependency chain of the 65 rounds
+    const uint32_t Q = pos_steps(L);
+    // values are parked in their slots in MONTGOMERY form (nothing but Poseidon segments reads them before the sweep of the last
+    // segment): no conversion sits on the dependency chain of the 65 rounds
     auto put = [&](uint32_t off, const Fr &m) { if (act) vm_store_val(V + 4ull * off, m); };
-    Fr s = fr_add(fr_to_mont(vm_load(x, x.aux[op.in_aux + j])), K[L.kC + j]);     // ark[0]
-    put(j, s);
+    Fr s;
+    uint32_t q = op.q0;
+    if (q == 0) { s = fr_add(fr_to_mont(vm_load(x, x.aux[op.in_aux + j])), K[L.kC + j]); put(j, s); q = 1; }     // step 0: ark[0]
+    else s = vm_load_val(V + 4ull * (pos_state_off(L, q - 1) + j));                                                // state after the previous segment
     auto full = [&](uint32_t F, uint32_t coff, uint32_t moff) {
         Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);
         put(F + 3 * j, x2); put(F + 3 * j + 1, x4); put(F + 3 * j + 2, x5);
@@ -103,34 +106,35 @@ __device__ void poseidon_warp(const VmCtx &x, const PoseidonOp op, const Fr *pk)
         for (uint32_t k = 0; k < t; k++) { Fr yk = shfl_fr(y, (int)k); acc = fr_add(acc, fr_mont(K[moff + k * t + j], yk)); }
         put(F + 4 * t + j, acc); s = acc;
     };
-    for (uint32_t f = 0; f < 4; f++) full(L.F1 + 5 * t * f, (f + 1) * t, f == 3 ? L.kP : L.kM);
 #pragma unroll 1
-    for (uint32_t r = 0; r < L.rp; r++) {
-        const uint32_t B = L.PB + r * (4 + t), so = (2 * t - 1) * r;
-        Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);                // meaningful on lane 0 only
-        Fr z0 = fr_add(x5, K[L.kC + 5 * t + r]);
-        if (lane == 0) { vm_store_val(V + 4ull * B, x2); vm_store_val(V + 4ull * (B + 1), x4); vm_store_val(V + 4ull * (B + 2), x5); vm_store_val(V + 4ull * (B + 3), z0); }
-        z0 = shfl_fr(z0, 0);
-        const Fr in = (lane == 0) ? z0 : s;
-        Fr prod = fr_mont(K[L.kS + so + j], in);                                          // S[so + i] * in[i]
-        Fr o0 = fr_zero();
-        for (uint32_t k = 0; k < t; k++) o0 = fr_add(o0, shfl_fr(prod, (int)k));
-        Fr oj = fr_add(s, fr_mont(z0, K[L.kS + so + t + (j ? j : 1) - 1]));                // lanes 1..t-1
-        s = (lane == 0) ? o0 : oj;
-        put(B + 4 + j, s);
+    for (; q < op.q1 && q < Q - 1; q++) {
+        if (q <= 4) { const uint32_t f = q - 1; full(L.F1 + 5 * t * f, (f + 1) * t, f == 3 ? L.kP : L.kM); }
+        else if (q < 5 + L.rp) {
+            const uint32_t r = q - 5, B = L.PB + r * (4 + t), so = (2 * t - 1) * r;
+            Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);                // meaningful on lane 0 only
+            Fr z0 = fr_add(x5, K[L.kC + 5 * t + r]);
+            if (lane == 0) { vm_store_val(V + 4ull * B, x2); vm_store_val(V + 4ull * (B + 1), x4); vm_store_val(V + 4ull * (B + 2), x5); vm_store_val(V + 4ull * (B + 3), z0); }
+            z0 = shfl_fr(z0, 0);
+            const Fr in = (lane == 0) ? z0 : s;
+            Fr prod = fr_mont(K[L.kS + so + j], in);                                          // S[so + i] * in[i]
+            Fr o0 = fr_zero();
+            for (uint32_t k = 0; k < t; k++) o0 = fr_add(o0, shfl_fr(prod, (int)k));
+            Fr oj = fr_add(s, fr_mont(z0, K[L.kS + so + t + (j ? j : 1) - 1]));                // lanes 1..t-1
+            s = (lane == 0) ? o0 : oj;
+            put(B + 4 + j, s);
+        } else { const uint32_t f = q - 5 - L.rp; full(L.SB + 5 * t * f, 5 * t + L.rp + f * t, L.kM); }
     }
-    for (uint32_t f = 0; f < 3; f++) full(L.SB + 5 * t * f, 5 * t + L.rp + f * t, L.kM);
-    {
+    if (op.q1 == Q) {                                                                          // last step
         Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);
         put(L.LB + 3 * j, x2); put(L.LB + 3 * j + 1, x4); put(L.LB + 3 * j + 2, x5);
         Fr prod = fr_mont(K[L.kM + j * t], x5), out = fr_zero();
         for (uint32_t k = 0; k < t; k++) out = fr_add(out, shfl_fr(prod, (int)k));
         if (lane == 0) vm_store_val(V + 4ull * (L.LB + 3 * t), out);
-    }
-    __syncwarp();
-    for (uint32_t i = (uint32_t)lane; i < L.total; i += 32) {         // all 32 lanes: Montgomery -> canonical, in place
-        uint64_t *p = V + 4ull * i;
-        vm_store_val(p, fr_from_mont(vm_load_val(p)));
+        __syncwarp();
+        for (uint32_t i = (uint32_t)lane; i < L.total; i += 32) {     // all 32 lanes: Montgomery -> canonical, in place
+            uint64_t *p = V + 4ull * i;
+            vm_store_val(p, fr_from_mont(vm_load_val(p)));
+        }
     }
 }
 
@@ -240,7 +244,8 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     mbar_wait(&s_bar, 0);
     cluster_sync_all();
     VmCtx x{U, a.val_base, a.konst, a.aux, a.invtab, &s_status};
-    const uint32_t gwarp = gt >> 5, nwarp = GT >> 5;
+    // warp ops are dealt round-robin over the CTAs of the cluster (the 17 absorbs of a level land on 8 SMs, not on one)
+    const uint32_t gwarp = (tid >> 5) * C + rank, nwarp = GT >> 5;
     for (uint32_t lv = 0; lv < a.n_levels; lv++) {
         if (a.prof && inst == 0 && gt == 0) a.prof[lv] = clock64();
         const Level L = s_levels[lv];

@@ -81,13 +81,27 @@ POB_HD uint32_t rw_out(int l) { return RW_OUT + l; }
 //   PB + (4+t)*r, r = 0..RP-1        partial round r: sigma (in2, in4, out), mixS.in[0] (= out + C), mixS.out[t]
 //   SB + 5t*f, f = 0..2              second-half full rounds (same shape)
 //   LB                               last sigmas (3t), then mixLast.out
-struct PoseidonOp { uint32_t t, in_aux, base, koff; };          // inputs: aux[in_aux .. +t) = initialState, inputs[]
+// One permutation is cut into POS_SEGMENTS warp ops of consecutive "steps" (step 0 = ark[0]; 1..4 first-half full rounds; then the RP
+// partial rounds; 3 second-half full rounds; the last step = final sigmas + mixLast + conversion sweep), scheduled in consecutive
+// levels: nothing but the last segment's result is consumed, so a 65-round dependency chain (~0.7 M cycles on one warp) no longer
+// holds up a whole level while every other warp of the cluster idles -- it proceeds alongside 8 levels of other work.  Between
+// segments the state is re-read from the value block (parked there in Montgomery form anyway).
+struct PoseidonOp { uint32_t t, in_aux, base, koff, q0, q1; };  // inputs: aux[in_aux .. +t) = initialState, inputs[]; steps [q0, q1)
+static const uint32_t POS_SEGMENTS = 8;
 struct PosLayout { uint32_t t, rp, F1, PB, SB, LB, total, kC, kS, kM, kP, ktotal; };
 POB_HD PosLayout pos_layout(uint32_t t) {
     PosLayout L; L.t = t; L.rp = (t == 3) ? 57u : (t == 4) ? 56u : 60u;
     L.F1 = t; L.PB = 21 * t; L.SB = L.PB + L.rp * (4 + t); L.LB = L.SB + 15 * t; L.total = L.LB + 3 * t + 1;
     L.kC = 0; L.kS = t * 8 + L.rp; L.kM = L.kS + L.rp * (2 * t - 1); L.kP = L.kM + t * t; L.ktotal = L.kP + t * t;
     return L;
+}
+POB_HD uint32_t pos_steps(const PosLayout &L) { return L.rp + 9; }
+// offset (in the value block) of state element 0 after step q (q < steps - 1)
+POB_HD uint32_t pos_state_off(const PosLayout &L, uint32_t q) {
+    if (q == 0) return 0;
+    if (q <= 4) return L.F1 + 5 * L.t * (q - 1) + 4 * L.t;
+    if (q < 5 + L.rp) return L.PB + (q - 5) * (4 + L.t) + 4;
+    return L.SB + 5 * L.t * (q - 5 - L.rp) + 4 * L.t;
 }
 
 // ---- warp op: prefix sum whose every partial sum is a signal (substring_check.circom:47-49 M[], :95 sums[]) -------

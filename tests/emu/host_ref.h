@@ -56,6 +56,8 @@ inline void vm_psum_scalar(const VmCtx &x, const PsumOp &op) {
 // Scalar reference of the Poseidon warp op (HOST ONLY users: tests/emu).  The device implementation is the
 // warp-cooperative poseidon_warp() in pob_b200.cu; both must fill the slot layout documented in program.h.
 inline void vm_poseidon_scalar(const VmCtx &x, const PoseidonOp &op, const Fr *pk) {
+    if (op.q0 != 0) return;      // the product runs a permutation as POS_SEGMENTS warp ops in consecutive levels; only the last segment's
+                                 // result is consumed, so the scalar reference may do the whole permutation at the first one
     const PosLayout L = pos_layout(op.t); const uint32_t t = op.t;
     const Fr *K = pk + op.koff;
     auto C = [&](uint32_t i) { return fr_from_mont(K[L.kC + i]); };
