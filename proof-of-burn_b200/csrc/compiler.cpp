@@ -1514,7 +1514,7 @@ static Blk T_RlpInteger(Builder &B, int N, Code in) {
     if (cs) { B.q_eqn(x.sig + n, d + bytes, n); B.q_lin(LC().s(x.sig + 2 * n).k(-(int64_t)n).s(d + length)); B.q_eqn(d + bigEndian, x.sig, n); }   // bigEndian <== ShiftLeft(N)(bytes, N - length)   :83
     x = T_LessThan(B, N * 8, in, c_const(128)); Code single = B.at(x.pos); B.at(isSingle) = single;
     if (cs) { B.q_eq(x.sig + 1, d + iIn); B.q_const(x.sig + 2, 128); B.q_eq(d + isSingle, x.sig); }           // isSingleByte <== LessThan(N*8)([in, 128])         :86
-    x = T_IsZero(B, in); Code iz = B.at(x.pos); B.at(isZero) = iz;
+    x = T_IsZero(B, in, /*likely_large=*/true); Code iz = B.at(x.pos); B.at(isZero) = iz;      // in = a balance: not a table-sized value
     if (cs) { B.q_eq(x.sig + 1, d + iIn); B.q_eq(d + isZero, x.sig); }                                        // isZero <== IsZero()(in)                           :89
     x = T_Mux1(B, B.add(c_const(0x80), len), in, single); B.at(first) = B.at(x.pos);
     if (cs) { B.q_lin(LC().s(x.sig + 1).k(-0x80).s(d + length, -1)); B.q_eq(x.sig + 2, d + iIn); B.q_eq(x.sig + 3, d + isSingle); B.q_eq(d + first, x.sig); }   // firstRlpByte <== Mux1()([0x80 + length, in], isSingleByte)   :95
@@ -2076,11 +2076,16 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     if (P.konst.empty()) P.konst.push_back(fr_zero());
     if (P.aux.empty()) P.aux.push_back(0);
     // ---- levelise ----
-    // OP_INV results (the `inv` hint signal of IsZero) are consumed by no other op, so they are pulled out of the
-    // dependency levels and run once at the end, batch-inverted (vm_inv_batch).
+    // OP_INV results (the `inv` hint signal of IsZero) are consumed by no other op.  The ones whose input is a small value (the
+    // overwhelming majority: differences of indices, bytes, lengths) are ordinary thread ops of their level -- a table lookup.  The
+    // ones expected to need a real field inversion (`likely_large`: SubstringCheck's exists[], RlpInteger's IsZero(balance)) are
+    // DEFERRED: batch-inverted with Montgomery's trick, one inversion per worker thread, and that inversion is spread over the
+    // levels that follow the one where their inputs are ready (kernels.cuh: k_eval) instead of sitting at the end of the kernel.
     std::vector<uint8_t> is_inv_slot(B.n_vals, 0);
-    size_t n_inv = 0;
-    for (auto &o : B.ops) if (op_opc(o.op) == OP_INV) { is_inv_slot[op_dst(o.op)] = 1; n_inv++; }
+    B.inv_generic.resize(B.n_vals, 0);
+    auto deferred = [&](const Op &o) { return op_opc(o) == OP_INV && B.inv_generic[op_dst(o)] != 0; };
+    size_t n_inv = 0; uint32_t ginv_ready = 0;
+    for (auto &o : B.ops) if (op_opc(o.op) == OP_INV) { is_inv_slot[op_dst(o.op)] = 1; if (deferred(o.op)) { n_inv++; ginv_ready = std::max(ginv_ready, o.level); } }
     auto uses_inv = [&](Code c) { return code_kind(c) == K_VAL && is_inv_slot[code_payload(c)]; };
     for (auto &o : B.ops) {
         uint32_t opc = op_opc(o.op);
@@ -2092,7 +2097,7 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     }
     for (Code c : B.aux) if (uses_inv(c)) throw std::runtime_error("pob: internal: an IsZero inverse is consumed by an operand list");
     uint32_t max_level = 0;
-    for (auto &o : B.ops) if (op_opc(o.op) != OP_INV) max_level = std::max(max_level, o.level);
+    for (auto &o : B.ops) if (!deferred(o.op)) max_level = std::max(max_level, o.level);
     for (auto &a : B.absorbs) max_level = std::max(max_level, a.level);
     for (auto &q : B.poseidons) max_level = std::max(max_level, q.level);
     for (auto &q : B.psums) max_level = std::max(max_level, q.level);
@@ -2110,18 +2115,16 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     P.pos_konst = B.pos_konst; if (P.pos_konst.empty()) P.pos_konst.push_back(fr_zero());
     for (auto &q : B.poseidons) for (uint32_t j = 0; j < q.op.t; j++) if (uses_inv(B.aux[q.op.in_aux + j])) throw std::runtime_error("pob: internal: an IsZero inverse feeds a Poseidon");
     std::vector<uint32_t> tcount(max_level + 2, 0), wcount(max_level + 2, 0);
-    for (auto &o : B.ops) if (op_opc(o.op) != OP_INV) tcount[o.level]++;
+    for (auto &o : B.ops) if (!deferred(o.op)) tcount[o.level]++;
     for (auto &a : B.absorbs) wcount[a.level]++;
     std::vector<uint32_t> tstart(max_level + 2, 0), wstart(max_level + 2, 0);
     for (uint32_t l = 1; l <= max_level + 1; l++) { tstart[l] = tstart[l - 1] + tcount[l - 1]; wstart[l] = wstart[l - 1] + wcount[l - 1]; }
     P.ops.resize(B.ops.size()); P.absorbs.resize(B.absorbs.size());
     P.inv_begin = (uint32_t)(B.ops.size() - n_inv); P.inv_end = (uint32_t)B.ops.size();
-    B.inv_generic.resize(B.n_vals, 0);
-    size_t n_ginv = 0; for (auto &o : B.ops) if (op_opc(o.op) == OP_INV && B.inv_generic[op_dst(o.op)]) n_ginv++;
-    P.ginv_begin = (uint32_t)(P.inv_end - n_ginv);
-    { std::vector<uint32_t> tp = tstart, wp = wstart; uint32_t ip = P.inv_begin, gp = P.ginv_begin;
+    P.ginv_begin = P.inv_begin;                              // (the table-sized group is no longer deferred)
+    { std::vector<uint32_t> tp = tstart, wp = wstart; uint32_t gp = P.ginv_begin;
       for (auto &o : B.ops) {
-          if (op_opc(o.op) == OP_INV) { if (B.inv_generic[op_dst(o.op)]) P.ops[gp++] = o.op; else P.ops[ip++] = o.op; }
+          if (deferred(o.op)) P.ops[gp++] = o.op;
           else P.ops[tp[o.level]++] = o.op;
       }
       for (auto &a : B.absorbs) P.absorbs[wp[a.level]++] = a.op; }
@@ -2136,8 +2139,10 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
     for (uint32_t l = 1; l <= max_level; l++) {
         if (tcount[l] == 0 && wcount[l] == 0 && pcount[l] == 0 && scount[l] == 0) continue;
         std::stable_sort(P.ops.begin() + tstart[l], P.ops.begin() + tstart[l] + tcount[l], [&](const Op &x, const Op &y) { return op_key(x) < op_key(y); });
+        if (n_inv && l >= ginv_ready && P.ginv_level == 0xffffffffu) P.ginv_level = (uint32_t)P.levels.size();   // first level that starts with every deferred input ready
         P.levels.push_back(Level{tstart[l], tstart[l] + tcount[l], wstart[l], wstart[l] + wcount[l], pstart[l], pstart[l] + pcount[l], sstart[l], sstart[l] + scount[l]});
     }
+    if (P.ginv_level == 0xffffffffu) P.ginv_level = (uint32_t)P.levels.size();
     // ---- renumber the value slots in execution order ----
     // Slot numbers are labels; after levelising and sorting they are scattered.  Renumbered in (level, op order) the 32 lanes of a
     // warp store 32 consecutive slots (one 1 KB run instead of 32 scattered sectors) and next-level operand loads fall into the

@@ -168,7 +168,25 @@ struct EvalArgs {
     long long *prof;                              // tuning only: per-level clock64 stamps of instance 0 (or null)
     uint32_t pos_konst_bytes, levels_bytes;       // sizes of the two TMA-staged tables (multiples of 16 bytes)
     uint32_t prefetch;                            // 1: fetch the next op record / prefetch its operand lines while the current op runs
+    uint32_t ginv_level;                          // first level at which every deferred inverse has its input (n_levels: none before the end)
 };
+
+// deferred IsZero inverses (comparators.circom:30): vm_exec.h vm_ginv_start / inv_eea_steps / vm_ginv_finish.  One inversion costs
+// about as much as twenty average levels; spread over the levels it costs a few thousand cycles per level on 8 warps per CTA.
+static const uint32_t INV_WORKERS = 256, INV_STEPS = 24;
+// parked state: word-major ([32 words][INV_WORKERS]) so that a warp's loads and stores are conflict-free
+__device__ __forceinline__ void inv_park(uint32_t *s, uint32_t t, const InvChain &c) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) { s[(k) * INV_WORKERS + t] = c.u.l[k]; s[(8 + k) * INV_WORKERS + t] = c.v.l[k];
+                                  s[(16 + k) * INV_WORKERS + t] = c.x1.l[k]; s[(24 + k) * INV_WORKERS + t] = c.x2.l[k]; }
+}
+__device__ __forceinline__ InvChain inv_unpark(const uint32_t *s, uint32_t t) {
+    InvChain c;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { c.u.l[k] = s[(k) * INV_WORKERS + t]; c.v.l[k] = s[(8 + k) * INV_WORKERS + t];
+                                  c.x1.l[k] = s[(16 + k) * INV_WORKERS + t]; c.x2.l[k] = s[(24 + k) * INV_WORKERS + t]; }
+    return c;
+}
 
 // ---- TMA (bulk async copy engine) and cluster primitives ---------------------------------------------------------------
 // cp.async.bulk global -> shared with mbarrier completion (SASS: UBLKCP.S.G + SYNCS.ARRIVE.TRANS64); the copies are issued by
@@ -227,6 +245,9 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     __shared__ __align__(8) uint64_t s_bar;
     Fr *s_pk = reinterpret_cast<Fr *>(dyn_smem);
     Level *s_levels = reinterpret_cast<Level *>(dyn_smem + a.pos_konst_bytes);
+    uint32_t *s_inv = reinterpret_cast<uint32_t *>(dyn_smem + a.pos_konst_bytes + a.levels_bytes);     // INV_WORKERS parked chains
+    uint32_t inv_phase = 0;                       // this worker's chain: 0 = nothing to invert, 1 = inversion running, 2 = inverse ready
+    const uint32_t wid = rank * INV_WORKERS + tid, NWK = C * INV_WORKERS;
     if (tid == 0) { s_status = STATUS_OK; mbar_init(&s_bar, 1); if (rank == 0) a.status[inst] = STATUS_OK; }
     __syncthreads();
     if (tid == 0) {
@@ -267,14 +288,29 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
           for (uint32_t w = L.w_begin + wv; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]);
           const uint32_t nw2 = (np + (L.w_end - L.w_begin)) % nwarp, sv = (gwarp + nwarp - nw2) % nwarp;
           for (uint32_t q = L.s_begin + sv; q < L.s_end; q += nwarp) psum_warp(x, a.psums[q]); }
+        if (tid < INV_WORKERS) {
+            if (lv == a.ginv_level) {                                               // start
+                InvChain c;
+                if (vm_ginv_start(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK, c)) { inv_park(s_inv, tid, c); inv_phase = 1; }
+            } else if (inv_phase == 1) {                                            // step
+                InvChain c = inv_unpark(s_inv, tid);
+                if (inv_eea_steps(c, INV_STEPS)) inv_phase = 2;
+                inv_park(s_inv, tid, c);
+            }
+        }
         cluster_sync_all();
     }
     if (a.prof && inst == 0 && gt == 0) a.prof[a.n_levels] = clock64();
-    // IsZero inverse hints: no consumers, done last.  Table-sized inputs are spread over all threads; the ones expected
-    // to need a real inversion go to 256 threads per CTA so that only 8 warps per SM pay for an inversion (one per thread).
-    vm_inv_batch(x, a.ops, a.inv_begin, a.ginv_begin, gt, GT);
-    if (tid < 256) vm_inv_batch(x, a.ops, a.ginv_begin, a.inv_end, rank * 256 + tid, C * 256);
-    if (a.prof && inst == 0) { cluster_sync_all(); if (gt == 0) a.prof[a.n_levels + 1] = clock64(); }
+    // finish the deferred inverses (or do all of it when their inputs only became ready in the last level)
+    if (tid < INV_WORKERS) {
+        if (a.ginv_level >= a.n_levels) vm_inv_batch(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK);
+        else if (inv_phase) {
+            InvChain c = inv_unpark(s_inv, tid);
+            if (inv_phase == 1) while (!inv_eea_steps(c, 64)) { }
+            vm_ginv_finish(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK, c.x1);
+        }
+    }
+    if (a.prof && inst == 0) { cluster_sync_all(); if (gt == 0) { a.prof[a.n_levels + 1] = clock64(); a.prof[a.n_levels + 2] = clock64(); } }
     __syncthreads();
     if (tid == 0 && s_status != STATUS_OK) atomicMin(a.status + inst, s_status);
     cluster_sync_all();

@@ -275,7 +275,7 @@ static void enqueue_eval(pob_handle *h, uint32_t c) {
     uint64_t *stores = h->d_stores + (size_t)r * E * h->store_stride;
     EvalArgs ea{h->d_ops, h->d_abs, h->d_pos, h->d_pos_konst, h->d_psums, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.ginv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
                 h->d_codes + P.out_code_off, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
-                h->d_status + first, h->d_outputs + (size_t)first * no * 4, (c == 0) ? h->d_prof : nullptr, h->pos_konst_bytes, h->levels_bytes, h->eval_prefetch};
+                h->d_status + first, h->d_outputs + (size_t)first * no * 4, (c == 0) ? h->d_prof : nullptr, h->pos_konst_bytes, h->levels_bytes, h->eval_prefetch, P.ginv_level};
     CU(cudaEventRecord(B.e0[c], h->s_eval));
     {   // one thread-block cluster per instance.  Cluster size: the largest power of two (<= 8) that still lets every instance of
         // the launch have its own SMs -- 8 CTAs for a single witness (latency), 4 for the 32-instance chunks of the main shape,
@@ -442,12 +442,13 @@ static int finish_batch(pob_handle *h, uint32_t *status, uint64_t *outputs, uint
     for (uint32_t c = 0; c < B.nchunks; c++) { float ms = 0; CU(cudaEventElapsedTime(&ms, B.e0[c], B.e1[c])); T.eval_ms += ms; }
     for (auto &G : B.groups) { float ms = 0; CU(cudaEventElapsedTime(&ms, G.t0, G.t1)); T.expand_ms += ms; }
     if (h->d_prof) {
-        std::vector<long long> st(P.levels.size() + 2);
+        std::vector<long long> st(P.levels.size() + 3);
         CU(cudaMemcpy(st.data(), h->d_prof, st.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         if (FILE *f = fopen(h->prof_path.c_str(), "w")) {
             for (size_t l = 0; l + 1 < st.size(); l++) {
                 if (l < P.levels.size()) fprintf(f, "level %zu ops %u absorbs %u poseidons %u cycles %lld\n", l, P.levels[l].t_end - P.levels[l].t_begin, P.levels[l].w_end - P.levels[l].w_begin, P.levels[l].p_end - P.levels[l].p_begin, st[l + 1] - st[l]);
-                else fprintf(f, "inverse-batch ops %u cycles %lld\n", P.inv_end - P.inv_begin, st[l + 1] - st[l]);
+                else if (l == P.levels.size()) fprintf(f, "inverse-batch(table) ops %u cycles %lld\n", P.ginv_begin - P.inv_begin, st[l + 1] - st[l]);
+                else fprintf(f, "inverse-batch(generic) ops %u cycles %lld\n", P.inv_end - P.ginv_begin, st[l + 1] - st[l]);
             }
             fclose(f);
         }
@@ -533,7 +534,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         CU(cudaSetDevice(device));
         h->d_ops = upload(P.ops); h->d_psums = upload(P.psums); h->d_pos = upload(P.poseidons); h->d_pos_konst = upload(P.pos_konst); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
         h->pos_konst_bytes = (uint32_t)(P.pos_konst.size() * sizeof(Fr)); h->levels_bytes = (uint32_t)(std::max<size_t>(1, P.levels.size()) * sizeof(Level));   // both multiples of 32
-        h->eval_smem = h->pos_konst_bytes + h->levels_bytes;
+        h->eval_smem = h->pos_konst_bytes + h->levels_bytes + (uint32_t)(INV_WORKERS * sizeof(InvChain));   // + the parked inversion state of 256 workers (32 KB)
         h->d_konst = upload(P.konst);
         { std::vector<Code> cd = P.codes; cd.resize(cd.size() + 8, 0); h->d_codes = upload(cd); }   // + 32 bytes: TMA copies whole 16-byte units
         if (const char *v = tune_env("POB_TILE_FILTER")) {      // TUNING build only: 1 = KeccakfRound tiles only, 2 = the others only (witness incomplete!)
@@ -560,7 +561,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         CU(cudaEventCreate(&h->ev_start)); CU(cudaEventCreate(&h->ev_end)); CU(cudaEventCreateWithFlags(&h->ev_tmp, cudaEventDisableTiming));
         // (an L2 persisting access-policy window for the code stream was tried and REDUCED the expand kernel to 4.9 TB/s: the
         // carve-out takes L2 away from write combining -- profiles/r01_expand_sweep.md)
-        if (const char *v = tune_env("POB_EVAL_PROFILE")) { h->prof_path = v; CU(cudaMalloc(&h->d_prof, (P.levels.size() + 2) * sizeof(long long))); }
+        if (const char *v = tune_env("POB_EVAL_PROFILE")) { h->prof_path = v; CU(cudaMalloc(&h->d_prof, (P.levels.size() + 3) * sizeof(long long))); }
         // witness slots: as many as fit in 80 % of free HBM after the store ring
         size_t free_b = 0, total_b = 0; CU(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t wbytes = 32ull * P.n_signals;

@@ -84,10 +84,10 @@ POB_HD uint32_t rw_out(int l) { return RW_OUT + l; }
 // One permutation is cut into POS_SEGMENTS warp ops of consecutive "steps" (step 0 = ark[0]; 1..4 first-half full rounds; then the RP
 // partial rounds; 3 second-half full rounds; the last step = final sigmas + mixLast + conversion sweep), scheduled in consecutive
 // levels: nothing but the last segment's result is consumed, so a 65-round dependency chain (~0.7 M cycles on one warp) no longer
-// holds up a whole level while every other warp of the cluster idles -- it proceeds alongside 8 levels of other work.  Between
+// holds up a whole level while every other warp of the cluster idles -- it proceeds alongside 16 levels of other work.  Between
 // segments the state is re-read from the value block (parked there in Montgomery form anyway).
 struct PoseidonOp { uint32_t t, in_aux, base, koff, q0, q1; };  // inputs: aux[in_aux .. +t) = initialState, inputs[]; steps [q0, q1)
-static const uint32_t POS_SEGMENTS = 8;
+static const uint32_t POS_SEGMENTS = 16;
 struct PosLayout { uint32_t t, rp, F1, PB, SB, LB, total, kC, kS, kM, kP, ktotal; };
 POB_HD PosLayout pos_layout(uint32_t t) {
     PosLayout L; L.t = t; L.rp = (t == 3) ? 57u : (t == 4) ? 56u : 60u;
@@ -157,8 +157,9 @@ struct Program {
     uint64_t store_u64() const { return (uint64_t)val_base + 4ull * n_vals; }
     // eval program
     std::vector<Op> ops;           // [0, inv_begin) sorted by level, then the deferred OP_INV ops
-    uint32_t inv_begin = 0, ginv_begin = 0, inv_end = 0;   // IsZero inverses feed no other op: they run last, batch-inverted
-                                   // per thread; [ginv_begin, inv_end) are the ones expected to miss the small-value table
+    uint32_t inv_begin = 0, ginv_begin = 0, inv_end = 0;   // [ginv_begin, inv_end): the DEFERRED IsZero inverses (expected to need a real
+                                   // inversion): batch-inverted per worker thread; inv_begin == ginv_begin (kept for the emulator)
+    uint32_t ginv_level = 0xffffffffu;   // index of the first level that starts with all their inputs ready (== levels.size(): none)
     std::vector<AbsorbOp> absorbs; // sorted by level
     std::vector<PoseidonOp> poseidons;   // sorted by level
     std::vector<PsumOp> psums;     // sorted by level

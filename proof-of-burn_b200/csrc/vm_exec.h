@@ -130,6 +130,52 @@ POB_HD void vm_inv_batch(const VmCtx &x, const Op *ops, uint32_t begin, uint32_t
     }
 }
 
+// ---- the deferred inverses as a state machine spread over the levels (k_eval; emulated 1:1 by tests/emu) ------------------------
+// Worker w of nw owns the deferred ops begin + w, + nw, ...  START (the first level at which all inputs are ready): zero /
+// table-sized inputs are answered at once, the others get their prefix product parked in the destination slot (Montgomery's
+// trick) and the worker's total product becomes an inversion in progress.  STEP (every later level): a bounded number of
+// iterations of fr_inv_eea's loop, state parked by the caller.  FINISH (after the last level): the products are unwound.
+struct InvChain { Fr u, v, x1, x2; };             // fr_inv_eea's state; once finished the inverse is in x1
+POB_HD bool inv_eea_steps(InvChain &c, uint32_t steps) {                           // true: finished
+    const Fr one = fr_from_u64(1);
+    for (uint32_t k = 0; k < steps; k++) {
+        if (fr_eq(c.u, one)) return true;
+        if (fr_eq(c.v, one)) { c.x1 = c.x2; c.u = one; return true; }
+        while (!(c.u.l[0] & 1u)) { fr_shr1(c.u); fr_half_mod(c.x1); }
+        while (!(c.v.l[0] & 1u)) { fr_shr1(c.v); fr_half_mod(c.x2); }
+        if (fr_geq(c.u, c.v)) { Fr t; fr_raw_sub(t, c.u, c.v); c.u = t; c.x1 = fr_sub(c.x1, c.x2); }
+        else { Fr t; fr_raw_sub(t, c.v, c.u); c.v = t; c.x2 = fr_sub(c.x2, c.x1); }
+    }
+    if (fr_eq(c.u, one)) return true;
+    if (fr_eq(c.v, one)) { c.x1 = c.x2; c.u = one; return true; }
+    return false;
+}
+POB_HD bool vm_ginv_start(const VmCtx &x, const Op *ops, uint32_t begin, uint32_t end, uint32_t w, uint32_t nw, InvChain &c) {
+    Fr acc = fr_from_u64(1); bool any = false;
+    for (uint32_t i = begin + w; i < end; i += nw) {
+        Fr a = vm_load(x, ops[i].a), d;
+        uint64_t *vd = x.U + x.val_base + 4ull * op_dst(ops[i]);
+        if (vm_inv_class(x, a, d) == 0) vm_store_val(vd, d);
+        else { vm_store_val(vd, acc); acc = fr_mul(acc, a); any = true; }
+    }
+    if (any) { c.u = acc; c.v = fr_p(); c.x1 = fr_from_u64(1); c.x2 = fr_zero(); }
+    return any;                                   // false: nothing left to do for this worker
+}
+POB_HD void vm_ginv_finish(const VmCtx &x, const Op *ops, uint32_t begin, uint32_t end, uint32_t w, uint32_t nw, Fr inv) {
+    uint32_t last = begin + w;
+    for (uint32_t i = last; i < end; i += nw) last = i;
+    for (uint32_t i = last;; i -= nw) {
+        Fr a = vm_load(x, ops[i].a), d;
+        if (vm_inv_class(x, a, d) != 0) {
+            uint64_t *vd = x.U + x.val_base + 4ull * op_dst(ops[i]);
+            Fr pre = vm_load_val(vd);
+            vm_store_val(vd, fr_mul(inv, pre));
+            inv = fr_mul(inv, a);
+        }
+        if (i < begin + w + nw) break;
+    }
+}
+
 // Keccak-f round constants and rotation tables (utils/keccak.circom:195, 200, 253-262)
 POB_HD uint64_t keccak_rc(int r) {
     constexpr uint64_t RC[24] = {

@@ -60,14 +60,27 @@ uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_
     }
     uint32_t status = STATUS_OK;
     VmCtx x{U.data(), P.val_base, P.konst.data(), P.aux.data(), e->invtab.data(), &status};
-    for (const Level &lv : P.levels) {
+    // deferred inverses: the same start / step / finish schedule as k_eval, with 8 workers and 24 steps per level
+    const uint32_t NW = 8, STEPS = 24;
+    std::vector<InvChain> chain(NW); std::vector<uint32_t> phase(NW, 0);
+    for (uint32_t li = 0; li < P.levels.size(); li++) {
+        const Level &lv = P.levels[li];
         for (uint32_t i = lv.t_begin; i < lv.t_end; i++) vm_exec_op(x, P.ops[i]);
         for (uint32_t i = lv.w_begin; i < lv.w_end; i++) vm_absorb_scalar(U.data(), P.absorbs[i]);
         for (uint32_t i = lv.p_begin; i < lv.p_end; i++) vm_poseidon_scalar(x, P.poseidons[i], P.pos_konst.data());
         for (uint32_t i = lv.s_begin; i < lv.s_end; i++) vm_psum_scalar(x, P.psums[i]);
+        for (uint32_t w = 0; w < NW; w++) {
+            if (li == P.ginv_level) phase[w] = vm_ginv_start(x, P.ops.data(), P.ginv_begin, P.inv_end, w, NW, chain[w]) ? 1 : 0;
+            else if (phase[w] == 1 && inv_eea_steps(chain[w], STEPS)) phase[w] = 2;
+        }
     }
-    for (uint32_t tid = 0; tid < 64; tid++) vm_inv_batch(x, P.ops.data(), P.inv_begin, P.ginv_begin, tid, 64);
-    for (uint32_t tid = 0; tid < 8; tid++) vm_inv_batch(x, P.ops.data(), P.ginv_begin, P.inv_end, tid, 8);
+    for (uint32_t w = 0; w < NW; w++) {
+        if (P.ginv_level >= P.levels.size()) vm_inv_batch(x, P.ops.data(), P.ginv_begin, P.inv_end, w, NW);
+        else if (phase[w]) {
+            if (phase[w] == 1) while (!inv_eea_steps(chain[w], 64)) { }
+            vm_ginv_finish(x, P.ops.data(), P.ginv_begin, P.inv_end, w, NW, chain[w].x1);
+        }
+    }
     if (witness)
         for (const Tile &t : P.tiles)
             for (uint32_t k = 0; k < t.n; k++) {
@@ -111,6 +124,11 @@ extern "C" uint32_t pob_emu_inv_selftest(uint32_t n) {
         if (fr_is_zero(a)) continue;
         Fr x = fr_inv_eea(a), y = fr_inv(a);
         if (!fr_eq(x, y) || !fr_eq(fr_mul(x, a), fr_from_u64(1))) bad++;
+        // the same inversion cut into slices (k_eval spreads it over the levels): any slicing gives the same result
+        InvChain c; c.u = a; c.v = fr_p(); c.x1 = fr_from_u64(1); c.x2 = fr_zero();
+        uint32_t slices = 0;
+        while (!inv_eea_steps(c, 1 + (i % 37))) slices++;
+        if (!fr_eq(c.x1, y) || slices * (1 + (i % 37)) > 520) bad++;
     }
     return bad;
 }
@@ -192,14 +210,14 @@ extern "C" void pob_emu_inv_miss_count(void *h, const uint64_t *inputs, uint64_t
         for (uint32_t i = lv.p_begin; i < lv.p_end; i++) vm_poseidon_scalar(x, P.poseidons[i], P.pos_konst.data());
         for (uint32_t i = lv.s_begin; i < lv.s_end; i++) vm_psum_scalar(x, P.psums[i]);
     }
-    out[0] = P.ginv_begin - P.inv_begin; out[1] = P.inv_end - P.ginv_begin; out[2] = out[3] = 0;
-    std::vector<uint8_t> thr(1024, 0);
-    for (uint32_t i = P.inv_begin; i < P.inv_end; i++) {
+    // out: 0 leveled INV ops, 1 deferred INV ops, 2 leveled ones that miss the table, 3 deferred ones that would have hit it,
+    //      4 first level with every deferred input ready, 5 number of levels
+    out[0] = out[2] = out[3] = 0; out[1] = P.inv_end - P.ginv_begin;
+    for (uint32_t i = 0; i < P.inv_end; i++) {
+        if (op_opc(P.ops[i]) != OP_INV) continue;
         Fr a = vm_load(x, P.ops[i].a), d;
         const bool miss = vm_inv_class(x, a, d) != 0;
-        if (i < P.ginv_begin) { if (miss) { out[2]++; thr[(i - P.inv_begin) % 1024] = 1; } } else if (!miss) out[3]++;
+        if (i < P.ginv_begin) { out[0]++; if (miss) out[2]++; } else if (!miss) out[3]++;
     }
-    out[4] = 0; for (uint8_t v : thr) out[4] += v;
-    uint64_t warps = 0; for (int w = 0; w < 32; w++) { bool any = false; for (int l = 0; l < 32; l++) any |= thr[w * 32 + l]; warps += any; }
-    out[5] = warps;
+    out[4] = P.ginv_level; out[5] = P.levels.size();
 }
