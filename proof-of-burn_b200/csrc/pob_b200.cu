@@ -155,14 +155,14 @@ struct pob_handle {
     // per SM: fewer concurrent write streams give the DRAM controllers longer same-row bursts -- measured 7.35 TB/s with
     // 2 CTAs/SM vs 7.26 / 7.19 / 7.09 / 6.97 TB/s with 3 / 4 / 5 / 8, and 5.96 TB/s with 1 (profiles/r01_expand_sweep.md)
     uint32_t round_dyn_smem = 85 * 1024;
-    uint32_t round_threads = 256, codes_dyn_smem = 0, codes_ug = 4; bool serialize = false;   // changed by POB_TUNING knobs only
+    uint32_t round_threads = 256, codes_dyn_smem = 0, codes_ug = 4, codes_overlap = 0; bool serialize = false;   // changed by POB_TUNING knobs only
     int eval_threads = 512; uint32_t eval_cluster = 0, eval_prefetch = 0;   // operand prefetch measured no gain (profiles/r02c_eval_sweep.log)   // k_eval: threads per CTA; CTAs per instance (0 = chosen per launch)
     uint32_t pos_konst_bytes = 0, levels_bytes = 0, eval_smem = 0;
     bool skip_eval = false;                     // tuning: evaluate only the first two chunks, then re-expand their stores (isolates the cost of concurrency)
     uint32_t expand_cs = 0, eval_l2_mb = 0;     // tuning: streaming witness stores; persisting-L2 window (MB) for the eval stream's store accesses
-    cudaStream_t s_eval = nullptr, s_exp = nullptr, s_h2d = nullptr;
+    cudaStream_t s_eval = nullptr, s_exp = nullptr, s_exp2 = nullptr, s_h2d = nullptr;
     cudaEvent_t ev_eval_done[RING] = {nullptr, nullptr}, ev_exp_done[RING] = {nullptr, nullptr}, ev_h2d[RING] = {nullptr, nullptr},
-                ev_start = nullptr, ev_end = nullptr, ev_tmp = nullptr;
+                ev_start = nullptr, ev_end = nullptr, ev_tmp = nullptr, ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
     // the batch in flight
     struct Group { uint32_t begin, end, chunk; cudaEvent_t t0, t1; };
@@ -321,7 +321,18 @@ static void enqueue_group(pob_handle *h, uint32_t g) {
     // launch 1: KeccakfRound tiles, tile-major (each CTA's tables are staged in shared memory);
     // launch 2: code tiles, INSTANCE-major, so that a tile's code stream is fetched from DRAM once and
     // served from L2 to the other witnesses of the group
+    // codes_overlap: the code-tile kernel (latency-bound gathers) runs on a second stream NEXT TO the round kernel (bandwidth-bound)
+    // instead of after it; 1 = round kernel launched first, 2 = code kernel launched first
     const uint32_t n_round = h->n_round_tiles, n_code = (uint32_t)P.tiles.size() - n_round;
+    const bool fork = h->codes_overlap && n_round && n_code;
+    cudaStream_t s_codes = fork ? h->s_exp2 : h->s_exp;
+    auto launch_codes = [&]() {
+        xa.tile0 = n_round;
+        if (h->codes_ug == 8) k_expand_codes<8><<<dim3(gc, n_code), 256, h->codes_dyn_smem, s_codes>>>(xa);
+        else k_expand_codes<4><<<dim3(gc, n_code), 256, h->codes_dyn_smem, s_codes>>>(xa);
+        B.T.other_launches++;
+    };
+    if (fork) { CU(cudaEventRecord(h->ev_fork, h->s_exp)); CU(cudaStreamWaitEvent(h->s_exp2, h->ev_fork, 0)); if (h->codes_overlap == 2) launch_codes(); }
     if (n_round) {
         xa.tile0 = 0;
         if (h->round_threads == 128) k_expand_round<128><<<dim3(n_round, gc), 128, h->round_dyn_smem, h->s_exp>>>(xa);
@@ -329,12 +340,8 @@ static void enqueue_group(pob_handle *h, uint32_t g) {
         else if (h->round_threads == 1024) k_expand_round<1024><<<dim3(n_round, gc), 1024, h->round_dyn_smem, h->s_exp>>>(xa);
         else k_expand_round<256><<<dim3(n_round, gc), 256, h->round_dyn_smem, h->s_exp>>>(xa);
     }
-    if (n_code) {
-        xa.tile0 = n_round;
-        if (h->codes_ug == 8) k_expand_codes<8><<<dim3(gc, n_code), 256, h->codes_dyn_smem, h->s_exp>>>(xa);
-        else k_expand_codes<4><<<dim3(gc, n_code), 256, h->codes_dyn_smem, h->s_exp>>>(xa);
-        B.T.other_launches++;
-    }
+    if (n_code && !(fork && h->codes_overlap == 2)) launch_codes();
+    if (fork) { CU(cudaEventRecord(h->ev_join, h->s_exp2)); CU(cudaStreamWaitEvent(h->s_exp, h->ev_join, 0)); }
     CU(cudaEventRecord(G.t1, h->s_exp));
     B.T.expand_launches++;
     if (B.digest) for (uint32_t k = G.begin; k < G.end; k++) {     // built-in on-GPU consumer: reads every entry of the witness once
@@ -500,6 +507,7 @@ void pob_destroy(pob_handle *h) {
     delete h->exporter; h->exporter = nullptr;
     for (void *p : h->cons.allocs) cudaFree(p);
     if (h->s_eval) cudaStreamSynchronize(h->s_eval);
+    if (h->s_exp2) cudaStreamSynchronize(h->s_exp2);
     if (h->s_exp) cudaStreamSynchronize(h->s_exp);
     if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
     for (void *p : {(void *)h->d_ops, (void *)h->d_psums, (void *)h->d_pos, (void *)h->d_pos_konst, (void *)h->d_abs, (void *)h->d_levels, (void *)h->d_aux, (void *)h->d_konst, (void *)h->d_codes,
@@ -515,8 +523,8 @@ void pob_destroy(pob_handle *h) {
         if (h->ev_exp_done[r]) cudaEventDestroy(h->ev_exp_done[r]);
         if (h->ev_h2d[r]) cudaEventDestroy(h->ev_h2d[r]);
     }
-    for (cudaEvent_t e : {h->ev_start, h->ev_end, h->ev_tmp}) if (e) cudaEventDestroy(e);
-    for (cudaStream_t s : {h->s_h2d, h->s_eval, h->s_exp}) if (s) cudaStreamDestroy(s);
+    for (cudaEvent_t e : {h->ev_start, h->ev_end, h->ev_tmp, h->ev_fork, h->ev_join}) if (e) cudaEventDestroy(e);
+    for (cudaStream_t s : {h->s_h2d, h->s_eval, h->s_exp, h->s_exp2}) if (s) cudaStreamDestroy(s);
     delete h;
 }
 
@@ -553,12 +561,14 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         CU(cudaStreamCreateWithPriority(&h->s_eval, cudaStreamNonBlocking, pr_greatest));
         CU(cudaStreamCreateWithPriority(&h->s_h2d, cudaStreamNonBlocking, pr_greatest));
         CU(cudaStreamCreateWithPriority(&h->s_exp, cudaStreamNonBlocking, pr_least));
+        CU(cudaStreamCreateWithPriority(&h->s_exp2, cudaStreamNonBlocking, pr_least));
         for (uint32_t r = 0; r < pob_handle::RING; r++) {
             CU(cudaEventCreateWithFlags(&h->ev_eval_done[r], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&h->ev_exp_done[r], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&h->ev_h2d[r], cudaEventDisableTiming));
         }
         CU(cudaEventCreate(&h->ev_start)); CU(cudaEventCreate(&h->ev_end)); CU(cudaEventCreateWithFlags(&h->ev_tmp, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
         // (an L2 persisting access-policy window for the code stream was tried and REDUCED the expand kernel to 4.9 TB/s: the
         // carve-out takes L2 away from write combining -- profiles/r01_expand_sweep.md)
         if (const char *v = tune_env("POB_EVAL_PROFILE")) { h->prof_path = v; CU(cudaMalloc(&h->d_prof, (P.levels.size() + 3) * sizeof(long long))); }
@@ -597,6 +607,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (const char *v = tune_env("POB_EXPAND_SMEM_KB")) h->round_dyn_smem = (uint32_t)atoi(v) * 1024u;
         if (const char *v = tune_env("POB_EXPAND_THREADS")) h->round_threads = (uint32_t)atoi(v);
         if (const char *v = tune_env("POB_CODES_UG")) h->codes_ug = (uint32_t)atoi(v);
+        if (const char *v = tune_env("POB_CODES_OVERLAP")) h->codes_overlap = (uint32_t)atoi(v);
         if (const char *v = tune_env("POB_CODES_SMEM_KB")) { h->codes_dyn_smem = (uint32_t)atoi(v) * 1024u; if (h->codes_dyn_smem > 48 * 1024) { CU(cudaFuncSetAttribute(k_expand_codes<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->codes_dyn_smem)); CU(cudaFuncSetAttribute(k_expand_codes<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->codes_dyn_smem)); } }
         if (h->round_dyn_smem > 48 * 1024) {
             CU(cudaFuncSetAttribute(k_expand_round<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));
