@@ -26,10 +26,16 @@ using namespace pob;
 
 namespace {
 
-__device__ __forceinline__ int inv_rot(int L) {      // i such that rot[i + 1] == L  (L = 1..24)
-    constexpr int INV[25] = {0, 23, 17, 5, 11, 6, 22, 1, 8, 21, 0, 2, 16, 15, 19, 12, 7, 3, 4, 14, 18, 9, 20, 13, 10};
-    return INV[L];
-}
+// Keccak tables in constant memory: a constexpr array inside a device function is rebuilt on the thread's stack at every use
+// (ptxas: 26 STL.128 + 3 dependent LDL per Keccak round), which tripled the latency of an absorb.
+__constant__ uint64_t c_keccak_rc[24] = {
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL, 0x000000000000808BULL,
+    0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008AULL, 0x0000000000000088ULL,
+    0x0000000080008009ULL, 0x000000008000000AULL, 0x000000008000808BULL, 0x800000000000008BULL, 0x8000000000008089ULL,
+    0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800AULL, 0x800000008000000AULL,
+    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};                        // keccak.circom:253-262
+__constant__ int c_keccak_rot[25] = {1, 10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};     // RhoPi lane walk, keccak.circom:195
+__constant__ int c_keccak_inv_rot[25] = {0, 23, 17, 5, 11, 6, 22, 1, 8, 21, 0, 2, 16, 15, 19, 12, 7, 3, 4, 14, 18, 9, 20, 13, 10};  // i such that rot[i + 1] == L  (L = 1..24)
 
 // One Absorb (utils/keccak.circom:304-323) by one warp; lane l < 25 owns state lane l.
 __device__ void absorb_warp(uint64_t *W, const AbsorbOp op) {
@@ -41,8 +47,12 @@ __device__ void absorb_warp(uint64_t *W, const AbsorbOp op) {
     if (lane < 17) st ^= W[op.blk_idx + lane];
     if (act) W[op.out_idx + l] = st;
     const int col = l % 5;
+    // lane constants of the round (hoisted: nothing below the loop header depends on memory except the round constant)
+    const int i = lane < 24 ? lane : 0;
+    const int rot_src = c_keccak_rot[i], shl = keccak_shl(i), rot_dst = c_keccak_inv_rot[l], cb_src = chi_b(l), cc_src = chi_c(l);
 #pragma unroll 1
     for (int r = 0; r < 24; r++) {
+        const uint64_t rc = c_keccak_rc[r];
         uint64_t *B = W + op.out_idx + RW * r;
         // Theta: Xor5 chain of my column (all lanes of a column compute it redundantly; lanes 0..4 store it)
         uint64_t v0 = __shfl_sync(FULL, st, col), v1 = __shfl_sync(FULL, st, col + 5), v2 = __shfl_sync(FULL, st, col + 10),
@@ -56,19 +66,16 @@ __device__ void absorb_warp(uint64_t *W, const AbsorbOp op) {
         uint64_t th = st ^ d;
         if (act) B[rw_th(l)] = th;
         // RhoPi: lane i < 24 performs step i on theta[rot[i]], the result belongs to lane rot[i+1]
-        const int i = lane < 24 ? lane : 0;
-        uint64_t a = __shfl_sync(FULL, th, keccak_rot(i));
-        const int shl = keccak_shl(i);
+        uint64_t a = __shfl_sync(FULL, th, rot_src);
         uint64_t a0 = a >> (64 - shl), a1 = a << shl, ro = a0 | a1;
         if (lane < 24) { B[rw_rp(lane, 0)] = a0; B[rw_rp(lane, 1)] = a1; B[rw_rp(lane, 2)] = ro; }
-        uint64_t rp = __shfl_sync(FULL, ro, inv_rot(l));
+        uint64_t rp = __shfl_sync(FULL, ro, rot_dst);
         if (lane == 0) rp = th;
         // Chi
-        uint64_t vb = __shfl_sync(FULL, rp, chi_b(l)), vc = __shfl_sync(FULL, rp, chi_c(l));
+        uint64_t vb = __shfl_sync(FULL, rp, cb_src), vc = __shfl_sync(FULL, rp, cc_src);
         uint64_t nb = ~vb, bc = nb & vc, ch = rp ^ bc;
         if (act) { B[rw_ch(l, 0)] = nb; B[rw_ch(l, 1)] = bc; B[rw_ch(l, 2)] = ch; }
         // Iota
-        const uint64_t rc = keccak_rc(r);
         if (lane == 0) { B[RW_RC] = rc; ch ^= rc; }
         if (act) B[rw_out(l)] = ch;
         st = ch;
@@ -171,20 +178,23 @@ struct EvalArgs {
     uint32_t ginv_level;                          // first level at which every deferred inverse has its input (n_levels: none before the end)
 };
 
-// deferred IsZero inverses (comparators.circom:30): vm_exec.h vm_ginv_start / inv_eea_steps / vm_ginv_finish.  One inversion costs
+// deferred IsZero inverses (comparators.circom:30): vm_exec.h vm_ginv_start / inv_chain_steps / vm_ginv_finish.  One inversion costs
 // about as much as twenty average levels; spread over the levels it costs a few thousand cycles per level on 8 warps per CTA.
-static const uint32_t INV_WORKERS = 256, INV_STEPS = 24;
-// parked state: word-major ([32 words][INV_WORKERS]) so that a warp's loads and stores are conflict-free
+static const uint32_t INV_WORKERS = 256, INV_STEPS = 64;
+// parked state: word-major ([33 words][INV_WORKERS]) so that a warp's loads and stores are conflict-free
+static const uint32_t INV_PARK_WORDS = 33;
 __device__ __forceinline__ void inv_park(uint32_t *s, uint32_t t, const InvChain &c) {
 #pragma unroll
     for (int k = 0; k < 8; k++) { s[(k) * INV_WORKERS + t] = c.u.l[k]; s[(8 + k) * INV_WORKERS + t] = c.v.l[k];
-                                  s[(16 + k) * INV_WORKERS + t] = c.x1.l[k]; s[(24 + k) * INV_WORKERS + t] = c.x2.l[k]; }
+                                  s[(16 + k) * INV_WORKERS + t] = c.r.l[k]; s[(24 + k) * INV_WORKERS + t] = c.s.l[k]; }
+    s[32 * INV_WORKERS + t] = c.k;
 }
 __device__ __forceinline__ InvChain inv_unpark(const uint32_t *s, uint32_t t) {
     InvChain c;
 #pragma unroll
     for (int k = 0; k < 8; k++) { c.u.l[k] = s[(k) * INV_WORKERS + t]; c.v.l[k] = s[(8 + k) * INV_WORKERS + t];
-                                  c.x1.l[k] = s[(16 + k) * INV_WORKERS + t]; c.x2.l[k] = s[(24 + k) * INV_WORKERS + t]; }
+                                  c.r.l[k] = s[(16 + k) * INV_WORKERS + t]; c.s.l[k] = s[(24 + k) * INV_WORKERS + t]; }
+    c.k = s[32 * INV_WORKERS + t];
     return c;
 }
 
@@ -246,8 +256,10 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     Fr *s_pk = reinterpret_cast<Fr *>(dyn_smem);
     Level *s_levels = reinterpret_cast<Level *>(dyn_smem + a.pos_konst_bytes);
     uint32_t *s_inv = reinterpret_cast<uint32_t *>(dyn_smem + a.pos_konst_bytes + a.levels_bytes);     // INV_WORKERS parked chains
-    uint32_t inv_phase = 0;                       // this worker's chain: 0 = nothing to invert, 1 = inversion running, 2 = inverse ready
-    const uint32_t wid = rank * INV_WORKERS + tid, NWK = C * INV_WORKERS;
+    bool inv_running = false;                     // this worker has an inversion in progress (state parked in s_inv)
+    // the workers are the LAST 8 warps of the CTA: warp ops (absorbs, Poseidon segments) are dealt from warp 0 upwards
+    const uint32_t wt = tid - (THREADS - INV_WORKERS), wid = rank * INV_WORKERS + wt, NWK = C * INV_WORKERS;
+    const bool inv_worker = tid >= THREADS - INV_WORKERS;
     if (tid == 0) { s_status = STATUS_OK; mbar_init(&s_bar, 1); if (rank == 0) a.status[inst] = STATUS_OK; }
     __syncthreads();
     if (tid == 0) {
@@ -288,26 +300,26 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
           for (uint32_t w = L.w_begin + wv; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]);
           const uint32_t nw2 = (np + (L.w_end - L.w_begin)) % nwarp, sv = (gwarp + nwarp - nw2) % nwarp;
           for (uint32_t q = L.s_begin + sv; q < L.s_end; q += nwarp) psum_warp(x, a.psums[q]); }
-        if (tid < INV_WORKERS) {
+        if (inv_worker) {
             if (lv == a.ginv_level) {                                               // start
                 InvChain c;
-                if (vm_ginv_start(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK, c)) { inv_park(s_inv, tid, c); inv_phase = 1; }
-            } else if (inv_phase == 1) {                                            // step
-                InvChain c = inv_unpark(s_inv, tid);
-                if (inv_eea_steps(c, INV_STEPS)) inv_phase = 2;
-                inv_park(s_inv, tid, c);
+                if (vm_ginv_start(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK, c)) { inv_park(s_inv, wt, c); inv_running = true; }
+            } else if (inv_running) {                                               // step; unwind as soon as the inverse is there
+                InvChain c = inv_unpark(s_inv, wt);
+                if (inv_chain_steps(c, INV_STEPS)) { vm_ginv_finish(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK, inv_chain_result(c)); inv_running = false; }
+                else inv_park(s_inv, wt, c);
             }
         }
         cluster_sync_all();
     }
     if (a.prof && inst == 0 && gt == 0) a.prof[a.n_levels] = clock64();
     // finish the deferred inverses (or do all of it when their inputs only became ready in the last level)
-    if (tid < INV_WORKERS) {
+    if (inv_worker) {
         if (a.ginv_level >= a.n_levels) vm_inv_batch(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK);
-        else if (inv_phase) {
-            InvChain c = inv_unpark(s_inv, tid);
-            if (inv_phase == 1) while (!inv_eea_steps(c, 64)) { }
-            vm_ginv_finish(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK, c.x1);
+        else if (inv_running) {
+            InvChain c = inv_unpark(s_inv, wt);
+            while (!inv_chain_steps(c, 64)) { }
+            vm_ginv_finish(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK, inv_chain_result(c));
         }
     }
     if (a.prof && inst == 0) { cluster_sync_all(); if (gt == 0) { a.prof[a.n_levels + 1] = clock64(); a.prof[a.n_levels + 2] = clock64(); } }
@@ -476,7 +488,7 @@ __global__ void __launch_bounds__(256) k_pow_grind(const GrindArgs a) {
         for (int i = 0; i < 24; i++) b[keccak_rot(i + 1)] = rotl64(s[keccak_rot(i)], keccak_shl(i));
 #pragma unroll
         for (int i = 0; i < 25; i++) s[i] = b[i] ^ (~b[chi_b(i)] & b[chi_c(i)]);
-        s[0] ^= keccak_rc(r);
+        s[0] ^= c_keccak_rc[r];
     }
     const uint64_t mask = a.zero_bytes >= 8 ? ~0ull : ((1ull << (8 * a.zero_bytes)) - 1);
     if ((s[0] & mask) == 0) atomicMin(a.hit, (unsigned long long)idx);
@@ -516,7 +528,7 @@ __global__ void __launch_bounds__(256) k_check_rounds(const uint64_t *wit, const
         for (int i = 0; i < 24; i++) b[keccak_rot(i + 1)] = rotl64(s[keccak_rot(i)], keccak_shl(i));
 #pragma unroll
         for (int i = 0; i < 25; i++) s[i] = b[i] ^ (~b[chi_b(i)] & b[chi_c(i)]);
-        s[0] ^= keccak_rc(r);
+        s[0] ^= c_keccak_rc[r];
 #pragma unroll
         for (int i = 0; i < 25; i++) bad |= (s[i] != o[i]);
         if (bad) atomicAdd(n_bad, 1ull);
@@ -547,7 +559,7 @@ __global__ void __launch_bounds__(256) k_check_kc(const CheckArgs a) {
     const uint64_t per = a.V.n_kc, total = per * (a.bases ? a.n_blocks : 1u);
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t blk = t / per, r = t - blk * per, base = a.bases ? a.bases[blk] : 0;
-        if (!cons_kc_ok(a.wit, base, a.V.kc[r], a.konst, keccak_rc((int)(blk % 24)))) check_fail(a, a.id0 + blk * a.V.n_records() + a.V.n_eq + r, false);
+        if (!cons_kc_ok(a.wit, base, a.V.kc[r], a.konst, c_keccak_rc[blk % 24])) check_fail(a, a.id0 + blk * a.V.n_records() + a.V.n_eq + r, false);
     }
 }
 __global__ void __launch_bounds__(256) k_check_r1(const CheckArgs a) {

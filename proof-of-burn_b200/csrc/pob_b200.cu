@@ -542,7 +542,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         CU(cudaSetDevice(device));
         h->d_ops = upload(P.ops); h->d_psums = upload(P.psums); h->d_pos = upload(P.poseidons); h->d_pos_konst = upload(P.pos_konst); h->d_abs = upload(P.absorbs); h->d_levels = upload(P.levels); h->d_aux = upload(P.aux);
         h->pos_konst_bytes = (uint32_t)(P.pos_konst.size() * sizeof(Fr)); h->levels_bytes = (uint32_t)(std::max<size_t>(1, P.levels.size()) * sizeof(Level));   // both multiples of 32
-        h->eval_smem = h->pos_konst_bytes + h->levels_bytes + (uint32_t)(INV_WORKERS * sizeof(InvChain));   // + the parked inversion state of 256 workers (32 KB)
+        h->eval_smem = h->pos_konst_bytes + h->levels_bytes + INV_WORKERS * INV_PARK_WORDS * 4u;   // + the parked inversion state of 256 workers (33 KB)
         h->d_konst = upload(P.konst);
         { std::vector<Code> cd = P.codes; cd.resize(cd.size() + 8, 0); h->d_codes = upload(cd); }   // + 32 bytes: TMA copies whole 16-byte units
         if (const char *v = tune_env("POB_TILE_FILTER")) {      // TUNING build only: 1 = KeccakfRound tiles only, 2 = the others only (witness incomplete!)

@@ -134,21 +134,67 @@ POB_HD void vm_inv_batch(const VmCtx &x, const Op *ops, uint32_t begin, uint32_t
 // Worker w of nw owns the deferred ops begin + w, + nw, ...  START (the first level at which all inputs are ready): zero /
 // table-sized inputs are answered at once, the others get their prefix product parked in the destination slot (Montgomery's
 // trick) and the worker's total product becomes an inversion in progress.  STEP (every later level): a bounded number of
-// iterations of fr_inv_eea's loop, state parked by the caller.  FINISH (after the last level): the products are unwound.
-struct InvChain { Fr u, v, x1, x2; };             // fr_inv_eea's state; once finished the inverse is in x1
-POB_HD bool inv_eea_steps(InvChain &c, uint32_t steps) {                           // true: finished
-    const Fr one = fr_from_u64(1);
-    for (uint32_t k = 0; k < steps; k++) {
-        if (fr_eq(c.u, one)) return true;
-        if (fr_eq(c.v, one)) { c.x1 = c.x2; c.u = one; return true; }
-        while (!(c.u.l[0] & 1u)) { fr_shr1(c.u); fr_half_mod(c.x1); }
-        while (!(c.v.l[0] & 1u)) { fr_shr1(c.v); fr_half_mod(c.x2); }
-        if (fr_geq(c.u, c.v)) { Fr t; fr_raw_sub(t, c.u, c.v); c.u = t; c.x1 = fr_sub(c.x1, c.x2); }
-        else { Fr t; fr_raw_sub(t, c.v, c.u); c.v = t; c.x2 = fr_sub(c.x2, c.x1); }
+// iterations of the inversion, state parked by the caller.  FINISH (after the last level): the products are unwound.
+// The inversion itself is Kaliski's "almost inverse" (phase 1 of the Montgomery inverse): per iteration one of four cheap cases
+// on (u, v, r, s) -- halve u, halve v, or subtract-and-halve -- with no modular halving and no inner loops (in SIMT the
+// per-lane `while (even) halve` loops of the textbook binary Euclid run for the maximum over the warp's lanes: measured 5x
+// slower).  After k iterations (254 <= k <= 508) r = -a^-1 2^k mod p; two Montgomery products remove the 2^k.
+struct InvChain { Fr u, v, r, s; uint32_t k; };
+POB_HD uint32_t bn_sub(Fr &d, const Fr &a, const Fr &b) {                           // d = a - b mod 2^256, returns the borrow
+#ifdef __CUDA_ARCH__
+    uint32_t br;
+    asm("sub.cc.u32 %0, %9, %17;\n\tsubc.cc.u32 %1, %10, %18;\n\tsubc.cc.u32 %2, %11, %19;\n\tsubc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\tsubc.cc.u32 %5, %14, %22;\n\tsubc.cc.u32 %6, %15, %23;\n\tsubc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(d.l[0]), "=r"(d.l[1]), "=r"(d.l[2]), "=r"(d.l[3]), "=r"(d.l[4]), "=r"(d.l[5]), "=r"(d.l[6]), "=r"(d.l[7]), "=r"(br)
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+    return br & 1u;
+#else
+    return fr_raw_sub(d, a, b);
+#endif
+}
+POB_HD void bn_add(Fr &d, const Fr &a, const Fr &b) {                               // d = a + b (the caller knows it fits)
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u32 %0, %8, %16;\n\taddc.cc.u32 %1, %9, %17;\n\taddc.cc.u32 %2, %10, %18;\n\taddc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\taddc.cc.u32 %5, %13, %21;\n\taddc.cc.u32 %6, %14, %22;\n\taddc.u32 %7, %15, %23;"
+        : "=r"(d.l[0]), "=r"(d.l[1]), "=r"(d.l[2]), "=r"(d.l[3]), "=r"(d.l[4]), "=r"(d.l[5]), "=r"(d.l[6]), "=r"(d.l[7])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+#else
+    fr_raw_add(d, a, b);
+#endif
+}
+POB_HD void bn_shl1(Fr &a) {
+#pragma unroll
+    for (int i = 7; i > 0; i--) a.l[i] = (a.l[i] << 1) | (a.l[i - 1] >> 31);
+    a.l[0] <<= 1;
+}
+POB_HD void inv_chain_init(InvChain &c, const Fr &a) { c.u = fr_p(); c.v = a; c.r = fr_zero(); c.s = fr_from_u64(1); c.k = 0; }
+POB_HD bool inv_chain_steps(InvChain &c, uint32_t steps) {                         // true: finished (v == 0)
+    for (uint32_t n = 0; n < steps; n++) {
+        if (fr_is_zero(c.v)) return true;
+        if (!(c.u.l[0] & 1u)) { fr_shr1(c.u); bn_shl1(c.s); }
+        else if (!(c.v.l[0] & 1u)) { fr_shr1(c.v); bn_shl1(c.r); }
+        else {
+            Fr d; const uint32_t lt = bn_sub(d, c.u, c.v);
+            if (!lt && !fr_is_zero(d)) { fr_shr1(d); c.u = d; bn_add(c.r, c.r, c.s); bn_shl1(c.s); }          // u > v
+            else { if (lt) bn_sub(d, c.v, c.u); fr_shr1(d); c.v = d; bn_add(c.s, c.s, c.r); bn_shl1(c.r); }      // v >= u
+        }
+        c.k++;
     }
-    if (fr_eq(c.u, one)) return true;
-    if (fr_eq(c.v, one)) { c.x1 = c.x2; c.u = one; return true; }
-    return false;
+    return fr_is_zero(c.v);
+}
+POB_HD Fr inv_chain_result(const InvChain &c) {                                     // a^-1 (canonical) once inv_chain_steps returned true
+    Fr r = c.r;
+    if (fr_geq_p(r)) { Fr t; fr_raw_sub(t, r, fr_p()); r = t; }                      // r < 2p
+    { Fr t; fr_raw_sub(t, fr_p(), r); r = t; }                                       // r = a^-1 2^k mod p, in [1, p-1] (r == 0 cannot happen for a != 0)
+    uint32_t k = c.k;                                                                // 254 <= k <= 508
+    if (k > 256) { r = fr_mont(r, fr_from_u64(1)); k -= 256; }                      // r * 2^-256; now 0 < k <= 256
+    const uint32_t e = 256 - k;                                                      // r * 2^e * 2^-256 = r * 2^-k
+    Fr pw = fr_zero(); pw.l[e >> 5] = 1u << (e & 31);
+    while (fr_geq_p(pw)) { Fr t; fr_raw_sub(t, pw, fr_p()); pw = t; }               // e = 254, 255 only
+    return fr_mont(r, pw);
 }
 POB_HD bool vm_ginv_start(const VmCtx &x, const Op *ops, uint32_t begin, uint32_t end, uint32_t w, uint32_t nw, InvChain &c) {
     Fr acc = fr_from_u64(1); bool any = false;
@@ -158,7 +204,7 @@ POB_HD bool vm_ginv_start(const VmCtx &x, const Op *ops, uint32_t begin, uint32_
         if (vm_inv_class(x, a, d) == 0) vm_store_val(vd, d);
         else { vm_store_val(vd, acc); acc = fr_mul(acc, a); any = true; }
     }
-    if (any) { c.u = acc; c.v = fr_p(); c.x1 = fr_from_u64(1); c.x2 = fr_zero(); }
+    if (any) inv_chain_init(c, acc);
     return any;                                   // false: nothing left to do for this worker
 }
 POB_HD void vm_ginv_finish(const VmCtx &x, const Op *ops, uint32_t begin, uint32_t end, uint32_t w, uint32_t nw, Fr inv) {

@@ -60,8 +60,8 @@ uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_
     }
     uint32_t status = STATUS_OK;
     VmCtx x{U.data(), P.val_base, P.konst.data(), P.aux.data(), e->invtab.data(), &status};
-    // deferred inverses: the same start / step / finish schedule as k_eval, with 8 workers and 24 steps per level
-    const uint32_t NW = 8, STEPS = 24;
+    // deferred inverses: the same start / step / finish schedule as k_eval, with 8 workers and 64 steps per level
+    const uint32_t NW = 8, STEPS = 64;
     std::vector<InvChain> chain(NW); std::vector<uint32_t> phase(NW, 0);
     for (uint32_t li = 0; li < P.levels.size(); li++) {
         const Level &lv = P.levels[li];
@@ -71,14 +71,16 @@ uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_
         for (uint32_t i = lv.s_begin; i < lv.s_end; i++) vm_psum_scalar(x, P.psums[i]);
         for (uint32_t w = 0; w < NW; w++) {
             if (li == P.ginv_level) phase[w] = vm_ginv_start(x, P.ops.data(), P.ginv_begin, P.inv_end, w, NW, chain[w]) ? 1 : 0;
-            else if (phase[w] == 1 && inv_eea_steps(chain[w], STEPS)) phase[w] = 2;
+            else if (phase[w] == 1 && inv_chain_steps(chain[w], STEPS)) {
+                vm_ginv_finish(x, P.ops.data(), P.ginv_begin, P.inv_end, w, NW, inv_chain_result(chain[w])); phase[w] = 0;
+            }
         }
     }
     for (uint32_t w = 0; w < NW; w++) {
         if (P.ginv_level >= P.levels.size()) vm_inv_batch(x, P.ops.data(), P.ginv_begin, P.inv_end, w, NW);
-        else if (phase[w]) {
-            if (phase[w] == 1) while (!inv_eea_steps(chain[w], 64)) { }
-            vm_ginv_finish(x, P.ops.data(), P.ginv_begin, P.inv_end, w, NW, chain[w].x1);
+        else if (phase[w] == 1) {
+            while (!inv_chain_steps(chain[w], 64)) { }
+            vm_ginv_finish(x, P.ops.data(), P.ginv_begin, P.inv_end, w, NW, inv_chain_result(chain[w]));
         }
     }
     if (witness)
@@ -124,11 +126,11 @@ extern "C" uint32_t pob_emu_inv_selftest(uint32_t n) {
         if (fr_is_zero(a)) continue;
         Fr x = fr_inv_eea(a), y = fr_inv(a);
         if (!fr_eq(x, y) || !fr_eq(fr_mul(x, a), fr_from_u64(1))) bad++;
-        // the same inversion cut into slices (k_eval spreads it over the levels): any slicing gives the same result
-        InvChain c; c.u = a; c.v = fr_p(); c.x1 = fr_from_u64(1); c.x2 = fr_zero();
+        // the deferred inverses' inversion (Kaliski almost-inverse, vm_exec.h) cut into slices: any slicing gives the Fermat result
+        InvChain c; inv_chain_init(c, a);
         uint32_t slices = 0;
-        while (!inv_eea_steps(c, 1 + (i % 37))) slices++;
-        if (!fr_eq(c.x1, y) || slices * (1 + (i % 37)) > 520) bad++;
+        while (!inv_chain_steps(c, 1 + (i % 37))) slices++;
+        if (c.k < 254 || c.k > 508 || !fr_eq(inv_chain_result(c), y)) bad++;
     }
     return bad;
 }
