@@ -98,13 +98,16 @@ __device__ void poseidon_warp(const VmCtx &x, const PoseidonOp op, const Fr *pk)
     const Fr *K = pk + op.koff;
     uint64_t *V = x.U + x.val_base + 4ull * op.base;
     const uint32_t Q = pos_steps(L);
-    // values are parked in their slots in MONTGOMERY form (nothing but Poseidon segments reads them before the sweep of the last
-    // segment): no conversion sits on the dependency chain of the 65 rounds
+    // values are parked in their slots in MONTGOMERY form until the end of the segment that wrote them (nothing but Poseidon segments
+    // reads them before the last segment is through): no conversion sits on the dependency chain of the 65 rounds
     auto put = [&](uint32_t off, const Fr &m) { if (act) vm_store_val(V + 4ull * off, m); };
     Fr s;
     uint32_t q = op.q0;
     if (q == 0) { s = fr_add(fr_to_mont(vm_load(x, x.aux[op.in_aux + j])), K[L.kC + j]); put(j, s); q = 1; }     // step 0: ark[0]
-    else s = vm_load_val(V + 4ull * (pos_state_off(L, q - 1) + j));                                                // state after the previous segment
+    else {                                                                                                          // state after the previous segment;
+        uint64_t *ps = V + 4ull * (pos_state_off(L, q - 1) + j);                                                    // its slots are the one thing that
+        s = vm_load_val(ps); if (act) vm_store_val(ps, fr_from_mont(s));                                            // segment left in Montgomery form
+    }
     auto full = [&](uint32_t F, uint32_t coff, uint32_t moff) {
         Fr x2 = fr_mont(s, s), x4 = fr_mont(x2, x2), x5 = fr_mont(x4, s);
         put(F + 3 * j, x2); put(F + 3 * j + 1, x4); put(F + 3 * j + 2, x5);
@@ -137,11 +140,14 @@ __device__ void poseidon_warp(const VmCtx &x, const PoseidonOp op, const Fr *pk)
         Fr prod = fr_mont(K[L.kM + j * t], x5), out = fr_zero();
         for (uint32_t k = 0; k < t; k++) out = fr_add(out, shfl_fr(prod, (int)k));
         if (lane == 0) vm_store_val(V + 4ull * (L.LB + 3 * t), out);
-        __syncwarp();
-        for (uint32_t i = (uint32_t)lane; i < L.total; i += 32) {     // all 32 lanes: Montgomery -> canonical, in place
-            uint64_t *p = V + 4ull * i;
-            vm_store_val(p, fr_from_mont(vm_load_val(p)));
-        }
+    }
+    // every segment converts what it wrote (all 32 lanes: Montgomery -> canonical, in place) except the state the next segment resumes from
+    __syncwarp();
+    const uint32_t keep = op.q1 < Q ? pos_state_off(L, op.q1 - 1) : L.total;
+    for (uint32_t i = pos_step_begin(L, op.q0) + (uint32_t)lane; i < pos_step_begin(L, op.q1); i += 32) {
+        if (i >= keep && i < keep + t) continue;
+        uint64_t *p = V + 4ull * i;
+        vm_store_val(p, fr_from_mont(vm_load_val(p)));
     }
 }
 
@@ -176,25 +182,26 @@ struct EvalArgs {
     uint32_t pos_konst_bytes, levels_bytes;       // sizes of the two TMA-staged tables (multiples of 16 bytes)
     uint32_t prefetch;                            // 1: fetch the next op record / prefetch its operand lines while the current op runs
     uint32_t ginv_level;                          // first level at which every deferred inverse has its input (n_levels: none before the end)
+    uint32_t solo_ops;                            // a level with at most this many thread ops (and <= SOLO_WARP_OPS warp ops) is run by CTA 0 alone; 0: never
 };
 
-// deferred IsZero inverses (comparators.circom:30): vm_exec.h vm_ginv_start / inv_chain_steps / vm_ginv_finish.  One inversion costs
-// about as much as twenty average levels; spread over the levels it costs a few thousand cycles per level on 8 warps per CTA.
-static const uint32_t INV_WORKERS = 256, INV_STEPS = 64;
-// parked state: word-major ([33 words][INV_WORKERS]) so that a warp's loads and stores are conflict-free
+// deferred IsZero inverses (comparators.circom:30): vm_exec.h vm_ginv_start / inv_chain_steps / vm_ginv_finish.  Every thread of the
+// cluster is a worker (the main shape has 7.7 K deferred inverses: two per thread of an 8-CTA cluster), one inversion each, INV_STEPS
+// iterations of it per level.
+static const uint32_t INV_STEPS = 64;
+static const uint32_t SOLO_OPS = 4096, SOLO_WARP_OPS = 8;       // k_eval: what one CTA runs alone (see small_level)
+// parked state: word-major ([33 words][workers]) so that a warp's loads and stores are conflict-free
 static const uint32_t INV_PARK_WORDS = 33;
-__device__ __forceinline__ void inv_park(uint32_t *s, uint32_t t, const InvChain &c) {
+__device__ __forceinline__ void inv_park(uint32_t *s, uint32_t nw, uint32_t t, const InvChain &c) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) { s[(k) * INV_WORKERS + t] = c.u.l[k]; s[(8 + k) * INV_WORKERS + t] = c.v.l[k];
-                                  s[(16 + k) * INV_WORKERS + t] = c.r.l[k]; s[(24 + k) * INV_WORKERS + t] = c.s.l[k]; }
-    s[32 * INV_WORKERS + t] = c.k;
+    for (int k = 0; k < 8; k++) { s[(k) * nw + t] = c.u.l[k]; s[(8 + k) * nw + t] = c.v.l[k]; s[(16 + k) * nw + t] = c.r.l[k]; s[(24 + k) * nw + t] = c.s.l[k]; }
+    s[32 * nw + t] = c.k;
 }
-__device__ __forceinline__ InvChain inv_unpark(const uint32_t *s, uint32_t t) {
+__device__ __forceinline__ InvChain inv_unpark(const uint32_t *s, uint32_t nw, uint32_t t) {
     InvChain c;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { c.u.l[k] = s[(k) * INV_WORKERS + t]; c.v.l[k] = s[(8 + k) * INV_WORKERS + t];
-                                  c.r.l[k] = s[(16 + k) * INV_WORKERS + t]; c.s.l[k] = s[(24 + k) * INV_WORKERS + t]; }
-    c.k = s[32 * INV_WORKERS + t];
+    for (int k = 0; k < 8; k++) { c.u.l[k] = s[(k) * nw + t]; c.v.l[k] = s[(8 + k) * nw + t]; c.r.l[k] = s[(16 + k) * nw + t]; c.s.l[k] = s[(24 + k) * nw + t]; }
+    c.k = s[32 * nw + t];
     return c;
 }
 
@@ -249,17 +256,14 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     const uint32_t C = cluster_nctarank(), rank = cluster_ctarank();
     const uint32_t inst = blockIdx.x / C, tid = threadIdx.x;
-    const uint32_t gt = rank * THREADS + tid, GT = C * THREADS;
+    const uint32_t gt_all = rank * THREADS + tid, GT_all = C * THREADS, gt = gt_all, GT = GT_all;
     uint64_t *U = a.stores + (uint64_t)inst * a.store_stride;
     __shared__ uint32_t s_status;
     __shared__ __align__(8) uint64_t s_bar;
     Fr *s_pk = reinterpret_cast<Fr *>(dyn_smem);
     Level *s_levels = reinterpret_cast<Level *>(dyn_smem + a.pos_konst_bytes);
-    uint32_t *s_inv = reinterpret_cast<uint32_t *>(dyn_smem + a.pos_konst_bytes + a.levels_bytes);     // INV_WORKERS parked chains
+    uint32_t *s_inv = reinterpret_cast<uint32_t *>(dyn_smem + a.pos_konst_bytes + a.levels_bytes);     // THREADS parked chains
     bool inv_running = false;                     // this worker has an inversion in progress (state parked in s_inv)
-    // the workers are the LAST 8 warps of the CTA: warp ops (absorbs, Poseidon segments) are dealt from warp 0 upwards
-    const uint32_t wt = tid - (THREADS - INV_WORKERS), wid = rank * INV_WORKERS + wt, NWK = C * INV_WORKERS;
-    const bool inv_worker = tid >= THREADS - INV_WORKERS;
     if (tid == 0) { s_status = STATUS_OK; mbar_init(&s_bar, 1); if (rank == 0) a.status[inst] = STATUS_OK; }
     __syncthreads();
     if (tid == 0) {
@@ -278,10 +282,25 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     cluster_sync_all();
     VmCtx x{U, a.val_base, a.konst, a.aux, a.invtab, &s_status};
     // warp ops are dealt round-robin over the CTAs of the cluster (the 17 absorbs of a level land on 8 SMs, not on one)
-    const uint32_t gwarp = (tid >> 5) * C + rank, nwarp = GT >> 5;
+    const uint32_t gwarp_all = (tid >> 5) * C + rank;
+    // A SMALL level (a few thousand thread ops, a handful of warp ops: the tails of reduction trees, the absorb chain of the block
+    // header) is run by CTA 0 alone, and two small levels in a row are separated by __syncthreads() instead of the cluster barrier
+    // (~3.5 K cycles each, 45 of the 64 levels of the main shape).  Every CTA evaluates the same predicate on the same level table, so
+    // all of them execute the same sequence of cluster barriers.  The level that starts the deferred inverses is never small (its
+    // workers sit in every CTA and need the barrier before it).
+    auto small_level = [&](uint32_t l) -> bool {
+        if (C == 1 || a.solo_ops == 0 || l >= a.n_levels || l == a.ginv_level) return false;
+        const Level &M = s_levels[l];
+        return M.t_end - M.t_begin <= a.solo_ops && (M.w_end - M.w_begin) + (M.p_end - M.p_begin) + (M.s_end - M.s_begin) <= SOLO_WARP_OPS;
+    };
+    bool solo = small_level(0);
     for (uint32_t lv = 0; lv < a.n_levels; lv++) {
-        if (a.prof && inst == 0 && gt == 0) a.prof[lv] = clock64();
+        if (a.prof && inst == 0 && gt_all == 0) a.prof[lv] = clock64();
         const Level L = s_levels[lv];
+        const bool next_solo = small_level(lv + 1);
+        const uint32_t gt = solo ? tid : gt_all, GT = solo ? (uint32_t)THREADS : GT_all;
+        const uint32_t gwarp = solo ? tid >> 5 : gwarp_all, nwarp = GT >> 5;
+        if (!solo || rank == 0) {
         // thread ops of one level are mutually independent: the next op record is fetched, and the cache lines of its operands
         // are requested (prefetch.global.L1), while the current op executes -- two of the three dependent memory latencies
         // of an op (record -> operand -> result) overlap with the previous op
@@ -300,27 +319,25 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
           for (uint32_t w = L.w_begin + wv; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]);
           const uint32_t nw2 = (np + (L.w_end - L.w_begin)) % nwarp, sv = (gwarp + nwarp - nw2) % nwarp;
           for (uint32_t q = L.s_begin + sv; q < L.s_end; q += nwarp) psum_warp(x, a.psums[q]); }
-        if (inv_worker) {
-            if (lv == a.ginv_level) {                                               // start
-                InvChain c;
-                if (vm_ginv_start(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK, c)) { inv_park(s_inv, wt, c); inv_running = true; }
-            } else if (inv_running) {                                               // step; unwind as soon as the inverse is there
-                InvChain c = inv_unpark(s_inv, wt);
-                if (inv_chain_steps(c, INV_STEPS)) { vm_ginv_finish(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK, inv_chain_result(c)); inv_running = false; }
-                else inv_park(s_inv, wt, c);
-            }
         }
-        cluster_sync_all();
+        if (lv == a.ginv_level) {                                                   // deferred inverses: start
+            InvChain c;
+            if (vm_ginv_start(x, a.ops, a.ginv_begin, a.inv_end, gt_all, GT_all, c)) { inv_park(s_inv, THREADS, tid, c); inv_running = true; }
+        } else if (inv_running) {                                                   // step; unwind as soon as the inverse is there
+            InvChain c = inv_unpark(s_inv, THREADS, tid);
+            if (inv_chain_steps(c, INV_STEPS)) { vm_ginv_finish(x, a.ops, a.ginv_begin, a.inv_end, gt_all, GT_all, inv_chain_result(c)); inv_running = false; }
+            else inv_park(s_inv, THREADS, tid, c);
+        }
+        if (solo && next_solo) { if (rank == 0) __syncthreads(); } else cluster_sync_all();
+        solo = next_solo;
     }
     if (a.prof && inst == 0 && gt == 0) a.prof[a.n_levels] = clock64();
     // finish the deferred inverses (or do all of it when their inputs only became ready in the last level)
-    if (inv_worker) {
-        if (a.ginv_level >= a.n_levels) vm_inv_batch(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK);
-        else if (inv_running) {
-            InvChain c = inv_unpark(s_inv, wt);
-            while (!inv_chain_steps(c, 64)) { }
-            vm_ginv_finish(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK, inv_chain_result(c));
-        }
+    if (a.ginv_level >= a.n_levels) vm_inv_batch(x, a.ops, a.ginv_begin, a.inv_end, gt_all, GT_all);
+    else if (inv_running) {
+        InvChain c = inv_unpark(s_inv, THREADS, tid);
+        while (!inv_chain_steps(c, 64)) { }
+        vm_ginv_finish(x, a.ops, a.ginv_begin, a.inv_end, gt_all, GT_all, inv_chain_result(c));
     }
     if (a.prof && inst == 0) { cluster_sync_all(); if (gt == 0) { a.prof[a.n_levels + 1] = clock64(); a.prof[a.n_levels + 2] = clock64(); } }
     __syncthreads();

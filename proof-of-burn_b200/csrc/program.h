@@ -82,7 +82,7 @@ POB_HD uint32_t rw_out(int l) { return RW_OUT + l; }
 //   SB + 5t*f, f = 0..2              second-half full rounds (same shape)
 //   LB                               last sigmas (3t), then mixLast.out
 // One permutation is cut into POS_SEGMENTS warp ops of consecutive "steps" (step 0 = ark[0]; 1..4 first-half full rounds; then the RP
-// partial rounds; 3 second-half full rounds; the last step = final sigmas + mixLast + conversion sweep), scheduled in consecutive
+// partial rounds; 3 second-half full rounds; the last step = final sigmas + mixLast), scheduled in consecutive
 // levels: nothing but the last segment's result is consumed, so a 65-round dependency chain (~0.7 M cycles on one warp) no longer
 // holds up a whole level while every other warp of the cluster idles -- it proceeds alongside 16 levels of other work.  Between
 // segments the state is re-read from the value block (parked there in Montgomery form anyway).
@@ -102,6 +102,15 @@ POB_HD uint32_t pos_state_off(const PosLayout &L, uint32_t q) {
     if (q <= 4) return L.F1 + 5 * L.t * (q - 1) + 4 * L.t;
     if (q < 5 + L.rp) return L.PB + (q - 5) * (4 + L.t) + 4;
     return L.SB + 5 * L.t * (q - 5 - L.rp) + 4 * L.t;
+}
+
+// first offset (in the value block) written by step q; step q writes [pos_step_begin(q), pos_step_begin(q + 1))
+POB_HD uint32_t pos_step_begin(const PosLayout &L, uint32_t q) {
+    if (q == 0) return 0;
+    if (q <= 4) return L.F1 + 5 * L.t * (q - 1);
+    if (q < 5 + L.rp) return L.PB + (q - 5) * (4 + L.t);
+    if (q < L.rp + 8) return L.SB + 5 * L.t * (q - 5 - L.rp);
+    return q == L.rp + 8 ? L.LB : L.total;
 }
 
 // ---- warp op: prefix sum whose every partial sum is a signal (substring_check.circom:47-49 M[], :95 sums[]) -------

@@ -170,16 +170,32 @@ POB_HD void bn_shl1(Fr &a) {
     for (int i = 7; i > 0; i--) a.l[i] = (a.l[i] << 1) | (a.l[i - 1] >> 31);
     a.l[0] <<= 1;
 }
+POB_HD uint32_t bn_sel(uint32_t m, uint32_t a, uint32_t b) { return b ^ ((a ^ b) & m); }      // m all-ones: a, zero: b
 POB_HD void inv_chain_init(InvChain &c, const Fr &a) { c.u = fr_p(); c.v = a; c.r = fr_zero(); c.s = fr_from_u64(1); c.k = 0; }
+// One iteration is written WITHOUT data-dependent branches (both differences, the sum and the doublings are computed, the case
+// picks among them): in a warp the four cases would run one after the other, each a dependent carry chain -- measured 625 cycles per
+// iteration with branches.
 POB_HD bool inv_chain_steps(InvChain &c, uint32_t steps) {                         // true: finished (v == 0)
     for (uint32_t n = 0; n < steps; n++) {
         if (fr_is_zero(c.v)) return true;
-        if (!(c.u.l[0] & 1u)) { fr_shr1(c.u); bn_shl1(c.s); }
-        else if (!(c.v.l[0] & 1u)) { fr_shr1(c.v); bn_shl1(c.r); }
-        else {
-            Fr d; const uint32_t lt = bn_sub(d, c.u, c.v);
-            if (!lt && !fr_is_zero(d)) { fr_shr1(d); c.u = d; bn_add(c.r, c.r, c.s); bn_shl1(c.s); }          // u > v
-            else { if (lt) bn_sub(d, c.v, c.u); fr_shr1(d); c.v = d; bn_add(c.s, c.s, c.r); bn_shl1(c.r); }      // v >= u
+        const bool ue = !(c.u.l[0] & 1u), ve = !(c.v.l[0] & 1u);
+        Fr d, e, sum;
+        const uint32_t lt = bn_sub(d, c.u, c.v); bn_sub(e, c.v, c.u); bn_add(sum, c.r, c.s);
+        const bool both_odd = !ue && !ve, gt = both_odd && !lt && !fr_is_zero(d);   // u > v
+        const bool side_u = ue || gt;                                               // the case halves u (else v)
+        const bool sub = both_odd;                                                  // ... after subtracting the other one
+        const uint32_t mu = 0u - (uint32_t)side_u, ms = 0u - (uint32_t)sub;        // masks: bitwise selects keep the compiler from branching
+        Fr t, r2 = c.r, s2 = c.s;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t.l[i] = bn_sel(mu, bn_sel(ms, d.l[i], c.u.l[i]), bn_sel(ms, e.l[i], c.v.l[i]));
+        fr_shr1(t); bn_shl1(r2); bn_shl1(s2);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            c.u.l[i] = bn_sel(mu, t.l[i], c.u.l[i]);
+            c.v.l[i] = bn_sel(mu, c.v.l[i], t.l[i]);
+            const uint32_t rs = bn_sel(ms, sum.l[i], bn_sel(mu, c.r.l[i], c.s.l[i]));   // the side that is not doubled: r (+ s) resp. s (+ r)
+            c.r.l[i] = bn_sel(mu, rs, r2.l[i]);
+            c.s.l[i] = bn_sel(mu, s2.l[i], rs);
         }
         c.k++;
     }

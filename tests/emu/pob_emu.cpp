@@ -101,6 +101,23 @@ uint64_t pob_emu_run(void *h, const uint64_t *inputs, uint64_t *witness, uint64_
 }
 }
 
+// per-level detail for tuning: out[24*i + opc] = thread ops of that opcode (opc < 16), [16] absorbs, [17] poseidon segments,
+// [18] prefix sums, [19] longest prefix sum, [20] sum of prefix-sum lengths, [21] sum of poseidon t
+extern "C" uint32_t pob_emu_level_detail(void *h, uint32_t *out, uint32_t max_levels) {
+    const Program &P = ((EmuProgram *)h)->P;
+    uint32_t n = (uint32_t)P.levels.size();
+    for (uint32_t i = 0; i < n && i < max_levels; i++) {
+        const Level &L = P.levels[i];
+        uint32_t *o = out + 24 * i;
+        for (int k = 0; k < 24; k++) o[k] = 0;
+        for (uint32_t k = L.t_begin; k < L.t_end; k++) { uint32_t opc = op_opc(P.ops[k]); if (opc < 16) o[opc]++; }
+        o[16] = L.w_end - L.w_begin; o[17] = L.p_end - L.p_begin; o[18] = L.s_end - L.s_begin;
+        for (uint32_t k = L.s_begin; k < L.s_end; k++) { o[19] = std::max(o[19], P.psums[k].n); o[20] += P.psums[k].n; }
+        for (uint32_t k = L.p_begin; k < L.p_end; k++) o[21] += P.poseidons[k].t;
+    }
+    return n;
+}
+
 // level histogram for tuning: out[3*i+0..2] = thread ops, absorb ops, INV ops of level i (up to max_levels)
 extern "C" uint32_t pob_emu_level_hist(void *h, uint32_t *out, uint32_t max_levels) {
     const Program &P = ((EmuProgram *)h)->P;
