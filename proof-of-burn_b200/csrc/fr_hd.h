@@ -74,6 +74,74 @@ POB_HD Fr fr_neg(const Fr &a) { if (fr_is_zero(a)) return a; Fr t; fr_raw_sub(t,
 // needs only the 8-step chain m_k = column_k * n0'.  Same number of IMAD.WIDE instructions as the word-serial CIOS
 // form; measured on B200 it is neither faster nor slower inside k_eval (a lone warp is bound by in-order issue, and the
 // 64-register cap spills the limb arrays -- ROADMAP.md).  Result < p (one conditional subtraction; inputs < p).
+#if defined(__CUDA_ARCH__) && !defined(POB_PORTABLE_MONT)
+// Device form: CIOS over two accumulators, E (limb k at weight 2^32k) and O (limb k at weight 2^32(k+1)), so that every 32x32
+// product lands on an aligned limb PAIR: ptxas fuses each `mad(c).lo.cc / madc.hi.cc` pair into one IMAD.WIDE.U32(.X) with
+// carry-in/out predicates -- 128 multiply-adds and ~70 other instructions per product instead of ~620 (the portable form below
+// splits every product into halves to keep its column sums inside 64 bits).  Per word b_i: E += a_even*b_i, O += a_odd*b_i,
+// m = E0*n0', E += p_even*m, O += p_odd*m, then t >>= 32 (E' = O, O' = E >> 64, E'[0] += E[1]) -- a renaming in unrolled code.
+// Bounds (a < p, b < 2^256): t < 2^288 before the shift, so E needs 9 limbs, O 8, and no O row carries out.  The algorithm
+// (same chains, same renaming) is checked against big-integer arithmetic by tests/test_host.py::test_even_odd_montgomery_model.
+#define POB_ROW(T, s0, s1, s2, s3, w)                                                                                              \
+    "mad.lo.cc.u32 %0, %" s0 ", %" w ", %0;\n\tmadc.hi.cc.u32 %1, %" s0 ", %" w ", %1;\n\t"                                         \
+    "madc.lo.cc.u32 %2, %" s1 ", %" w ", %2;\n\tmadc.hi.cc.u32 %3, %" s1 ", %" w ", %3;\n\t"                                        \
+    "madc.lo.cc.u32 %4, %" s2 ", %" w ", %4;\n\tmadc.hi.cc.u32 %5, %" s2 ", %" w ", %5;\n\t"                                        \
+    "madc.lo.cc.u32 %6, %" s3 ", %" w ", %6;\n\tmadc.hi.cc.u32 %7, %" s3 ", %" w ", %7;\n\t"
+__device__ __forceinline__ void mont_row_e(uint32_t *T, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t w) {   // T[0..7] += s*w, carry into T[8]
+    asm(POB_ROW(T, "9", "10", "11", "12", "13") "addc.u32 %8, %8, 0;"
+        : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "+r"(T[8])
+        : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(w));
+}
+__device__ __forceinline__ void mont_row_o(uint32_t *T, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t w) {   // T[0..7] += s*w (never carries out)
+    uint32_t unused = 0;
+    asm(POB_ROW(T, "9", "10", "11", "12", "13") "addc.u32 %8, %8, 0;"
+        : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "+r"(unused)
+        : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(w));
+}
+// e0 += x, the carry of that limb (weight 2^32 = O's first limb) enters the row T[0..7] += s*w
+__device__ __forceinline__ void mont_row_o_carry(uint32_t &e0, uint32_t x, uint32_t *T, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t w) {
+    asm("add.cc.u32 %8, %8, %14;\n\t"
+        "madc.lo.cc.u32 %0, %9, %13, %0;\n\tmadc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\tmadc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\tmadc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\tmadc.hi.u32 %7, %12, %13, %7;"
+        : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "+r"(e0)
+        : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(w), "r"(x));
+}
+__device__ __forceinline__ Fr fr_mont(const Fr &a, const Fr &b) {
+    uint32_t E[9], O[9], x = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) E[k] = O[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t bi = b.l[i];
+        mont_row_o_carry(E[0], x, O, a.l[1], a.l[3], a.l[5], a.l[7], bi);
+        mont_row_e(E, a.l[0], a.l[2], a.l[4], a.l[6], bi);
+        const uint32_t m = E[0] * POB_N0;
+        mont_row_o(O, fr_p_limb(1), fr_p_limb(3), fr_p_limb(5), fr_p_limb(7), m);
+        mont_row_e(E, fr_p_limb(0), fr_p_limb(2), fr_p_limb(4), fr_p_limb(6), m);                    // E[0] is 0 now
+        x = E[1];
+        uint32_t N[9];
+#pragma unroll
+        for (int k = 0; k < 7; k++) N[k] = E[k + 2];
+        N[7] = 0; N[8] = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) E[k] = O[k];
+        E[8] = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) O[k] = N[k];
+    }
+    Fr r;
+    asm("add.cc.u32 %0, %8, %16;\n\taddc.cc.u32 %1, %9, %17;\n\taddc.cc.u32 %2, %10, %18;\n\taddc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\taddc.cc.u32 %5, %13, %21;\n\taddc.cc.u32 %6, %14, %22;\n\taddc.u32 %7, %15, %23;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
+          "r"(x), "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
+    if (fr_geq_p(r)) { Fr sub; fr_raw_sub(sub, r, fr_p()); return sub; }                               // r < 2p
+    return r;
+}
+#undef POB_ROW
+#else
 POB_HD Fr fr_mont(const Fr &a, const Fr &b) {
     uint32_t T[16];
     uint64_t c = 0;
@@ -110,6 +178,7 @@ POB_HD Fr fr_mont(const Fr &a, const Fr &b) {
     if (c || fr_geq_p(r)) { Fr sub; fr_raw_sub(sub, r, fr_p()); return sub; }
     return r;
 }
+#endif
 POB_HD Fr fr_r2() { Fr r; for (int i = 0; i < 8; i++) r.l[i] = fr_r2_limb(i); return r; }
 POB_HD Fr fr_to_mont(const Fr &a) { return fr_mont(a, fr_r2()); }
 POB_HD Fr fr_from_mont(const Fr &a) { Fr one = fr_from_u64(1); return fr_mont(a, one); }

@@ -182,14 +182,13 @@ struct EvalArgs {
     uint32_t pos_konst_bytes, levels_bytes;       // sizes of the two TMA-staged tables (multiples of 16 bytes)
     uint32_t prefetch;                            // 1: fetch the next op record / prefetch its operand lines while the current op runs
     uint32_t ginv_level;                          // first level at which every deferred inverse has its input (n_levels: none before the end)
-    uint32_t solo_ops;                            // a level with at most this many thread ops (and <= SOLO_WARP_OPS warp ops) is run by CTA 0 alone; 0: never
 };
 
-// deferred IsZero inverses (comparators.circom:30): vm_exec.h vm_ginv_start / inv_chain_steps / vm_ginv_finish.  Every thread of the
-// cluster is a worker (the main shape has 7.7 K deferred inverses: two per thread of an 8-CTA cluster), one inversion each, INV_STEPS
-// iterations of it per level.
-static const uint32_t INV_STEPS = 64;
-static const uint32_t SOLO_OPS = 4096, SOLO_WARP_OPS = 8;       // k_eval: what one CTA runs alone (see small_level)
+// deferred IsZero inverses (comparators.circom:30): vm_exec.h vm_ginv_start / inv_chain_steps / vm_ginv_finish.  INV_WORKERS threads per
+// CTA (its last 8 warps: warp ops are dealt from warp 0 upwards) run one inversion each, INV_STEPS iterations of it per level.  The
+// iterations are issue-bound: with every thread a worker (half as many products to unwind per worker) the levels that carry them
+// took 60-65 K cycles instead of 45 K (profiles/r02o_eval_levels.log).
+static const uint32_t INV_WORKERS = 256, INV_STEPS = 64;
 // parked state: word-major ([33 words][workers]) so that a warp's loads and stores are conflict-free
 static const uint32_t INV_PARK_WORDS = 33;
 __device__ __forceinline__ void inv_park(uint32_t *s, uint32_t nw, uint32_t t, const InvChain &c) {
@@ -256,13 +255,15 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     const uint32_t C = cluster_nctarank(), rank = cluster_ctarank();
     const uint32_t inst = blockIdx.x / C, tid = threadIdx.x;
-    const uint32_t gt_all = rank * THREADS + tid, GT_all = C * THREADS, gt = gt_all, GT = GT_all;
+    const uint32_t gt = rank * THREADS + tid, GT = C * THREADS;
     uint64_t *U = a.stores + (uint64_t)inst * a.store_stride;
     __shared__ uint32_t s_status;
     __shared__ __align__(8) uint64_t s_bar;
     Fr *s_pk = reinterpret_cast<Fr *>(dyn_smem);
     Level *s_levels = reinterpret_cast<Level *>(dyn_smem + a.pos_konst_bytes);
-    uint32_t *s_inv = reinterpret_cast<uint32_t *>(dyn_smem + a.pos_konst_bytes + a.levels_bytes);     // THREADS parked chains
+    uint32_t *s_inv = reinterpret_cast<uint32_t *>(dyn_smem + a.pos_konst_bytes + a.levels_bytes);     // INV_WORKERS parked chains
+    const bool inv_worker = tid >= THREADS - INV_WORKERS;
+    const uint32_t wt = tid - (THREADS - INV_WORKERS), wid = rank * INV_WORKERS + wt, NWK = C * INV_WORKERS;
     bool inv_running = false;                     // this worker has an inversion in progress (state parked in s_inv)
     if (tid == 0) { s_status = STATUS_OK; mbar_init(&s_bar, 1); if (rank == 0) a.status[inst] = STATUS_OK; }
     __syncthreads();
@@ -282,25 +283,10 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     cluster_sync_all();
     VmCtx x{U, a.val_base, a.konst, a.aux, a.invtab, &s_status};
     // warp ops are dealt round-robin over the CTAs of the cluster (the 17 absorbs of a level land on 8 SMs, not on one)
-    const uint32_t gwarp_all = (tid >> 5) * C + rank;
-    // A SMALL level (a few thousand thread ops, a handful of warp ops: the tails of reduction trees, the absorb chain of the block
-    // header) is run by CTA 0 alone, and two small levels in a row are separated by __syncthreads() instead of the cluster barrier
-    // (~3.5 K cycles each, 45 of the 64 levels of the main shape).  Every CTA evaluates the same predicate on the same level table, so
-    // all of them execute the same sequence of cluster barriers.  The level that starts the deferred inverses is never small (its
-    // workers sit in every CTA and need the barrier before it).
-    auto small_level = [&](uint32_t l) -> bool {
-        if (C == 1 || a.solo_ops == 0 || l >= a.n_levels || l == a.ginv_level) return false;
-        const Level &M = s_levels[l];
-        return M.t_end - M.t_begin <= a.solo_ops && (M.w_end - M.w_begin) + (M.p_end - M.p_begin) + (M.s_end - M.s_begin) <= SOLO_WARP_OPS;
-    };
-    bool solo = small_level(0);
+    const uint32_t gwarp = (tid >> 5) * C + rank, nwarp = GT >> 5;
     for (uint32_t lv = 0; lv < a.n_levels; lv++) {
-        if (a.prof && inst == 0 && gt_all == 0) a.prof[lv] = clock64();
+        if (a.prof && inst == 0 && gt == 0) a.prof[lv] = clock64();
         const Level L = s_levels[lv];
-        const bool next_solo = small_level(lv + 1);
-        const uint32_t gt = solo ? tid : gt_all, GT = solo ? (uint32_t)THREADS : GT_all;
-        const uint32_t gwarp = solo ? tid >> 5 : gwarp_all, nwarp = GT >> 5;
-        if (!solo || rank == 0) {
         // thread ops of one level are mutually independent: the next op record is fetched, and the cache lines of its operands
         // are requested (prefetch.global.L1), while the current op executes -- two of the three dependent memory latencies
         // of an op (record -> operand -> result) overlap with the previous op
@@ -319,25 +305,27 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
           for (uint32_t w = L.w_begin + wv; w < L.w_end; w += nwarp) absorb_warp(U, a.absorbs[w]);
           const uint32_t nw2 = (np + (L.w_end - L.w_begin)) % nwarp, sv = (gwarp + nwarp - nw2) % nwarp;
           for (uint32_t q = L.s_begin + sv; q < L.s_end; q += nwarp) psum_warp(x, a.psums[q]); }
+        if (inv_worker) {
+            if (lv == a.ginv_level) {                                               // deferred inverses: start
+                InvChain c;
+                if (vm_ginv_start(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK, c)) { inv_park(s_inv, INV_WORKERS, wt, c); inv_running = true; }
+            } else if (inv_running) {                                               // step; unwind as soon as the inverse is there
+                InvChain c = inv_unpark(s_inv, INV_WORKERS, wt);
+                if (inv_chain_steps(c, INV_STEPS)) { vm_ginv_finish(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK, inv_chain_result(c)); inv_running = false; }
+                else inv_park(s_inv, INV_WORKERS, wt, c);
+            }
         }
-        if (lv == a.ginv_level) {                                                   // deferred inverses: start
-            InvChain c;
-            if (vm_ginv_start(x, a.ops, a.ginv_begin, a.inv_end, gt_all, GT_all, c)) { inv_park(s_inv, THREADS, tid, c); inv_running = true; }
-        } else if (inv_running) {                                                   // step; unwind as soon as the inverse is there
-            InvChain c = inv_unpark(s_inv, THREADS, tid);
-            if (inv_chain_steps(c, INV_STEPS)) { vm_ginv_finish(x, a.ops, a.ginv_begin, a.inv_end, gt_all, GT_all, inv_chain_result(c)); inv_running = false; }
-            else inv_park(s_inv, THREADS, tid, c);
-        }
-        if (solo && next_solo) { if (rank == 0) __syncthreads(); } else cluster_sync_all();
-        solo = next_solo;
+        cluster_sync_all();
     }
     if (a.prof && inst == 0 && gt == 0) a.prof[a.n_levels] = clock64();
     // finish the deferred inverses (or do all of it when their inputs only became ready in the last level)
-    if (a.ginv_level >= a.n_levels) vm_inv_batch(x, a.ops, a.ginv_begin, a.inv_end, gt_all, GT_all);
-    else if (inv_running) {
-        InvChain c = inv_unpark(s_inv, THREADS, tid);
-        while (!inv_chain_steps(c, 64)) { }
-        vm_ginv_finish(x, a.ops, a.ginv_begin, a.inv_end, gt_all, GT_all, inv_chain_result(c));
+    if (inv_worker) {
+        if (a.ginv_level >= a.n_levels) vm_inv_batch(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK);
+        else if (inv_running) {
+            InvChain c = inv_unpark(s_inv, INV_WORKERS, wt);
+            while (!inv_chain_steps(c, 64)) { }
+            vm_ginv_finish(x, a.ops, a.ginv_begin, a.inv_end, wid, NWK, inv_chain_result(c));
+        }
     }
     if (a.prof && inst == 0) { cluster_sync_all(); if (gt == 0) { a.prof[a.n_levels + 1] = clock64(); a.prof[a.n_levels + 2] = clock64(); } }
     __syncthreads();

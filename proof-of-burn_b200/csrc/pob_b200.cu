@@ -155,7 +155,7 @@ struct pob_handle {
     // per SM: fewer concurrent write streams give the DRAM controllers longer same-row bursts -- measured 7.35 TB/s with
     // 2 CTAs/SM vs 7.26 / 7.19 / 7.09 / 6.97 TB/s with 3 / 4 / 5 / 8, and 5.96 TB/s with 1 (profiles/r01_expand_sweep.md)
     uint32_t round_dyn_smem = 85 * 1024;
-    uint32_t round_threads = 256, codes_dyn_smem = 0, codes_ug = 4, codes_overlap = 0, eval_solo_ops = SOLO_OPS; bool serialize = false;   // changed by POB_TUNING knobs only
+    uint32_t round_threads = 256, codes_dyn_smem = 0, codes_ug = 4, codes_overlap = 0; bool serialize = false;   // changed by POB_TUNING knobs only
     int eval_threads = 512; uint32_t eval_cluster = 0, eval_prefetch = 0;   // operand prefetch measured no gain (profiles/r02c_eval_sweep.log)   // k_eval: threads per CTA; CTAs per instance (0 = chosen per launch)
     uint32_t pos_konst_bytes = 0, levels_bytes = 0, eval_smem = 0;
     bool skip_eval = false;                     // tuning: evaluate only the first two chunks, then re-expand their stores (isolates the cost of concurrency)
@@ -275,7 +275,7 @@ static void enqueue_eval(pob_handle *h, uint32_t c) {
     uint64_t *stores = h->d_stores + (size_t)r * E * h->store_stride;
     EvalArgs ea{h->d_ops, h->d_abs, h->d_pos, h->d_pos_konst, h->d_psums, h->d_levels, (uint32_t)P.levels.size(), P.inv_begin, P.ginv_begin, P.inv_end, h->d_aux, h->d_konst, h->d_invtab,
                 h->d_codes + P.out_code_off, P.n_outputs, P.n_inputs, P.val_base, stores, h->store_stride, d_in,
-                h->d_status + first, h->d_outputs + (size_t)first * no * 4, (c == 0) ? h->d_prof : nullptr, h->pos_konst_bytes, h->levels_bytes, h->eval_prefetch, P.ginv_level, h->eval_solo_ops};
+                h->d_status + first, h->d_outputs + (size_t)first * no * 4, (c == 0) ? h->d_prof : nullptr, h->pos_konst_bytes, h->levels_bytes, h->eval_prefetch, P.ginv_level};
     CU(cudaEventRecord(B.e0[c], h->s_eval));
     {   // one thread-block cluster per instance.  Cluster size: the largest power of two (<= 8) that still lets every instance of
         // the launch have its own SMs -- 8 CTAs for a single witness (latency), 4 for the 32-instance chunks of the main shape,
@@ -598,7 +598,7 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (const char *v = tune_env("POB_EXPAND_CS")) h->expand_cs = (uint32_t)(atoi(v) != 0);
         if (const char *v = tune_env("POB_EVAL_L2_MB")) h->eval_l2_mb = (uint32_t)std::max(0, atoi(v));
         if (h->eval_threads != 256 && h->eval_threads != 512) h->eval_threads = 1024;
-        h->eval_smem = h->pos_konst_bytes + h->levels_bytes + h->eval_threads * INV_PARK_WORDS * 4u;   // + the parked inversion state of every thread (66 KB for 512)
+        h->eval_smem = h->pos_konst_bytes + h->levels_bytes + INV_WORKERS * INV_PARK_WORDS * 4u;   // + the parked inversion state of 256 workers (33 KB)
         if (h->eval_smem > 200 * 1024) throw std::runtime_error("the Poseidon constant table, the level table and the parked inversions do not fit in shared memory");
         CU(cudaFuncSetAttribute(k_eval<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->eval_smem));
         CU(cudaFuncSetAttribute(k_eval<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->eval_smem));
@@ -608,7 +608,6 @@ int pob_create(const char *main_name, const uint64_t *params, int nparams, int h
         if (const char *v = tune_env("POB_EXPAND_THREADS")) h->round_threads = (uint32_t)atoi(v);
         if (const char *v = tune_env("POB_CODES_UG")) h->codes_ug = (uint32_t)atoi(v);
         if (const char *v = tune_env("POB_CODES_OVERLAP")) h->codes_overlap = (uint32_t)atoi(v);
-        if (const char *v = tune_env("POB_EVAL_SOLO")) h->eval_solo_ops = (uint32_t)atoi(v);
         if (const char *v = tune_env("POB_CODES_SMEM_KB")) { h->codes_dyn_smem = (uint32_t)atoi(v) * 1024u; if (h->codes_dyn_smem > 48 * 1024) { CU(cudaFuncSetAttribute(k_expand_codes<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->codes_dyn_smem)); CU(cudaFuncSetAttribute(k_expand_codes<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->codes_dyn_smem)); } }
         if (h->round_dyn_smem > 48 * 1024) {
             CU(cudaFuncSetAttribute(k_expand_round<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->round_dyn_smem));

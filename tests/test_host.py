@@ -159,3 +159,72 @@ def test_bench_helpers():
     assert bench.N_SIGNALS_MAIN == pob_b200.layout_info(bench.MAIN_EXPR)["n_signals"]
     assert 1 <= bench.mem_limited_procs(64, 34 * bench.N_SIGNALS_MAIN) <= 64
     assert bench.mem_limited_procs(64, 1 << 60) == 1            # nothing fits: still one process
+
+
+def test_even_odd_montgomery_model():
+    """The device form of fr_mont (csrc/fr_hd.h, inline PTX: two accumulators E / O, every product on an aligned limb pair, one
+    carry chain per row, the shift a renaming) modelled limb by limb with Python integers -- same rows, same carry hand-overs,
+    same bounds (no O row carries out, E needs 9 limbs, result < 2p) -- against a*b*2^-256 mod p.  The PTX itself runs in the
+    `-m gpu` parity tests (every Poseidon value of every witness goes through it)."""
+    import random
+    P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    M32 = (1 << 32) - 1
+    N0 = (-pow(P, -1, 1 << 32)) % (1 << 32)
+    assert N0 == 0xefffffff                                           # POB_N0
+    pl = [(P >> (32 * i)) & M32 for i in range(8)]
+
+    class Chain:                                                      # a PTX carry chain (add.cc / addc.cc / mad.lo.cc / madc.hi.cc)
+        def __init__(self):
+            self.c = 0
+
+        def add(self, x, y, cin):
+            s = x + y + (self.c if cin else 0)
+            self.c = s >> 32
+            return s & M32
+
+    def row(T, src, w, ch, first_cin):                                # T[0..7] += sum_k src[k] * w << 64k: four lo/hi pairs on one chain
+        cin = first_cin
+        for k in range(4):
+            T[2 * k] = ch.add(T[2 * k], (src[k] * w) & M32, cin)
+            cin = True
+            T[2 * k + 1] = ch.add(T[2 * k + 1], (src[k] * w) >> 32, True)
+
+    def mont(a, b):
+        al = [(a >> (32 * i)) & M32 for i in range(8)]
+        bl = [(b >> (32 * i)) & M32 for i in range(8)]
+        E, O, x = [0] * 9, [0] * 8, 0
+        for i in range(8):
+            ch = Chain()                                              # mont_row_o_carry
+            E[0] = ch.add(E[0], x, False)
+            row(O, al[1::2], bl[i], ch, True)
+            assert ch.c == 0
+            ch = Chain()                                              # mont_row_e
+            row(E, al[0::2], bl[i], ch, False)
+            E[8] = ch.add(E[8], 0, True)
+            m = (E[0] * N0) & M32
+            ch = Chain()                                              # mont_row_o
+            row(O, pl[1::2], m, ch, False)
+            assert ch.c == 0
+            ch = Chain()                                              # mont_row_e
+            row(E, pl[0::2], m, ch, False)
+            E[8] = ch.add(E[8], 0, True)
+            assert ch.c == 0 and E[0] == 0
+            x, E, O = E[1], O[:] + [0], E[2:9] + [0]                  # t >>= 32
+        ch = Chain()
+        r = [ch.add(E[0], x, False)] + [0] * 7
+        for k in range(1, 8):
+            r[k] = ch.add(E[k], O[k - 1], True)
+        assert ch.c == 0 and O[7] == 0 and E[8] == 0
+        v = sum(r[k] << (32 * k) for k in range(8))
+        assert v < 2 * P
+        return v - P if v >= P else v
+
+    rinv = pow(1 << 256, -1, P)
+    rng = random.Random(7)
+    vals = [0, 1, 2, P - 1, P - 2, 1 << 253, M32, (1 << 64) - 1, (1 << 224) - 1] + [rng.randrange(P) for _ in range(3000)]
+    for i, a in enumerate(vals):
+        b = vals[(i * 7 + 3) % len(vals)]
+        assert mont(a, b) == a * b * rinv % P
+    for _ in range(500):                                              # second operand only needs to be < 2^256 (inv_chain_result's 2^e)
+        a, b = rng.randrange(P), rng.randrange(1 << 256)
+        assert mont(a, b) == a * b * rinv % P
