@@ -292,12 +292,30 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
         // of an op (record -> operand -> result) overlap with the previous op
         {
             uint32_t i = L.t_begin + gt;
-            Op nxt = i < L.t_end ? ldg_op(a.ops + i) : Op{0, 0, 0, 0};
-            for (; i < L.t_end; i += GT) {
+            Op nxt = i < L.t_sel ? ldg_op(a.ops + i) : Op{0, 0, 0, 0};
+            for (; i < L.t_sel; i += GT) {
                 const Op cur = nxt;
-                if (i + GT < L.t_end) { nxt = ldg_op(a.ops + i + GT); if (a.prefetch) prefetch_operands(x, nxt); }
+                if (i + GT < L.t_sel) { nxt = ldg_op(a.ops + i + GT); if (a.prefetch) prefetch_operands(x, nxt); }
                 vm_exec_op(x, cur);
             }
+        }
+        // SELSUM ops (selector.circom:31-41; 128 K of them in one level of the main shape) are three dependent loads and nothing else:
+        // four of a thread's ops go through each hop together
+        for (uint32_t i = L.t_sel + gt; i < L.t_end; i += 4 * GT) {
+            Op o[4]; Fr sel[4], r[4]; Code src[4]; bool live[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { live[k] = i + k * GT < L.t_end; o[k] = ldg_op(a.ops + (live[k] ? i + k * GT : i)); }
+#pragma unroll
+            for (int k = 0; k < 4; k++) sel[k] = vm_load(x, o[k].a);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const bool hit = fr_fits64(sel[k]) && fr_lo64(sel[k]) <= (uint64_t)o[k].c;
+                src[k] = hit ? x.aux[o[k].b + (uint32_t)fr_lo64(sel[k])] : c_const(0);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) r[k] = vm_load(x, src[k]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (live[k]) vm_store_val(U + a.val_base + 4ull * op_dst(o[k]), r[k]);
         }
         // warp ops: Poseidons take the first warps (long), Keccak absorbs the next ones
         for (uint32_t q = L.p_begin + gwarp; q < L.p_end; q += nwarp) poseidon_warp(x, a.poseidons[q], s_pk);
