@@ -44,28 +44,79 @@ POB_HD bool fr_fits64(const Fr &a) { uint32_t o = 0; for (int i = 2; i < 8; i++)
 POB_HD uint64_t fr_lo64(const Fr &a) { return (uint64_t)a.l[0] | ((uint64_t)a.l[1] << 32); }
 // a >= p ?
 POB_HD bool fr_geq_p(const Fr &a) {
+#ifdef __CUDA_ARCH__
+    uint32_t br;                                                       // borrow of a - p
+    asm("sub.cc.u32 %0, %1, %9;\n\tsubc.cc.u32 %0, %2, %10;\n\tsubc.cc.u32 %0, %3, %11;\n\tsubc.cc.u32 %0, %4, %12;\n\t"
+        "subc.cc.u32 %0, %5, %13;\n\tsubc.cc.u32 %0, %6, %14;\n\tsubc.cc.u32 %0, %7, %15;\n\tsubc.cc.u32 %0, %8, %16;\n\t"
+        "subc.u32 %0, 0, 0;"
+        : "=&r"(br)
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(fr_p_limb(0)), "r"(fr_p_limb(1)), "r"(fr_p_limb(2)), "r"(fr_p_limb(3)), "r"(fr_p_limb(4)), "r"(fr_p_limb(5)), "r"(fr_p_limb(6)), "r"(fr_p_limb(7)));
+    return br == 0;
+#else
     for (int i = 7; i >= 0; i--) { uint32_t p = fr_p_limb(i); if (a.l[i] > p) return true; if (a.l[i] < p) return false; }
     return true;
+#endif
 }
+// r = a + b / a - b mod 2^256, returning the carry / borrow.  On the device one carry chain (add.cc / addc.cc): the portable form
+// costs four instructions per limb.
 POB_HD uint32_t fr_raw_add(Fr &r, const Fr &a, const Fr &b) {
+#ifdef __CUDA_ARCH__
+    uint32_t c;
+    asm("add.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, %18;\n\taddc.cc.u32 %2, %11, %19;\n\taddc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\taddc.cc.u32 %5, %14, %22;\n\taddc.cc.u32 %6, %15, %23;\n\taddc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]), "=r"(c)
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+    return c;
+#else
     uint64_t c = 0;
     for (int i = 0; i < 8; i++) { c += (uint64_t)a.l[i] + b.l[i]; r.l[i] = (uint32_t)c; c >>= 32; }
     return (uint32_t)c;
+#endif
 }
 POB_HD uint32_t fr_raw_sub(Fr &r, const Fr &a, const Fr &b) {
+#ifdef __CUDA_ARCH__
+    uint32_t br;
+    asm("sub.cc.u32 %0, %9, %17;\n\tsubc.cc.u32 %1, %10, %18;\n\tsubc.cc.u32 %2, %11, %19;\n\tsubc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\tsubc.cc.u32 %5, %14, %22;\n\tsubc.cc.u32 %6, %15, %23;\n\tsubc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]), "=r"(br)
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+    return br & 1u;
+#else
     uint64_t br = 0;
     for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)a.l[i] - b.l[i] - br; r.l[i] = (uint32_t)d; br = (d >> 32) & 1; }
     return (uint32_t)br;
+#endif
 }
 POB_HD Fr fr_p() { Fr r; for (int i = 0; i < 8; i++) r.l[i] = fr_p_limb(i); return r; }
 POB_HD Fr fr_add(const Fr &a, const Fr &b) {
+#ifdef __CUDA_ARCH__
+    Fr r, t; fr_raw_add(r, a, b);                                     // a, b < p < 2^254: no carry out
+    const uint32_t keep = 0u - fr_raw_sub(t, r, fr_p());              // all-ones: r < p
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.l[i] ^= (t.l[i] ^ r.l[i]) & keep;
+    return t;
+#else
     Fr r; uint32_t c = fr_raw_add(r, a, b);
     if (c || fr_geq_p(r)) { Fr t; fr_raw_sub(t, r, fr_p()); return t; }
     return r;
+#endif
 }
 POB_HD Fr fr_sub(const Fr &a, const Fr &b) {
+#ifdef __CUDA_ARCH__
+    Fr r, t; const uint32_t wrap = 0u - fr_raw_sub(r, a, b);         // all-ones: a < b
+    fr_raw_add(t, r, fr_p());
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] ^= (r.l[i] ^ t.l[i]) & wrap;
+    return r;
+#else
     Fr r; if (fr_raw_sub(r, a, b)) { Fr t; fr_raw_add(t, r, fr_p()); return t; }
     return r;
+#endif
 }
 POB_HD Fr fr_neg(const Fr &a) { if (fr_is_zero(a)) return a; Fr t; fr_raw_sub(t, fr_p(), a); return t; }
 

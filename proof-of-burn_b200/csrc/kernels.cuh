@@ -302,18 +302,25 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
         // SELSUM ops (selector.circom:31-41; 128 K of them in one level of the main shape) are three dependent loads and nothing else:
         // four of a thread's ops go through each hop together
         for (uint32_t i = L.t_sel + gt; i < L.t_end; i += 4 * GT) {
-            Op o[4]; Fr sel[4], r[4]; Code src[4]; bool live[4];
+            // the loads of a hop are issued unconditionally (a slot address for every code; non-slot codes are rare and patched
+            // afterwards): a load under a branch on the code kind would be waited for at the branch's join
+            const uint64_t *V = U + a.val_base;
+            Op o[4]; Fr sel[4], r[4]; Code src[4]; bool live[4], hit[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) { live[k] = i + k * GT < L.t_end; o[k] = ldg_op(a.ops + (live[k] ? i + k * GT : i)); }
 #pragma unroll
-            for (int k = 0; k < 4; k++) sel[k] = vm_load(x, o[k].a);
+            for (int k = 0; k < 4; k++) sel[k] = vm_load_val(V + 4ull * (code_kind(o[k].a) == K_VAL ? code_payload(o[k].a) : 0u));
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (code_kind(o[k].a) != K_VAL) sel[k] = vm_load(x, o[k].a);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const bool hit = fr_fits64(sel[k]) && fr_lo64(sel[k]) <= (uint64_t)o[k].c;
-                src[k] = hit ? x.aux[o[k].b + (uint32_t)fr_lo64(sel[k])] : c_const(0);
+                hit[k] = fr_fits64(sel[k]) && fr_lo64(sel[k]) <= (uint64_t)o[k].c;
+                src[k] = x.aux[o[k].b + (hit[k] ? (uint32_t)fr_lo64(sel[k]) : 0u)];
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) r[k] = vm_load(x, src[k]);
+            for (int k = 0; k < 4; k++) r[k] = vm_load_val(V + 4ull * (code_kind(src[k]) == K_VAL ? code_payload(src[k]) : 0u));
+#pragma unroll
+            for (int k = 0; k < 4; k++) { if (!hit[k]) r[k] = fr_zero(); else if (code_kind(src[k]) != K_VAL) r[k] = vm_load(x, src[k]); }
 #pragma unroll
             for (int k = 0; k < 4; k++) if (live[k]) vm_store_val(U + a.val_base + 4ull * op_dst(o[k]), r[k]);
         }

@@ -140,31 +140,8 @@ POB_HD void vm_inv_batch(const VmCtx &x, const Op *ops, uint32_t begin, uint32_t
 // per-lane `while (even) halve` loops of the textbook binary Euclid run for the maximum over the warp's lanes: measured 5x
 // slower).  After k iterations (254 <= k <= 508) r = -a^-1 2^k mod p; two Montgomery products remove the 2^k.
 struct InvChain { Fr u, v, r, s; uint32_t k; };
-POB_HD uint32_t bn_sub(Fr &d, const Fr &a, const Fr &b) {                           // d = a - b mod 2^256, returns the borrow
-#ifdef __CUDA_ARCH__
-    uint32_t br;
-    asm("sub.cc.u32 %0, %9, %17;\n\tsubc.cc.u32 %1, %10, %18;\n\tsubc.cc.u32 %2, %11, %19;\n\tsubc.cc.u32 %3, %12, %20;\n\t"
-        "subc.cc.u32 %4, %13, %21;\n\tsubc.cc.u32 %5, %14, %22;\n\tsubc.cc.u32 %6, %15, %23;\n\tsubc.cc.u32 %7, %16, %24;\n\t"
-        "subc.u32 %8, 0, 0;"
-        : "=r"(d.l[0]), "=r"(d.l[1]), "=r"(d.l[2]), "=r"(d.l[3]), "=r"(d.l[4]), "=r"(d.l[5]), "=r"(d.l[6]), "=r"(d.l[7]), "=r"(br)
-        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
-          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
-    return br & 1u;
-#else
-    return fr_raw_sub(d, a, b);
-#endif
-}
-POB_HD void bn_add(Fr &d, const Fr &a, const Fr &b) {                               // d = a + b (the caller knows it fits)
-#ifdef __CUDA_ARCH__
-    asm("add.cc.u32 %0, %8, %16;\n\taddc.cc.u32 %1, %9, %17;\n\taddc.cc.u32 %2, %10, %18;\n\taddc.cc.u32 %3, %11, %19;\n\t"
-        "addc.cc.u32 %4, %12, %20;\n\taddc.cc.u32 %5, %13, %21;\n\taddc.cc.u32 %6, %14, %22;\n\taddc.u32 %7, %15, %23;"
-        : "=r"(d.l[0]), "=r"(d.l[1]), "=r"(d.l[2]), "=r"(d.l[3]), "=r"(d.l[4]), "=r"(d.l[5]), "=r"(d.l[6]), "=r"(d.l[7])
-        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
-          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
-#else
-    fr_raw_add(d, a, b);
-#endif
-}
+POB_HD uint32_t bn_sub(Fr &d, const Fr &a, const Fr &b) { return fr_raw_sub(d, a, b); }   // d = a - b mod 2^256, returns the borrow (one carry chain on the device)
+POB_HD void bn_add(Fr &d, const Fr &a, const Fr &b) { fr_raw_add(d, a, b); }                // d = a + b (the caller knows it fits)
 POB_HD void bn_shl1(Fr &a) {
 #pragma unroll
     for (int i = 7; i > 0; i--) a.l[i] = (a.l[i] << 1) | (a.l[i - 1] >> 31);
