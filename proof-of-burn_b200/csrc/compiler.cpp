@@ -2140,9 +2140,7 @@ Program compile_circuit(const std::string &main_name, const std::vector<Fr> &par
         if (tcount[l] == 0 && wcount[l] == 0 && pcount[l] == 0 && scount[l] == 0) continue;
         std::stable_sort(P.ops.begin() + tstart[l], P.ops.begin() + tstart[l] + tcount[l], [&](const Op &x, const Op &y) { return op_key(x) < op_key(y); });
         if (n_inv && l >= ginv_ready && P.ginv_level == 0xffffffffu) P.ginv_level = (uint32_t)P.levels.size();   // first level that starts with every deferred input ready
-        uint32_t t_sel = tstart[l] + tcount[l];
-        while (t_sel > tstart[l] && op_opc(P.ops[t_sel - 1]) == OP_SELSUM) t_sel--;                  // op_key puts them last
-        P.levels.push_back(Level{tstart[l], tstart[l] + tcount[l], wstart[l], wstart[l] + wcount[l], pstart[l], pstart[l] + pcount[l], sstart[l], sstart[l] + scount[l], t_sel, 0, 0, 0});
+        P.levels.push_back(Level{tstart[l], tstart[l] + tcount[l], wstart[l], wstart[l] + wcount[l], pstart[l], pstart[l] + pcount[l], sstart[l], sstart[l] + scount[l]});
     }
     if (P.ginv_level == 0xffffffffu) P.ginv_level = (uint32_t)P.levels.size();
     // ---- renumber the value slots in execution order ----

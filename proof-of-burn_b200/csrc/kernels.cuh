@@ -251,7 +251,10 @@ __device__ __forceinline__ void prefetch_operands(const VmCtx &x, const Op &o) {
 // cluster barrier; the instance store lives in global memory (L2-resident).  Poseidon round / MDS constants (C, S, M, P of
 // circomlib/circuits/poseidon_constants.circom, Montgomery form) and the level table are staged in shared memory by TMA.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
+// Register cap 104 for the 512-thread shape: 512 x 104 leaves 12 K registers of the SM, enough for one k_expand_round CTA (256 x 32) to
+// stay resident next to a k_eval CTA.  At 117 registers the SM belonged to k_eval alone: the kernel ran faster (1.14 instead of
+// 1.89 ms per chunk under load) and the batch slower (1032 instead of 1043 witnesses/s, profiles/r02r_bench_default.json).
+__global__ void __maxnreg__(THREADS == 1024 ? 64 : 104) k_eval(const EvalArgs a) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     const uint32_t C = cluster_nctarank(), rank = cluster_ctarank();
     const uint32_t inst = blockIdx.x / C, tid = threadIdx.x;
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
     Fr *s_pk = reinterpret_cast<Fr *>(dyn_smem);
     Level *s_levels = reinterpret_cast<Level *>(dyn_smem + a.pos_konst_bytes);
     uint32_t *s_inv = reinterpret_cast<uint32_t *>(dyn_smem + a.pos_konst_bytes + a.levels_bytes);     // INV_WORKERS parked chains
-    const bool inv_worker = tid >= THREADS - INV_WORKERS;
+    const bool inv_worker = tid + INV_WORKERS >= THREADS;
     const uint32_t wt = tid - (THREADS - INV_WORKERS), wid = rank * INV_WORKERS + wt, NWK = C * INV_WORKERS;
     bool inv_running = false;                     // this worker has an inversion in progress (state parked in s_inv)
     if (tid == 0) { s_status = STATUS_OK; mbar_init(&s_bar, 1); if (rank == 0) a.status[inst] = STATUS_OK; }
@@ -292,37 +295,12 @@ __global__ void __launch_bounds__(THREADS) k_eval(const EvalArgs a) {
         // of an op (record -> operand -> result) overlap with the previous op
         {
             uint32_t i = L.t_begin + gt;
-            Op nxt = i < L.t_sel ? ldg_op(a.ops + i) : Op{0, 0, 0, 0};
-            for (; i < L.t_sel; i += GT) {
+            Op nxt = i < L.t_end ? ldg_op(a.ops + i) : Op{0, 0, 0, 0};
+            for (; i < L.t_end; i += GT) {
                 const Op cur = nxt;
-                if (i + GT < L.t_sel) { nxt = ldg_op(a.ops + i + GT); if (a.prefetch) prefetch_operands(x, nxt); }
+                if (i + GT < L.t_end) { nxt = ldg_op(a.ops + i + GT); if (a.prefetch) prefetch_operands(x, nxt); }
                 vm_exec_op(x, cur);
             }
-        }
-        // SELSUM ops (selector.circom:31-41; 128 K of them in one level of the main shape) are three dependent loads and nothing else:
-        // four of a thread's ops go through each hop together
-        for (uint32_t i = L.t_sel + gt; i < L.t_end; i += 4 * GT) {
-            // the loads of a hop are issued unconditionally (a slot address for every code; non-slot codes are rare and patched
-            // afterwards): a load under a branch on the code kind would be waited for at the branch's join
-            const uint64_t *V = U + a.val_base;
-            Op o[4]; Fr sel[4], r[4]; Code src[4]; bool live[4], hit[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) { live[k] = i + k * GT < L.t_end; o[k] = ldg_op(a.ops + (live[k] ? i + k * GT : i)); }
-#pragma unroll
-            for (int k = 0; k < 4; k++) sel[k] = vm_load_val(V + 4ull * (code_kind(o[k].a) == K_VAL ? code_payload(o[k].a) : 0u));
-#pragma unroll
-            for (int k = 0; k < 4; k++) if (code_kind(o[k].a) != K_VAL) sel[k] = vm_load(x, o[k].a);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                hit[k] = fr_fits64(sel[k]) && fr_lo64(sel[k]) <= (uint64_t)o[k].c;
-                src[k] = x.aux[o[k].b + (hit[k] ? (uint32_t)fr_lo64(sel[k]) : 0u)];
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) r[k] = vm_load_val(V + 4ull * (code_kind(src[k]) == K_VAL ? code_payload(src[k]) : 0u));
-#pragma unroll
-            for (int k = 0; k < 4; k++) { if (!hit[k]) r[k] = fr_zero(); else if (code_kind(src[k]) != K_VAL) r[k] = vm_load(x, src[k]); }
-#pragma unroll
-            for (int k = 0; k < 4; k++) if (live[k]) vm_store_val(U + a.val_base + 4ull * op_dst(o[k]), r[k]);
         }
         // warp ops: Poseidons take the first warps (long), Keccak absorbs the next ones
         for (uint32_t q = L.p_begin + gwarp; q < L.p_end; q += nwarp) poseidon_warp(x, a.poseidons[q], s_pk);

@@ -117,9 +117,7 @@ POB_HD uint32_t pos_step_begin(const PosLayout &L, uint32_t q) {
 //   V[dst + k] = x0 + sum_{i <= k} aux[aux0 + i]      (k < n); lanes own contiguous ranges, totals combined by a warp scan
 struct PsumOp { uint32_t aux0, n, dst; Code x0; };
 
-// thread ops [t_begin, t_end), of which [t_sel, t_end) are the level's SELSUM ops (sorted last; k_eval runs them four at a time so
-// that their three dependent loads -- selector, operand-list entry, value -- overlap); absorbs, Poseidon segments, prefix sums
-struct Level { uint32_t t_begin, t_end, w_begin, w_end, p_begin, p_end, s_begin, s_end, t_sel, pad0, pad1, pad2; };   // 48 bytes: TMA copies 16-byte units
+struct Level { uint32_t t_begin, t_end, w_begin, w_end, p_begin, p_end, s_begin, s_end; };
 
 // ---- expand tiles: a contiguous run of witness entries and where its codes live -------------------------------
 struct Tile { uint64_t dst; uint32_t n, code_off, ubase, pad; };  // BIT codes are relative to ubase; pad = 1: round tile (all BIT)

@@ -21,15 +21,30 @@ struct VmCtx {
     uint32_t *status;       // min over failing constraints of (component base + 1); STATUS_OK if none
 };
 
+// A value slot is 32 bytes, 32-byte aligned (val_base is a multiple of 4 words, the store stride of 32, witness entries are 32 bytes):
+// on the device one 256-bit access per value.  As four 64-bit accesses a warp's 32 values (a contiguous 1 KB run) cost four
+// instructions of 32 half-used sectors each, and the thread-op levels of k_eval were bound by exactly that.
 POB_HD Fr vm_load_val(const uint64_t *p) {
     Fr r;
+#ifdef __CUDA_ARCH__
+    uint64_t v[4];
+    asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p) : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; i++) { r.l[2 * i] = (uint32_t)v[i]; r.l[2 * i + 1] = (uint32_t)(v[i] >> 32); }
+#else
 #pragma unroll
     for (int i = 0; i < 4; i++) { uint64_t v = p[i]; r.l[2 * i] = (uint32_t)v; r.l[2 * i + 1] = (uint32_t)(v >> 32); }
+#endif
     return r;
 }
 POB_HD void vm_store_val(uint64_t *p, const Fr &v) {
+#ifdef __CUDA_ARCH__
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" :: "l"(p), "l"((uint64_t)v.l[0] | ((uint64_t)v.l[1] << 32)), "l"((uint64_t)v.l[2] | ((uint64_t)v.l[3] << 32)),
+                 "l"((uint64_t)v.l[4] | ((uint64_t)v.l[5] << 32)), "l"((uint64_t)v.l[6] | ((uint64_t)v.l[7] << 32)) : "memory");
+#else
 #pragma unroll
     for (int i = 0; i < 4; i++) p[i] = (uint64_t)v.l[2 * i] | ((uint64_t)v.l[2 * i + 1] << 32);
+#endif
 }
 POB_HD Fr vm_load(const VmCtx &x, Code c) {
     uint32_t k = code_kind(c), p = code_payload(c);
