@@ -204,13 +204,16 @@ POB_HD Fr inv_chain_result(const InvChain &c) {                                 
     while (fr_geq_p(pw)) { Fr t; fr_raw_sub(t, pw, fr_p()); pw = t; }               // e = 254, 255 only
     return fr_mont(r, pw);
 }
+// Products are taken with the bare Montgomery product (x * y * R^-1, R = 2^256), never converted: acc_i = acc_{i-1} (*) a_i is
+// a_1..a_i * R^-i, its field inverse I_n = (a_1..a_n)^-1 * R^n, and then I_n (*) acc_{n-1} = a_n^-1 exactly and I_n (*) a_n = I_{n-1}:
+// one product per element on the way up, two on the way down (fr_mul would be twice that).
 POB_HD bool vm_ginv_start(const VmCtx &x, const Op *ops, uint32_t begin, uint32_t end, uint32_t w, uint32_t nw, InvChain &c) {
     Fr acc = fr_from_u64(1); bool any = false;
     for (uint32_t i = begin + w; i < end; i += nw) {
         Fr a = vm_load(x, ops[i].a), d;
         uint64_t *vd = x.U + x.val_base + 4ull * op_dst(ops[i]);
         if (vm_inv_class(x, a, d) == 0) vm_store_val(vd, d);
-        else { vm_store_val(vd, acc); acc = fr_mul(acc, a); any = true; }
+        else { vm_store_val(vd, acc); acc = fr_mont(acc, a); any = true; }
     }
     if (any) inv_chain_init(c, acc);
     return any;                                   // false: nothing left to do for this worker
@@ -223,8 +226,8 @@ POB_HD void vm_ginv_finish(const VmCtx &x, const Op *ops, uint32_t begin, uint32
         if (vm_inv_class(x, a, d) != 0) {
             uint64_t *vd = x.U + x.val_base + 4ull * op_dst(ops[i]);
             Fr pre = vm_load_val(vd);
-            vm_store_val(vd, fr_mul(inv, pre));
-            inv = fr_mul(inv, a);
+            vm_store_val(vd, fr_mont(inv, pre));
+            inv = fr_mont(inv, a);
         }
         if (i < begin + w + nw) break;
     }
