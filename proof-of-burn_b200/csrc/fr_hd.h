@@ -120,11 +120,10 @@ POB_HD Fr fr_sub(const Fr &a, const Fr &b) {
 }
 POB_HD Fr fr_neg(const Fr &a) { if (fr_is_zero(a)) return a; Fr t; fr_raw_sub(t, fr_p(), a); return t; }
 
-// Montgomery product a*b*2^-256 mod p, column-wise (product scanning): the 64 limb products of the 512-bit product are
-// mutually independent (each column keeps a split lo/hi accumulator, so no carry chain links them), and the reduction
-// needs only the 8-step chain m_k = column_k * n0'.  Same number of IMAD.WIDE instructions as the word-serial CIOS
-// form; measured on B200 it is neither faster nor slower inside k_eval (a lone warp is bound by in-order issue, and the
-// 64-register cap spills the limb arrays -- ROADMAP.md).  Result < p (one conditional subtraction; inputs < p).
+// Montgomery product a*b*2^-256 mod p.  Result < p (one conditional subtraction); a < p, b < 2^256.
+// Portable form (host, emulator, `make portable`): column-wise (product scanning) -- the 64 limb products of the 512-bit product
+// are mutually independent (each column keeps a split lo/hi accumulator, so no carry chain links them), and the reduction needs
+// only the 8-step chain m_k = column_k * n0'.  On the device it compiles to 620 instructions (130 IMAD.WIDE + 354 adds).
 #if defined(__CUDA_ARCH__) && !defined(POB_PORTABLE_MONT)
 // Device form: CIOS over two accumulators, E (limb k at weight 2^32k) and O (limb k at weight 2^32(k+1)), so that every 32x32
 // product lands on an aligned limb PAIR: ptxas fuses each `mad(c).lo.cc / madc.hi.cc` pair into one IMAD.WIDE.U32(.X) with

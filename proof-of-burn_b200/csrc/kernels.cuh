@@ -2,12 +2,15 @@
 //
 //   k_eval    one thread-block cluster (1, 2, 4 or 8 CTAs) per proof instance: runs the levelised witness program over the
 //             instance store, levels separated by a cluster barrier.  Thread ops: BN254-Fr FMA / IsZero / inverse / div-mod /
-//             byte packing / constraint checks (vm_exec.h).  Warp ops: one Keccak absorb per warp, state lane l held by
+//             byte packing / constraint checks (vm_exec.h; field arithmetic in fr_hd.h: inline-PTX Montgomery product, carry-chain
+//             add / sub; one 256-bit access per value slot).  Warp ops: one Keccak absorb per warp, state lane l held by
 //             thread l, Theta column parities / D, RhoPi lane walk and Chi neighbours exchanged with warp shuffles; every
 //             intermediate lane word the bit-level circuit exposes (utils/keccak.circom:58-297) is written to the store
-//             (238 words per round).  One Poseidon permutation per warp (state element j in Montgomery form on lane j,
-//             Mix/MixS via shuffles; round constants and MDS matrices staged in shared memory by TMA).  Prefix sums by warp
-//             scan.  IsZero inverse hints batch-inverted at the end (table for small inputs, one inversion per thread).
+//             (238 words per round).  Poseidon permutations, one warp each, cut into POS_SEGMENTS segments over consecutive levels
+//             (state element j in Montgomery form on lane j, Mix/MixS via shuffles; round constants and MDS matrices staged in
+//             shared memory by TMA).  Prefix sums by warp scan.  IsZero inverse hints: table lookups in their level for small
+//             inputs; the ones that need a field inversion are batch-inverted (one inversion per worker thread) by a state machine
+//             that advances INV_STEPS iterations per level.
 //   k_expand_round / k_expand_codes  the HBM-bound kernels: materialise every witness entry as a 32-byte little-endian
 //             field element with one 256-bit store (STG.E.ENL2.256).  Algorithmic bytes = 32 * n_signals per instance
 //             (6.909 GB for main_proof_of_burn).  KeccakfRound blocks (95.8 %) are driven by 8-byte group descriptors

@@ -149,7 +149,7 @@ POB_HD void vm_inv_batch(const VmCtx &x, const Op *ops, uint32_t begin, uint32_t
 // Worker w of nw owns the deferred ops begin + w, + nw, ...  START (the first level at which all inputs are ready): zero /
 // table-sized inputs are answered at once, the others get their prefix product parked in the destination slot (Montgomery's
 // trick) and the worker's total product becomes an inversion in progress.  STEP (every later level): a bounded number of
-// iterations of the inversion, state parked by the caller.  FINISH (after the last level): the products are unwound.
+// iterations of the inversion, state parked by the caller.  FINISH (as soon as the inversion is through, at the latest after the last level): the products are unwound.
 // The inversion itself is Kaliski's "almost inverse" (phase 1 of the Montgomery inverse): per iteration one of four cheap cases
 // on (u, v, r, s) -- halve u, halve v, or subtract-and-halve -- with no modular halving and no inner loops (in SIMT the
 // per-lane `while (even) halve` loops of the textbook binary Euclid run for the maximum over the warp's lanes: measured 5x
