@@ -124,3 +124,27 @@ def test_config5_shapes_program_matches_oracle(layers):
     expr = "ProofOfBurn(%d, 4, 16, 50, 31, 2, 10 ** 19, 10 ** 20)" % layers
     prog = _compare(expr, [synth.to_json(inst, shape)])
     assert prog.stats["n_signals"] == 51277058 + 10289431 * layers
+
+
+def test_inverse_classes_on_valid_inputs():
+    """The layout compiler sorts IsZero's inverse hints into two classes: table-sized inputs (ordinary thread ops of their level, a
+    2 MB table lookup on the GPU) and the ones that need a field inversion (deferred, batch-inverted by the state machine of
+    k_eval).  On valid ProofOfBurn inputs no leveled inverse may miss the table (it would pay an inline inversion inside a level),
+    the deferred ones must start before the last level, and nearly all of them must really need the inversion."""
+    import ctypes, emu
+    from pob_b200 import synth
+    shape = (4, 4, 5, 50, 31, 2, 10 ** 19, 10 ** 20)
+    name, params = oracle.parse_main("ProofOfBurn(4, 4, 5, 50, 31, 2, 10 ** 19, 10 ** 20)")
+    prog = emu.EmuProgram(name, oracle.to_limbs(params), len(params))
+    L = emu.lib()
+    L.pob_emu_inv_miss_count.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    cases = [pob_fixture()] + [synth.to_json(inst, shape) for inst in synth.make_batch(3, shape, seed=11)]
+    for inp in cases:
+        flat = oracle.to_limbs(oracle.flatten_inputs(oracle.schema(name, params), inp))
+        out = np.zeros(8, dtype=np.uint64)
+        L.pob_emu_inv_miss_count(prog.h, flat.ctypes.data, out.ctypes.data)
+        leveled, deferred, leveled_miss, deferred_hit, ginv_level, n_levels = (int(v) for v in out[:6])
+        assert leveled > 1000 and deferred > 100
+        assert leveled_miss == 0
+        assert deferred_hit * 20 < deferred
+        assert ginv_level < n_levels
