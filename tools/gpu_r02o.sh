@@ -1,5 +1,6 @@
 #!/bin/bash
 # round 2, GPU session O: small levels on CTA 0 alone, Poseidon conversion per segment, branch-free inversion steps on every thread
+# (the small-level path and tools/solo_sweep.py were removed after this session: measured slower, profiles/r02o_solo_sweep.log)
 TAG=${1:-r02o}; OUT=gpurun_out; mkdir -p $OUT
 echo "== pytest -m gpu"; timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee $OUT/pytest_gpu_$TAG.log
 echo "== level profile"; timeout 600 python tools/eval_levels.py $OUT 2>&1 | tee $OUT/eval_levels_$TAG.log
